@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Headline benchmark: ResNet-50 KFAC.update images/sec on synthetic ImageNet-shaped batches (BASELINE.json).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 # the reference algorithm on the host CPU
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU, weak scaling
+
+A "step" is one pass of the hot path -- `KFAC.update(batch)` over one recorded batch: for each of the 54
+Conv2d/Linear layers the fused implicit-im2col SYRK for A and the SYRK for G, accumulated into the factor arena.
+`value` times exactly K such steps with the recorded activations / output gradients already resident in HBM
+(10.2 + 10.6 GiB per 256-batch: far larger than the 126 MB L2, so no flush is needed between iterations);
+`e2e` times the user-visible loop of scripts/factors.py:46-61 (pinned host batch -> H2D -> forward -> sampled
+labels -> backward -> update -> loss read back).  With N > 1 every rank processes its own batches and one
+all-reduce of the arena per pass (inside the timed region) merges them; time = max over ranks.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import warnings
+
+import torch
+
+warnings.filterwarnings("ignore", category=FutureWarning)
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ResNet-50 KFAC update images/sec"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="resnet50", choices=["resnet18", "resnet50", "resnet152", "lenet5"])
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 256; 100 for lenet5)")
+    ap.add_argument("--precision", default=os.environ.get("CURVATURE_B200_PRECISION", "fp32"))
+    ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--per-layer", default=None, help="write a per-layer SYRK timing table (JSON) to this path")
+    return ap.parse_args()
+
+
+def make_model(name):
+    torch.manual_seed(0)
+    if name == "lenet5":
+        nn = torch.nn                                 # curvature/lenet5.py:11-24 (architecture)
+        return nn.Sequential(nn.Conv2d(1, 6, 5, padding=2), nn.ReLU(), nn.MaxPool2d(2, 2), nn.Conv2d(6, 16, 5),
+                             nn.ReLU(), nn.MaxPool2d(2, 2), nn.Flatten(), nn.Linear(400, 120), nn.ReLU(),
+                             nn.Linear(120, 84), nn.ReLU(), nn.Linear(84, 10)), (1, 28, 28)
+    import torchvision
+    return getattr(torchvision.models, name)(weights=None), (3, 224, 224)
+
+
+def fisher_step(model, x):
+    """Loop body of scripts/factors.py:51-59: forward, sample labels from the model's own predictive
+    distribution, mean cross-entropy, zero_grad, backward."""
+    logits = model(x)
+    labels = torch.distributions.Categorical(logits=logits.detach()).sample()
+    loss = torch.nn.functional.cross_entropy(logits, labels)
+    model.zero_grad()
+    loss.backward()
+    return loss
+
+
+def algorithmic_flops(kfac):
+    """sum over layers of R*K(K+1) + R*M(M+1) (one multiply-add per unique element of each
+    symmetric factor per contraction row)."""
+    total = 0
+    rows = []
+    for layer, (x, g) in kfac.record.items():
+        bias = layer.bias is not None
+        if layer.__class__.__name__ == "Conv2d":
+            R = g.shape[0] * g.shape[2] * g.shape[3]
+            K = layer.weight[0].numel() + bias
+        else:
+            R = g.shape[0]
+            K = layer.weight.shape[1] + bias
+        M = layer.weight.shape[0]
+        f = R * (K * (K + 1) + M * (M + 1))
+        rows.append((layer, K, M, R, f))
+        total += f
+    return total, rows
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(args, steps, warmup, model_name, batch):
+    """The reference algorithm (oracle port of curvatures.py:312-350; the reference is pure Python + ATen and
+    has no separately compilable kernel) on the host cores: `KFAC.update` on a bounded batch."""
+    import oracle.curvature_oracle as orc
+    model, shape = make_model(model_name)
+    model.train()
+    kfac = orc.KFAC(model)
+    torch.manual_seed(1000)
+    x = torch.randn(batch, *shape)
+    fisher_step(model, x)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        kfac.update(batch)
+        t1 = time.perf_counter()
+        if i >= warmup:
+            times.append(t1 - t0)
+    total = sum(times)
+    return {"value": batch * len(times) / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{model_name} KFAC.update on one {batch}-image 224^2 batch x {len(times)} timed calls "
+                      f"({warmup} warm-up), torch {torch.__version__} CPU, {os.cpu_count()} logical cpus",
+            "ms_per_step": 1e3 * total / len(times)}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    batch = args.batch or (100 if args.model == "lenet5" else 256)
+    workload = {"lenet5": "LeNet-5 KFAC.update, synthetic 28x28 batches of 100 (BASELINE configs[0])",
+                "resnet18": "ResNet-18 KFAC.update, synthetic 224x224 batch 256 (BASELINE configs[2])",
+                "resnet50": "ResNet-50 KFAC.update, synthetic 224x224 batch 256 per GPU (BASELINE metric config)",
+                "resnet152": "ResNet-152 KFAC.update, synthetic 224x224 batch 256 (BASELINE configs[4])"}[args.model]
+    metric = METRIC if args.model == "resnet50" else METRIC.replace("ResNet-50", args.model)
+    config = {"workload": workload, "model": args.model, "batch_per_gpu": batch, "global_batch": batch * world,
+              "image": "3x224x224" if args.model != "lenet5" else "1x28x28", "parallelism": f"dp{world}",
+              "l2": "inputs larger than L2 (recorded activations + gradients >> 126 MB); no flush needed"
+                    if args.model != "lenet5" else "inputs smaller than L2; 256 MB buffer written between iterations"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb_ = batch if args.model == "lenet5" else min(args.cpu_batch, batch)
+        res = cpu_reference_run(args, args.steps, args.warmup, args.model, cb_)
+        line = {"impl": "reference", "metric": metric, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": dict(config, cpu_sample_batch=cb_),
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import curvature_b200 as cb
+    from curvature_b200 import _native as nat
+
+    model, shape = make_model(args.model)
+    model = model.to(dev).train()
+    kfac = cb.KFAC(model, precision=args.precision)
+    torch.manual_seed(1000 + rank)
+    x_host = torch.randn(batch, *shape).pin_memory()
+    x_dev = torch.empty(batch, *shape, device=dev)
+    x_dev.copy_(x_host, non_blocking=True)
+    fisher_step(model, x_dev)            # records activations and output gradients (resident from here on)
+    flops, rows = algorithmic_flops(kfac)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.model == "lenet5" else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- update-only (inputs resident in HBM) ----------------
+    for _ in range(args.warmup):
+        kfac.update(batch)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = nat.launch_calls
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev[0].record()
+    for i in range(args.steps):
+        if flush is not None:
+            flush.fill_(i)
+        ev[1 + 2 * i].record()
+        kfac.update(batch)
+        ev[2 + 2 * i].record()
+    if world > 1:
+        cb.allreduce_arena(kfac)          # the one collective of the estimation pass
+    ev[-1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = nat.launch_calls - launches0
+    clocks = sampler.stop() if sampler else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    update_ms = [ev[1 + 2 * i].elapsed_time(ev[2 + 2 * i]) for i in range(args.steps)]
+    if flush is not None:
+        total_ms = sum(update_ms)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = t.item()
+    value = world * batch * args.steps / (total_ms / 1e3)
+
+    # ---------------- per-layer table (optional, outside the timed region) ----------------
+    if args.per_layer and rank == 0:
+        table = []
+        for layer, K, M, R, f in rows:
+            x, g = kfac.record[layer]
+            xs, gs = x.detach().contiguous(), g.detach().contiguous()
+            first, second = kfac.state[layer]
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            bias = layer.bias is not None
+            ta, tg = [], []
+            for rep in range(4):
+                e[0].record()
+                if layer.__class__.__name__ == "Conv2d":
+                    nat.syrk_conv_accum(xs, layer.kernel_size, layer.stride, layer.padding, bias, 1.0 / R, first,
+                                        kfac.precision)
+                else:
+                    nat.syrk_rows_accum(xs, bias, 1.0 / R, first, kfac.precision)
+                e[1].record()
+                nat.syrk_rows_accum(gs, False, 1.0 / R, second, kfac.precision)
+                e[2].record()
+                torch.cuda.synchronize(dev)
+                if rep:
+                    ta.append(e[0].elapsed_time(e[1]))
+                    tg.append(e[1].elapsed_time(e[2]))
+            a_ms, g_ms = statistics.median(ta), statistics.median(tg)
+            table.append({"layer": str(layer), "K": K, "M": M, "R": R, "A_ms": a_ms, "G_ms": g_ms,
+                          "A_tflops": R * K * (K + 1) / a_ms / 1e9, "G_tflops": R * M * (M + 1) / g_ms / 1e9,
+                          "A_gbs": 4 * x.numel() / a_ms / 1e6, "G_gbs": 4 * g.numel() / g_ms / 1e6})
+        os.makedirs(os.path.dirname(os.path.abspath(args.per_layer)), exist_ok=True)
+        json.dump(table, open(args.per_layer, "w"), indent=1)
+
+    # ---------------- end to end through the public API with host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            x_dev.copy_(x_host, non_blocking=True)
+            loss = fisher_step(model, x_dev)
+            kfac.update(batch)
+            return loss.item()        # device -> host read of the step's result
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        if world > 1:
+            cb.allreduce_arena(kfac)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * batch * args.steps / dt.item(), "unit": UNIT,
+               "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4,
+               "what": "pinned host batch -> H2D -> forward -> sampled labels -> backward -> KFAC.update -> loss.item()"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (1.4 PF sustained bf16"
+    tier = args.precision
+    if tier in ("tf32", "tf32x3", "fp32"):
+        peak, peak_note = bf16 / 2.0, peak_src + " / 2: kind::tf32 issues at half the bf16 rate)"
+    else:
+        peak, peak_note = bf16, peak_src + ")"
+    step_ms = statistics.mean(update_ms)
+    achieved = flops / (step_ms / 1e3) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "crv SYRK family (all launches of one KFAC.update)",
+                "algorithmic_flops_per_step": flops, "peak_source": peak_note, "tier": tier}
+    line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3", "bf16": "bf16"}[tier],
+            "data": "synthetic", "config": config, "roofline": roofline, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "wall_s_timed_region": t_wall, "update_ms_mean": step_ms}
+    if world == 1 and not args.no_cpu_baseline:
+        cb_ = batch if args.model == "lenet5" else min(args.cpu_batch, batch)
+        res = cpu_reference_run(args, 2, 1, args.model, cb_)
+        line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

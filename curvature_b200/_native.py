@@ -1,0 +1,260 @@
+"""ctypes binding of libcurvature_b200.so (the C ABI declared in include/curvature_b200.h).
+
+There is no fallback of any kind: if the shared library is missing this module raises at
+import, and every compute call raises ``RuntimeError`` with the library's own message when the
+kernel launch fails (e.g. no CUDA device).  torch is used only for device memory and streams.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcurvature_b200.so")
+
+PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_BF16 = 0, 1, 2, 3
+PRECISION_NAMES = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16}
+OP_SYRK_CONV, OP_SYRK_ROWS, OP_EFB_PROJECT, OP_CHOL_INV, OP_SAMPLE_MN = range(5)
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -m curvature_b200.build` "
+        "(nvcc, sm_100a).  curvature_b200 has no CPU or PyTorch fallback.")
+
+_lib = ctypes.CDLL(LIB_PATH)
+
+_f32p = c_void_p  # device pointers travel as integers
+
+
+def _sig(name, restype, *argtypes):
+    fn = getattr(_lib, name)
+    fn.restype = restype
+    fn.argtypes = list(argtypes)
+    return fn
+
+
+_abi_version = _sig("crv_abi_version", c_int)
+_last_error = _sig("crv_last_error", c_char_p)
+_sm_count = _sig("crv_device_sm_count", c_int)
+_workspace_bytes = _sig("crv_workspace_bytes", c_size_t, c_int, POINTER(c_int64), c_int)
+_syrk_conv = _sig("crv_syrk_conv_accum", c_int, _f32p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                  c_int, c_int, c_int, c_float, _f32p, c_void_p, c_size_t, c_int, c_void_p)
+_syrk_rows = _sig("crv_syrk_rows_accum", c_int, _f32p, c_int, c_int, c_int, c_int, c_float, _f32p, c_void_p,
+                  c_size_t, c_int, c_void_p)
+_diag_accum = _sig("crv_diag_accum", c_int, _f32p, _f32p, c_int, c_int, c_float, _f32p, _f32p, c_void_p)
+_efb_project = _sig("crv_efb_project_accum", c_int, _f32p, _f32p, _f32p, c_int, c_int, _f32p, c_void_p,
+                    c_size_t, c_int, c_void_p)
+_chol_inv = _sig("crv_chol_inv_batched", c_int, POINTER(c_void_p), POINTER(c_int), c_int, POINTER(c_float),
+                 POINTER(c_float), POINTER(c_void_p), c_void_p, c_void_p, c_size_t, c_void_p)
+_sample_mn = _sig("crv_sample_matrix_normal", c_int, _f32p, _f32p, _f32p, _f32p, c_int, c_int, c_int, _f32p,
+                  _f32p, _f32p, _f32p, _f32p, c_void_p, c_size_t, c_int, c_void_p)
+_inv_sqrt = _sig("crv_elementwise_inv_sqrt", c_int, _f32p, c_float, c_float, _f32p, c_size_t, c_void_p)
+_diag_sample = _sig("crv_diag_sample", c_int, _f32p, _f32p, c_int, c_int, c_int, _f32p, _f32p, _f32p, _f32p,
+                    _f32p, c_void_p)
+_gemm = _sig("crv_gemm", c_int, _f32p, c_int, c_int, _f32p, c_int, c_int, _f32p, c_int, c_int, c_int, c_int,
+             c_float, c_float, c_int, c_void_p)
+
+ABI_VERSION = _abi_version()
+EXPORTED_SYMBOLS = (
+    "crv_abi_version", "crv_last_error", "crv_device_sm_count", "crv_workspace_bytes",
+    "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_diag_accum", "crv_efb_project_accum",
+    "crv_chol_inv_batched", "crv_sample_matrix_normal", "crv_elementwise_inv_sqrt", "crv_diag_sample",
+    "crv_gemm")
+
+# counts kernel-launching C-ABI calls (bench.py reports launches from it)
+launch_calls = 0
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"curvature_b200::{what} failed: {_last_error().decode(errors='replace')}")
+
+
+def _dev(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"curvature_b200: {what} must live on a CUDA device "
+                           "(there is no CPU fallback; the CUDA kernels are the only implementation)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"curvature_b200: {what} must be float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"curvature_b200: {what} must be contiguous")
+    return t.data_ptr()
+
+
+def _opt(t, what):
+    return None if t is None else _dev(t, what)
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def default_precision():
+    name = os.environ.get("CURVATURE_B200_PRECISION", "fp32").lower()
+    if name not in PRECISION_NAMES:
+        raise ValueError(f"CURVATURE_B200_PRECISION={name!r}; expected one of {sorted(PRECISION_NAMES)}")
+    return PRECISION_NAMES[name]
+
+
+def resolve_precision(p):
+    if p is None:
+        return default_precision()
+    if isinstance(p, str):
+        return PRECISION_NAMES[p.lower()]
+    return int(p)
+
+
+_workspaces = {}
+
+
+def workspace(nbytes, device):
+    """Grow-only scratch buffer per device (kernels never allocate)."""
+    nbytes = max(int(nbytes), 256)
+    buf = _workspaces.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[device] = buf
+    return buf
+
+
+def workspace_bytes(op, dims):
+    arr = (c_int64 * len(dims))(*[int(d) for d in dims])
+    return _workspace_bytes(op, arr, len(dims))
+
+
+def sm_count():
+    return _sm_count()
+
+
+def syrk_conv_accum(x, kernel_size, stride, padding, has_bias, alpha, out, precision=PREC_FP32):
+    """out (K,K) += alpha * unfold(x) unfold(x)^T  with the optional ones row (K1a)."""
+    global launch_calls
+    N, C, H, W = x.shape
+    kh, kw = kernel_size
+    sh, sw = stride
+    ph, pw = padding
+    K = C * kh * kw + int(bool(has_bias))
+    if tuple(out.shape) != (K, K):
+        raise ValueError(f"factor has shape {tuple(out.shape)}, expected {(K, K)}")
+    nb = workspace_bytes(OP_SYRK_CONV, [N, C, H, W, kh, kw, sh, sw, ph, pw, int(bool(has_bias)), precision])
+    ws = workspace(nb, x.device)
+    launch_calls += 1
+    _check(_syrk_conv(_dev(x, "activation"), N, C, H, W, kh, kw, sh, sw, ph, pw, int(bool(has_bias)),
+                      float(alpha), _dev(out, "factor"), ws.data_ptr(), ws.numel(), precision, _stream(x)),
+           "crv_syrk_conv_accum")
+
+
+def syrk_rows_accum(g, has_bias, alpha, out, precision=PREC_FP32):
+    """out (D,D) += alpha * sum_{n,l} g[n,:,l] g[n,:,l]^T for g viewed as (N, M, L) (K1b)."""
+    global launch_calls
+    N, M = g.shape[0], g.shape[1]
+    L = 1
+    for s in g.shape[2:]:
+        L *= s
+    D = M + int(bool(has_bias))
+    if tuple(out.shape) != (D, D):
+        raise ValueError(f"factor has shape {tuple(out.shape)}, expected {(D, D)}")
+    nb = workspace_bytes(OP_SYRK_ROWS, [N, M, L, int(bool(has_bias)), precision])
+    ws = workspace(nb, g.device)
+    launch_calls += 1
+    _check(_syrk_rows(_dev(g, "operand"), N, M, L, int(bool(has_bias)), float(alpha), _dev(out, "factor"),
+                      ws.data_ptr(), ws.numel(), precision, _stream(g)), "crv_syrk_rows_accum")
+
+
+def diag_accum(wgrad, bgrad, scale, state=None, grads_out=None):
+    """state (M,K) += scale * [wgrad | bgrad]^2; optionally also emit the concatenated grads (K2)."""
+    global launch_calls
+    M = wgrad.shape[0]
+    K0 = wgrad.numel() // M
+    launch_calls += 1
+    _check(_diag_accum(_dev(wgrad, "weight.grad"), _opt(bgrad, "bias.grad"), M, K0, float(scale),
+                       _opt(state, "state"), _opt(grads_out, "grads_out"), _stream(wgrad)), "crv_diag_accum")
+
+
+def efb_project_accum(QG, QA, G, lambdas, precision=PREC_FP32):
+    """lambdas (M,K) += (QG^T G QA)^2 (K3)."""
+    global launch_calls
+    M, K = G.shape
+    ws = workspace(workspace_bytes(OP_EFB_PROJECT, [M, K]), G.device)
+    launch_calls += 2
+    _check(_efb_project(_dev(QG, "QG"), _dev(QA, "QA"), _dev(G, "grads"), M, K, _dev(lambdas, "lambdas"),
+                        ws.data_ptr(), ws.numel(), precision, _stream(G)), "crv_efb_project_accum")
+
+
+def chol_inv_batched(factors, adds, muls, outs):
+    """outs[i] = chol_lower(inv(sym(sqrt(mul_i) F_i + sqrt(add_i) I)))  (K4).  Returns the device
+    int32 info tensor (0 = ok)."""
+    global launch_calls
+    count = len(factors)
+    dev = factors[0].device
+    dims = [int(f.shape[0]) for f in factors]
+    for f, o in zip(factors, outs):
+        if f.shape[0] != f.shape[1] or tuple(o.shape) != tuple(f.shape):
+            raise ValueError("factors must be square and outputs must match them")
+    Fp = (c_void_p * count)(*[_dev(f, "factor") for f in factors])
+    Lp = (c_void_p * count)(*[_dev(o, "output") for o in outs])
+    dm = (c_int * count)(*dims)
+    ad = (c_float * count)(*[float(a) for a in adds])
+    mu = (c_float * count)(*[float(m) for m in muls])
+    info = torch.empty(count, dtype=torch.int32, device=dev)
+    ws = workspace(workspace_bytes(OP_CHOL_INV, [count] + dims), dev)
+    launch_calls += 4 + 3 * ((max(dims) + 31) // 32)
+    _check(_chol_inv(Fp, dm, count, ad, mu, Lp, info.data_ptr(), ws.data_ptr(), ws.numel(),
+                     torch.cuda.current_stream(dev).cuda_stream), "crv_chol_inv_batched")
+    return info
+
+
+def sample_matrix_normal(LG, LA, z, has_bias, row_scale=None, mu_w=None, mu_b=None, w_out=None, b_out=None,
+                         s_out=None, precision=PREC_FP32):
+    """S = LG z^T LA^T, optionally written as mean + S into weight / bias (K5)."""
+    global launch_calls
+    M = LG.shape[0]
+    K = LA.shape[0]
+    K0 = K - int(bool(has_bias))
+    if tuple(z.shape) != (K, M):
+        raise ValueError(f"noise has shape {tuple(z.shape)}, expected {(K, M)}")
+    ws = workspace(workspace_bytes(OP_SAMPLE_MN, [M, K]), LG.device)
+    launch_calls += 2 + int(row_scale is not None)
+    _check(_sample_mn(_dev(LG, "LG"), _dev(LA, "LA"), _dev(z, "noise"), _opt(row_scale, "row_scale"), M, K0,
+                      int(bool(has_bias)), _opt(mu_w, "mu_w"), _opt(mu_b, "mu_b"), _opt(w_out, "weight"),
+                      _opt(b_out, "bias"), _opt(s_out, "sample"), ws.data_ptr(), ws.numel(), precision,
+                      _stream(LG)), "crv_sample_matrix_normal")
+
+
+def elementwise_inv_sqrt(v, add, mul, out):
+    global launch_calls
+    launch_calls += 1
+    _check(_inv_sqrt(_dev(v, "value"), float(add), float(mul), _dev(out, "out"), v.numel(), _stream(v)),
+           "crv_elementwise_inv_sqrt")
+
+
+def diag_sample(z, inv, has_bias, mu_w=None, mu_b=None, w_out=None, b_out=None, s_out=None):
+    global launch_calls
+    M, K = inv.shape
+    K0 = K - int(bool(has_bias))
+    launch_calls += 1
+    _check(_diag_sample(_dev(z, "noise"), _dev(inv, "inv_state"), M, K0, int(bool(has_bias)),
+                        _opt(mu_w, "mu_w"), _opt(mu_b, "mu_b"), _opt(w_out, "weight"), _opt(b_out, "bias"),
+                        _opt(s_out, "sample"), _stream(z)), "crv_diag_sample")
+
+
+def gemm(A, B, transA=False, transB=False, alpha=1.0, beta=0.0, out=None, precision=PREC_FP32):
+    """Row-major C = alpha op(A) op(B) + beta C through the library's own GEMM kernel."""
+    global launch_calls
+    m = A.shape[1] if transA else A.shape[0]
+    k = A.shape[0] if transA else A.shape[1]
+    kb = B.shape[1] if transB else B.shape[0]
+    n = B.shape[0] if transB else B.shape[1]
+    if k != kb:
+        raise ValueError(f"inner dimensions differ: {k} vs {kb}")
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=A.device)
+    if m == 0 or n == 0:
+        return out
+    if k == 0:
+        return out.zero_() if beta == 0.0 else out.mul_(beta)
+    launch_calls += 1
+    _check(_gemm(_dev(A, "A"), A.shape[1], int(transA), _dev(B, "B"), B.shape[1], int(transB), _dev(out, "C"),
+                 out.shape[1], m, n, k, float(alpha), float(beta), precision, _stream(A)), "crv_gemm")
+    return out

@@ -1,0 +1,179 @@
+// extern "C" boundary of libcurvature_b200.so (see include/curvature_b200.h).
+#include "../../include/curvature_b200.h"
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace crv {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int device_sm_count() {
+  static thread_local int cached_dev = -1, cached_sms = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (dev != cached_dev) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    cached_dev = dev;
+    cached_sms = sms;
+  }
+  return cached_sms;
+}
+
+static int syrk_dispatch(const ConvGeom& g, float alpha, float* F, void* ws, size_t ws_bytes, int precision,
+                         cudaStream_t s) {
+  if (precision == CRV_PREC_FP32) return syrk_simt_launch(g, alpha, F, s);
+  if (precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32X3 || precision == CRV_PREC_BF16)
+    return syrk_tc_launch(g, alpha, F, precision, ws, ws_bytes, s);
+  set_error("unknown precision tier %d", precision);
+  return 1;
+}
+
+}  // namespace crv
+
+using namespace crv;
+
+extern "C" {
+
+int crv_abi_version(void) { return CRV_ABI_VERSION; }
+const char* crv_last_error(void) { return last_error(); }
+int crv_device_sm_count(void) { return device_sm_count(); }
+
+size_t crv_workspace_bytes(int op, const int64_t* dims, int ndims) {
+  switch (op) {
+    case CRV_OP_SYRK_CONV: {
+      if (ndims < 12) return 0;
+      ConvGeom g;
+      static const float dummy = 0.f;
+      if (make_geom(g, &dummy, (int)dims[0], (int)dims[1], (int)dims[2], (int)dims[3], (int)dims[4],
+                    (int)dims[5], (int)dims[6], (int)dims[7], (int)dims[8], (int)dims[9], (int)dims[10]))
+        return 0;
+      return dims[11] == CRV_PREC_FP32 ? 0 : syrk_tc_workspace(g, (int)dims[11]);
+    }
+    case CRV_OP_SYRK_ROWS: {
+      if (ndims < 5) return 0;
+      ConvGeom g;
+      static const float dummy = 0.f;
+      if (make_geom(g, &dummy, (int)dims[0], (int)dims[1], 1, (int)dims[2], 1, 1, 1, 1, 0, 0, (int)dims[3]))
+        return 0;
+      return dims[4] == CRV_PREC_FP32 ? 0 : syrk_tc_workspace(g, (int)dims[4]);
+    }
+    case CRV_OP_EFB_PROJECT:
+    case CRV_OP_SAMPLE_MN:
+      if (ndims < 2) return 0;
+      return (size_t)dims[0] * (size_t)dims[1] * sizeof(float) * (op == CRV_OP_SAMPLE_MN ? 2 : 1);
+    case CRV_OP_CHOL_INV: {
+      if (ndims < 1 || ndims < 1 + dims[0]) return 0;
+      const int count = (int)dims[0];
+      int* d = new int[count];
+      for (int i = 0; i < count; ++i) d[i] = (int)dims[1 + i];
+      const size_t b = chol_workspace(d, count);
+      delete[] d;
+      return b;
+    }
+    default:
+      return 0;
+  }
+}
+
+int crv_syrk_conv_accum(const float* x, int N, int C, int H, int W, int kh, int kw, int sh, int sw, int ph,
+                        int pw, int has_bias, float alpha, float* A, void* ws, size_t ws_bytes,
+                        int precision, crv_stream_t stream) {
+  ConvGeom g;
+  if (int rc = make_geom(g, x, N, C, H, W, kh, kw, sh, sw, ph, pw, has_bias)) return rc;
+  return syrk_dispatch(g, alpha, A, ws, ws_bytes, precision, (cudaStream_t)stream);
+}
+
+int crv_syrk_rows_accum(const float* gptr, int N, int M, int L, int has_bias, float alpha, float* F,
+                        void* ws, size_t ws_bytes, int precision, crv_stream_t stream) {
+  ConvGeom g;
+  if (int rc = make_geom(g, gptr, N, M, 1, L, 1, 1, 1, 1, 0, 0, has_bias)) return rc;
+  return syrk_dispatch(g, alpha, F, ws, ws_bytes, precision, (cudaStream_t)stream);
+}
+
+int crv_diag_accum(const float* wgrad, const float* bgrad, int M, int K0, float scale, float* state,
+                   float* grads_out, crv_stream_t stream) {
+  return diag_accum_launch(wgrad, bgrad, M, K0, scale, state, grads_out, (cudaStream_t)stream);
+}
+
+int crv_gemm(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc,
+             int m, int n, int k, float alpha, float beta, int precision, crv_stream_t stream) {
+  CRV_CHECK(precision == CRV_PREC_FP32, "crv_gemm: only the fp32 tier is built");
+  // op(A)(i,kk): A[i*lda + kk] or, transposed, A[kk*lda + i]
+  const long long sa_m = transA ? 1 : lda, sa_k = transA ? lda : 1;
+  const long long sb_k = transB ? 1 : ldb, sb_n = transB ? ldb : 1;
+  return gemm_simt_launch(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, m, n, k, alpha, beta, EPI_STORE, nullptr,
+                          (cudaStream_t)stream);
+}
+
+int crv_efb_project_accum(const float* QG, const float* QA, const float* G, int M, int K, float* lambdas,
+                          void* ws, size_t ws_bytes, int precision, crv_stream_t stream) {
+  CRV_CHECK(precision == CRV_PREC_FP32, "crv_efb_project_accum: only the fp32 tier is built");
+  CRV_CHECK(QG && QA && G && lambdas, "null pointer");
+  CRV_CHECK(ws && ws_bytes >= (size_t)M * K * sizeof(float), "workspace too small");
+  float* T = (float*)ws;
+  // T = QG^T * G        (M x M)^T (M x K)
+  if (int rc = gemm_simt_launch(QG, 1, M, G, K, 1, T, K, M, K, M, 1.f, 0.f, EPI_STORE, nullptr,
+                                (cudaStream_t)stream))
+    return rc;
+  // lambdas += (T * QA)^2   (M x K)(K x K)
+  return gemm_simt_launch(T, K, 1, QA, K, 1, lambdas, K, M, K, K, 1.f, 0.f, EPI_SQUARE_ACCUM, nullptr,
+                          (cudaStream_t)stream);
+}
+
+int crv_chol_inv_batched(const float* const* F, const int* dims, int count, const float* add,
+                         const float* mul, float* const* L_out, int* info, void* ws, size_t ws_bytes,
+                         crv_stream_t stream) {
+  return chol_inv_batched_launch(F, dims, count, add, mul, L_out, info, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int crv_sample_matrix_normal(const float* LG, const float* LA, const float* z, const float* row_scale, int M,
+                             int K0, int has_bias, const float* mu_w, const float* mu_b, float* w_out,
+                             float* b_out, float* s_out, void* ws, size_t ws_bytes, int precision,
+                             crv_stream_t stream) {
+  CRV_CHECK(precision == CRV_PREC_FP32, "crv_sample_matrix_normal: only the fp32 tier is built");
+  CRV_CHECK(LG && LA && z, "null pointer");
+  CRV_CHECK(M > 0 && K0 > 0, "bad shape");
+  CRV_CHECK(!w_out || mu_w, "w_out needs mu_w");
+  CRV_CHECK(!b_out || mu_b, "b_out needs mu_b");
+  const int K = K0 + (has_bias ? 1 : 0);
+  const size_t mk = (size_t)M * K;
+  CRV_CHECK(ws && ws_bytes >= mk * sizeof(float) * (row_scale ? 2 : 1), "workspace too small");
+  float* T = (float*)ws;
+  const float* zz = z;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (row_scale) {
+    float* Z2 = T + mk;
+    if (int rc = scale_transpose_launch(z, row_scale, K, M, Z2, s)) return rc;
+    zz = Z2;
+  }
+  // T = LG * z^T : A = LG (M x M), B(kk, n) = z[n, kk]  -> sb_k = 1, sb_n = M
+  if (int rc = gemm_simt_launch(LG, M, 1, zz, 1, M, T, K, M, K, M, 1.f, 0.f, EPI_STORE, nullptr, s)) return rc;
+  // S = T * LA^T : B(kk, n) = LA[n, kk] -> sb_k = 1, sb_n = K
+  SampleEpilogue se;
+  se.mu_w = mu_w; se.mu_b = mu_b; se.w_out = w_out; se.b_out = b_out; se.s_out = s_out;
+  se.K0 = K0; se.has_bias = has_bias ? 1 : 0;
+  return gemm_simt_launch(T, K, 1, LA, 1, K, nullptr, K, M, K, K, 1.f, 0.f, 2, &se, s);
+}
+
+int crv_elementwise_inv_sqrt(const float* v, float add, float mul, float* out, size_t n, crv_stream_t stream) {
+  return inv_sqrt_launch(v, add, mul, out, n, (cudaStream_t)stream);
+}
+
+int crv_diag_sample(const float* z, const float* inv, int M, int K0, int has_bias, const float* mu_w,
+                    const float* mu_b, float* w_out, float* b_out, float* s_out, crv_stream_t stream) {
+  return diag_sample_launch(z, inv, M, K0, has_bias, mu_w, mu_b, w_out, b_out, s_out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+// K4: batched damped "Cholesky of the inverse" (KFAC.invert, curvature/curvatures.py:368-379).
+//
+// The reference computes L = chol_lower(inverse(reg)) with reg = sym(sqrt(s) F + sqrt(n) I).
+// That L is reproduced WITHOUT forming an inverse and without an LU:
+//     P = J reg J  (J = exchange matrix),   P = C C^T  (lower Cholesky),
+//     reg = (J C J)(J C J)^T = U U^T with U upper  =>  reg^{-1} = U^{-T} U^{-1},
+// and U^{-T} is lower triangular with a positive diagonal, i.e. it is THE Cholesky factor of
+// reg^{-1}:  L = U^{-T} = J C^{-T} J,  L[i][j] = Cinv[D-1-j][D-1-i].
+// (C^{-T} alone -- the obvious "invert the Cholesky factor" -- is an upper factor of the same
+// covariance and gives different samples for the same noise)
+//
+// Blocked right-looking factorisation with 32-wide panels (diagonal blocks factored and inverted
+// in fp64 in shared memory, panel solves and trailing updates in fp32 FMA), followed by a
+// column-parallel blocked triangular inversion.  All matrices of a call advance together:
+// gridDim.z indexes the matrix, CTAs of finished / smaller matrices exit at once.
+#include "common.cuh"
+#include <math.h>
+
+namespace crv {
+namespace {
+
+constexpr int NB = 32;
+
+struct MatDesc {
+  const float* F;   // input factor (D x D)
+  float* W;         // workspace: flipped damped matrix -> its lower Cholesky factor C
+  float* X;         // workspace: inverse of C (lower part)
+  float* Dinv;      // workspace: nb inverted diagonal blocks, 32 x 32 each
+  float* L;         // output
+  int D, nb;
+  float sqrt_mul, sqrt_add;
+};
+
+// ---- prologue: W = J * sym(sqrt(s) F + sqrt(n) I) * J -----------------------------------------
+__global__ void __launch_bounds__(256) chol_prologue_kernel(const MatDesc* __restrict__ descs) {
+  const MatDesc d = descs[blockIdx.z];
+  const size_t total = (size_t)d.D * d.D;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const int i = (int)(e / d.D), j = (int)(e - (size_t)i * d.D);
+    const int a = d.D - 1 - i, b = d.D - 1 - j;
+    // same rounding sequence as the reference: (s*F + diag) then (reg + reg^T) / 2
+    float rab = __fmul_rn(d.sqrt_mul, __ldg(d.F + (size_t)a * d.D + b));
+    float rba = __fmul_rn(d.sqrt_mul, __ldg(d.F + (size_t)b * d.D + a));
+    if (a == b) { rab = __fadd_rn(rab, d.sqrt_add); rba = __fadd_rn(rba, d.sqrt_add); }
+    d.W[e] = __fadd_rn(rab, rba) / 2.0f;
+  }
+}
+
+// ---- step 1: factor + invert the diagonal block of panel j (fp64 in smem) ----------------------
+__global__ void __launch_bounds__(256) chol_potf2_kernel(const MatDesc* __restrict__ descs, int j, int* info) {
+  const MatDesc d = descs[blockIdx.x];
+  if (j >= d.nb) return;
+  __shared__ double S[NB][NB + 1];
+  __shared__ double Iv[NB][NB + 1];
+  __shared__ int bad;
+  const int o = j * NB;
+  const int bs = min(NB, d.D - o);
+  const int t = threadIdx.x;
+  if (t == 0) bad = 0;
+  for (int e = t; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    double v = 0.0;
+    if (r < bs && c < bs && c <= r) v = (double)d.W[(size_t)(o + r) * d.D + o + c];
+    if (r >= bs && r == c) v = 1.0;   // pad to a full 32x32 block with the identity
+    S[r][c] = v;
+  }
+  __syncthreads();
+  for (int c = 0; c < NB; ++c) {
+    if (t == 0) {
+      const double p = S[c][c];
+      if (!(p > 0.0)) { if (!bad) bad = o + c + 1; }
+      S[c][c] = sqrt(p);
+    }
+    __syncthreads();
+    const double piv = S[c][c];
+    if (t > c && t < NB) S[t][c] /= piv;
+    __syncthreads();
+    // trailing update of the block: rows r > c, columns c < cc <= r
+    for (int e = t; e < NB * NB; e += 256) {
+      const int r = e / NB, cc = e % NB;
+      if (r > c && cc > c && cc <= r) S[r][cc] -= S[r][c] * S[cc][c];
+    }
+    __syncthreads();
+  }
+  // inverse of the lower-triangular block, one column per thread (forward substitution)
+  if (t < NB) {
+    const int c = t;
+    for (int r = 0; r < NB; ++r) {
+      double acc = (r == c) ? 1.0 : 0.0;
+      if (r < c) { Iv[r][c] = 0.0; continue; }
+      for (int k = c; k < r; ++k) acc -= S[r][k] * Iv[k][c];
+      Iv[r][c] = acc / S[r][r];
+    }
+  }
+  __syncthreads();
+  for (int e = t; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    if (r < bs && c < bs) d.W[(size_t)(o + r) * d.D + o + c] = (c <= r) ? (float)S[r][c] : 0.f;
+    d.Dinv[(size_t)j * NB * NB + e] = (float)Iv[r][c];
+  }
+  if (t == 0 && bad && info[blockIdx.x] == 0) info[blockIdx.x] = bad;
+}
+
+// ---- step 2: panel solve  W[ib][j] <- W[ib][j] * inv(C_jj)^T  for ib > j -----------------------
+__global__ void __launch_bounds__(256) chol_trsm_kernel(const MatDesc* __restrict__ descs, int j) {
+  const MatDesc d = descs[blockIdx.z];
+  const int ib = j + 1 + blockIdx.x;
+  if (ib >= d.nb) return;
+  __shared__ float Ab[NB][NB + 1];
+  __shared__ float Iv[NB][NB + 1];
+  const int t = threadIdx.x;
+  const int ro = ib * NB, co = j * NB;
+  for (int e = t; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    Ab[r][c] = (ro + r < d.D && co + c < d.D) ? d.W[(size_t)(ro + r) * d.D + co + c] : 0.f;
+    Iv[r][c] = d.Dinv[(size_t)j * NB * NB + e];
+  }
+  __syncthreads();
+  for (int e = t; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < NB; ++k) acc = fmaf(Ab[r][k], Iv[c][k], acc);
+    if (ro + r < d.D && co + c < d.D) d.W[(size_t)(ro + r) * d.D + co + c] = acc;
+  }
+}
+
+// ---- step 3: trailing update  W[I][K] -= C[I][j] * C[K][j]^T  on 64x64 tiles, I >= K -----------
+__global__ void __launch_bounds__(256) chol_update_kernel(const MatDesc* __restrict__ descs, int j) {
+  const MatDesc d = descs[blockIdx.z];
+  const int start = (j + 1) * NB;          // first trailing row/col
+  if (start >= d.D) return;
+  const int nt = (d.D - start + 63) / 64;  // 64-wide tiles in the trailing matrix
+  const int p = blockIdx.x;
+  if (p >= nt * (nt + 1) / 2) return;
+  int ti = (int)((sqrtf(8.f * (float)p + 1.f) - 1.f) * 0.5f);
+  while (ti * (ti + 1) / 2 > p) --ti;
+  while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
+  const int tj = p - ti * (ti + 1) / 2;
+  __shared__ __align__(16) float Ps[NB][68];   // Ps[k][row]  panel rows of tile ti
+  __shared__ __align__(16) float Qs[NB][68];   // Qs[k][row]  panel rows of tile tj
+  const int t = threadIdx.x;
+  const int r0 = start + ti * 64, c0 = start + tj * 64, ko = j * NB;
+  for (int e = t; e < 64 * NB; e += 256) {
+    const int r = e / NB, k = e % NB;   // lanes along k: contiguous 128-byte panel rows
+    Ps[k][r] = (r0 + r < d.D) ? d.W[(size_t)(r0 + r) * d.D + ko + k] : 0.f;
+    Qs[k][r] = (c0 + r < d.D) ? d.W[(size_t)(c0 + r) * d.D + ko + k] : 0.f;
+  }
+  __syncthreads();
+  const int ty = t >> 4, tx = t & 15;
+  float acc[4][4] = {};
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    const float4 a4 = *reinterpret_cast<const float4*>(&Ps[k][ty * 4]);
+    const float4 b4 = *reinterpret_cast<const float4*>(&Qs[k][tx * 4]);
+    const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+    const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(a[i], b[jj], acc[i][jj]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty * 4 + i;
+    if (r >= d.D) continue;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int c = c0 + tx * 4 + jj;
+      if (c < d.D && c <= r) d.W[(size_t)r * d.D + c] -= acc[i][jj];
+    }
+  }
+}
+
+// ---- triangular inverse X = C^{-1}: one CTA per 16-column strip, forward over block rows ------
+constexpr int CW = 16;
+__global__ void __launch_bounds__(256) chol_trtri_kernel(const MatDesc* __restrict__ descs) {
+  const MatDesc d = descs[blockIdx.z];
+  const int c0 = blockIdx.x * CW;
+  if (c0 >= d.D) return;
+  __shared__ float Cb[NB][NB + 1];
+  __shared__ float Xb[NB][CW + 1];
+  __shared__ float Tb[NB][CW + 1];
+  const int t = threadIdx.x;
+  const int ib0 = c0 / NB;
+  // each thread owns two accumulators of the (32 x 16) strip block: (r, c) and (r + 16, c)
+  const int r1 = t / CW, cc = t % CW;   // r1 in 0..15
+  for (int i = ib0; i < d.nb; ++i) {
+    float acc0 = 0.f, acc1 = 0.f;
+    for (int k = ib0; k < i; ++k) {
+      for (int e = t; e < NB * NB; e += 256) {
+        const int r = e / NB, c = e % NB;
+        Cb[r][c] = (i * NB + r < d.D && k * NB + c < d.D) ? d.W[(size_t)(i * NB + r) * d.D + k * NB + c] : 0.f;
+      }
+      for (int e = t; e < NB * CW; e += 256) {
+        const int r = e / CW, c = e % CW;
+        Xb[r][c] = (k * NB + r < d.D && c0 + c < d.D) ? d.X[(size_t)(k * NB + r) * d.D + c0 + c] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int q = 0; q < NB; ++q) {
+        const float xv = Xb[q][cc];
+        acc0 = fmaf(Cb[r1][q], xv, acc0);
+        acc1 = fmaf(Cb[r1 + 16][q], xv, acc1);
+      }
+      __syncthreads();
+    }
+    // T = E_i - acc, then X_i = inv(C_ii) * T
+    Tb[r1][cc] = ((i * NB + r1) == (c0 + cc) ? 1.f : 0.f) - acc0;
+    Tb[r1 + 16][cc] = ((i * NB + r1 + 16) == (c0 + cc) ? 1.f : 0.f) - acc1;
+    for (int e = t; e < NB * NB; e += 256) Cb[e / NB][e % NB] = d.Dinv[(size_t)i * NB * NB + e];
+    __syncthreads();
+    float x0 = 0.f, x1 = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < NB; ++q) {
+      const float tv = Tb[q][cc];
+      x0 = fmaf(Cb[r1][q], tv, x0);
+      x1 = fmaf(Cb[r1 + 16][q], tv, x1);
+    }
+    if (c0 + cc < d.D) {
+      if (i * NB + r1 < d.D) d.X[(size_t)(i * NB + r1) * d.D + c0 + cc] = x0;
+      if (i * NB + r1 + 16 < d.D) d.X[(size_t)(i * NB + r1 + 16) * d.D + c0 + cc] = x1;
+    }
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
+// ---- epilogue: L[i][j] = X[D-1-j][D-1-i] for j <= i, 0 above the diagonal ----------------------
+__global__ void __launch_bounds__(256) chol_epilogue_kernel(const MatDesc* __restrict__ descs) {
+  const MatDesc d = descs[blockIdx.z];
+  const size_t total = (size_t)d.D * d.D;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const int i = (int)(e / d.D), j = (int)(e - (size_t)i * d.D);
+    d.L[e] = (j <= i) ? d.X[(size_t)(d.D - 1 - j) * d.D + (d.D - 1 - i)] : 0.f;
+  }
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+size_t chol_workspace(const int* dims, int count) {
+  size_t bytes = align_up(sizeof(MatDesc) * (size_t)count, 256);
+  for (int i = 0; i < count; ++i) {
+    const size_t D = (size_t)dims[i];
+    const size_t nb = (D + NB - 1) / NB;
+    bytes += align_up(D * D * 4, 256) * 2 + align_up(nb * NB * NB * 4, 256);
+  }
+  return bytes;
+}
+
+int chol_inv_batched_launch(const float* const* F, const int* dims, int count, const float* add,
+                            const float* mul, float* const* L_out, int* info, void* ws, size_t ws_bytes,
+                            cudaStream_t s) {
+  CRV_CHECK(count > 0, "empty batch");
+  CRV_CHECK(F && dims && add && mul && L_out && info && ws, "null pointer");
+  CRV_CHECK(count <= 65535, "too many matrices in one call");
+  CRV_CHECK(ws_bytes >= chol_workspace(dims, count), "workspace too small: %zu < %zu", ws_bytes,
+            chol_workspace(dims, count));
+  MatDesc* host = new MatDesc[count];
+  char* base = (char*)ws;
+  size_t off = align_up(sizeof(MatDesc) * (size_t)count, 256);
+  int maxD = 0;
+  for (int i = 0; i < count; ++i) {
+    const size_t D = (size_t)dims[i];
+    if (dims[i] <= 0 || !F[i] || !L_out[i] || !(mul[i] >= 0.f) || !(add[i] >= 0.f)) {
+      delete[] host;
+      set_error("bad matrix %d: D=%d add=%g mul=%g", i, dims[i], (double)add[i], (double)mul[i]);
+      return 1;
+    }
+    const size_t nb = (D + NB - 1) / NB;
+    host[i].F = F[i];
+    host[i].L = L_out[i];
+    host[i].D = dims[i];
+    host[i].nb = (int)nb;
+    host[i].sqrt_mul = (float)sqrt((double)mul[i]);
+    host[i].sqrt_add = (float)sqrt((double)add[i]);
+    host[i].W = (float*)(base + off); off += align_up(D * D * 4, 256);
+    host[i].X = (float*)(base + off); off += align_up(D * D * 4, 256);
+    host[i].Dinv = (float*)(base + off); off += align_up(nb * NB * NB * 4, 256);
+    if (dims[i] > maxD) maxD = dims[i];
+  }
+  cudaError_t e = cudaMemcpyAsync(ws, host, sizeof(MatDesc) * (size_t)count, cudaMemcpyHostToDevice, s);
+  // pageable source: the copy has been staged when the call returns, so `host` can go
+  delete[] host;
+  CRV_CUDA(e);
+  CRV_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * (size_t)count, s));
+  const MatDesc* descs = (const MatDesc*)ws;
+  const int nbmax = (maxD + NB - 1) / NB;
+  const unsigned ew = (unsigned)min((size_t)1024, ((size_t)maxD * maxD + 255) / 256);
+  chol_prologue_kernel<<<dim3(ew, 1, count), 256, 0, s>>>(descs);
+  for (int j = 0; j < nbmax; ++j) {
+    chol_potf2_kernel<<<count, 256, 0, s>>>(descs, j, info);
+    const int below = nbmax - j - 1;
+    if (below > 0) {
+      chol_trsm_kernel<<<dim3(below, 1, count), 256, 0, s>>>(descs, j);
+      const int nt = (maxD - (j + 1) * NB + 63) / 64;
+      chol_update_kernel<<<dim3(nt * (nt + 1) / 2, 1, count), 256, 0, s>>>(descs, j);
+    }
+  }
+  chol_trtri_kernel<<<dim3((maxD + CW - 1) / CW, 1, count), 256, 0, s>>>(descs);
+  chol_epilogue_kernel<<<dim3(ew, 1, count), 256, 0, s>>>(descs);
+  CRV_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace crv

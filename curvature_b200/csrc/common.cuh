@@ -1,0 +1,99 @@
+// Shared declarations of the curvature_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace crv {
+
+// thread-local last-error text surfaced through crv_last_error()
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define CRV_CHECK(cond, ...)                 \
+  do {                                       \
+    if (!(cond)) {                           \
+      ::crv::set_error(__VA_ARGS__);         \
+      return 1;                              \
+    }                                        \
+  } while (0)
+
+#define CRV_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      ::crv::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),     \
+                       __FILE__, __LINE__);                                         \
+      return 2;                                                                     \
+    }                                                                               \
+  } while (0)
+
+// The (D x R) matrix whose Gram matrix a SYRK call accumulates, described implicitly:
+// row k = c*kh*kw + i*kw + j (+ one trailing row of ones iff has_bias), column
+// r = n*L + oh*OW + ow, element x[n, c, oh*sh - ph + i, ow*sw - pw + j] or 0 outside.
+// An (N, M, L) "rows" operand is the special case C=M, H=1, W=L, 1x1 kernel.
+struct ConvGeom {
+  const float* x;
+  int N, C, H, W;
+  int kh, kw, sh, sw, ph, pw;
+  int OH, OW;
+  int L;         // OH*OW
+  int K0;        // C*kh*kw
+  int D;         // K0 + has_bias
+  int has_bias;
+  long long R;   // N*L
+};
+
+inline int make_geom(ConvGeom& g, const float* x, int N, int C, int H, int W, int kh, int kw, int sh,
+                     int sw, int ph, int pw, int has_bias) {
+  CRV_CHECK(x != nullptr, "null input pointer");
+  CRV_CHECK(N > 0 && C > 0 && H > 0 && W > 0, "bad tensor shape N=%d C=%d H=%d W=%d", N, C, H, W);
+  CRV_CHECK(kh > 0 && kw > 0 && sh > 0 && sw > 0 && ph >= 0 && pw >= 0,
+            "bad conv geometry k=(%d,%d) s=(%d,%d) p=(%d,%d)", kh, kw, sh, sw, ph, pw);
+  CRV_CHECK(H + 2 * ph >= kh && W + 2 * pw >= kw, "kernel larger than padded input");
+  g.x = x; g.N = N; g.C = C; g.H = H; g.W = W;
+  g.kh = kh; g.kw = kw; g.sh = sh; g.sw = sw; g.ph = ph; g.pw = pw;
+  g.OH = (H + 2 * ph - kh) / sh + 1;
+  g.OW = (W + 2 * pw - kw) / sw + 1;
+  g.L = g.OH * g.OW;
+  g.K0 = C * kh * kw;
+  g.has_bias = has_bias ? 1 : 0;
+  g.D = g.K0 + g.has_bias;
+  g.R = (long long)N * g.L;
+  CRV_CHECK((long long)N * C * H * W < (1LL << 31), "input tensor too large for 32-bit indexing");
+  return 0;
+}
+
+int device_sm_count();
+
+// ---- kernel launchers (one per .cu file) -------------------------------------------------
+int syrk_simt_launch(const ConvGeom& g, float alpha, float* F, cudaStream_t s);
+int syrk_tc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,
+                   cudaStream_t s);
+size_t syrk_tc_workspace(const ConvGeom& g, int precision);
+
+enum GemmEpilogue {
+  EPI_STORE = 0,       // C = alpha*acc + beta*C
+  EPI_SQUARE_ACCUM = 1 // C += acc*acc
+};
+struct SampleEpilogue {   // EPI for K5: split (M,K) result into weight/bias with the mean added
+  const float* mu_w; const float* mu_b; float* w_out; float* b_out; float* s_out; int K0; int has_bias;
+};
+int gemm_simt_launch(const float* A, long long sa_m, long long sa_k, const float* B, long long sb_k,
+                     long long sb_n, float* C, int ldc, int m, int n, int k, float alpha, float beta,
+                     int epilogue, const SampleEpilogue* sample, cudaStream_t s);
+
+int diag_accum_launch(const float* wgrad, const float* bgrad, int M, int K0, float scale, float* state,
+                      float* grads_out, cudaStream_t s);
+int inv_sqrt_launch(const float* v, float add, float mul, float* out, size_t n, cudaStream_t s);
+int diag_sample_launch(const float* z, const float* inv, int M, int K0, int has_bias, const float* mu_w,
+                       const float* mu_b, float* w_out, float* b_out, float* s_out, cudaStream_t s);
+int scale_transpose_launch(const float* z, const float* row_scale, int K, int M, float* out, cudaStream_t s);
+
+size_t chol_workspace(const int* dims, int count);
+int chol_inv_batched_launch(const float* const* F, const int* dims, int count, const float* add,
+                            const float* mul, float* const* L_out, int* info, void* ws, size_t ws_bytes,
+                            cudaStream_t s);
+
+}  // namespace crv

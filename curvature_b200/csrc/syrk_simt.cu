@@ -1,0 +1,177 @@
+// K1 (fp32 tier): fused implicit-im2col + SYRK + running-sum epilogue on the CUDA cores.
+//
+//   F[k1,k2] += alpha * sum_r X[k1,r] * X[k2,r]
+//
+// X is never materialised: every staged element is gathered straight from the NCHW
+// activation tensor through the index map of ConvGeom (bit-exact restatement of the
+// reference's F.unfold row/column order, curvature/curvatures.py:329-336).  Exact fp32
+// products and fp32 FMA accumulation -> this is the 1e-5 parity tier and the checker for the
+// tensor-core tiers.  Only lower-triangular 64x64 tile pairs are computed; off-diagonal tiles
+// are mirrored in the epilogue.  The contraction axis R is split across CTAs so that small
+// factors with huge R (ResNet stem: 147^2 over R = 3.2M) still fill 148 SMs; partial sums are
+// merged with fp32 red.global.add straight into the factor arena (the `state +=` of
+// curvatures.py:346-350 is the same RMW, so no separate accumulate pass exists).
+#include "common.cuh"
+
+namespace crv {
+namespace {
+
+constexpr int BM = 64;     // tile edge (rows of X per operand tile)
+constexpr int BK = 32;     // contraction chunk = one warp-wide coalesced read along r
+constexpr int PITCH = 68;  // smem pitch in floats: 16B-aligned rows, conflict-free float4 access
+constexpr int NT = 256;
+
+// Row descriptor: channel base offset c*H*W (>= 0), or ROW_ONES / ROW_NONE.
+constexpr int ROW_NONE = -1;
+constexpr int ROW_ONES = -2;
+
+__device__ __forceinline__ void decode_row(const ConvGeom& g, int k, int& base, int& dij) {
+  if (k < g.K0) {
+    const int khw = g.kh * g.kw;
+    const int c = k / khw;
+    const int t = k - c * khw;
+    const int i = t / g.kw;
+    const int j = t - i * g.kw;
+    base = c * g.H * g.W;
+    dij = ((i - g.ph) << 16) | ((j - g.pw) & 0xffff);
+  } else {
+    base = (k < g.D) ? ROW_ONES : ROW_NONE;
+    dij = 0;
+  }
+}
+
+__global__ void __launch_bounds__(NT, 2)
+syrk_simt_kernel(const ConvGeom g, const float alpha, float* __restrict__ F, const int chunks_per_split) {
+  __shared__ __align__(16) float As[BK][PITCH];
+  __shared__ __align__(16) float Bs[BK][PITCH];
+
+  // lower-triangular tile pair (ti >= tj) from the linear block index
+  const int p = blockIdx.x;
+  int ti = (int)((sqrtf(8.f * (float)p + 1.f) - 1.f) * 0.5f);
+  while (ti * (ti + 1) / 2 > p) --ti;
+  while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
+  const int tj = p - ti * (ti + 1) / 2;
+  const bool diag = (ti == tj);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // Each thread stages, per operand tile, two quads of 4 consecutive rows at one r:
+  // rows 4*(warp + 8*q) .. +3, q = 0,1.  One float4 st.shared per quad (conflict-free).
+  int baseA[8], dA[8], baseB[8], dB[8];
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int row = 4 * (warp + 8 * q) + e;
+      decode_row(g, ti * BM + row, baseA[q * 4 + e], dA[q * 4 + e]);
+      decode_row(g, tj * BM + row, baseB[q * 4 + e], dB[q * 4 + e]);
+    }
+
+  const long long r_begin = (long long)blockIdx.y * chunks_per_split * BK;
+  long long r_end = r_begin + (long long)chunks_per_split * BK;
+  if (r_end > g.R) r_end = g.R;
+
+  float va[8], vb[8];
+  auto fetch = [&](long long r0) {
+    const long long r = r0 + lane;
+    const bool valid = r < r_end;
+    int n = 0, oh = 0, ow = 0;
+    if (valid) {
+      n = (int)(r / g.L);
+      const int l = (int)(r - (long long)n * g.L);
+      oh = l / g.OW;
+      ow = l - oh * g.OW;
+    }
+    const float* __restrict__ img = g.x + (size_t)n * g.C * g.H * g.W;
+    const int ih0 = oh * g.sh, iw0 = ow * g.sw;
+    auto load = [&](int base, int dij) -> float {
+      if (!valid || base == ROW_NONE) return 0.f;
+      if (base == ROW_ONES) return 1.f;
+      const int ih = ih0 + (dij >> 16);
+      const int iw = iw0 + (int)(short)(dij & 0xffff);
+      if ((unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W) return __ldg(img + base + ih * g.W + iw);
+      return 0.f;
+    };
+#pragma unroll
+    for (int e = 0; e < 8; ++e) va[e] = load(baseA[e], dA[e]);
+    if (!diag) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) vb[e] = load(baseB[e], dB[e]);
+    }
+  };
+
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+  if (r_begin < r_end) fetch(r_begin);
+  for (long long r0 = r_begin; r0 < r_end; r0 += BK) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      *reinterpret_cast<float4*>(&As[lane][4 * (warp + 8 * q)]) =
+          make_float4(va[q * 4 + 0], va[q * 4 + 1], va[q * 4 + 2], va[q * 4 + 3]);
+      if (!diag)
+        *reinterpret_cast<float4*>(&Bs[lane][4 * (warp + 8 * q)]) =
+            make_float4(vb[q * 4 + 0], vb[q * 4 + 1], vb[q * 4 + 2], vb[q * 4 + 3]);
+    }
+    __syncthreads();
+    if (r0 + BK < r_end) fetch(r0 + BK);  // next chunk's global loads fly during the FMAs
+    const float(*Bp)[PITCH] = diag ? As : Bs;
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bp[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // epilogue: F += alpha * acc (and the mirrored element for off-diagonal tiles)
+  const int D = g.D;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = ti * BM + ty * 4 + i;
+    if (row >= D) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = tj * BM + tx * 4 + j;
+      if (col >= D) continue;
+      const float v = alpha * acc[i][j];
+      atomicAdd(&F[(size_t)row * D + col], v);
+      if (!diag) atomicAdd(&F[(size_t)col * D + row], v);
+    }
+  }
+}
+
+}  // namespace
+
+int syrk_simt_launch(const ConvGeom& g, float alpha, float* F, cudaStream_t s) {
+  CRV_CHECK(F != nullptr, "null factor pointer");
+  const int T = (g.D + BM - 1) / BM;
+  const long long pairs = (long long)T * (T + 1) / 2;
+  const long long chunks = (g.R + BK - 1) / BK;
+  const int sms = device_sm_count();
+  CRV_CHECK(sms > 0, "no CUDA device");
+  const long long target = (long long)sms * 2 * 3;  // ~3 waves of 2 resident CTAs per SM
+  long long splits = (target + pairs - 1) / pairs;
+  if (splits > chunks / 4) splits = chunks / 4;     // keep >= 4 chunks per CTA
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  const long long cps = (chunks + splits - 1) / splits;
+  splits = (chunks + cps - 1) / cps;
+  CRV_CHECK(pairs < (1LL << 31), "factor too large");
+  dim3 grid((unsigned)pairs, (unsigned)splits, 1);
+  syrk_simt_kernel<<<grid, NT, 0, s>>>(g, alpha, F, (int)cps);
+  CRV_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace crv

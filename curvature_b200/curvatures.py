@@ -1,0 +1,626 @@
+"""Fisher information approximations with the reference's Python surface, computed by sm_100a kernels.
+
+Drop-in for ``curvature/curvatures.py`` of DLR-RM/curvature: the class names, constructor
+arguments, ``update`` / ``invert`` / ``sample`` / ``sample_and_replace``, the ``state`` / ``inv_state``
+layouts (dicts keyed by the module objects, in ``model.modules()`` order) and the assertion messages
+are the reference's (curvatures.py:17-672).  The bodies contain no ``torch.mm`` / ``unfold`` / ``cat``:
+hooks stash device pointers and ``update`` hands them to the C-ABI kernels in ``libcurvature_b200.so``
+(include/curvature_b200.h).  There is no CPU path: tensors must be CUDA fp32.
+
+Differences a caller can observe (all documented in DESIGN.md):
+  * ``KFAC.record[layer][1]`` holds the *unscaled* output gradient; the reference's ``* batch`` of
+    curvatures.py:310 is folded into the SYRK epilogue scale.  ``KFAC.scaled_record(layer)`` returns the
+    reference's tensor.
+  * ``sample`` / ``sample_and_replace`` accept an optional ``noise`` argument (the Gaussian tensor the
+    reference would draw) so that posterior samples can be compared with identical noise.
+  * every estimator keeps its state in one flat fp32 arena (``.arena``); the per-layer tensors in ``state``
+    are views into it, which is what a single NCCL all-reduce per estimation pass operates on.
+  * ``add`` / ``multiply`` may be ints as well as floats for every estimator.
+"""
+from abc import ABC, abstractmethod
+import copy
+import warnings
+from typing import Any, Dict, List, Optional, Sequence, Union
+
+import torch
+from torch import Tensor
+from torch.nn import Module, Sequential
+
+from . import _native as nat
+from .utils import get_eigenvectors, kron
+
+# the reference registers the same (non-full) backward hook kind; torch warns about it on every forward
+warnings.filterwarnings("ignore", message="Using a non-full backward hook")
+
+_SUPPORTED = ['Linear', 'Conv2d', 'MultiheadAttention']
+_SCALARS = (float, int)
+
+
+def _pair(v):
+    if isinstance(v, (tuple, list)):
+        if len(v) == 1:
+            return int(v[0]), int(v[0])
+        return int(v[0]), int(v[1])
+    return int(v), int(v)
+
+
+class FactorArena:
+    """One flat, zero-initialised fp32 buffer carved into per-layer matrices (256-byte aligned views)."""
+
+    ALIGN = 64  # floats
+
+    def __init__(self, shapes: Sequence[Sequence[int]], device, dtype=torch.float32):
+        offsets, total = [], 0
+        for shape in shapes:
+            n = 1
+            for s in shape:
+                n *= int(s)
+            offsets.append(total)
+            total += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.flat = torch.zeros(max(total, self.ALIGN), dtype=dtype, device=device)
+        self.views = []
+        for off, shape in zip(offsets, shapes):
+            n = 1
+            for s in shape:
+                n *= int(s)
+            self.views.append(self.flat[off:off + n].view(*shape))
+
+
+def _damping(add, multiply, index, count):
+    """Scalar or per-layer damping (curvatures.py:183-187, 361-365)."""
+    if not isinstance(add, _SCALARS) and not isinstance(multiply, _SCALARS):
+        assert len(add) == len(multiply) == count
+        return float(add[index]), float(multiply[index])
+    return float(add), float(multiply)
+
+
+def _grad_of(p: Tensor, what: str) -> Tensor:
+    if p.grad is None:
+        raise RuntimeError(f"{what}.grad is None. Did you call 'backward' prior to 'update'?")
+    g = p.grad
+    return g if g.is_contiguous() else g.contiguous()
+
+
+class Curvature(ABC):
+    """Base class of all approximations (reference: curvatures.py:17-129)."""
+
+    def __init__(self,
+                 model: Union[Module, Sequential],
+                 layer_types: Union[List[str], str] = None,
+                 precision: Union[str, int, None] = None):
+        """
+        Args:
+            model: Any (pre-trained) PyTorch model, on a CUDA device.
+            layer_types: `Linear`, `Conv2d`, `MultiheadAttention`; all three if `None` or `[]`.
+            precision: arithmetic tier of the dense contractions (`'fp32'`, `'tf32'`, `'tf32x3'`, `'bf16'`);
+                       default from `CURVATURE_B200_PRECISION`, else fp32.
+        """
+        self.model = model
+        self.model_state = copy.deepcopy(model.state_dict())
+        self.layer_types = list()
+        if isinstance(layer_types, str):
+            self.layer_types.append(layer_types)
+        elif isinstance(layer_types, list):
+            if layer_types:
+                self.layer_types.extend(layer_types)
+            else:
+                self.layer_types.extend(_SUPPORTED)
+        elif layer_types is None:
+            self.layer_types.extend(_SUPPORTED)
+        else:
+            raise TypeError
+        for _type in self.layer_types:
+            assert _type in _SUPPORTED
+        self.state = dict()
+        self.inv_state = dict()
+        self.precision = nat.resolve_precision(precision)
+        self.arena: Optional[FactorArena] = None
+
+    # -- helpers ---------------------------------------------------------------------------------------
+    def _selected(self):
+        for layer in self.model.modules():
+            name = layer.__class__.__name__
+            if name in self.layer_types:
+                yield name, layer
+
+    @staticmethod
+    def _layer_dims(layer: Module):
+        """(M, K0, has_bias) of a Linear / Conv2d weight viewed as (M, K0)."""
+        M = layer.weight.shape[0]
+        return M, layer.weight.numel() // M, layer.bias is not None
+
+    @staticmethod
+    def _replace(sample: Tensor,
+                 weight: Tensor,
+                 bias: Tensor = None):
+        """Adds `sample` (M, K) to the parameters: last column to `bias`, the rest to `weight`
+        (reference: curvatures.py:67-82).  Kept for API compatibility; `sample_and_replace` itself writes
+        mean + sample from inside the sampling kernel's epilogue."""
+        if bias is not None:
+            bias.data.add_(sample[:, -1].contiguous().view(*bias.shape))
+            sample = sample[:, :-1]
+        weight.data.add_(sample.contiguous().view(*weight.shape))
+
+    @abstractmethod
+    def update(self, *args: Any, **kwargs: Any):
+        raise NotImplementedError
+
+    @abstractmethod
+    def invert(self,
+               add: Union[float, list, tuple] = 0.,
+               multiply: Union[float, list, tuple] = 1.):
+        raise NotImplementedError
+
+    @abstractmethod
+    def sample(self, layer: Module, noise: Optional[Tensor] = None) -> Tensor:
+        raise NotImplementedError
+
+    def _sample_into(self, key, weight: Tensor, bias: Optional[Tensor], mean_w: Tensor, mean_b: Optional[Tensor],
+                     noise: Optional[Tensor]):
+        """Write mean + sample into (weight, bias).  Default: sample, then add (two passes)."""
+        s = self.sample(key, noise)
+        weight.data.copy_(mean_w)
+        if bias is not None:
+            bias.data.copy_(mean_b)
+        self._replace(s, weight, bias)
+
+    def _param_names(self):
+        """Map id(parameter tensor) -> state_dict key, to find each layer's posterior mean."""
+        return {id(v): k for k, v in self.model.state_dict(keep_vars=True).items()}
+
+    def sample_and_replace(self, noise: Optional[Dict] = None):
+        """Samples new model parameters and replaces old ones for selected layers, skipping all others
+        (reference: curvatures.py:117-129).  Equivalent to reloading the mean (`load_state_dict`) and adding a
+        fresh sample to every selected layer; parameters of selected layers are written once, as mean + sample,
+        by the sampling kernel.  `noise` optionally maps layer (or 'attn_in'/'attn_out') -> Gaussian tensor."""
+        names = self._param_names()
+        current = self.model.state_dict(keep_vars=True)
+        written = set()
+        for name, layer in self._selected():
+            if name in ['Linear', 'Conv2d']:
+                targets = [(layer, layer.weight, layer.bias)]
+            else:
+                targets = [('attn_in', layer.in_proj_weight, layer.in_proj_bias),
+                           ('attn_out', layer.out_proj.weight, layer.out_proj.bias)]
+            for key, weight, bias in targets:
+                mean_w = self.model_state[names[id(weight)]]
+                mean_b = self.model_state[names[id(bias)]] if bias is not None else None
+                z = None if noise is None else noise[key]
+                self._sample_into(key, weight, bias, mean_w, mean_b, z)
+                written.add(names[id(weight)])
+                if bias is not None:
+                    written.add(names[id(bias)])
+        with torch.no_grad():   # everything else: restore the mean, as load_state_dict would
+            for k, v in current.items():
+                if k not in written:
+                    v.data.copy_(self.model_state[k])
+
+
+class Diagonal(Curvature):
+    r"""Diagonal Fisher: `state[layer] += batch_size * [wgrad | bgrad]**2` (reference: curvatures.py:132-193),
+    through the streaming kernel `crv_diag_accum` (K2)."""
+
+    def _entries(self):
+        """(key, weight, bias) for every selected parameter group, in `model.modules()` order."""
+        for name, layer in self._selected():
+            if name in ['Linear', 'Conv2d']:
+                yield layer, layer.weight, layer.bias
+            elif name == 'MultiheadAttention':
+                yield 'attn_in', layer.in_proj_weight, layer.in_proj_bias
+                yield 'attn_out', layer.out_proj.weight, layer.out_proj.bias
+
+    def _ensure_arena(self):
+        if self.arena is None:
+            entries = list(self._entries())
+            shapes = [(w.shape[0], w.numel() // w.shape[0] + (b is not None)) for _, w, b in entries]
+            self.arena = FactorArena(shapes, entries[0][1].device)
+            self._views = {key: v for (key, _, _), v in zip(entries, self.arena.views)}
+
+    def update(self,
+               batch_size: int):
+        """Accumulates the squared gradients of all selected layers (call after `backward`)."""
+        self._ensure_arena()
+        for key, weight, bias in self._entries():
+            wg = _grad_of(weight, 'weight')
+            bg = _grad_of(bias, 'bias') if bias is not None else None
+            if key not in self.state:
+                self.state[key] = self._views[key]
+            nat.diag_accum(wg, bg, batch_size, state=self.state[key])
+
+    def invert(self,
+               add: Union[float, list, tuple] = 0.,
+               multiply: Union[float, list, tuple] = 1.):
+        assert self.state, "State dict is empty. Did you call 'update' prior to this?"
+        if self.inv_state:
+            Warning("State has already been inverted. Is this expected?")
+        for index, (layer, value) in enumerate(self.state.items()):
+            n, s = _damping(add, multiply, index, len(self.state))
+            out = torch.empty_like(value)
+            nat.elementwise_inv_sqrt(value, n, s, out)
+            self.inv_state[layer] = out
+
+    def sample(self,
+               layer: Union[Module, str],
+               noise: Optional[Tensor] = None) -> Tensor:
+        assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
+        inv = self.inv_state[layer]
+        z = torch.empty_like(inv).normal_() if noise is None else noise
+        out = torch.empty_like(inv)
+        nat.diag_sample(z, inv, False, s_out=out)
+        return out
+
+    def _sample_into(self, key, weight, bias, mean_w, mean_b, noise):
+        assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
+        inv = self.inv_state[key]
+        z = torch.empty_like(inv).normal_() if noise is None else noise
+        nat.diag_sample(z, inv, bias is not None, mu_w=mean_w, mu_b=mean_b, w_out=weight.data,
+                        b_out=None if bias is None else bias.data)
+
+
+class KFAC(Curvature):
+    r"""Kronecker-factored Fisher (reference: curvatures.py:264-392).
+
+    `update` computes, per selected layer, A = X X^T / R from the recorded layer input (implicit im2col for
+    convolutions, trailing ones row for the bias) and G = g g^T * N^2 / R from the recorded output gradient, and
+    adds both to the running sums -- one fused kernel per factor (K1), accumulating straight into the arena.
+    `invert` is one batched damped Cholesky-of-inverse call (K4); `sample` is the fused two-GEMM matrix-normal
+    draw (K5)."""
+
+    def __init__(self,
+                 model: Union[Module, Sequential],
+                 layer_types: Union[List[str], str] = None,
+                 precision: Union[str, int, None] = None):
+        super().__init__(model, layer_types, precision)
+        self.hooks = list()
+        self.record = dict()
+
+        for layer in model.modules():
+            if layer.__class__.__name__ in self.layer_types:
+                if layer.__class__.__name__ in ['Linear', 'Conv2d']:
+                    if layer.__class__.__name__ == 'Conv2d':
+                        self._check_conv(layer)
+                    self.record[layer] = [None, None]
+                    self.hooks.append(layer.register_forward_pre_hook(self._save_input))
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        # same (non-full) hook kind as the reference, curvatures.py:302
+                        self.hooks.append(layer.register_backward_hook(self._save_output))
+                elif layer.__class__.__name__ == 'MultiheadAttention':
+                    raise NotImplementedError
+
+    @staticmethod
+    def _check_conv(layer):
+        # the reference calls F.unfold(x, kernel_size, padding=, stride=) only (curvatures.py:329)
+        if _pair(layer.dilation) != (1, 1) or layer.groups != 1:
+            raise NotImplementedError("KFAC supports Conv2d with dilation=1 and groups=1 only (as the reference)")
+        if isinstance(layer.padding, str) or layer.padding_mode != 'zeros':
+            raise NotImplementedError("KFAC supports integer zero padding only (as the reference)")
+
+    # hooks: pointer stashes only -- no kernel launch, no copy (they also fire on eval forwards)
+    def _save_input(self, module, input):
+        self.record[module][0] = input[0]
+
+    def _save_output(self, module, grad_input, grad_output):
+        self.record[module][1] = grad_output[0]
+
+    _save_grad_output = _save_output
+
+    def scaled_record(self, layer: Module) -> Tensor:
+        """The tensor the reference stores in `record[layer][1]` (curvatures.py:310)."""
+        g = self.record[layer][1]
+        return g * g.size(0)
+
+    def _ensure_arena(self):
+        if self.arena is None:
+            layers = list(self.record.keys())
+            shapes = []
+            for layer in layers:
+                M, K0, hb = self._layer_dims(layer)
+                shapes += [(K0 + hb, K0 + hb), (M, M)]
+            self.arena = FactorArena(shapes, layers[0].weight.device)
+            self._views = {l: [self.arena.views[2 * i], self.arena.views[2 * i + 1]] for i, l in enumerate(layers)}
+
+    def update(self,
+               batch_size: int):
+        """Adds the Kronecker factors of the recorded batch to the running sums of every selected layer.
+        `batch_size` is accepted for API compatibility; like the reference the factors are normalised by the
+        recorded tensors' own shapes."""
+        self._ensure_arena()
+        for layer in self.model.modules():
+            module_class = layer.__class__.__name__
+            if module_class in self.layer_types:
+                if module_class in ['Linear', 'Conv2d']:
+                    forward, backward = self.record[layer]
+                    if forward is None or backward is None:
+                        raise RuntimeError("KFAC.update: no recorded input / output gradient for "
+                                           f"{module_class}; run a forward and backward pass first")
+                    x = forward.detach()
+                    g = backward.detach()
+                    if not x.is_contiguous():
+                        x = x.contiguous()
+                    if not g.is_contiguous():
+                        g = g.contiguous()
+                    if layer not in self.state:
+                        self.state[layer] = self._views[layer]
+                    first, second = self.state[layer]
+                    has_bias = layer.bias is not None
+                    n_g = g.size(0)
+                    if module_class == 'Conv2d':
+                        N, _, H, W = x.shape
+                        kh, kw = _pair(layer.kernel_size)
+                        sh, sw = _pair(layer.stride)
+                        ph, pw = _pair(layer.padding)
+                        r_x = N * ((H + 2 * ph - kh) // sh + 1) * ((W + 2 * pw - kw) // sw + 1)
+                        nat.syrk_conv_accum(x, (kh, kw), (sh, sw), (ph, pw), has_bias, 1.0 / r_x, first,
+                                            self.precision)
+                        r_g = n_g * g.shape[2] * g.shape[3]
+                    else:
+                        if x.dim() != 2:
+                            raise NotImplementedError("KFAC supports 2-D Linear inputs only (as the reference)")
+                        nat.syrk_rows_accum(x, has_bias, 1.0 / x.size(0), first, self.precision)
+                        r_g = n_g
+                    # reference: (g * N)(g * N)^T / R  ==  g g^T * N^2 / R
+                    nat.syrk_rows_accum(g, False, float(n_g) * float(n_g) / float(r_g), second, self.precision)
+                elif module_class == 'MultiheadAttention':
+                    raise NotImplementedError
+
+    def invert(self,
+               add: Union[float, list, tuple] = 0.,
+               multiply: Union[float, list, tuple] = 1.):
+        assert self.state, "State dict is empty. Did you call 'update' prior to this?"
+        if self.inv_state:
+            Warning("State has already been inverted. Is this expected?")
+        factors, adds, muls = [], [], []
+        for index, (layer, value) in enumerate(self.state.items()):
+            n, s = _damping(add, multiply, index, len(self.state))
+            first, second = value
+            factors += [first, second]
+            adds += [n, n]
+            muls += [s, s]
+        inv_arena = FactorArena([f.shape for f in factors], factors[0].device)
+        info = nat.chol_inv_batched(factors, adds, muls, inv_arena.views)
+        bad = torch.nonzero(info).flatten().tolist()   # one sync per invert; invert is not the hot loop
+        if bad:
+            raise RuntimeError("KFAC.invert: damped factor is not positive definite for matrices "
+                               f"{bad[:8]} (factor index = 2*layer + {{0: A, 1: G}}); increase `add`. "
+                               "(The reference falls back to numpy here; this implementation has no CPU path.)")
+        self._inv_arena = inv_arena
+        for i, layer in enumerate(self.state.keys()):
+            self.inv_state[layer] = (inv_arena.views[2 * i], inv_arena.views[2 * i + 1])
+
+    def _noise(self, first: Tensor, second: Tensor, noise: Optional[Tensor]) -> Tensor:
+        if noise is None:   # same draw as the reference (curvatures.py:391)
+            return torch.randn(first.size(0), second.size(0), device=first.device, dtype=first.dtype)
+        return noise if noise.is_contiguous() else noise.contiguous()
+
+    def sample(self,
+               layer: Module,
+               noise: Optional[Tensor] = None) -> Tensor:
+        assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
+        first, second = self.inv_state[layer]
+        z = self._noise(first, second, noise)
+        out = torch.empty(second.size(0), first.size(0), device=first.device, dtype=first.dtype)
+        nat.sample_matrix_normal(second, first, z, False, s_out=out, precision=nat.PREC_FP32)
+        return out
+
+    def _sample_into(self, key, weight, bias, mean_w, mean_b, noise):
+        assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
+        first, second = self.inv_state[key]
+        z = self._noise(first, second, noise)
+        nat.sample_matrix_normal(second, first, z, bias is not None, mu_w=mean_w, mu_b=mean_b,
+                                 w_out=weight.data, b_out=None if bias is None else bias.data,
+                                 precision=nat.PREC_FP32)
+
+
+class EFB(Curvature):
+    """Eigenvalue-corrected Kronecker factorisation (reference: curvatures.py:395-460):
+    `state[layer] += (QG^T [wgrad|bgrad] QA)**2`, `diags[layer] += batch_size * [wgrad|bgrad]**2`."""
+
+    def __init__(self,
+                 model: Union[Module, Sequential],
+                 factors: Dict[Module, Tensor],
+                 layer_types: Union[List[str], str] = None,
+                 precision: Union[str, int, None] = None,
+                 eigvecs: Optional[Dict] = None):
+        """`eigvecs` optionally supplies precomputed eigenbases {layer: (QA, QG)} (eigenvectors are only defined
+        up to sign / rotation inside degenerate eigenspaces, so parity tests feed the oracle's)."""
+        super().__init__(model, layer_types, precision)
+        self.eigvecs = get_eigenvectors(factors) if eigvecs is None else eigvecs
+        self.diags = dict()
+
+    def _ensure_arena(self):
+        if self.arena is None:
+            layers = [l for n, l in self._selected() if n in ['Linear', 'Conv2d']]
+            shapes = []
+            for layer in layers:
+                M, K0, hb = self._layer_dims(layer)
+                shapes += [(M, K0 + hb), (M, K0 + hb)]
+            self.arena = FactorArena(shapes, layers[0].weight.device)
+            self._views = {l: (self.arena.views[2 * i], self.arena.views[2 * i + 1]) for i, l in enumerate(layers)}
+
+    def update(self,
+               batch_size: int):
+        self._ensure_arena()
+        for name, layer in self._selected():
+            if name in ['Linear', 'Conv2d']:
+                wg = _grad_of(layer.weight, 'weight')
+                bg = _grad_of(layer.bias, 'bias') if layer.bias is not None else None
+                if layer not in self.state:
+                    self.state[layer], self.diags[layer] = self._views[layer]
+                grads = torch.empty_like(self.state[layer])
+                nat.diag_accum(wg, bg, batch_size, state=self.diags[layer], grads_out=grads)
+                qa, qg = self.eigvecs[layer]
+                nat.efb_project_accum(qg, qa, grads, self.state[layer], nat.PREC_FP32)
+            elif name == 'MultiheadAttention':
+                raise NotImplementedError
+
+    def invert(self,
+               add: Union[float, list, tuple] = 0.,
+               multiply: Union[float, list, tuple] = 1.):
+        assert self.state, "State dict is empty. Did you call 'update' prior to this?"
+        if self.inv_state:
+            Warning("State has already been inverted. Is this expected?")
+        for index, (layer, value) in enumerate(self.state.items()):
+            n, s = _damping(add, multiply, index, len(self.state))
+            out = torch.empty_like(value)
+            nat.elementwise_inv_sqrt(value, n, s, out)
+            self.inv_state[layer] = out
+
+    def _noise(self, first, second, noise):
+        if noise is None:
+            return torch.randn(first.size(0), second.size(0), device=first.device, dtype=first.dtype)
+        return noise if noise.is_contiguous() else noise.contiguous()
+
+    def sample(self,
+               layer: Module,
+               noise: Optional[Tensor] = None) -> Tensor:
+        assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
+        first, second = self.eigvecs[layer]
+        z = self._noise(first, second, noise)
+        out = torch.empty(second.size(0), first.size(0), device=first.device, dtype=first.dtype)
+        nat.sample_matrix_normal(second, first, z, False, row_scale=self.inv_state[layer], s_out=out)
+        return out
+
+    def _sample_into(self, key, weight, bias, mean_w, mean_b, noise):
+        assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
+        first, second = self.eigvecs[key]
+        z = self._noise(first, second, noise)
+        nat.sample_matrix_normal(second, first, z, bias is not None, row_scale=self.inv_state[key],
+                                 mu_w=mean_w, mu_b=mean_b, w_out=weight.data,
+                                 b_out=None if bias is None else bias.data)
+
+
+class INF(Curvature):
+    """Low-rank "information form" estimator (reference: curvatures.py:463-672).
+
+    No data pass and no north-star kernel of its own: the rank selection is host-side index logic exactly as in
+    the reference; the dense algebra runs on the device through the library's GEMM (`crv_gemm`), with the
+    Kronecker products of the reference replaced by the equivalent small GEMMs
+    (`_diagonal_accumulator(QA,QG,l) == ((QA*QA) L (QG*QG)^T).flatten()`); the general (non-symmetric) matrix
+    inverses of `pre_sampler` use `torch.linalg` (cuSOLVER), as they are one-shot, LeNet-sized operations."""
+
+    def __init__(self,
+                 model: Union[Module, Sequential],
+                 diags: Dict[Module, Tensor],
+                 factors: Dict[Module, Tensor],
+                 lambdas: Dict[Module, Tensor],
+                 layer_types: Union[List[str], str] = None,
+                 precision: Union[str, int, None] = None,
+                 eigvecs: Optional[Dict] = None):
+        super().__init__(model, layer_types, precision)
+        assert diags.keys() == factors.keys() == lambdas.keys()
+        self.eigvecs = get_eigenvectors(factors) if eigvecs is None else eigvecs
+        self.lambdas = lambdas
+        self.diags = diags
+
+    def update(self,
+               rank: int = 100):
+        values = zip(list(self.diags.keys()),
+                     list(self.eigvecs.values()),
+                     list(self.lambdas.values()),
+                     list(self.diags.values()))
+        for layer, eigvecs, lambdas, diags in values:
+            xxt_eigvecs, ggt_eigvecs = eigvecs
+            lambda_vec = lambdas.t().contiguous().view(-1)
+            diag_vec = diags.t().contiguous().view(-1)
+            lr_xxt_eigvecs, lr_ggt_eigvecs, lr_lambda = self._dim_reduction(xxt_eigvecs, ggt_eigvecs, lambda_vec, rank)
+            sif_diag = self._diagonal_accumulator(lr_xxt_eigvecs, lr_ggt_eigvecs, lr_lambda)
+            self.state[layer] = (lr_xxt_eigvecs, lr_ggt_eigvecs, lr_lambda, diag_vec - sif_diag)
+
+    def invert(self,
+               add: Union[float, list, tuple] = 0.,
+               multiply: Union[float, list, tuple] = 1.):
+        assert self.state, "State dict is empty. Did you call 'update' prior to this?"
+        if self.inv_state:
+            Warning("State has already been inverted. Is this expected?")
+        for index, (layer, value) in enumerate(self.state.items()):
+            n, s = _damping(add, multiply, index, len(self.state))
+            lr_frst_eigvecs, lr_scnd_eigvecs, lr_lambda, correction = value
+            correction[correction < 0] = 0     # in place, like the reference (curvatures.py:523)
+            reg_lr_lambda = (s * lr_lambda).sqrt()
+            reg_inv_correction = torch.empty_like(correction)
+            nat.elementwise_inv_sqrt(correction, n, s, reg_inv_correction)
+            pre_sample = self.pre_sampler(lr_frst_eigvecs, lr_scnd_eigvecs, reg_lr_lambda, reg_inv_correction)
+            self.inv_state[layer] = (lr_frst_eigvecs, lr_scnd_eigvecs, reg_inv_correction, pre_sample)
+
+    def sample(self,
+               layer: Module,
+               noise: Optional[Tensor] = None) -> Tensor:
+        assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
+        a, b, c, d = self.inv_state[layer]
+        return self.sampler(a, b, c, d, noise).reshape(a.shape[0], b.shape[0]).t()
+
+    @staticmethod
+    def pre_sampler(frst_eigvecs: Tensor,
+                    scnd_eigvecs: Tensor,
+                    reg_lambda: Tensor,
+                    reg_inv_correction: Tensor) -> Tensor:
+        """reference: curvatures.py:538-572.  V = diag(c) kron(QA,QG) diag(l) is never formed:
+        V^T V = (QA^T diag-weighted QA) combined with QG through the per-row weights c^2 reshaped (K, M):
+        (V^T V)[(a,b),(a',b')] = l_ab l_a'b' sum_{k,m} c_km^2 QA[k,a] QA[k,a'] QG[m,b] QG[m,b']."""
+        K, ra = frst_eigvecs.shape
+        M, rg = scnd_eigvecs.shape
+        c2 = (reg_inv_correction ** 2).view(K, M).contiguous()
+        # pair products of eigenvector columns: PA[k,(a,a')] = QA[k,a] QA[k,a'];  PG[m,(b,b')] likewise
+        PA = (frst_eigvecs[:, :, None] * frst_eigvecs[:, None, :]).reshape(K, ra * ra).contiguous()
+        PG = (scnd_eigvecs[:, :, None] * scnd_eigvecs[:, None, :]).reshape(M, rg * rg).contiguous()
+        T = nat.gemm(c2, PG)                                  # (K, rg*rg)
+        W = nat.gemm(PA, T, transA=True)                      # (ra*ra, rg*rg): W[(a,a'),(b,b')]
+        vtv = W.view(ra, ra, rg, rg).permute(0, 2, 1, 3).reshape(ra * rg, ra * rg)
+        vtv = reg_lambda[:, None] * vtv * reg_lambda[None, :]
+        vtv = (vtv + vtv.t()) / 2.
+        eye = torch.eye(vtv.shape[0], device=vtv.device, dtype=vtv.dtype)
+        A_c_inv = torch.linalg.inv(torch.linalg.cholesky(vtv))
+        B_c = torch.linalg.cholesky(vtv + eye)
+        C = nat.gemm(nat.gemm(A_c_inv, (B_c - eye).contiguous(), transA=True), A_c_inv)
+        L_c = torch.linalg.inv(torch.linalg.inv(C) + vtv)
+        return reg_lambda[:, None] * L_c * reg_lambda[None, :]
+
+    @staticmethod
+    def sampler(frst_eigvecs: Tensor,
+                scnd_eigvecs: Tensor,
+                reg_inv_correction: Tensor,
+                pre_sample: Tensor,
+                noise: Optional[Tensor] = None) -> Tensor:
+        """reference: curvatures.py:574-600."""
+        K, M = frst_eigvecs.shape[0], scnd_eigvecs.shape[0]
+        X = torch.randn(K * M, device=frst_eigvecs.device, dtype=frst_eigvecs.dtype) if noise is None else noise
+        Y_l = reg_inv_correction * X
+        unvec_Y_l = Y_l.reshape(M, K)
+        Xq = nat.gemm(nat.gemm(scnd_eigvecs, unvec_Y_l, transA=True), frst_eigvecs)          # (rg, ra)
+        Qx = nat.gemm(pre_sample, Xq.t().contiguous().view(-1, 1)).view(-1)
+        unvec_Qx = Qx.reshape(scnd_eigvecs.shape[1], frst_eigvecs.shape[1])
+        X_p_s = nat.gemm(nat.gemm(scnd_eigvecs, unvec_Qx), frst_eigvecs, transB=True)        # (M, K)
+        Y_r = reg_inv_correction ** 2 * X_p_s.t().contiguous().view(-1)
+        return Y_l - Y_r
+
+    @staticmethod
+    def _dim_reduction(frst_eigvecs: Tensor,
+                       scnd_eigvecs: Tensor,
+                       lambda_vec: Tensor,
+                       rank: int):
+        """reference: curvatures.py:602-647 (host-side index selection, 1-based like the reference)."""
+        if rank >= lambda_vec.shape[0]:
+            return frst_eigvecs, scnd_eigvecs, lambda_vec
+        m = scnd_eigvecs.shape[1]
+        order = (torch.argsort(-torch.abs(lambda_vec))[:rank] + 1).tolist()
+        idx_left = sorted({int((t - 1.) / m + 1.) for t in order})
+        idx_right = sorted({t - m * (int((t - 1.) / m + 1.) - 1) for t in order})
+        dev = lambda_vec.device
+        picks = torch.tensor([m * (i - 1) + j - 1 for i in idx_left for j in idx_right], device=dev)
+        left = torch.tensor([i - 1 for i in idx_left], device=dev)
+        right = torch.tensor([j - 1 for j in idx_right], device=dev)
+        return (frst_eigvecs.index_select(1, left).contiguous(),
+                scnd_eigvecs.index_select(1, right).contiguous(),
+                lambda_vec.index_select(0, picks))
+
+    @staticmethod
+    def _diagonal_accumulator(xxt_eigvecs: Tensor,
+                              ggt_eigvecs: Tensor,
+                              lambda_vec: Tensor):
+        """reference: curvatures.py:649-672, kron-free: out[i*m + p] = sum_{a,b} QA[i,a]^2 QG[p,b]^2 l[a*rg+b]."""
+        ra, rg = xxt_eigvecs.shape[1], ggt_eigvecs.shape[1]
+        lam = lambda_vec.view(ra, rg).contiguous()
+        qa2 = (xxt_eigvecs ** 2).contiguous()
+        qg2 = (ggt_eigvecs ** 2).contiguous()
+        return nat.gemm(nat.gemm(qa2, lam), qg2, transB=True).view(-1)

@@ -1,0 +1,133 @@
+/*
+ * curvature_b200 -- C ABI of the B200 (sm_100a) kernels behind the Fisher-estimation
+ * hot path of DLR-RM/curvature.
+ *
+ * The reference has no FFI of its own: its boundary is the Python class API of
+ * curvature/curvatures.py, and every "kernel" is an ATen call made from there.  Each entry
+ * point below replaces the ATen call sequence cited beside it (file:line in the reference
+ * tree); INTEGRATION.md shows the ctypes stub a maintainer would add to the reference.
+ *
+ * Conventions (all entry points):
+ *   - every data pointer is a DEVICE pointer to fp32 memory owned by the caller (torch);
+ *   - `stream` is a cudaStream_t (pass torch.cuda.current_stream().cuda_stream); calls only
+ *     enqueue work, never synchronise the device, never allocate persistent memory;
+ *   - scratch memory is passed in as (ws, ws_bytes); size it with crv_workspace_bytes();
+ *   - return value 0 = ok, non-zero = error; crv_last_error() gives the message (thread-local);
+ *   - there is no CPU fallback: without a CUDA device every compute call returns an error.
+ *   - matrices are dense row-major.
+ */
+#ifndef CURVATURE_B200_H
+#define CURVATURE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRV_ABI_VERSION 1
+
+typedef void* crv_stream_t; /* cudaStream_t */
+
+/* Arithmetic tier of the dense contractions (SYRK / GEMM kernels). */
+enum crv_precision {
+  CRV_PREC_FP32   = 0, /* CUDA-core fp32 FMA (exact fp32 products); parity tier 1e-5            */
+  CRV_PREC_TF32   = 1, /* tcgen05 kind::tf32, operands rounded to nearest (cvt.rna), fp32 accum  */
+  CRV_PREC_TF32X3 = 2, /* tcgen05 3xTF32 error-compensated split (hi*hi + hi*lo + lo*hi)          */
+  CRV_PREC_BF16   = 3  /* tcgen05 kind::f16 with bf16 operands, fp32 accum; parity tier 1e-3      */
+};
+
+/* Operations for crv_workspace_bytes(). dims as documented per op. */
+enum crv_op {
+  CRV_OP_SYRK_CONV   = 0, /* dims = {N,C,H,W,kh,kw,sh,sw,ph,pw,has_bias,precision} */
+  CRV_OP_SYRK_ROWS   = 1, /* dims = {N,M,L,has_bias,precision}                     */
+  CRV_OP_EFB_PROJECT = 2, /* dims = {M,K}                                          */
+  CRV_OP_CHOL_INV    = 3, /* dims = {count, d_0, ..., d_{count-1}}                 */
+  CRV_OP_SAMPLE_MN   = 4  /* dims = {M,K}                                          */
+};
+
+int         crv_abi_version(void);
+const char* crv_last_error(void);
+/* Number of SMs of the current device (0 if there is none). */
+int         crv_device_sm_count(void);
+size_t      crv_workspace_bytes(int op, const int64_t* dims, int ndims);
+
+/* K1a -- first Kronecker factor of a Conv2d layer, fused implicit im2col + SYRK + running sum:
+ *   A[k1,k2] += alpha * sum_r X[k1,r] X[k2,r],   X = unfold(x) in the reference's row order
+ *   k = c*kh*kw + i*kw + j, r = n*OH*OW + oh*OW + ow, zero padding, dilation 1, groups 1,
+ *   plus a trailing row of ones iff has_bias.  A is (K,K), K = C*kh*kw + has_bias.
+ * Replaces F.unfold + permute/contiguous + ones/cat + torch.mm + div + add_
+ * (curvature/curvatures.py:329-336, 346-350).  The patch matrix is never written to HBM. */
+int crv_syrk_conv_accum(const float* x, int N, int C, int H, int W,
+                        int kh, int kw, int sh, int sw, int ph, int pw,
+                        int has_bias, float alpha, float* A,
+                        void* ws, size_t ws_bytes, int precision, crv_stream_t stream);
+
+/* K1b -- Gram matrix over the non-channel axes of an (N, M, L) tensor (L = 1 for Linear):
+ *   F[m1,m2] += alpha * sum_{n,l} g[n,m1,l] g[n,m2,l]    (+ trailing ones row iff has_bias)
+ * Second factor G (curvatures.py:339-343, 346-350) and first factor of Linear layers
+ * (curvatures.py:332-336).  F is (D,D), D = M + has_bias. */
+int crv_syrk_rows_accum(const float* g, int N, int M, int L, int has_bias, float alpha, float* F,
+                        void* ws, size_t ws_bytes, int precision, crv_stream_t stream);
+
+/* K2 -- squared-gradient accumulation (Diagonal.update, curvatures.py:151-158; the `diags`
+ * part of EFB.update, curvatures.py:431-434):
+ *   state[m, k] += scale * G[m,k]^2,  G = [wgrad.view(M,K0) | bgrad]  (bias column last).
+ * bgrad may be NULL (no bias -> K = K0).  If grads_out != NULL the concatenated G (M, K) is
+ * also written there (input of crv_efb_project_accum).  state may be NULL. */
+int crv_diag_accum(const float* wgrad, const float* bgrad, int M, int K0, float scale,
+                   float* state, float* grads_out, crv_stream_t stream);
+
+/* K3 -- EFB eigenbasis projection (curvatures.py:427-433):
+ *   lambdas[m,k] += ((QG^T * G * QA)[m,k])^2,   QG (M,M), G (M,K), QA (K,K).
+ * ws holds the (M,K) intermediate. */
+int crv_efb_project_accum(const float* QG, const float* QA, const float* G, int M, int K,
+                          float* lambdas, void* ws, size_t ws_bytes, int precision,
+                          crv_stream_t stream);
+
+/* K4 -- batched damped Cholesky-of-inverse (KFAC.invert, curvatures.py:368-379):
+ *   reg = sqrt(mul_i) * F_i + sqrt(add_i) * I;  reg = (reg + reg^T)/2;
+ *   L_i = lower Cholesky factor of inv(reg)     (L_i L_i^T = reg^{-1}).
+ * F / L_out are HOST arrays of `count` device pointers, dims[i] the matrix orders, add / mul
+ * host arrays of per-matrix scalars.  info is a DEVICE int array (count): 0 = ok, j > 0 = the
+ * j-th leading minor of the flipped matrix is not positive (reference: RuntimeError -> numpy
+ * fallback at curvatures.py:380-383; here the caller raises -- no CPU fallback). */
+int crv_chol_inv_batched(const float* const* F, const int* dims, int count,
+                         const float* add, const float* mul, float* const* L_out, int* info,
+                         void* ws, size_t ws_bytes, crv_stream_t stream);
+
+/* K5 -- matrix-normal posterior draw fused with the parameter write-back
+ * (KFAC.sample curvatures.py:391-392 + Curvature._replace :78-82 + the load_state_dict
+ * reload of the mean at :119):
+ *   S = LG * z^T * LA^T  (M,K);  w_out[m, 0:K0] = mu_w + S[:, 0:K0];  b_out[m] = mu_b + S[:, K0]
+ * z is (K, M) exactly as the reference draws it, LA (K,K), LG (M,M), K = K0 + has_bias.
+ * If row_scale != NULL (EFB.sample, curvatures.py:458-460) z is first multiplied elementwise
+ * by row_scale^T where row_scale is (M,K).  s_out (M,K), if non-NULL, receives S itself
+ * (KFAC.sample's return value); w_out / b_out / mu_* may be NULL when only S is wanted. */
+int crv_sample_matrix_normal(const float* LG, const float* LA, const float* z, const float* row_scale,
+                             int M, int K0, int has_bias,
+                             const float* mu_w, const float* mu_b, float* w_out, float* b_out,
+                             float* s_out, void* ws, size_t ws_bytes, int precision,
+                             crv_stream_t stream);
+
+/* out[i] = sqrt(1 / (mul * v[i] + add))  (Diagonal.invert :188, EFB.invert :450, INF :526). */
+int crv_elementwise_inv_sqrt(const float* v, float add, float mul, float* out, size_t n,
+                             crv_stream_t stream);
+
+/* w_out = mu_w + (z * inv)[:, 0:K0], b_out = mu_b + (z * inv)[:, K0]   (Diagonal.sample :193 +
+ * _replace); z, inv are (M,K); s_out (nullable) receives z * inv. */
+int crv_diag_sample(const float* z, const float* inv, int M, int K0, int has_bias,
+                    const float* mu_w, const float* mu_b, float* w_out, float* b_out, float* s_out,
+                    crv_stream_t stream);
+
+/* Plain row-major GEMM used by the INF low-rank algebra (curvatures.py:538-600) and tests:
+ *   C (m,n) = alpha * op(A) * op(B) + beta * C,  op = transpose iff trans* != 0. */
+int crv_gemm(const float* A, int lda, int transA, const float* B, int ldb, int transB,
+             float* C, int ldc, int m, int n, int k, float alpha, float beta, int precision,
+             crv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CURVATURE_B200_H */

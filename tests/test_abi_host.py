@@ -1,0 +1,135 @@
+"""CPU: the C-ABI library loads and exports every symbol include/*.h declares; host-side logic of the
+drop-in classes (argument handling, assertion messages, index selection, arena, sharding).  No kernel runs."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from helpers import ROOT, orc
+
+import curvature_b200 as cb
+from curvature_b200 import _native as nat
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "curvature_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(crv_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(nat.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 13
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/curvature_b200.h but not exported"
+    assert sorted(nat.EXPORTED_SYMBOLS) == declared
+    assert nat.ABI_VERSION == 1
+
+
+def test_workspace_queries_are_host_only():
+    assert nat.workspace_bytes(nat.OP_EFB_PROJECT, [10, 20]) == 10 * 20 * 4
+    assert nat.workspace_bytes(nat.OP_SAMPLE_MN, [10, 20]) == 10 * 20 * 4 * 2
+    assert nat.workspace_bytes(nat.OP_CHOL_INV, [2, 6, 401]) >= 2 * (36 + 401 * 401) * 4
+    assert nat.workspace_bytes(nat.OP_SYRK_CONV, [2, 3, 8, 8, 3, 3, 1, 1, 1, 1, 1, nat.PREC_FP32]) == 0
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are refused loudly instead of being routed to some other implementation."""
+    model = torch.nn.Sequential(torch.nn.Linear(3, 2))
+    kfac = cb.KFAC(model)
+    model(torch.randn(4, 3)).sum().backward()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        kfac.update(4)
+    diag = cb.Diagonal(model)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        diag.update(4)
+
+
+def test_layer_types_and_messages():
+    model = orc.lenet5()
+    assert cb.Diagonal(model).layer_types == ['Linear', 'Conv2d', 'MultiheadAttention']
+    assert cb.Diagonal(model, []).layer_types == ['Linear', 'Conv2d', 'MultiheadAttention']
+    assert cb.Diagonal(model, 'Linear').layer_types == ['Linear']
+    assert cb.Diagonal(model, ['Conv2d']).layer_types == ['Conv2d']
+    with pytest.raises(TypeError):
+        cb.Diagonal(model, 3)
+    with pytest.raises(AssertionError):
+        cb.Diagonal(model, ['BatchNorm2d'])
+    for cls in (cb.Diagonal, cb.KFAC):
+        est = cls(model)
+        with pytest.raises(AssertionError, match="State dict is empty. Did you call 'update' prior to this\\?"):
+            est.invert()
+        with pytest.raises(AssertionError, match="Inverse state dict is empty. Did you call 'invert' prior to this\\?"):
+            est.sample(model[0])
+    kfac = cb.KFAC(model, 'Conv2d')
+    assert len(kfac.record) == 2 and len(kfac.hooks) == 4
+    assert cb.KFAC._save_grad_output is cb.KFAC._save_output
+    mha = torch.nn.Sequential(torch.nn.MultiheadAttention(8, 2))
+    with pytest.raises(NotImplementedError):
+        cb.KFAC(mha)
+    with pytest.raises(NotImplementedError):
+        cb.KFAC(torch.nn.Sequential(torch.nn.Conv2d(4, 4, 3, groups=2)))
+
+
+def test_hooks_are_pointer_stashes():
+    model = orc.lenet5()
+    kfac = cb.KFAC(model)
+    x = torch.rand(3, 1, 28, 28)
+    out = model(x)
+    assert kfac.record[model[0]][0] is x                       # reference: no copy (curvatures.py:307)
+    out.sum().backward()
+    g = kfac.record[model[11]][1]
+    assert g.shape == (3, 10)
+    assert torch.equal(kfac.scaled_record(model[11]), g * 3)   # what the reference stores (curvatures.py:310)
+    with torch.no_grad():
+        model(x)                                               # eval-style forward still only stashes
+
+
+def test_dim_reduction_matches_oracle():
+    torch.manual_seed(3)
+    qa, qg = torch.randn(12, 12), torch.randn(7, 7)
+    lam = torch.randn(84).abs()
+    for rank in (5, 20, 83, 84, 200):
+        a, b, c = cb.INF._dim_reduction(qa, qg, lam, rank)
+        ao, bo, co = orc.INF._dim_reduction(qa, qg, lam, rank)
+        assert torch.equal(a, ao) and torch.equal(b, bo) and torch.equal(c, co)
+
+
+def test_kron_and_eigen_helpers():
+    a = torch.tensor([[1, 2], [3, 4]])
+    b = torch.tensor([[0, 5], [6, 7]])
+    assert torch.equal(cb.kron(a, b), orc.kron(a, b))
+    torch.manual_seed(0)
+    A = torch.randn(9, 9); A = A @ A.t()
+    G = torch.randn(5, 5); G = G @ G.t()
+    ev = cb.get_eigenvectors({"l": (A, G)})["l"]
+    evo = orc.eigenvectors_of_factors({"l": (A, G)})["l"]
+    for q, qo, Fm in ((ev[0], evo[0], A), (ev[1], evo[1], G)):
+        assert q.is_contiguous()
+        assert torch.allclose(q.abs(), qo.abs(), atol=1e-5)
+        assert torch.allclose(q.t() @ (2 * Fm) @ q, torch.diag(torch.diag(q.t() @ (2 * Fm) @ q)), atol=1e-3)
+    vals = cb.get_eigenvalues([(A, G), torch.ones(3, 2)])
+    assert vals.numel() == 45 + 6
+    assert torch.allclose(vals, orc.eigenvalues_of_factors([(A, G), torch.ones(3, 2)]), rtol=1e-4, atol=1e-4)
+
+
+def test_arena_views_alias_flat_buffer():
+    arena = cb.FactorArena([(3, 3), (5, 2), (1,)], "cpu")
+    assert arena.flat.numel() % cb.FactorArena.ALIGN == 0
+    arena.views[1].fill_(2.0)
+    assert arena.flat.sum().item() == 20.0
+    for v in arena.views:
+        assert v.data_ptr() % 256 == arena.flat.data_ptr() % 256
+
+
+def test_shard_indices():
+    assert cb.shard_indices(5, 0, 2) == [0, 2, 4]
+    assert cb.shard_indices(5, 1, 2) == [1, 3]
+    costs = [100, 1, 1, 1, 50, 50]
+    parts = [cb.shard_indices(6, r, 2, costs) for r in range(2)]
+    assert sorted(parts[0] + parts[1]) == list(range(6))
+    loads = [sum(costs[i] for i in p) for p in parts]
+    assert max(loads) <= 103

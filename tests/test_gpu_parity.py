@@ -1,0 +1,399 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the golden fixtures
+produced by the real reference.  Tolerances are the north-star's: bit-exact where the arithmetic is integer
+(im2col indexing on integer-valued data), relative Frobenius 1e-5 for fp32 factors and diagonals, a stated
+1e-3 for the tensor-core tiers; samples are compared with the same supplied Gaussian noise."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import orc, rel_fro, model_from_golden, selected_layers, n_batches, conv_zoo
+
+pytestmark = pytest.mark.gpu
+
+import curvature_b200 as cb                      # noqa: E402
+from curvature_b200 import _native as nat        # noqa: E402
+
+DEV = "cuda:0"
+FACTOR_TOL = {nat.PREC_FP32: 1e-5, nat.PREC_TF32: 1e-3, nat.PREC_TF32X3: 1e-5, nat.PREC_BF16: 1e-3}
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    # the model's own conv fwd/bwd (cuDNN, not ours) must not run in TF32 or it perturbs the inputs
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def tiers():
+    out = [nat.PREC_FP32]
+    import os
+    for name in os.environ.get("CURVATURE_B200_TEST_TIERS", "tf32").split(","):
+        if name and name != "fp32":
+            out.append(nat.PRECISION_NAMES[name])
+    return out
+
+
+def oracle_A(x, k, s, p, has_bias, dtype=torch.float64):
+    cols = orc.unfold_patches(x.to(dtype), k, p, s)
+    X = cols.permute(1, 0, 2).reshape(cols.shape[1], -1)
+    if has_bias:
+        X = torch.cat([X, torch.ones_like(X[:1])], 0)
+    return X @ X.t(), X.shape[1]
+
+
+GEOMS = [
+    # N, C, H, W, kernel, stride, padding, bias
+    (2, 1, 5, 5, (3, 3), (1, 1), (1, 1), True),
+    (3, 3, 7, 6, (3, 2), (2, 1), (1, 0), True),
+    (2, 2, 8, 8, (1, 1), (2, 2), (0, 0), False),
+    (2, 4, 9, 11, (5, 5), (1, 1), (2, 2), True),
+    (1, 3, 12, 12, (7, 7), (2, 2), (3, 3), False),
+    (2, 2, 6, 9, (1, 3), (1, 2), (0, 2), True),
+    (2, 5, 4, 4, (4, 4), (1, 1), (0, 0), False),
+    (1, 1, 10, 3, (3, 3), (3, 1), (2, 2), True),
+    (5, 8, 14, 14, (3, 3), (1, 1), (1, 1), False),     # K = 72: two 64-row tiles
+    (3, 16, 7, 7, (3, 3), (2, 2), (1, 1), True),       # K = 145: three tiles, odd sizes
+    (70, 3, 6, 6, (3, 3), (1, 1), (1, 1), True),       # R = 2520: several contraction splits
+]
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+@pytest.mark.parametrize("prec", tiers())
+def test_implicit_im2col_syrk_bit_exact_on_integers(geom, prec):
+    """Integer-valued activations make every product and partial sum exactly representable (also in tf32 /
+    bf16), so any indexing error -- wrong tap, wrong padding, wrong row order, lost bias row -- shows up as an
+    exact mismatch.  This is the 'bit-exact for im2col indexing' gate."""
+    N, C, H, W, k, s, p, bias = geom
+    gen = torch.Generator().manual_seed(hash(geom) % (2 ** 31))
+    x = torch.randint(0, 4, (N, C, H, W), generator=gen).float()
+    want, R = oracle_A(x, k, s, p, bias)
+    K = want.shape[0]
+    out = torch.zeros(K, K, device=DEV)
+    nat.syrk_conv_accum(x.to(DEV), k, s, p, bias, 1.0, out, prec)
+    assert torch.equal(out.cpu().double(), want), f"max diff {(out.cpu().double() - want).abs().max()}"
+    # running sum: a second call with alpha = 2 adds twice the factor (curvatures.py:346-350 is a plain +=)
+    nat.syrk_conv_accum(x.to(DEV), k, s, p, bias, 2.0, out, prec)
+    assert torch.equal(out.cpu().double(), 3 * want)
+
+
+@pytest.mark.parametrize("shape,bias", [((4, 6), True), ((5, 10), False), ((3, 7, 5, 4), False), ((2, 70, 3, 3), False),
+                                        ((9, 130), True), ((1, 1), True), ((300, 3, 2, 2), False)])
+@pytest.mark.parametrize("prec", tiers())
+def test_rows_syrk_bit_exact_on_integers(shape, bias, prec):
+    gen = torch.Generator().manual_seed(len(shape) * 1000 + shape[1])
+    g = torch.randint(-3, 4, shape, generator=gen).float()
+    M = shape[1]
+    X = g.reshape(shape[0], M, -1).permute(1, 0, 2).reshape(M, -1).double()
+    if bias:
+        X = torch.cat([X, torch.ones_like(X[:1])], 0)
+    want = X @ X.t()
+    out = torch.zeros(want.shape[0], want.shape[0], device=DEV)
+    nat.syrk_rows_accum(g.to(DEV), bias, 1.0, out, prec)
+    assert torch.equal(out.cpu().double(), want)
+
+
+@pytest.mark.parametrize("prec", tiers())
+def test_kfac_layer_factors_from_recorded_tensors(golden, prec):
+    """Kernel-level parity on the exact tensors the reference's hooks recorded (convzoo: strides, asymmetric
+    padding, non-square kernels, bias / no bias, Linear with and without bias)."""
+    g = golden("convzoo")
+    model = conv_zoo()
+    for li, layer in enumerate(selected_layers(model)):
+        x = torch.from_numpy(g[f"last_input/{li}"])
+        go = torch.from_numpy(g[f"last_gradout/{li}"])          # already scaled by N, as the reference records it
+        A_ref, G_ref = orc.kfac_factors(x, go, layer)
+        bias = layer.bias is not None
+        K, M = A_ref.shape[0], G_ref.shape[0]
+        A = torch.zeros(K, K, device=DEV)
+        G = torch.zeros(M, M, device=DEV)
+        if layer.__class__.__name__ == "Conv2d":
+            R = x.shape[0] * go.shape[2] * go.shape[3]
+            nat.syrk_conv_accum(x.to(DEV), layer.kernel_size, layer.stride, layer.padding, bias, 1.0 / R, A, prec)
+        else:
+            R = x.shape[0]
+            nat.syrk_rows_accum(x.to(DEV), bias, 1.0 / R, A, prec)
+        nat.syrk_rows_accum(go.to(DEV).contiguous(), False, 1.0 / R, G, prec)
+        assert rel_fro(A, A_ref) <= FACTOR_TOL[prec], (li, rel_fro(A, A_ref))
+        assert rel_fro(G, G_ref) <= FACTOR_TOL[prec], (li, rel_fro(G, G_ref))
+        assert torch.equal(A, A.t()) and torch.equal(G, G.t())
+
+
+def run_estimation(name, g, prec):
+    """The reference's estimation loop (scripts/factors.py:46-61) on the GPU with the fixture's inputs and labels."""
+    model = model_from_golden(name, g, DEV)
+    layers = selected_layers(model)
+    N = int(g["meta/batch"])
+    kfac = cb.KFAC(model, precision=prec)
+    diag = cb.Diagonal(model)
+    for b in range(n_batches(g)):
+        orc.fisher_step(model, torch.from_numpy(g[f"x/{b}"]).to(DEV), labels=torch.from_numpy(g[f"labels/{b}"]).to(DEV))
+        kfac.update(N)
+        diag.update(N)
+    eig = {l: (torch.from_numpy(g[f"eig_QA/{li}"]).to(DEV), torch.from_numpy(g[f"eig_QG/{li}"]).to(DEV))
+           for li, l in enumerate(layers)}
+    efb = cb.EFB(model, kfac.state, eigvecs=eig)
+    for b in range(n_batches(g)):
+        orc.fisher_step(model, torch.from_numpy(g[f"x/{b}"]).to(DEV), labels=torch.from_numpy(g[f"labels/{b}"]).to(DEV))
+        efb.update(N)
+    return model, layers, kfac, diag, efb, eig
+
+
+@pytest.mark.parametrize("name", ["convzoo", "lenet5"])
+@pytest.mark.parametrize("prec", tiers())
+def test_estimators_match_reference_fixtures(name, golden, prec):
+    g = golden(name)
+    model, layers, kfac, diag, efb, eig = run_estimation(name, g, prec)
+    assert list(kfac.state.keys()) == layers                     # model.modules() order, module-keyed
+    for li, l in enumerate(layers):
+        assert isinstance(kfac.state[l], list) and len(kfac.state[l]) == 2
+        eA, eG = rel_fro(kfac.state[l][0], g[f"kfac_A/{li}"]), rel_fro(kfac.state[l][1], g[f"kfac_G/{li}"])
+        assert eA <= FACTOR_TOL[prec] and eG <= FACTOR_TOL[prec], (name, li, eA, eG)
+        assert rel_fro(diag.state[l], g[f"diag/{li}"]) <= 1e-5, (name, li, rel_fro(diag.state[l], g[f"diag/{li}"]))
+        assert rel_fro(efb.state[l], g[f"efb_lambda/{li}"]) <= 5e-5, (name, li, rel_fro(efb.state[l], g[f"efb_lambda/{li}"]))
+        assert rel_fro(efb.diags[l], g[f"diag/{li}"]) <= 1e-5
+    # A[-1,-1] counts the updates (ones-row) wherever the layer has a bias: plain-sum accumulation
+    for l in layers:
+        if l.bias is not None:
+            assert abs(kfac.state[l][0][-1, -1].item() - n_batches(g)) < 1e-5
+
+    # ---- invert + samples with the supplied noise (fp32 kernels; the factors come from the fixture so that the
+    #      comparison isolates K4 / K5 from the estimation tier) ----
+    for li, l in enumerate(layers):
+        kfac.state[l][0].copy_(torch.from_numpy(g[f"kfac_A/{li}"]))
+        kfac.state[l][1].copy_(torch.from_numpy(g[f"kfac_G/{li}"]))
+        efb.state[l].copy_(torch.from_numpy(g[f"efb_lambda/{li}"]))
+        diag.state[l].copy_(torch.from_numpy(g[f"diag/{li}"]))
+    kfac.invert(*g["meta/kfac_damp"].tolist())
+    diag.invert(*g["meta/diag_damp"].tolist())
+    efb.invert(*g["meta/diag_damp"].tolist())
+    for li, l in enumerate(layers):
+        LA, LG = kfac.inv_state[l]
+        assert isinstance(kfac.inv_state[l], tuple)
+        eA, eG = rel_fro(LA, g[f"kfac_LA/{li}"]), rel_fro(LG, g[f"kfac_LG/{li}"])
+        assert eA <= 1e-4 and eG <= 1e-4, (name, li, eA, eG)
+        assert torch.equal(LA, torch.tril(LA))
+        z = torch.from_numpy(g[f"noise_KM/{li}"]).to(DEV)
+        assert rel_fro(kfac.sample(l, z), g[f"kfac_sample/{li}"]) <= 1e-4
+        assert rel_fro(efb.sample(l, z), g[f"efb_sample/{li}"]) <= 1e-4
+        if f"diag_sample/{li}" in g.files:
+            zd = torch.from_numpy(g[f"noise_MK/{li}"]).to(DEV)
+            assert rel_fro(diag.sample(l, zd), g[f"diag_sample/{li}"]) <= 1e-6
+            assert rel_fro(diag.inv_state[l], g[f"diag_inv/{li}"]) <= 1e-6
+            assert rel_fro(efb.inv_state[l], g[f"efb_inv/{li}"]) <= 1e-6
+
+    # ---- sample_and_replace with the same noise: end state of every parameter ----
+    noise = {l: torch.from_numpy(g[f"noise_KM/{li}"]).to(DEV) for li, l in enumerate(layers)}
+    kfac.sample_and_replace(noise=noise)
+    sd = model.state_dict()
+    if any(k.startswith("replaced/") for k in g.files):
+        for k, v in sd.items():
+            assert rel_fro(v, g[f"replaced/{k}"]) <= 1e-5, k
+    else:
+        for li, l in enumerate(layers):
+            s = torch.from_numpy(g[f"kfac_sample/{li}"])
+            w0 = kfac.model_state[[k for k, v in model.state_dict(keep_vars=True).items() if v is l.weight][0]].cpu()
+            want_w = w0 + s[:, :w0[0].numel()].reshape(w0.shape)
+            assert rel_fro(l.weight.data, want_w) <= 1e-5
+    # a second call starts again from the mean (load_state_dict semantics, curvatures.py:119)
+    kfac.sample_and_replace(noise=noise)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd[k]) or rel_fro(v, sd[k]) <= 1e-7
+
+
+@pytest.mark.parametrize("name", ["convzoo", "lenet5"])
+def test_inf_matches_reference_fixtures(name, golden):
+    g = golden(name)
+    model = model_from_golden(name, g, DEV)
+    layers = selected_layers(model)
+    dev = lambda key, li: torch.from_numpy(g[f"{key}/{li}"]).to(DEV)   # noqa: E731
+    diags = {l: dev("diag", li) for li, l in enumerate(layers)}
+    factors = {l: [dev("kfac_A", li), dev("kfac_G", li)] for li, l in enumerate(layers)}
+    lambdas = {l: dev("efb_lambda", li) for li, l in enumerate(layers)}
+    eig = {l: (dev("eig_QA", li), dev("eig_QG", li)) for li, l in enumerate(layers)}
+    inf = cb.INF(model, diags, factors, lambdas, eigvecs=eig)
+    inf.update(rank=int(g["meta/rank"]))
+    for li, l in enumerate(layers):
+        a, b, lam, corr = inf.state[l]
+        assert torch.equal(a.cpu(), torch.from_numpy(g[f"inf_state_lrQA/{li}"]))       # pure index selection
+        assert torch.equal(b.cpu(), torch.from_numpy(g[f"inf_state_lrQG/{li}"]))
+        assert torch.equal(lam.cpu(), torch.from_numpy(g[f"inf_state_lrlambda/{li}"]))
+        # the correction is a difference of two nearly equal diagonals: compare on the scale of the diagonal
+        scale = np.linalg.norm(g[f"diag/{li}"])
+        assert (corr.cpu() - torch.from_numpy(g[f"inf_state_correction/{li}"])).norm().item() <= 1e-5 * scale
+    for li, l in enumerate(layers):     # isolate invert / sample from the small differences above
+        inf.state[l] = (inf.state[l][0], inf.state[l][1], inf.state[l][2], dev("inf_state_correction", li))
+    inf.invert(*g["meta/inf_damp"].tolist())
+    for li, l in enumerate(layers):
+        pre = inf.inv_state[l][3]
+        if f"inf_pre/{li}" in g.files:
+            assert rel_fro(pre, g[f"inf_pre/{li}"]) <= 2e-3, (li, rel_fro(pre, g[f"inf_pre/{li}"]))
+        else:
+            assert rel_fro(pre[:128, :128], g[f"inf_pre_corner/{li}"]) <= 2e-3
+            assert abs(pre.double().norm().item() / float(g[f"inf_pre_fro/{li}"]) - 1) <= 2e-3
+        z = dev("noise_KM", li).reshape(-1)
+        assert rel_fro(inf.sample(l, z), g[f"inf_sample/{li}"]) <= 1e-3, (li, rel_fro(inf.sample(l, z), g[f"inf_sample/{li}"]))
+
+
+RESNET_LAYERS = [
+    # name, N, C, H, W, k, s, p
+    ("stem 7x7 s2", 2, 3, 224, 224, 7, 2, 3),
+    ("3x3 64ch 56^2", 2, 64, 56, 56, 3, 1, 1),
+    ("3x3 s2 128ch", 2, 128, 56, 56, 3, 2, 1),
+    ("1x1 256ch 56^2", 2, 256, 56, 56, 1, 1, 0),
+    ("1x1 s2 256ch", 2, 256, 56, 56, 1, 2, 0),
+    ("3x3 256ch 14^2", 4, 256, 14, 14, 3, 1, 1),
+    ("3x3 512ch 7^2", 4, 512, 7, 7, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("layer", RESNET_LAYERS, ids=[l[0] for l in RESNET_LAYERS])
+@pytest.mark.parametrize("prec", tiers())
+def test_resnet_shaped_factors_against_fp64(layer, prec):
+    """BASELINE config shapes (ResNet-18/50/152 layer geometries) at a reduced batch, against an fp64
+    unfold + matmul on the same device (size-independent check of the fused kernel on real tile counts)."""
+    name, N, C, H, W, k, s, p = layer
+    torch.manual_seed(1)
+    x = torch.relu(torch.randn(N, C, H, W, device=DEV))            # post-ReLU-like activations
+    cols = F.unfold(x.double(), k, padding=p, stride=s)
+    X = cols.permute(1, 0, 2).reshape(cols.shape[1], -1)
+    want = (X @ X.t()) / X.shape[1]
+    out = torch.zeros_like(want, dtype=torch.float32)
+    nat.syrk_conv_accum(x, (k, k), (s, s), (p, p), False, 1.0 / X.shape[1], out, prec)
+    err = rel_fro(out, want)
+    assert err <= FACTOR_TOL[prec], (name, err)
+    assert torch.equal(out, out.t())
+    # G-type operand of the same layer: (N, M, OH, OW) gradient-like tensor
+    OH = (H + 2 * p - k) // s + 1
+    gten = torch.randn(N, min(C, 256), OH, OH, device=DEV) * 1e-3
+    Xg = gten.double().permute(1, 0, 2, 3).reshape(gten.shape[1], -1)
+    wantg = (Xg @ Xg.t()) * (N * N / Xg.shape[1])
+    outg = torch.zeros_like(wantg, dtype=torch.float32)
+    nat.syrk_rows_accum(gten, False, N * N / Xg.shape[1], outg, prec)
+    assert rel_fro(outg, wantg) <= FACTOR_TOL[prec], (name, rel_fro(outg, wantg))
+
+
+@pytest.mark.parametrize("D", [1, 6, 31, 32, 33, 85, 401, 1000])
+def test_damped_cholesky_of_inverse(D):
+    torch.manual_seed(D)
+    X = torch.randn(D, 2 * D + 3, device=DEV)
+    Fm = (X @ X.t() / X.shape[1]).contiguous()
+    Fm = Fm + 1e-3 * torch.randn_like(Fm)                 # slightly asymmetric, like a summed factor
+    add, mul = 0.3, 2.5
+    out = torch.empty_like(Fm)
+    info = nat.chol_inv_batched([Fm], [add], [mul], [out])
+    assert info.item() == 0
+    reg = mul ** 0.5 * Fm.double() + add ** 0.5 * torch.eye(D, device=DEV, dtype=torch.float64)
+    reg = (reg + reg.t()) / 2
+    want = torch.linalg.cholesky(torch.linalg.inv(reg))
+    assert rel_fro(out, want) <= 1e-4, rel_fro(out, want)
+    resid = out.double() @ out.double().t() @ reg - torch.eye(D, device=DEV, dtype=torch.float64)
+    assert resid.norm().item() / D ** 0.5 <= 1e-4
+    assert torch.equal(out, torch.tril(out))
+
+
+def test_cholesky_batch_mixed_sizes_and_failure_flag():
+    torch.manual_seed(0)
+    mats = []
+    for D in (5, 70, 33, 128):
+        X = torch.randn(D, 3 * D, device=DEV)
+        mats.append((X @ X.t() / X.shape[1]).contiguous())
+    mats.append(-torch.eye(4, device=DEV))                   # not positive definite after damping
+    outs = [torch.empty_like(m) for m in mats]
+    info = nat.chol_inv_batched(mats, [0.5] * 5, [1.0] * 5, outs).cpu()
+    assert info[:4].tolist() == [0, 0, 0, 0] and info[4].item() > 0
+    for m, o in zip(mats[:4], outs[:4]):
+        want = orc.damped_inverse_cholesky(m.cpu(), 0.5, 1.0)
+        assert rel_fro(o, want) <= 1e-4
+    model = torch.nn.Sequential(torch.nn.Linear(3, 2)).to(DEV)
+    kfac = cb.KFAC(model)
+    model(torch.randn(4, 3, device=DEV)).sum().backward()
+    kfac.update(4)
+    kfac.state[model[0]][0].copy_(-torch.eye(4))
+    with pytest.raises(RuntimeError, match="not positive definite"):
+        kfac.invert(0.5, 1.0)
+
+
+@pytest.mark.parametrize("M,K0,bias", [(6, 25, True), (16, 150, True), (7, 64, False), (1000, 2048, True), (3, 1, True)])
+def test_streaming_kernels(M, K0, bias):
+    torch.manual_seed(M)
+    w = torch.randn(M, K0, device=DEV)
+    b = torch.randn(M, device=DEV) if bias else None
+    grads = torch.cat([w, b[:, None]], 1) if bias else w
+    K = grads.shape[1]
+    state = torch.rand(M, K, device=DEV)
+    want = state + grads ** 2 * 32
+    gout = torch.empty(M, K, device=DEV)
+    nat.diag_accum(w, b, 32, state=state, grads_out=gout)
+    assert rel_fro(state, want) <= 1e-6 and torch.equal(gout, grads)
+    inv = torch.empty_like(state)
+    nat.elementwise_inv_sqrt(state, 0.1, 1e3, inv)
+    assert rel_fro(inv, torch.reciprocal(1e3 * state + 0.1).sqrt()) <= 1e-6
+    z = torch.randn(M, K, device=DEV)
+    mu_w, mu_b = torch.randn(M, K0, device=DEV), (torch.randn(M, device=DEV) if bias else None)
+    w_out, b_out = torch.empty_like(mu_w), (torch.empty_like(mu_b) if bias else None)
+    s_out = torch.empty_like(z)
+    nat.diag_sample(z, inv, bias, mu_w=mu_w, mu_b=mu_b, w_out=w_out, b_out=b_out, s_out=s_out)
+    assert torch.equal(s_out, z * inv)
+    assert torch.equal(w_out, mu_w + (z * inv)[:, :K0])
+    if bias:
+        assert torch.equal(b_out, mu_b + (z * inv)[:, K0])
+
+
+@pytest.mark.parametrize("M,K0,bias", [(10, 84, True), (120, 400, True), (64, 576, False), (256, 1152, False)])
+def test_efb_projection_and_matrix_normal_draw(M, K0, bias):
+    torch.manual_seed(K0)
+    K = K0 + bias
+    QA = torch.linalg.qr(torch.randn(K, K, device=DEV))[0].contiguous()
+    QG = torch.linalg.qr(torch.randn(M, M, device=DEV))[0].contiguous()
+    G = torch.randn(M, K, device=DEV)
+    lam = torch.rand(M, K, device=DEV)
+    want = lam.double() + (QG.double().t() @ G.double() @ QA.double()) ** 2
+    nat.efb_project_accum(QG, QA, G, lam)
+    assert rel_fro(lam, want) <= 1e-5
+    LA = torch.tril(torch.randn(K, K, device=DEV)).contiguous()
+    LG = torch.tril(torch.randn(M, M, device=DEV)).contiguous()
+    z = torch.randn(K, M, device=DEV)
+    S_want = (LA.double() @ z.double() @ LG.double().t()).t()             # curvatures.py:392
+    mu_w, mu_b = torch.randn(M, K0, device=DEV), torch.randn(M, device=DEV)
+    w_out, b_out, s_out = torch.empty_like(mu_w), torch.empty_like(mu_b), torch.empty(M, K, device=DEV)
+    nat.sample_matrix_normal(LG, LA, z, bias, mu_w=mu_w, mu_b=mu_b if bias else None, w_out=w_out,
+                             b_out=b_out if bias else None, s_out=s_out)
+    assert rel_fro(s_out, S_want) <= 1e-5
+    assert rel_fro(w_out, mu_w.double() + S_want[:, :K0]) <= 1e-5
+    if bias:
+        assert rel_fro(b_out, mu_b.double() + S_want[:, K0]) <= 1e-5
+    rs = torch.rand(M, K, device=DEV)
+    nat.sample_matrix_normal(QG, QA, z, False, row_scale=rs, s_out=s_out)   # EFB.sample, curvatures.py:458-460
+    want_efb = (QA.double() @ (z.double() * rs.double().t()) @ QG.double().t()).t()
+    assert rel_fro(s_out, want_efb) <= 1e-5
+
+
+def test_diagonal_multihead_attention_keys():
+    torch.manual_seed(0)
+    mha = torch.nn.MultiheadAttention(16, 4).to(DEV)
+    model = torch.nn.ModuleList([mha])
+    x = torch.randn(5, 3, 16, device=DEV)
+    out, _ = mha(x, x, x)
+    out.sum().backward()
+    diag = cb.Diagonal(model)
+    diag.update(3)
+    assert list(diag.state.keys()) == ['attn_in', 'attn_out']
+    want_in = torch.cat([mha.in_proj_weight.grad, mha.in_proj_bias.grad[:, None]], 1) ** 2 * 3
+    assert rel_fro(diag.state['attn_in'], want_in) <= 1e-6
+    diag.invert(0.1, 10.0)
+    diag.sample_and_replace()
+    assert not torch.equal(mha.in_proj_weight.data, diag.model_state['0.in_proj_weight'])
+
+
+def test_gemm_entry_point():
+    torch.manual_seed(0)
+    A, B = torch.randn(70, 33, device=DEV), torch.randn(33, 129, device=DEV)
+    assert rel_fro(nat.gemm(A, B), A.double() @ B.double()) <= 1e-6
+    assert rel_fro(nat.gemm(A, torch.randn(70, 5, device=DEV), transA=True).shape[0], 33) == 0
+    Bt = B.t().contiguous()
+    assert rel_fro(nat.gemm(A, Bt, transB=True), A.double() @ B.double()) <= 1e-6
+    C = torch.ones(70, 129, device=DEV)
+    nat.gemm(A, B, alpha=2.0, beta=3.0, out=C)
+    assert rel_fro(C, 2 * (A.double() @ B.double()) + 3) <= 1e-6
