@@ -242,6 +242,8 @@ def diag_sample(z, inv, has_bias, mu_w=None, mu_b=None, w_out=None, b_out=None, 
 def gemm(A, B, transA=False, transB=False, alpha=1.0, beta=0.0, out=None, precision=PREC_FP32):
     """Row-major C = alpha op(A) op(B) + beta C through the library's own GEMM kernel."""
     global launch_calls
+    A = A if A.is_contiguous() else A.contiguous()
+    B = B if B.is_contiguous() else B.contiguous()
     m = A.shape[1] if transA else A.shape[0]
     k = A.shape[0] if transA else A.shape[1]
     kb = B.shape[1] if transB else B.shape[0]

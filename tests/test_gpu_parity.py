@@ -29,7 +29,7 @@ def _strict_fp32():
 def tiers():
     out = [nat.PREC_FP32]
     import os
-    for name in os.environ.get("CURVATURE_B200_TEST_TIERS", "tf32").split(","):
+    for name in os.environ.get("CURVATURE_B200_TEST_TIERS", "").split(","):
         if name and name != "fp32":
             out.append(nat.PRECISION_NAMES[name])
     return out
