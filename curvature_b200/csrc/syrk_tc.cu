@@ -1,9 +1,469 @@
-// placeholder until the tcgen05 kernel lands
+// K1 (tensor-core tier): fused implicit-im2col + SYRK on the 5th-generation tensor cores.
+//
+//   F[k1,k2] += alpha * sum_r X[k1,r] * X[k2,r]       X = im2col(x) (+ ones row), never in HBM
+//
+// Structure (one work item per CTA, 17 warps, 1 CTA / SM):
+//   * the factor is cut into 256-row blocks; only block pairs (I >= J) are computed, and the
+//     contraction axis R is split S ways so that pairs*S items fill the 148 SMs;
+//   * 16 PRODUCER warps gather activations straight from the NCHW tensor (lane <-> contraction
+//     position r, so global reads are coalesced along ow), round them to TF32 with cvt.rna and
+//     store them into shared memory in the canonical K-major SWIZZLE_128B layout that tcgen05
+//     expects (row = 128 bytes = 32 positions; 16-byte chunk index XOR (row & 7));
+//     rows of a block are enumerated TAP-MAJOR (k' = (i*kw+j)*C + c) so that the 32 consecutive
+//     rows a warp owns share one filter tap: one bounds test / offset per tap instead of per row;
+//   * ONE thread of the MMA warp issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N<=256, K=8):
+//     per stage 2 row halves x 4 k-steps, accumulating a 256x256 fp32 tile in TMEM (2 x 256 columns
+//     = all 512 columns); tcgen05.commit releases the smem stage / signals the epilogue;
+//   * mbarrier full/empty ring of 3 x 64 KB stages between producers and the MMA thread;
+//   * EPILOGUE (producer warps 0-3): tcgen05.ld the accumulator (32 lanes x 16 columns per
+//     instruction) and store the partial tile to the workspace; a second, small kernel sums the S
+//     partial tiles in a fixed order (deterministic), scales by alpha, undoes the tap-major
+//     permutation and adds the tile and its mirror image into the factor arena.
 #include "common.cuh"
+#include "../../include/curvature_b200.h"
+#include <math.h>
+
 namespace crv {
-size_t syrk_tc_workspace(const ConvGeom&, int) { return 0; }
-int syrk_tc_launch(const ConvGeom&, float, float*, int precision, void*, size_t, cudaStream_t) {
-  set_error("tensor-core tier %d is not built yet", precision);
-  return 1;
+namespace {
+
+constexpr int TB = 256;                       // rows of X per block (tile edge)
+constexpr int STAGE_ROWS = 512;               // (row, 32-position segment) slots per pipeline stage
+constexpr int STAGE_BYTES = STAGE_ROWS * 128; // 64 KB
+constexpr int NSTAGE = 3;
+constexpr int NPROD = 16;                     // producer warps
+constexpr int NTHREADS = (NPROD + 1) * 32;
+constexpr int TILE_ELEMS = TB * TB;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr uint32_t SPIN_LIMIT = 1u << 21;     // watchdog: trap instead of hanging the GPU
+
+__device__ float g_zero_page[64];   // zeros: where padded / out-of-range positions read from
+
+struct FastDiv {
+  uint32_t mul, shift, one;  // q = one ? n : umulhi(n, mul) >> shift   (exact for n < 2^31)
+};
+
+struct TcParams {
+  ConvGeom g;
+  FastDiv divL, divOW, divC, divKW;
+  int T, pairs, splits, chunks, cps;  // blocks, block pairs, R-splits, 32-chunks, chunks per split
+  int HW, CHW, KK;
+  float* ws;
+};
+
+__host__ FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  if (d <= 1) { f.mul = 0; f.shift = 0; f.one = 1; return f; }
+  uint32_t s = 0;
+  while ((1u << (s + 1)) <= d) ++s;          // s = floor(log2 d)
+  if ((d & (d - 1)) == 0) {                  // power of two: mul = 2^(32-s) would overflow for s = 0 only
+    f.mul = (uint32_t)(1ull << (32 - s));
+    f.shift = 0;
+    f.one = 0;
+    return f;
+  }
+  f.mul = (uint32_t)(((1ull << (32 + s)) / d) + 1);
+  f.shift = s;
+  f.one = 0;
+  return f;
 }
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  return f.one ? n : (__umulhi(n, f.mul) >> f.shift);
+}
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > SPIN_LIMIT) asm volatile("trap;");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cvt_tf32(float f) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(f));
+  return u;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in bits
+// [0,14), leading byte offset (unused for one swizzle atom along K) in [16,30), stride byte offset
+// = 1024 B between 8-row groups in [32,46), descriptor version 1 in [46,48), swizzle mode 2 (128 B)
+// in [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D = fp32 (bits 4-5 = 1), A and B = TF32 (format 2 at bits 7-9 / 10-12),
+// both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+__device__ __forceinline__ uint32_t umma_idesc(uint32_t M, uint32_t N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+__device__ __forceinline__ void decode_pair(int pair, int T, int& I, int& J) {
+  const int noff = T * (T - 1) / 2;  // off-diagonal pairs first (they are the heavy items)
+  if (pair < noff) {
+    int i = (int)((1.f + sqrtf(1.f + 8.f * (float)pair)) * 0.5f);
+    while (i * (i - 1) / 2 > pair) --i;
+    while ((i + 1) * i / 2 <= pair) ++i;
+    I = i;
+    J = pair - i * (i - 1) / 2;
+  } else {
+    I = J = pair - noff;
+  }
+}
+
+// ---- main kernel ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1) syrk_tc_kernel(const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;     // swizzle-128B atoms need 1024-byte alignment
+  const uint32_t bars = sbase + NSTAGE * STAGE_BYTES;
+  // full[s] = bars + 8 s ; empty[s] = bars + 8 (NSTAGE + s) ; tmem_full = bars + 8 * 2 NSTAGE
+  const uint32_t bar_tmem_full = bars + 8 * (2 * NSTAGE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (sbase - raw) + NSTAGE * STAGE_BYTES + 8 * (2 * NSTAGE + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvGeom& g = p.g;
+
+  const int item = blockIdx.x;
+  const int pair = item / p.splits, split = item - pair * p.splits;
+  int I, J;
+  decode_pair(pair, p.T, I, J);
+  const bool diag = (I == J);
+  const int rowsA = min(TB, g.D - I * TB);
+  const int mh = (rowsA + 127) >> 7;                               // 128-row halves of the A block
+  const int ncols = diag ? ((rowsA + 15) & ~15) : TB;              // UMMA N
+  const int RP = diag ? (rowsA <= 128 ? 128 : 256) : 512;          // rows per sub-chunk in a stage
+  const int SC = STAGE_ROWS / RP;                                  // 32-position sub-chunks per stage
+  const int cb = split * p.cps;
+  const int ce = min(p.chunks, cb + p.cps);
+  const int nstage_it = (ce - cb + SC - 1) / SC;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(bars + 8 * s, NPROD);
+      mbar_init(bars + 8 * (NSTAGE + s), 1);
+    }
+    mbar_init(bar_tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == NPROD) {  // TMEM: all 512 columns (two 128 x 256 fp32 accumulators)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < NPROD) {
+    // ================= producers =================
+    const int q0 = warp * 32;
+    const int sc = q0 / RP;
+    const int row0 = q0 - sc * RP;                         // first of this warp's 32 rows in the sub-chunk
+    int kp0;                                               // tap-major row index of that row
+    if (diag) kp0 = I * TB + row0;
+    else kp0 = (row0 < TB) ? (I * TB + row0) : (J * TB + row0 - TB);
+    const bool active = kp0 < g.D && (diag || row0 >= TB || row0 < mh * 128);
+    const int t0 = (int)fdiv((uint32_t)min(kp0, g.K0), p.divC);
+    const int c0 = min(kp0, g.K0) - t0 * g.C;
+    uint32_t swz[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) swz[j] = ((((uint32_t)lane >> 2) ^ (uint32_t)j) << 4) | (((uint32_t)lane & 3u) << 2);
+    const uint32_t sub_off = (uint32_t)(sc * RP + row0) * 128u;
+    const uint32_t r_end = (uint32_t)min((long long)ce * 32, g.R);
+
+    // Stage hand-over shared by both producer paths: wait until the MMAs that read this slot have retired,
+    // store the 32 staged rows (TF32-rounded) into the swizzled layout, publish to the async proxy, arrive.
+    auto commit_stage = [&](int it, const float (&v)[32], bool has_data) {
+      const int s = it % NSTAGE;
+      const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+      mbar_wait(bars + 8 * (NSTAGE + s), ph ^ 1u);
+      if (has_data) {
+        const uint32_t dst = sbase + (uint32_t)s * STAGE_BYTES + sub_off;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sts32(dst + (uint32_t)j * 128u + swz[j & 7], cvt_tf32(v[j]));
+      }
+      fence_proxy_async();                                 // generic-proxy stores -> visible to the MMA (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * s);
+    };
+
+    // FAST PATH: the warp's 32 rows are 32 consecutive channels of ONE filter tap (true for every row group
+    // of a layer whose channel count is a multiple of 32, i.e. all ResNet 1x1 / 3x3 convolutions and all
+    // output-gradient operands).  Per stage each lane derives one pointer (or the zero page when its position
+    // is padding / beyond the item) and walks the channels with a constant stride: 2 instructions per row,
+    // no predicates.  Loads of stage it+1 are issued before stage it is stored (register double buffer), so
+    // global/L2 latency overlaps the previous stage's stores and the tensor core never waits on a cold load.
+    const bool fast = active && (kp0 + 32 <= g.K0) && (c0 + 32 <= g.C);
+    if (fast) {
+      const int ti = (int)fdiv((uint32_t)t0, p.divKW);
+      const int tj = t0 - ti * g.kw;
+      const int dih = ti - g.ph, diw = tj - g.pw;
+      const int cbase = c0 * p.HW;
+      auto issue_stage = [&](int it, float (&v)[32]) {
+        const uint32_t chunk = (uint32_t)(cb + it * SC + sc);
+        uint32_t r = chunk * 32u + (uint32_t)lane;
+        const bool vr = r < r_end;
+        if (!vr) r = 0;
+        const uint32_t n = fdiv(r, p.divL);
+        const uint32_t l = r - n * (uint32_t)g.L;
+        const uint32_t oh = fdiv(l, p.divOW);
+        const uint32_t ow = l - oh * (uint32_t)g.OW;
+        const int ih = (int)oh * g.sh + dih, iw = (int)ow * g.sw + diw;
+        const bool ok = vr && (unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W;
+        const float* __restrict__ ptr = ok ? (g.x + (size_t)n * (size_t)p.CHW + (size_t)(cbase + ih * g.W + iw))
+                                           : g_zero_page;
+        const size_t stride = ok ? (size_t)p.HW : 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __ldg(ptr);
+          ptr += stride;
+        }
+      };
+      float va[32], vb[32];
+      issue_stage(0, va);
+      for (int it = 0; it < nstage_it; it += 2) {
+        if (it + 1 < nstage_it) issue_stage(it + 1, vb);
+        commit_stage(it, va, true);
+        if (it + 1 < nstage_it) {
+          if (it + 2 < nstage_it) issue_stage(it + 2, va);
+          commit_stage(it + 1, vb, true);
+        }
+      }
+    } else {
+    // GENERIC PATH: any geometry (channel counts that are not multiples of 32, the bias row, ragged ends).
+    for (int it = 0; it < nstage_it; ++it) {
+      float v[32];
+      if (active) {
+        const uint32_t chunk = (uint32_t)(cb + it * SC + sc);
+        uint32_t r = chunk * 32u + (uint32_t)lane;
+        const bool vr = r < r_end;
+        if (!vr) r = 0;
+        const uint32_t n = fdiv(r, p.divL);
+        const uint32_t l = r - n * (uint32_t)g.L;
+        const uint32_t oh = fdiv(l, p.divOW);
+        const uint32_t ow = l - oh * (uint32_t)g.OW;
+        const int ihb = (int)oh * g.sh - g.ph, iwb = (int)ow * g.sw - g.pw;
+        const float* __restrict__ xn = g.x + (size_t)n * (size_t)p.CHW;
+        int t = t0, c = c0, coff = c0 * p.HW, kp = kp0, toff = 0;
+        bool ok = false;
+        auto settap = [&]() {
+          ok = false;
+          if (t < p.KK) {
+            const int i = (int)fdiv((uint32_t)t, p.divKW);
+            const int jj = t - i * g.kw;
+            const int ih = ihb + i, iw = iwb + jj;
+            ok = vr && (unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W;
+            toff = ih * g.W + iw;
+          }
+        };
+        settap();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float val = 0.f;
+          if (t < p.KK) {
+            if (ok) val = __ldg(xn + (toff + coff));
+          } else if (kp == g.K0 && g.has_bias && vr) {
+            val = 1.f;                                     // the ones row of the bias
+          }
+          v[j] = val;
+          ++kp; ++c; coff += p.HW;
+          if (c == g.C) { c = 0; coff = 0; ++t; settap(); }
+        }
+      }
+      commit_stage(it, v, active);
+    }
+    }
+
+    // ================= epilogue (warps 0-3: TMEM lane quadrant = warp index) =================
+    if (warp < 4) {
+      mbar_wait(bar_tmem_full, 0);
+      tc_fence_after();
+      float* __restrict__ wsp = p.ws + (size_t)item * TILE_ELEMS;
+      for (int h = 0; h < mh; ++h) {
+        const int row = h * 128 + warp * 32 + lane;
+        for (int cc = 0; cc < ncols; cc += 16) {
+          uint32_t a[16];
+          const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(h * 256 + cc);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+                "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (row < rowsA) {
+            uint4* dst = reinterpret_cast<uint4*>(wsp + (size_t)row * TB + cc);
+            dst[0] = make_uint4(a[0], a[1], a[2], a[3]);
+            dst[1] = make_uint4(a[4], a[5], a[6], a[7]);
+            dst[2] = make_uint4(a[8], a[9], a[10], a[11]);
+            dst[3] = make_uint4(a[12], a[13], a[14], a[15]);
+          }
+        }
+      }
+    }
+  } else {
+    // ================= MMA issuer: one thread =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(128, (uint32_t)ncols);
+      uint32_t acc = 0;
+      for (int it = 0; it < nstage_it; ++it) {
+        const int s = it % NSTAGE;
+        const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+        mbar_wait(bars + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t st = sbase + (uint32_t)s * STAGE_BYTES;
+        for (int q = 0; q < SC; ++q) {
+          const uint32_t sub = st + (uint32_t)(q * RP) * 128u;
+          const uint32_t bsub = diag ? sub : sub + TB * 128u;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t bdesc = umma_desc(bsub + ks * 32);
+            for (int h = 0; h < mh; ++h) {
+              const uint64_t adesc = umma_desc(sub + (uint32_t)h * (128u * 128u) + ks * 32);
+              tc_mma_tf32(tmem + (uint32_t)h * 256u, adesc, bdesc, idesc, acc);
+            }
+            acc = 1;
+          }
+        }
+        tc_commit(bars + 8 * (NSTAGE + s));                // frees the stage when these MMAs retire
+      }
+      tc_commit(bar_tmem_full);                            // accumulator complete -> epilogue
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NPROD) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// ---- fixed-order reduction of the S partial tiles into the factor ------------------------------
+__global__ void __launch_bounds__(256) syrk_tc_reduce_kernel(const TcParams p, const float alpha, float* __restrict__ F) {
+  const int pair = blockIdx.x >> 4, rg = blockIdx.x & 15;
+  int I, J;
+  decode_pair(pair, p.T, I, J);
+  const bool diag = (I == J);
+  const ConvGeom& g = p.g;
+  const int rowsA = min(TB, g.D - I * TB);
+  const int colsB = diag ? rowsA : TB;
+  const int col = threadIdx.x;
+  if (col >= colsB) return;
+  auto perm = [&](int kp) -> int {        // tap-major k' -> the reference's row index c*kh*kw + tap
+    if (kp >= g.K0) return kp;
+    const int t = (int)fdiv((uint32_t)kp, p.divC);
+    const int c = kp - t * g.C;
+    return c * p.KK + t;
+  };
+  const int gj = perm(J * TB + col);
+  const float* __restrict__ base = p.ws + (size_t)pair * p.splits * TILE_ELEMS;
+  for (int rr = 0; rr < 16; ++rr) {
+    const int row = rg * 16 + rr;
+    if (row >= rowsA) break;
+    if (diag && col > row) continue;     // diagonal blocks: lower triangle only, mirrored below (exact symmetry)
+    float sum = 0.f;
+    for (int s = 0; s < p.splits; ++s) sum += base[(size_t)s * TILE_ELEMS + row * TB + col];
+    const float v = alpha * sum;
+    const int gi = perm(I * TB + row);
+    F[(size_t)gi * g.D + gj] += v;
+    if (!(diag && col == row)) F[(size_t)gj * g.D + gi] += v;
+  }
+}
+
+struct Plan {
+  int T, pairs, splits, chunks, cps;
+  size_t ws_bytes;
+};
+
+Plan make_plan(const ConvGeom& g, int sms) {
+  Plan pl;
+  pl.T = (g.D + TB - 1) / TB;
+  pl.pairs = pl.T * (pl.T + 1) / 2;
+  pl.chunks = (int)((g.R + 31) / 32);
+  if (sms <= 0) sms = 148;
+  // choose the number of R-splits: estimated makespan (in chunk units) = waves * (chunks/S + fixed overhead)
+  // + cost of reducing S partial tiles per pair
+  const int maxS = pl.chunks / 16 > 0 ? pl.chunks / 16 : 1;
+  double best = 1e300;
+  int bestS = 1;
+  for (int S = 1; S <= maxS && S <= 8 * sms; ++S) {
+    const long long items = (long long)pl.pairs * S;
+    const long long waves = (items + sms - 1) / sms;
+    const double est = (double)waves * ((double)pl.chunks / S + 10.0) + 0.14 * (double)items;
+    if (est < best * 0.999) { best = est; bestS = S; }
+  }
+  pl.cps = (pl.chunks + bestS - 1) / bestS;
+  pl.cps = (pl.cps + 3) & ~3;                         // whole stages for every sub-chunk count (1, 2, 4)
+  pl.splits = (pl.chunks + pl.cps - 1) / pl.cps;
+  pl.ws_bytes = (size_t)pl.pairs * pl.splits * TILE_ELEMS * sizeof(float);
+  return pl;
+}
+
+}  // namespace
+
+size_t syrk_tc_workspace(const ConvGeom& g, int precision) {
+  (void)precision;
+  return make_plan(g, device_sm_count()).ws_bytes;
+}
+
+int syrk_tc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,
+                   cudaStream_t s) {
+  CRV_CHECK(precision == CRV_PREC_TF32, "tensor-core tier %d is not built (available: tf32)", precision);
+  CRV_CHECK(F != nullptr, "null factor pointer");
+  const int sms = device_sm_count();
+  CRV_CHECK(sms > 0, "no CUDA device");
+  CRV_CHECK(g.R < (1LL << 31) - 64, "contraction length too large");
+  const Plan pl = make_plan(g, sms);
+  CRV_CHECK(ws != nullptr && ws_bytes >= pl.ws_bytes, "workspace too small: %zu < %zu", ws_bytes, pl.ws_bytes);
+  CRV_CHECK(((uintptr_t)ws & 15) == 0, "workspace must be 16-byte aligned");
+  TcParams p;
+  p.g = g;
+  p.divL = make_fastdiv((uint32_t)g.L);
+  p.divOW = make_fastdiv((uint32_t)g.OW);
+  p.divC = make_fastdiv((uint32_t)g.C);
+  p.divKW = make_fastdiv((uint32_t)g.kw);
+  p.T = pl.T; p.pairs = pl.pairs; p.splits = pl.splits; p.chunks = pl.chunks; p.cps = pl.cps;
+  p.HW = g.H * g.W; p.CHW = g.C * g.H * g.W; p.KK = g.kh * g.kw;
+  p.ws = (float*)ws;
+  CRV_CUDA(cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  syrk_tc_kernel<<<pl.pairs * pl.splits, NTHREADS, SMEM_BYTES, s>>>(p);
+  CRV_CUDA(cudaGetLastError());
+  syrk_tc_reduce_kernel<<<pl.pairs * 16, 256, 0, s>>>(p, alpha, F);
+  CRV_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace crv

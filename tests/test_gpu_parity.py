@@ -29,7 +29,7 @@ def _strict_fp32():
 def tiers():
     out = [nat.PREC_FP32]
     import os
-    for name in os.environ.get("CURVATURE_B200_TEST_TIERS", "").split(","):
+    for name in os.environ.get("CURVATURE_B200_TEST_TIERS", "tf32").split(","):
         if name and name != "fp32":
             out.append(nat.PRECISION_NAMES[name])
     return out
@@ -263,7 +263,10 @@ def test_resnet_shaped_factors_against_fp64(layer, prec):
     nat.syrk_conv_accum(x, (k, k), (s, s), (p, p), False, 1.0 / X.shape[1], out, prec)
     err = rel_fro(out, want)
     assert err <= FACTOR_TOL[prec], (name, err)
-    assert torch.equal(out, out.t())
+    if prec == nat.PREC_FP32:   # split-R partials meet in fp32 atomics: symmetric up to summation order
+        assert rel_fro(out, out.t()) <= 1e-6
+    else:                       # tensor-core tiers reduce partial tiles in a fixed order and mirror: exact
+        assert torch.equal(out, out.t())
     # G-type operand of the same layer: (N, M, OH, OW) gradient-like tensor
     OH = (H + 2 * p - k) // s + 1
     gten = torch.randn(N, min(C, 256), OH, OH, device=DEV) * 1e-3
