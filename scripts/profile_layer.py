@@ -1,0 +1,70 @@
+"""Run single ResNet-shaped SYRK launches through the C ABI (for ncu captures and quick timing).
+
+    python scripts/profile_layer.py [--prec tf32] [--reps 3] name[,name...]
+Layer names: see LAYERS below.  Prints the median CUDA-event time and the achieved algorithmic TFLOP/s / GB/s.
+"""
+import argparse
+import os
+import statistics
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from curvature_b200 import _native as nat  # noqa: E402
+
+# name: (kind, N, C, H, W, k, s, p)   kind 'A' = conv input factor, 'G' = (N, M, OH, OW) gradient factor
+LAYERS = {
+    "a2304": ("A", 256, 256, 14, 14, 3, 1, 1),
+    "a4608": ("A", 256, 512, 7, 7, 3, 1, 1),
+    "a1152": ("A", 256, 128, 28, 28, 3, 1, 1),
+    "a576": ("A", 256, 64, 56, 56, 3, 1, 1),
+    "a1024": ("A", 256, 1024, 14, 14, 1, 1, 0),
+    "a256": ("A", 256, 256, 56, 56, 1, 1, 0),
+    "a64": ("A", 256, 64, 56, 56, 1, 1, 0),
+    "stem": ("A", 256, 3, 224, 224, 7, 2, 3),
+    "g64": ("G", 256, 64, 56, 56, 1, 1, 0),
+    "g256": ("G", 256, 256, 56, 56, 1, 1, 0),
+    "g1024": ("G", 256, 1024, 14, 14, 1, 1, 0),
+    "g2048": ("G", 256, 2048, 7, 7, 1, 1, 0),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("names")
+    ap.add_argument("--prec", default="tf32")
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    prec = nat.PRECISION_NAMES[args.prec]
+    dev = "cuda:0"
+    for name in args.names.split(","):
+        kind, N, C, H, W, k, s, p = LAYERS[name]
+        torch.manual_seed(0)
+        x = torch.relu(torch.randn(N, C, H, W, device=dev))
+        if kind == "A":
+            K = C * k * k
+            OH = (H + 2 * p - k) // s + 1
+            R = N * OH * OH
+            out = torch.zeros(K, K, device=dev)
+            fn = lambda: nat.syrk_conv_accum(x, (k, k), (s, s), (p, p), False, 1.0 / R, out, prec)  # noqa: E731
+        else:
+            K = C
+            R = N * H * W
+            out = torch.zeros(K, K, device=dev)
+            fn = lambda: nat.syrk_rows_accum(x, False, 1.0 / R, out, prec)  # noqa: E731
+        times = []
+        for _ in range(args.reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = statistics.median(times[1:])
+        print(f"{name:6s} K={K:5d} R={R:8d}  {ms:8.3f} ms  {R * K * (K + 1) / ms / 1e9:7.1f} TFLOP/s (algorithmic)  "
+              f"{4 * x.numel() / ms / 1e6:7.0f} GB/s (input once)")
+
+
+if __name__ == "__main__":
+    main()
