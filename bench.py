@@ -318,7 +318,7 @@ def main():
     bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (1.4 PF sustained bf16"
     tier = args.precision
-    if tier in ("tf32", "tf32x3", "fp32"):
+    if tier in ("tf32", "tf32x3", "fp32", "tf32_tma"):
         peak, peak_note = bf16 / 2.0, peak_src + " / 2: kind::tf32 issues at half the bf16 rate)"
     else:
         peak, peak_note = bf16, peak_src + ")"
@@ -329,7 +329,7 @@ def main():
                 "algorithmic_flops_per_step": flops, "peak_source": peak_note, "tier": tier}
     line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3", "bf16": "bf16"}[tier],
+            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3", "bf16": "bf16", "tf32_tma": "tf32"}[tier],
             "data": "synthetic", "config": config, "roofline": roofline, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "wall_s_timed_region": t_wall, "update_ms_mean": step_ms}
     if world == 1 and not args.no_cpu_baseline:

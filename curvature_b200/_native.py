@@ -13,8 +13,9 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcurvature_b200.so")
 
-PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_BF16 = 0, 1, 2, 3
-PRECISION_NAMES = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16}
+PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_BF16, PREC_TF32_TMA = 0, 1, 2, 3, 4
+PRECISION_NAMES = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16,
+                   "tf32_tma": PREC_TF32_TMA}
 OP_SYRK_CONV, OP_SYRK_ROWS, OP_EFB_PROJECT, OP_CHOL_INV, OP_SAMPLE_MN = range(5)
 
 if not os.path.exists(LIB_PATH):

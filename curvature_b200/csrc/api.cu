@@ -34,7 +34,8 @@ int device_sm_count() {
 static int syrk_dispatch(const ConvGeom& g, float alpha, float* F, void* ws, size_t ws_bytes, int precision,
                          cudaStream_t s) {
   if (precision == CRV_PREC_FP32) return syrk_simt_launch(g, alpha, F, s);
-  if (precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32X3 || precision == CRV_PREC_BF16)
+  if (precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32X3 || precision == CRV_PREC_BF16 ||
+      precision == CRV_PREC_TF32_TMA)
     return syrk_tc_launch(g, alpha, F, precision, ws, ws_bytes, s);
   set_error("unknown precision tier %d", precision);
   return 1;

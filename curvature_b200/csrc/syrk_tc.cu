@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "../../include/curvature_b200.h"
 #include <math.h>
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace crv {
 namespace {
@@ -49,6 +50,15 @@ struct TcParams {
   int HW, CHW, KK;
   int vec_ok;                         // operand rows are 16-byte aligned runs of 4 positions (LDG.128 path)
   float* ws;
+};
+
+struct TmaGeom {          // position patches and channel segments of the TMA-fed variant
+  FastDiv divPPI, divPCW; // patches per image, patches per patch-row
+  int bw, bh;             // patch = bh x bw output positions (bw * bh = 32)
+  int chbox;              // channels per TMA box = rows per segment (min(C, 256))
+  int flat;               // 1: (L, 1, C, N) view of a 1x1 operand; 0: (W, H, C, N)
+  int pcw, ppi;           // patches per patch-row, patches per image
+  int nimg;               // N
 };
 
 __host__ FastDiv make_fastdiv(uint32_t d) {
@@ -116,6 +126,17 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in bits
 // [0,14), leading byte offset (unused for one swizzle atom along K) in [16,30), stride byte offset
 // = 1024 B between 8-row groups in [32,46), descriptor version 1 in [46,48), swizzle mode 2 (128 B)
@@ -139,6 +160,176 @@ __device__ __forceinline__ void decode_pair(int pair, int T, int& I, int& J) {
     J = pair - i * (i - 1) / 2;
   } else {
     I = J = pair - noff;
+  }
+}
+
+// ---- pieces shared by the thread-staged and the TMA-fed kernels ------------------------------------
+struct ItemShape {
+  int I, J, rowsA, mh, ncols, RP, SC, cb, ce, nstage_it;
+  bool diag;
+};
+__device__ __forceinline__ ItemShape item_shape(const TcParams& p, int item) {
+  ItemShape t;
+  const int pair = item / p.splits, split = item - pair * p.splits;
+  decode_pair(pair, p.T, t.I, t.J);
+  t.diag = (t.I == t.J);
+  t.rowsA = min(TB, p.g.D - t.I * TB);
+  t.mh = (t.rowsA + 127) >> 7;                                   // 128-row halves of the A block
+  t.ncols = t.diag ? ((t.rowsA + 15) & ~15) : TB;                // UMMA N
+  t.RP = t.diag ? (t.rowsA <= 128 ? 128 : 256) : 512;            // rows per sub-chunk in a stage
+  t.SC = STAGE_ROWS / t.RP;                                      // 32-position sub-chunks per stage
+  t.cb = split * p.cps;
+  t.ce = min(p.chunks, t.cb + p.cps);
+  t.nstage_it = (t.ce - t.cb + t.SC - 1) / t.SC;
+  return t;
+}
+
+// One thread: for every stage wait for the operands, issue 4 k-steps x mh row halves of
+// tcgen05.mma.kind::tf32 (M=128, N=ncols, K=8) per sub-chunk, then commit to free the stage.
+__device__ __forceinline__ void mma_issue_all(const ItemShape& t, uint32_t sbase, uint32_t bars, uint32_t bar_tmem_full,
+                                              uint32_t tmem) {
+  const uint32_t idesc = umma_idesc(128, (uint32_t)t.ncols);
+  uint32_t acc = 0;
+  for (int it = 0; it < t.nstage_it; ++it) {
+    const int s = it % NSTAGE;
+    const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+    mbar_wait(bars + 8 * s, ph);
+    tc_fence_after();
+    const uint32_t st = sbase + (uint32_t)s * STAGE_BYTES;
+    for (int q = 0; q < t.SC; ++q) {
+      const uint32_t sub = st + (uint32_t)(q * t.RP) * 128u;
+      const uint32_t bsub = t.diag ? sub : sub + TB * 128u;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t bdesc = umma_desc(bsub + ks * 32);
+        for (int h = 0; h < t.mh; ++h) {
+          const uint64_t adesc = umma_desc(sub + (uint32_t)h * (128u * 128u) + ks * 32);
+          tc_mma_tf32(tmem + (uint32_t)h * 256u, adesc, bdesc, idesc, acc);
+        }
+        acc = 1;
+      }
+    }
+    tc_commit(bars + 8 * (NSTAGE + s));                // frees the stage when these MMAs retire
+  }
+  tc_commit(bar_tmem_full);                            // accumulator complete -> epilogue
+}
+
+// One warp (TMEM lane quadrant `quad`): accumulator -> registers -> partial tile in the workspace.
+__device__ __forceinline__ void epilogue_store(const ItemShape& t, uint32_t bar_tmem_full, uint32_t tmem,
+                                               float* __restrict__ wsp, int quad, int lane) {
+  mbar_wait(bar_tmem_full, 0);
+  tc_fence_after();
+  for (int h = 0; h < t.mh; ++h) {
+    const int row = h * 128 + quad * 32 + lane;
+    for (int cc = 0; cc < t.ncols; cc += 16) {
+      uint32_t a[16];
+      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * 256 + cc);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+            "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < t.rowsA) {
+        uint4* dst = reinterpret_cast<uint4*>(wsp + (size_t)row * TB + cc);
+        dst[0] = make_uint4(a[0], a[1], a[2], a[3]);
+        dst[1] = make_uint4(a[4], a[5], a[6], a[7]);
+        dst[2] = make_uint4(a[8], a[9], a[10], a[11]);
+        dst[3] = make_uint4(a[12], a[13], a[14], a[15]);
+      }
+    }
+  }
+}
+
+// ---- TMA-fed kernel ---------------------------------------------------------------------------------
+// Same tiles, same MMA loop, same epilogue; the operands are fetched by the TMA unit instead of by threads:
+// one cp.async.bulk.tensor.4d per (filter tap, channel segment) box of [channels][bh x bw positions] lands
+// directly in the K-major SWIZZLE_128B layout, with the hardware's out-of-bounds zero fill providing the
+// convolution padding (box coordinates are shifted by the tap offset and may be negative).  No LSU traffic, no
+// per-element instructions.  The tensor core reads the fp32 words as TF32 (low 13 mantissa bits ignored), so this
+// variant has TF32-truncation accuracy (stated 1e-3 tier) instead of the round-to-nearest of the staged path.
+// Warps: 0 = TMA producer (one thread), 1 = MMA issuer (one thread) + TMEM owner, 2..5 = epilogue.
+constexpr int TMA_THREADS = 6 * 32;
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+syrk_tc_tma_kernel(const TcParams p, const TmaGeom tg, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  const uint32_t bars = sbase + NSTAGE * STAGE_BYTES;
+  const uint32_t bar_tmem_full = bars + 8 * (2 * NSTAGE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (sbase - raw) + NSTAGE * STAGE_BYTES + 8 * (2 * NSTAGE + 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvGeom& g = p.g;
+  const ItemShape t = item_shape(p, blockIdx.x);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(bars + 8 * s, 1);
+      mbar_init(bars + 8 * (NSTAGE + s), 1);
+    }
+    mbar_init(bar_tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // channel segments of the two blocks: rows [sg*chbox, +chbox) <-> tap-major index k' = blk*256 + sg*chbox
+      const int segs = TB / tg.chbox;
+      const int nsegA = min(segs, (g.K0 - t.I * TB + tg.chbox - 1) / tg.chbox);
+      const int nsegB = t.diag ? 0 : segs;                      // off-diagonal: block J is always complete
+      const uint32_t box_bytes = (uint32_t)tg.chbox * 128u;
+      const uint32_t stage_tx = (uint32_t)(t.SC * (nsegA + nsegB)) * box_bytes;
+      for (int it = 0; it < t.nstage_it; ++it) {
+        const int s = it % NSTAGE;
+        const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+        mbar_wait(bars + 8 * (NSTAGE + s), ph ^ 1u);
+        mbar_arrive_expect_tx(bars + 8 * s, stage_tx);
+        const uint32_t st = sbase + (uint32_t)s * STAGE_BYTES;
+        for (int q = 0; q < t.SC; ++q) {
+          // chunk -> (image, patch row, patch column); chunks past the end map to image index >= N: all zero fill
+          const uint32_t chunk = (uint32_t)(t.cb + it * t.SC + q);
+          const uint32_t n = fdiv(chunk, tg.divPPI);
+          const uint32_t rem = chunk - n * (uint32_t)tg.ppi;
+          const uint32_t pr = fdiv(rem, tg.divPCW);
+          const uint32_t pc = rem - pr * (uint32_t)tg.pcw;
+          const int w0 = (int)pc * tg.bw, h0 = (int)pr * tg.bh;
+          const uint32_t sub = st + (uint32_t)(q * t.RP) * 128u;
+          for (int sg = 0; sg < nsegA + nsegB; ++sg) {
+            const bool isB = sg >= nsegA;
+            const int kp = (isB ? t.J * TB + (sg - nsegA) * tg.chbox : t.I * TB + sg * tg.chbox);
+            const int tap = (int)fdiv((uint32_t)kp, p.divC);
+            const int c0 = kp - tap * g.C;
+            const int ti = (int)fdiv((uint32_t)tap, p.divKW);
+            const int tj = tap - ti * g.kw;
+            const uint32_t dst = sub + (uint32_t)((isB ? TB + (sg - nsegA) * tg.chbox : sg * tg.chbox)) * 128u;
+            tma_load_4d(dst, &tmap, w0 + tj - g.pw, h0 + ti - g.ph, c0, (int)n, bars + 8 * s);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) mma_issue_all(t, sbase, bars, bar_tmem_full, tmem);
+    __syncwarp();
+  } else {
+    epilogue_store(t, bar_tmem_full, tmem, p.ws + (size_t)blockIdx.x * TILE_ELEMS, warp & 3, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
 }
 
@@ -423,40 +614,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) syrk_tc_kernel(const TcParams p) 
 }
 
 // ---- fixed-order reduction of the S partial tiles into the factor ------------------------------
-// One CTA per (block pair, tile row); a thread owns one column and sums the S partials in split order
-// (deterministic), 8 loads in flight at a time.
+// One CTA per 32x32 sub-tile of a block pair.  A lane owns one column and sums the S partials in split
+// order (deterministic, 8 loads in flight); the direct block is added row-wise and the mirror image is
+// added through a shared-memory transpose, so both read-modify-writes of the factor are coalesced.
 __global__ void __launch_bounds__(256) syrk_tc_reduce_kernel(const TcParams p, const float alpha, float* __restrict__ F) {
-  const int pair = blockIdx.x >> 8, row = blockIdx.x & 255;
+  __shared__ float tile[32][33];
+  const int pair = blockIdx.x >> 6, sub = blockIdx.x & 63;
+  const int br = sub >> 3, bc = sub & 7;
   int I, J;
   decode_pair(pair, p.T, I, J);
   const bool diag = (I == J);
+  if (diag && bc > br) return;            // diagonal blocks: lower triangle only, mirrored below (exact symmetry)
   const ConvGeom& g = p.g;
   const int rowsA = min(TB, g.D - I * TB);
   const int colsB = diag ? rowsA : TB;
-  const int col = threadIdx.x;
-  if (row >= rowsA || col >= colsB) return;
-  if (diag && col > row) return;         // diagonal blocks: lower triangle only, mirrored below (exact symmetry)
+  if (br * 32 >= rowsA || bc * 32 >= colsB) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   auto perm = [&](int kp) -> int {        // tap-major k' -> the reference's row index c*kh*kw + tap
     if (kp >= g.K0) return kp;
     const int t = (int)fdiv((uint32_t)kp, p.divC);
     const int c = kp - t * g.C;
     return c * p.KK + t;
   };
-  const float* __restrict__ base = p.ws + (size_t)pair * p.splits * TILE_ELEMS + row * TB + col;
-  float sum = 0.f;
-  int s = 0;
-  for (; s + 8 <= p.splits; s += 8) {
-    float t[8];
+  const float* __restrict__ base = p.ws + (size_t)pair * p.splits * TILE_ELEMS;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) t[u] = base[(size_t)(s + u) * TILE_ELEMS];
+  for (int q = 0; q < 4; ++q) {
+    const int row = br * 32 + w * 4 + q, col = bc * 32 + lane;
+    const bool valid = row < rowsA && col < colsB;
+    float v = 0.f;
+    if (valid) {
+      const float* __restrict__ b = base + row * TB + col;
+      float sum = 0.f;
+      int s = 0;
+      for (; s + 8 <= p.splits; s += 8) {
+        float t[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) sum += t[u];
+        for (int u = 0; u < 8; ++u) t[u] = b[(size_t)(s + u) * TILE_ELEMS];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sum += t[u];
+      }
+      for (; s < p.splits; ++s) sum += b[(size_t)s * TILE_ELEMS];
+      v = alpha * sum;
+      if (!(diag && col > row)) F[(size_t)perm(I * TB + row) * g.D + perm(J * TB + col)] += v;
+    }
+    tile[w * 4 + q][lane] = v;
   }
-  for (; s < p.splits; ++s) sum += base[(size_t)s * TILE_ELEMS];
-  const float v = alpha * sum;
-  const int gi = perm(I * TB + row), gj = perm(J * TB + col);
-  F[(size_t)gi * g.D + gj] += v;
-  if (!(diag && col == row)) F[(size_t)gj * g.D + gi] += v;
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {           // mirror image: lanes run along the original rows
+    const int col = bc * 32 + w * 4 + q, row = br * 32 + lane;
+    if (row < rowsA && col < colsB && !(diag && col >= row))
+      F[(size_t)perm(J * TB + col) * g.D + perm(I * TB + row)] += tile[lane][w * 4 + q];
+  }
 }
 
 struct Plan {
@@ -464,11 +673,11 @@ struct Plan {
   size_t ws_bytes;
 };
 
-Plan make_plan(const ConvGeom& g, int sms) {
+Plan make_plan(const ConvGeom& g, int sms, int chunks) {
   Plan pl;
   pl.T = (g.D + TB - 1) / TB;
   pl.pairs = pl.T * (pl.T + 1) / 2;
-  pl.chunks = (int)((g.R + 31) / 32);
+  pl.chunks = chunks;
   if (sms <= 0) sms = 148;
   // choose the number of R-splits: estimated makespan (in chunk units) = waves * (chunks/S + fixed overhead)
   // + cost of reducing S partial tiles per pair
@@ -488,21 +697,85 @@ Plan make_plan(const ConvGeom& g, int sms) {
   return pl;
 }
 
+// Can this operand be fetched by TMA?  Needs a 1x1 / unit-stride / unpadded operand (its flattened (L, C, N) view
+// lets the out-of-bounds fill zero the ragged last chunk of every image), no bias row, a power-of-two channel
+// count (boxes of min(C,256) channels) and 16-byte aligned rows (L % 4 == 0).
+bool tma_geometry(const ConvGeom& g, TmaGeom& tg, int& chunks) {
+  if (g.has_bias || g.sh != 1 || g.sw != 1) return false;
+  if (((uintptr_t)g.x & 15) != 0) return false;
+  if (g.C < 16 || (g.C & (g.C - 1)) != 0) return false;
+  tg.chbox = g.C < TB ? g.C : TB;
+  tg.nimg = g.N;
+  const int KK = g.kh * g.kw;
+  tg.flat = (KK == 1 && g.ph == 0 && g.pw == 0) ? 1 : 0;
+  int pch;
+  if (tg.flat) {
+    if (g.L % 4) return false;
+    tg.bw = 32; tg.bh = 1;
+    tg.pcw = (g.L + 31) / 32;
+    pch = 1;
+  } else {
+    // Measured on B200 (scripts/experiments/tma_align_probe.cu): cp.async.bulk.tensor raises an illegal-instruction
+    // fault when the innermost start coordinate is not a multiple of 16 bytes, so the +-1 column shifts of a k x k
+    // filter cannot be expressed as TMA box coordinates on fp32 NCHW data.  k x k operands stay thread-staged.
+    return false;
+  }
+  tg.ppi = tg.pcw * pch;
+  tg.divPPI = make_fastdiv((uint32_t)tg.ppi);
+  tg.divPCW = make_fastdiv((uint32_t)tg.pcw);
+  const long long c = (long long)g.N * tg.ppi;
+  if (c >= (1LL << 26)) return false;
+  chunks = (int)c;
+  return true;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
 }  // namespace
 
 size_t syrk_tc_workspace(const ConvGeom& g, int precision) {
-  (void)precision;
-  return make_plan(g, device_sm_count()).ws_bytes;
+  const int sms = device_sm_count();
+  size_t b = make_plan(g, sms, (int)((g.R + 31) / 32)).ws_bytes;
+  if (precision == CRV_PREC_TF32_TMA) {
+    TmaGeom tg;
+    int chunks = 0;
+    if (tma_geometry(g, tg, chunks)) {
+      const size_t b2 = make_plan(g, sms, chunks).ws_bytes;
+      if (b2 > b) b = b2;
+    }
+  }
+  return b;
 }
 
 int syrk_tc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,
                    cudaStream_t s) {
-  CRV_CHECK(precision == CRV_PREC_TF32, "tensor-core tier %d is not built (available: tf32)", precision);
+  CRV_CHECK(precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32_TMA,
+            "tensor-core tier %d is not built (available: tf32, tf32_tma)", precision);
   CRV_CHECK(F != nullptr, "null factor pointer");
   const int sms = device_sm_count();
   CRV_CHECK(sms > 0, "no CUDA device");
   CRV_CHECK(g.R < (1LL << 31) - 64, "contraction length too large");
-  const Plan pl = make_plan(g, sms);
+  TmaGeom tg;
+  int tma_chunks = 0;
+  const bool use_tma = precision == CRV_PREC_TF32_TMA && tma_geometry(g, tg, tma_chunks) && tensor_map_encoder();
+  const Plan pl = make_plan(g, sms, use_tma ? tma_chunks : (int)((g.R + 31) / 32));
   CRV_CHECK(ws != nullptr && ws_bytes >= pl.ws_bytes, "workspace too small: %zu < %zu", ws_bytes, pl.ws_bytes);
   CRV_CHECK(((uintptr_t)ws & 15) == 0, "workspace must be 16-byte aligned");
   TcParams p;
@@ -516,10 +789,26 @@ int syrk_tc_launch(const ConvGeom& g, float alpha, float* F, int precision, void
   p.ws = (float*)ws;
   p.vec_ok = (p.KK == 1 && g.sh == 1 && g.sw == 1 && g.ph == 0 && g.pw == 0 && (g.L % 4) == 0 &&
               ((uintptr_t)g.x & 15) == 0) ? 1 : 0;
-  CRV_CUDA(cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  syrk_tc_kernel<<<pl.pairs * pl.splits, NTHREADS, SMEM_BYTES, s>>>(p);
+  if (use_tma) {
+    CUtensorMap map;
+    const cuuint64_t Wd = tg.flat ? (cuuint64_t)g.L : (cuuint64_t)g.W;
+    const cuuint64_t Hd = tg.flat ? 1 : (cuuint64_t)g.H;
+    const cuuint64_t gdim[4] = {Wd, Hd, (cuuint64_t)g.C, (cuuint64_t)g.N};
+    const cuuint64_t gstr[3] = {Wd * 4, Hd * Wd * 4, (cuuint64_t)g.C * Hd * Wd * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)tg.bw, (cuuint32_t)tg.bh, (cuuint32_t)tg.chbox, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult rc = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)g.x, gdim, gstr, box,
+                                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CRV_CHECK(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)rc);
+    CRV_CUDA(cudaFuncSetAttribute(syrk_tc_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    syrk_tc_tma_kernel<<<pl.pairs * pl.splits, TMA_THREADS, SMEM_BYTES, s>>>(p, tg, map);
+  } else {
+    CRV_CUDA(cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    syrk_tc_kernel<<<pl.pairs * pl.splits, NTHREADS, SMEM_BYTES, s>>>(p);
+  }
   CRV_CUDA(cudaGetLastError());
-  syrk_tc_reduce_kernel<<<pl.pairs * 256, 256, 0, s>>>(p, alpha, F);
+  syrk_tc_reduce_kernel<<<pl.pairs * 64, 256, 0, s>>>(p, alpha, F);
   CRV_CUDA(cudaGetLastError());
   return 0;
 }

@@ -35,7 +35,9 @@ enum crv_precision {
   CRV_PREC_FP32   = 0, /* CUDA-core fp32 FMA (exact fp32 products); parity tier 1e-5            */
   CRV_PREC_TF32   = 1, /* tcgen05 kind::tf32, operands rounded to nearest (cvt.rna), fp32 accum  */
   CRV_PREC_TF32X3 = 2, /* tcgen05 3xTF32 error-compensated split (hi*hi + hi*lo + lo*hi)          */
-  CRV_PREC_BF16   = 3  /* tcgen05 kind::f16 with bf16 operands, fp32 accum; parity tier 1e-3      */
+  CRV_PREC_BF16   = 3, /* tcgen05 kind::f16 with bf16 operands, fp32 accum; parity tier 1e-3      */
+  CRV_PREC_TF32_TMA = 4 /* tcgen05 kind::tf32 fed by TMA where the geometry allows (hardware TF32
+                           truncation of the fp32 operands; parity tier 1e-3), else as CRV_PREC_TF32 */
 };
 
 /* Operations for crv_workspace_bytes(). dims as documented per op. */
