@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="resnet50", choices=["resnet18", "resnet50", "resnet152", "lenet5"])
     ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 256; 100 for lenet5)")
-    ap.add_argument("--precision", default=os.environ.get("CURVATURE_B200_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("CURVATURE_B200_PRECISION", "tf32"))
     ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
