@@ -569,11 +569,17 @@ class INF(Curvature):
         vtv = W.view(ra, ra, rg, rg).permute(0, 2, 1, 3).reshape(ra * rg, ra * rg)
         vtv = reg_lambda[:, None] * vtv * reg_lambda[None, :]
         vtv = (vtv + vtv.t()) / 2.
-        eye = torch.eye(vtv.shape[0], device=vtv.device, dtype=vtv.dtype)
-        A_c_inv = torch.linalg.inv(torch.linalg.cholesky(vtv))
-        B_c = torch.linalg.cholesky(vtv + eye)
-        C = nat.gemm(nat.gemm(A_c_inv, (B_c - eye).contiguous(), transA=True), A_c_inv)
-        L_c = torch.linalg.inv(torch.linalg.inv(C) + vtv)
+        # The r x r chain below (Cholesky + three explicit inverses, curvatures.py:564-570) has condition numbers
+        # of 1e6..1e8 on LeNet-5: evaluated in fp32 it is O(0.1..1) away from the exact result (the reference's own
+        # fp32 output is, too).  It is a one-shot, r <= ~1.5k operation, so it runs in fp64 on the device
+        # (torch.linalg -> cuSOLVER, the library call the north star allows for one-shot factorizations); measured
+        # against the fp64 oracle this is 1e-7 instead of 1e-1.
+        v64 = vtv.double()
+        eye = torch.eye(v64.shape[0], device=v64.device, dtype=v64.dtype)
+        A_c_inv = torch.linalg.inv(torch.linalg.cholesky(v64))
+        B_c = torch.linalg.cholesky(v64 + eye)
+        C = A_c_inv.t() @ (B_c - eye) @ A_c_inv
+        L_c = torch.linalg.inv(torch.linalg.inv(C) + v64).to(vtv.dtype)
         return reg_lambda[:, None] * L_c * reg_lambda[None, :]
 
     @staticmethod
