@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--model", default="resnet50", choices=["resnet18", "resnet50", "resnet152", "lenet5"])
     ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 256; 100 for lenet5)")
     ap.add_argument("--precision", default=os.environ.get("CURVATURE_B200_PRECISION", "tf32"))
+    ap.add_argument("--layout", default="channels_last", choices=["channels_last", "nchw"],
+                    help="memory format the model runs in (the logical tensors are identical; channels_last lets "
+                         "every factor operand reach the tensor core through TMA)")
     ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -175,6 +178,7 @@ def main():
     metric = METRIC if args.model == "resnet50" else METRIC.replace("ResNet-50", args.model)
     config = {"workload": workload, "model": args.model, "batch_per_gpu": batch, "global_batch": batch * world,
               "image": "3x224x224" if args.model != "lenet5" else "1x28x28", "parallelism": f"dp{world}",
+              "memory_format": args.layout if args.model != "lenet5" else "nchw",
               "l2": "inputs larger than L2 (recorded activations + gradients >> 126 MB); no flush needed"
                     if args.model != "lenet5" else "inputs smaller than L2; 256 MB buffer written between iterations"}
 
@@ -203,6 +207,8 @@ def main():
 
     model, shape = make_model(args.model)
     model = model.to(dev).train()
+    if args.layout == "channels_last" and args.model != "lenet5":
+        model = model.to(memory_format=torch.channels_last)
     kfac = cb.KFAC(model, precision=args.precision)
     torch.manual_seed(1000 + rank)
     x_host = torch.randn(batch, *shape).pin_memory()

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libcurvature_b200.so")
 PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_BF16, PREC_TF32_TMA = 0, 1, 2, 3, 4
 PRECISION_NAMES = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16,
                    "tf32_tma": PREC_TF32_TMA}
-OP_SYRK_CONV, OP_SYRK_ROWS, OP_EFB_PROJECT, OP_CHOL_INV, OP_SAMPLE_MN = range(5)
+OP_SYRK_CONV, OP_SYRK_ROWS, OP_EFB_PROJECT, OP_CHOL_INV, OP_SAMPLE_MN, OP_SYRK_CONV_NHWC, OP_SYRK_ROWS_NHWC = range(7)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -43,6 +43,10 @@ _syrk_conv = _sig("crv_syrk_conv_accum", c_int, _f32p, c_int, c_int, c_int, c_in
                   c_int, c_int, c_int, c_float, _f32p, c_void_p, c_size_t, c_int, c_void_p)
 _syrk_rows = _sig("crv_syrk_rows_accum", c_int, _f32p, c_int, c_int, c_int, c_int, c_float, _f32p, c_void_p,
                   c_size_t, c_int, c_void_p)
+_syrk_conv_nhwc = _sig("crv_syrk_conv_accum_nhwc", c_int, _f32p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                       c_int, c_int, c_int, c_int, c_float, _f32p, c_void_p, c_size_t, c_int, c_void_p)
+_syrk_rows_nhwc = _sig("crv_syrk_rows_accum_nhwc", c_int, _f32p, c_int, c_int, c_int, c_int, c_float, _f32p,
+                       c_void_p, c_size_t, c_int, c_void_p)
 _diag_accum = _sig("crv_diag_accum", c_int, _f32p, _f32p, c_int, c_int, c_float, _f32p, _f32p, c_void_p)
 _efb_project = _sig("crv_efb_project_accum", c_int, _f32p, _f32p, _f32p, c_int, c_int, _f32p, c_void_p,
                     c_size_t, c_int, c_void_p)
@@ -59,7 +63,8 @@ _gemm = _sig("crv_gemm", c_int, _f32p, c_int, c_int, _f32p, c_int, c_int, _f32p,
 ABI_VERSION = _abi_version()
 EXPORTED_SYMBOLS = (
     "crv_abi_version", "crv_last_error", "crv_device_sm_count", "crv_workspace_bytes",
-    "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_diag_accum", "crv_efb_project_accum",
+    "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc",
+    "crv_diag_accum", "crv_efb_project_accum",
     "crv_chol_inv_batched", "crv_sample_matrix_normal", "crv_elementwise_inv_sqrt", "crv_diag_sample",
     "crv_gemm")
 
@@ -128,8 +133,31 @@ def sm_count():
     return _sm_count()
 
 
+def _dense(t, what):
+    """Device pointer of a dense fp32 CUDA tensor in ANY dense layout (the caller states the layout)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"curvature_b200: {what} must live on a CUDA device "
+                           "(there is no CPU fallback; the CUDA kernels are the only implementation)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"curvature_b200: {what} must be float32, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _is_channels_last(t):
+    """True if the 4-D tensor is dense in [N][H][W][C] order and NOT also dense in [N][C][H][W] order."""
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
+
+
+def _tensor_core(precision):
+    return precision in (PREC_TF32, PREC_TF32_TMA)
+
+
 def syrk_conv_accum(x, kernel_size, stride, padding, has_bias, alpha, out, precision=PREC_FP32):
-    """out (K,K) += alpha * unfold(x) unfold(x)^T  with the optional ones row (K1a)."""
+    """out (K,K) += alpha * unfold(x) unfold(x)^T  with the optional ones row (K1a / K1c).
+
+    x is the logical (N,C,H,W) activation.  A channels-last tensor goes to the TMA-fed MN-major kernel
+    (crv_syrk_conv_accum_nhwc) when the tier is a tensor-core one and the geometry qualifies; every other case
+    uses the NCHW kernel (crv_syrk_conv_accum), on a contiguous copy if the tensor is not NCHW-dense."""
     global launch_calls
     N, C, H, W = x.shape
     kh, kw = kernel_size
@@ -138,16 +166,31 @@ def syrk_conv_accum(x, kernel_size, stride, padding, has_bias, alpha, out, preci
     K = C * kh * kw + int(bool(has_bias))
     if tuple(out.shape) != (K, K):
         raise ValueError(f"factor has shape {tuple(out.shape)}, expected {(K, K)}")
-    nb = workspace_bytes(OP_SYRK_CONV, [N, C, H, W, kh, kw, sh, sw, ph, pw, int(bool(has_bias)), precision])
+    dims = [N, C, H, W, kh, kw, sh, sw, ph, pw, int(bool(has_bias)), precision]
+    if _tensor_core(precision) and not has_bias and _is_channels_last(x):
+        nb = workspace_bytes(OP_SYRK_CONV_NHWC, dims)
+        if nb and x.data_ptr() % 16 == 0:
+            ws = workspace(nb, x.device)
+            launch_calls += 2 + int(precision == PREC_TF32)
+            _check(_syrk_conv_nhwc(_dense(x, "activation"), N, C, H, W, kh, kw, sh, sw, ph, pw, 0, float(alpha),
+                                   _dev(out, "factor"), ws.data_ptr(), ws.numel(), precision, _stream(x)),
+                   "crv_syrk_conv_accum_nhwc")
+            return
+    if not x.is_contiguous():
+        x = x.contiguous()
+    nb = workspace_bytes(OP_SYRK_CONV, dims)
     ws = workspace(nb, x.device)
-    launch_calls += 1
+    launch_calls += 1 if precision == PREC_FP32 else 2
     _check(_syrk_conv(_dev(x, "activation"), N, C, H, W, kh, kw, sh, sw, ph, pw, int(bool(has_bias)),
                       float(alpha), _dev(out, "factor"), ws.data_ptr(), ws.numel(), precision, _stream(x)),
            "crv_syrk_conv_accum")
 
 
 def syrk_rows_accum(g, has_bias, alpha, out, precision=PREC_FP32):
-    """out (D,D) += alpha * sum_{n,l} g[n,:,l] g[n,:,l]^T for g viewed as (N, M, L) (K1b)."""
+    """out (D,D) += alpha * sum_{n,l} g[n,:,l] g[n,:,l]^T for g viewed as (N, M, L) (K1b / K1d).
+
+    Channels-last 4-D operands and 2-D (Linear) operands are [R][M] matrices in memory: they go to the TMA-fed
+    MN-major kernel when the tier is a tensor-core one and the geometry qualifies."""
     global launch_calls
     N, M = g.shape[0], g.shape[1]
     L = 1
@@ -156,9 +199,21 @@ def syrk_rows_accum(g, has_bias, alpha, out, precision=PREC_FP32):
     D = M + int(bool(has_bias))
     if tuple(out.shape) != (D, D):
         raise ValueError(f"factor has shape {tuple(out.shape)}, expected {(D, D)}")
+    rows_major = _is_channels_last(g) or (g.dim() == 2 and g.is_contiguous()) or \
+        (g.dim() == 4 and L == 1 and g.is_contiguous())
+    if _tensor_core(precision) and not has_bias and rows_major:
+        nb = workspace_bytes(OP_SYRK_ROWS_NHWC, [N, M, L, 0, precision])
+        if nb and g.data_ptr() % 16 == 0:
+            ws = workspace(nb, g.device)
+            launch_calls += 2 + int(precision == PREC_TF32)
+            _check(_syrk_rows_nhwc(_dense(g, "operand"), N, M, L, 0, float(alpha), _dev(out, "factor"),
+                                   ws.data_ptr(), ws.numel(), precision, _stream(g)), "crv_syrk_rows_accum_nhwc")
+            return
+    if not g.is_contiguous():
+        g = g.contiguous()
     nb = workspace_bytes(OP_SYRK_ROWS, [N, M, L, int(bool(has_bias)), precision])
     ws = workspace(nb, g.device)
-    launch_calls += 1
+    launch_calls += 1 if precision == PREC_FP32 else 2
     _check(_syrk_rows(_dev(g, "operand"), N, M, L, int(bool(has_bias)), float(alpha), _dev(out, "factor"),
                       ws.data_ptr(), ws.numel(), precision, _stream(g)), "crv_syrk_rows_accum")
 

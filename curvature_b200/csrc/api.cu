@@ -70,6 +70,25 @@ size_t crv_workspace_bytes(int op, const int64_t* dims, int ndims) {
         return 0;
       return dims[4] == CRV_PREC_FP32 ? 0 : syrk_tc_workspace(g, (int)dims[4]);
     }
+    case CRV_OP_SYRK_CONV_NHWC: {
+      if (ndims < 12) return 0;
+      ConvGeom g;
+      static const float dummy = 0.f;
+      if (make_geom(g, &dummy, (int)dims[0], (int)dims[1], (int)dims[2], (int)dims[3], (int)dims[4],
+                    (int)dims[5], (int)dims[6], (int)dims[7], (int)dims[8], (int)dims[9], (int)dims[10]))
+        return 0;
+      g.x = nullptr;   // alignment of the real pointer is checked at launch
+      return syrk_nhwc_workspace(g, (int)dims[11]);
+    }
+    case CRV_OP_SYRK_ROWS_NHWC: {
+      if (ndims < 5) return 0;
+      ConvGeom g;
+      static const float dummy = 0.f;
+      if (make_geom(g, &dummy, (int)dims[0], (int)dims[1], 1, (int)dims[2], 1, 1, 1, 1, 0, 0, (int)dims[3]))
+        return 0;
+      g.x = nullptr;
+      return syrk_nhwc_workspace(g, (int)dims[4]);
+    }
     case CRV_OP_EFB_PROJECT:
     case CRV_OP_SAMPLE_MN:
       if (ndims < 2) return 0;
@@ -101,6 +120,21 @@ int crv_syrk_rows_accum(const float* gptr, int N, int M, int L, int has_bias, fl
   ConvGeom g;
   if (int rc = make_geom(g, gptr, N, M, 1, L, 1, 1, 1, 1, 0, 0, has_bias)) return rc;
   return syrk_dispatch(g, alpha, F, ws, ws_bytes, precision, (cudaStream_t)stream);
+}
+
+int crv_syrk_conv_accum_nhwc(const float* x, int N, int C, int H, int W, int kh, int kw, int sh, int sw, int ph,
+                             int pw, int has_bias, float alpha, float* A, void* ws, size_t ws_bytes,
+                             int precision, crv_stream_t stream) {
+  ConvGeom g;
+  if (int rc = make_geom(g, x, N, C, H, W, kh, kw, sh, sw, ph, pw, has_bias)) return rc;
+  return syrk_nhwc_launch(g, alpha, A, precision, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int crv_syrk_rows_accum_nhwc(const float* gptr, int N, int M, int L, int has_bias, float alpha, float* F,
+                             void* ws, size_t ws_bytes, int precision, crv_stream_t stream) {
+  ConvGeom g;
+  if (int rc = make_geom(g, gptr, N, M, 1, L, 1, 1, 1, 1, 0, 0, has_bias)) return rc;
+  return syrk_nhwc_launch(g, alpha, F, precision, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int crv_diag_accum(const float* wgrad, const float* bgrad, int M, int K0, float scale, float* state,

@@ -72,6 +72,11 @@ int syrk_simt_launch(const ConvGeom& g, float alpha, float* F, cudaStream_t s);
 int syrk_tc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,
                    cudaStream_t s);
 size_t syrk_tc_workspace(const ConvGeom& g, int precision);
+// channels-last operands (g.x is [N][H][W][C]); tensor-core tiers only
+bool syrk_nhwc_supported(const ConvGeom& g, int precision);
+size_t syrk_nhwc_workspace(const ConvGeom& g, int precision);
+int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,
+                     cudaStream_t s);
 
 enum GemmEpilogue {
   EPI_STORE = 0,       // C = alpha*acc + beta*C

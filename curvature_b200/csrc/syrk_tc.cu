@@ -748,6 +748,286 @@ EncodeTiledFn tensor_map_encoder() {
   return fn;
 }
 
+
+// ---- channels-last (NHWC) operands: MN-major, TMA-fed kernel -------------------------------------------
+// When the recorded tensor is channels-last -- [N][H][W][C] for activations / output gradients, [N][F] for
+// Linear operands -- the channel axis is contiguous, so for a fixed position the 32 channels of a chunk are one
+// 128-byte run: exactly one row of the MN-major SWIZZLE_128B operand layout of tcgen05 (rows = contraction
+// index = position, 128 bytes = 32 consecutive operand rows).  A filter tap is then a shift of the box
+// COORDINATES in the W / H dimensions (never of the innermost dimension), which TMA handles at any alignment,
+// with out-of-bounds zero fill supplying the convolution padding and elementStrides supplying the stride.
+// Every operand of every layer (k x k A, 1 x 1 A, G, Linear) becomes the same thing: per stage, per 32-channel
+// chunk, NB boxes of [bh x bw positions] x [32 channels] fetched by one cp.async.bulk.tensor each.  No thread
+// touches the data on its way from L2 to the tensor core.
+//
+// Positions of a box that do not exist are never loaded: box extents divide the output grid (bw | OW, bh | OH),
+// and where bw*bh is not a multiple of 8 (the contraction depth of one tf32 MMA) the remaining rows of the
+// box's shared-memory slot are zeroed once at kernel start -- TMA never writes them.
+constexpr int NH_THREADS = 6 * 32;
+constexpr int NH_MAXSTAGE = 8;
+constexpr int NH_DATA_BYTES = 216 * 1024;
+constexpr int NH_SMEM_BYTES = NH_DATA_BYTES + 1024 /*barriers, chunk table*/ + 1024 /*alignment slack*/;
+constexpr int NH_STAGE_TARGET = 64 * 1024;
+
+struct NhParams {
+  int D, C, KK, kw;
+  FastDiv divC, divKW;
+  int T, splits;
+  int nbox, bps;             // boxes in total / per split
+  int PB, PBv;               // rows per box slot (multiple of 8) / rows a box really holds
+  int NBoff, NBdiag;         // boxes per pipeline stage for off-diagonal / diagonal items
+  FastDiv divPPI, divPCW;
+  int ppi, pcw, bw, bh;      // boxes per image, boxes per box-row, box extent in output positions
+  int sh, sw, ph, pw, flat;
+  float* ws;
+};
+
+// MN-major SWIZZLE_128B descriptor: 128-byte rows (32 fp32 along M/N), 8 consecutive rows (contraction) per
+// 1024-byte atom; leading byte offset = distance between 32-row chunks along M/N; stride byte offset = distance
+// between 8-position groups (unused by a K = 8 instruction but kept consistent).
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint32_t umma_idesc_mn(uint32_t M, uint32_t N) {
+  return umma_idesc(M, N) | (1u << 15) | (1u << 16);   // A and B both MN-major
+}
+
+__global__ void __launch_bounds__(NH_THREADS, 1)
+syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  const uint32_t bars = sbase + NH_DATA_BYTES;                 // full[8] | empty[8] | tmem_full
+  const uint32_t bar_tmem_full = bars + 8 * (2 * NH_MAXSTAGE);
+  uint8_t* aux = smem_raw + (sbase - raw) + NH_DATA_BYTES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 8 * (2 * NH_MAXSTAGE + 1));
+  int4* tab = reinterpret_cast<int4*>(aux + 256);              // per loaded chunk: {c0, dx, dy, slot}
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int pair = blockIdx.x / p.splits, split = blockIdx.x - pair * p.splits;
+  int I, J;
+  decode_pair(pair, p.T, I, J);
+  const bool diag = (I == J);
+  const int rowsA = min(TB, p.D - I * TB);
+  const int mh = (rowsA + 127) >> 7;
+  const int ncols = diag ? ((rowsA + 15) & ~15) : TB;
+  const int nchA = (rowsA + 31) >> 5, nchB = diag ? 0 : TB / 32;
+  const int slotsA = mh * 4, nslots = slotsA + nchB, loaded = nchA + nchB;
+  const int NB = diag ? p.NBdiag : p.NBoff;
+  const uint32_t chunk_bytes = (uint32_t)(NB * p.PB) * 128u;
+  const uint32_t stage_bytes = (uint32_t)nslots * chunk_bytes;
+  const int nstage = min(NH_MAXSTAGE, (int)(NH_DATA_BYTES / stage_bytes));
+  const int b_begin = split * p.bps, b_end = min(p.nbox, b_begin + p.bps);
+  const int nit = (b_end - b_begin + NB - 1) / NB;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NH_MAXSTAGE; ++s) {
+      mbar_init(bars + 8 * s, 1);
+      mbar_init(bars + 8 * (NH_MAXSTAGE + s), 1);
+    }
+    mbar_init(bar_tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+  }
+  if (warp == 0 && lane < loaded) {
+    const bool isB = lane >= nchA;
+    const int kp = isB ? J * TB + (lane - nchA) * 32 : I * TB + lane * 32;
+    const int tap = (int)fdiv((uint32_t)kp, p.divC);
+    const int ti = (int)fdiv((uint32_t)tap, p.divKW);
+    tab[lane] = make_int4(kp - tap * p.C, p.flat ? 0 : (tap - ti * p.kw) - p.pw, p.flat ? 0 : ti - p.ph,
+                          isB ? slotsA + (lane - nchA) : lane);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (p.PB > p.PBv) {   // zero the rows of every box slot that no box ever writes
+    const int pad16 = (p.PB - p.PBv) * 8;                       // 16-byte words per box slot
+    const int total = nstage * nslots * NB * pad16;
+    for (int e = threadIdx.x; e < total; e += NH_THREADS) {
+      const int slot = e / pad16, w = e - slot * pad16;
+      const uint32_t a = sbase + (uint32_t)slot * (uint32_t)p.PB * 128u + (uint32_t)p.PBv * 128u + (uint32_t)w * 16u;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0) : "memory");
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t box_bytes = (uint32_t)p.PBv * 128u;
+      for (int it = 0; it < nit; ++it) {
+        const int s = it % nstage;
+        const uint32_t ph = (uint32_t)(it / nstage) & 1u;
+        mbar_wait(bars + 8 * (NH_MAXSTAGE + s), ph ^ 1u);
+        const int b0 = b_begin + it * NB;
+        const int nv = min(NB, b_end - b0);
+        mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)(nv * loaded) * box_bytes);
+        const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+        for (int j = 0; j < nv; ++j) {
+          const uint32_t b = (uint32_t)(b0 + j);
+          int X0, Y0, Nn;
+          if (p.flat) {
+            X0 = (int)b * p.PB; Y0 = 0; Nn = 0;
+          } else {
+            const uint32_t n = fdiv(b, p.divPPI);
+            const uint32_t rem = b - n * (uint32_t)p.ppi;
+            const uint32_t pr = fdiv(rem, p.divPCW);
+            const uint32_t pc = rem - pr * (uint32_t)p.pcw;
+            X0 = (int)pc * p.bw * p.sw; Y0 = (int)pr * p.bh * p.sh; Nn = (int)n;
+          }
+          const uint32_t dstj = st + (uint32_t)(j * p.PB) * 128u;
+          for (int q = 0; q < loaded; ++q) {
+            const int4 e = tab[q];
+            tma_load_4d(dstj + (uint32_t)e.w * chunk_bytes, &tmap, e.x, X0 + e.y, Y0 + e.z, Nn, bars + 8 * s);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_mn(128, (uint32_t)ncols);
+      uint32_t acc = 0;
+      for (int it = 0; it < nit; ++it) {
+        const int s = it % nstage;
+        const uint32_t ph = (uint32_t)(it / nstage) & 1u;
+        mbar_wait(bars + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+        const uint32_t bst = diag ? st : st + (uint32_t)slotsA * chunk_bytes;
+        const int nv = min(NB, b_end - (b_begin + it * NB));
+        const int nkg = nv * (p.PB >> 3);
+        for (int kg = 0; kg < nkg; ++kg) {
+          const uint64_t bdesc = umma_desc_mn(bst + (uint32_t)kg * 1024u, chunk_bytes);
+          for (int h = 0; h < mh; ++h) {
+            const uint64_t adesc = umma_desc_mn(st + (uint32_t)(h * 4) * chunk_bytes + (uint32_t)kg * 1024u, chunk_bytes);
+            tc_mma_tf32(tmem + (uint32_t)h * 256u, adesc, bdesc, idesc, acc);
+          }
+          acc = 1;
+        }
+        tc_commit(bars + 8 * (NH_MAXSTAGE + s));
+      }
+      tc_commit(bar_tmem_full);
+    }
+    __syncwarp();
+  } else {
+    ItemShape t;
+    t.mh = mh; t.ncols = ncols; t.rowsA = rowsA;
+    epilogue_store(t, bar_tmem_full, tmem, p.ws + (size_t)blockIdx.x * TILE_ELEMS, warp & 3, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// out[i] = round-to-nearest TF32 of in[i] (layout preserved): the rounding pre-pass of the `tf32` tier.
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+    const float4 v = __ldg(in + i);
+    float4 o;
+    o.x = __uint_as_float(cvt_tf32(v.x)); o.y = __uint_as_float(cvt_tf32(v.y));
+    o.z = __uint_as_float(cvt_tf32(v.z)); o.w = __uint_as_float(cvt_tf32(v.w));
+    out[i] = o;
+  }
+}
+
+struct NhPlan {
+  NhParams p;
+  int pairs;
+  size_t partial_bytes, copy_bytes;
+};
+
+bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
+  const int KK = g.kh * g.kw;
+  if (g.has_bias || g.C < 32 || (g.C & 3) != 0) return false;
+  if (KK > 1 && (g.C & 31) != 0) return false;
+  if (((uintptr_t)g.x & 15) != 0) return false;
+  if (g.sh > 8 || g.sw > 8) return false;
+  if (g.R >= (1LL << 31) - 512) return false;
+  NhParams& p = pl.p;
+  p.D = g.D; p.C = g.C; p.KK = KK; p.kw = g.kw;
+  p.divC = make_fastdiv((uint32_t)g.C);
+  p.divKW = make_fastdiv((uint32_t)g.kw);
+  p.T = (g.D + TB - 1) / TB;
+  pl.pairs = p.T * (p.T + 1) / 2;
+  p.sh = g.sh; p.sw = g.sw; p.ph = g.ph; p.pw = g.pw;
+  p.flat = (KK == 1 && g.sh == 1 && g.sw == 1 && g.ph == 0 && g.pw == 0) ? 1 : 0;
+  // chunk slots per stage of the two item kinds
+  const int mhd = ((p.T > 1 ? TB : g.D) + 127) >> 7;
+  const int slots_diag = mhd * 4, slots_off = 8 + 8;
+  const int slots_max = p.T > 1 ? slots_off : slots_diag;
+  const int pcap = NH_STAGE_TARGET / (slots_max * 128);       // positions per stage at the target stage size
+  if (p.flat) {
+    long long pb = pcap < 256 ? pcap : 256;
+    const long long r8 = (g.R + 7) & ~7LL;
+    if (pb > r8) pb = r8;
+    p.PB = p.PBv = (int)pb;
+    p.bw = (int)pb; p.bh = 1; p.pcw = 1; p.ppi = 1;
+    p.nbox = (int)((g.R + pb - 1) / pb);
+  } else {
+    int best_bw = 0, best_bh = 0, best_pb = 0;
+    double best_eff = -1.0;
+    for (int bw = 1; bw <= g.OW; ++bw) {
+      if (g.OW % bw || bw * g.sw > 256) continue;
+      for (int bh = 1; bh <= g.OH; ++bh) {
+        if (g.OH % bh || bh * g.sh > 256) continue;
+        const int pbv = bw * bh, pb = (pbv + 7) & ~7;
+        if (pb > pcap) continue;
+        const double eff = (double)pbv / pb;
+        const bool better = eff > best_eff + 1e-9 ||
+                            (eff > best_eff - 1e-9 && (pb > best_pb || (pb == best_pb && bw > best_bw)));
+        if (better) { best_eff = eff; best_bw = bw; best_bh = bh; best_pb = pb; }
+      }
+    }
+    if (best_bw == 0) return false;
+    p.bw = best_bw; p.bh = best_bh; p.PBv = best_bw * best_bh; p.PB = best_pb;
+    p.pcw = g.OW / best_bw;
+    p.ppi = p.pcw * (g.OH / best_bh);
+    const long long nb = (long long)g.N * p.ppi;
+    if (nb >= (1LL << 30)) return false;
+    p.nbox = (int)nb;
+  }
+  p.divPPI = make_fastdiv((uint32_t)p.ppi);
+  p.divPCW = make_fastdiv((uint32_t)p.pcw);
+  auto boxes_per_stage = [&](int slots) {
+    int nb = NH_STAGE_TARGET / (slots * p.PB * 128);
+    return nb < 1 ? 1 : nb;
+  };
+  p.NBoff = boxes_per_stage(slots_off);
+  p.NBdiag = boxes_per_stage(slots_diag);
+  if (p.T > 1) p.NBdiag = p.NBoff * (p.NBdiag / p.NBoff > 0 ? p.NBdiag / p.NBoff : 1);
+  if (slots_max * p.NBoff * p.PB * 128 * 2 > NH_DATA_BYTES && p.T > 1) return false;   // needs >= 2 stages
+  if (slots_diag * p.NBdiag * p.PB * 128 * 2 > NH_DATA_BYTES) return false;
+  // contraction splits: same makespan model as the staged kernel, in units of 32 positions
+  const double units = (double)p.nbox * p.PB / 32.0;
+  const int maxS = (int)(units / 16) > 0 ? (int)(units / 16) : 1;
+  double best = 1e300;
+  int bestS = 1;
+  for (int S = 1; S <= maxS && S <= 8 * sms; ++S) {
+    const long long items = (long long)pl.pairs * S;
+    const long long waves = (items + sms - 1) / sms;
+    const double est = (double)waves * (units / S + 10.0) + 0.14 * (double)items;
+    if (est < best * 0.999) { best = est; bestS = S; }
+  }
+  const int nbmax = p.NBdiag > p.NBoff ? p.NBdiag : p.NBoff;
+  int bps = (p.nbox + bestS - 1) / bestS;
+  bps = (bps + nbmax - 1) / nbmax * nbmax;
+  p.bps = bps;
+  p.splits = (p.nbox + bps - 1) / bps;
+  pl.partial_bytes = (size_t)pl.pairs * p.splits * TILE_ELEMS * sizeof(float);
+  pl.copy_bytes = precision == CRV_PREC_TF32 ? (((size_t)g.N * g.C * g.H * g.W * sizeof(float) + 1023) & ~(size_t)1023) : 0;
+  return true;
+}
+
 }  // namespace
 
 size_t syrk_tc_workspace(const ConvGeom& g, int precision) {
@@ -809,6 +1089,78 @@ int syrk_tc_launch(const ConvGeom& g, float alpha, float* F, int precision, void
   }
   CRV_CUDA(cudaGetLastError());
   syrk_tc_reduce_kernel<<<pl.pairs * 64, 256, 0, s>>>(p, alpha, F);
+  CRV_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+// ---- channels-last entry points ----------------------------------------------------------------------
+bool syrk_nhwc_supported(const ConvGeom& g, int precision) {
+  if (precision != CRV_PREC_TF32 && precision != CRV_PREC_TF32_TMA) return false;
+  NhPlan pl;
+  return nhwc_plan(g, precision, 148, pl);
+}
+
+size_t syrk_nhwc_workspace(const ConvGeom& g, int precision) {
+  NhPlan pl;
+  if (!nhwc_plan(g, precision, device_sm_count(), pl)) return 0;
+  return pl.partial_bytes + 1024 + pl.copy_bytes;
+}
+
+int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,
+                     cudaStream_t s) {
+  CRV_CHECK(precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32_TMA,
+            "channels-last SYRK: tier %d is not built (available: tf32, tf32_tma)", precision);
+  CRV_CHECK(F != nullptr, "null factor pointer");
+  const int sms = device_sm_count();
+  CRV_CHECK(sms > 0, "no CUDA device");
+  NhPlan pl;
+  CRV_CHECK(nhwc_plan(g, precision, sms, pl),
+            "channels-last SYRK: unsupported geometry (needs no bias row, C %% 4 == 0, C >= 32, C %% 32 == 0 for k x k)");
+  CRV_CHECK(tensor_map_encoder() != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
+  const size_t need = pl.partial_bytes + 1024 + pl.copy_bytes;
+  CRV_CHECK(ws != nullptr && ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
+  CRV_CHECK(((uintptr_t)ws & 1023) == 0, "workspace must be 1024-byte aligned");
+  NhParams& p = pl.p;
+  p.ws = (float*)ws;
+  const float* src = g.x;
+  if (precision == CRV_PREC_TF32) {   // rounding pre-pass: TF32 round-to-nearest copy, same layout
+    float* copy = (float*)((char*)ws + ((pl.partial_bytes + 1023) & ~(size_t)1023));
+    const size_t n4 = (size_t)g.N * g.C * g.H * g.W / 4;
+    const unsigned blocks = (unsigned)((n4 + 255) / 256 < (size_t)sms * 16 ? (n4 + 255) / 256 : (size_t)sms * 16);
+    round_tf32_kernel<<<blocks, 256, 0, s>>>((const float4*)g.x, (float4*)copy, n4);
+    CRV_CUDA(cudaGetLastError());
+    src = copy;
+  }
+  CUtensorMap map;
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t box[4], estr[4];
+  if (p.flat) {
+    gdim[0] = (cuuint64_t)g.C; gdim[1] = (cuuint64_t)g.R; gdim[2] = 1; gdim[3] = 1;
+    gstr[0] = (cuuint64_t)g.C * 4; gstr[1] = (cuuint64_t)g.R * g.C * 4; gstr[2] = gstr[1];
+    box[0] = 32; box[1] = (cuuint32_t)p.PB; box[2] = 1; box[3] = 1;
+    estr[0] = estr[1] = estr[2] = estr[3] = 1;
+  } else {
+    gdim[0] = (cuuint64_t)g.C; gdim[1] = (cuuint64_t)g.W; gdim[2] = (cuuint64_t)g.H; gdim[3] = (cuuint64_t)g.N;
+    gstr[0] = (cuuint64_t)g.C * 4; gstr[1] = (cuuint64_t)g.W * g.C * 4; gstr[2] = (cuuint64_t)g.H * g.W * g.C * 4;
+    box[0] = 32; box[1] = (cuuint32_t)(p.bw * g.sw); box[2] = (cuuint32_t)(p.bh * g.sh); box[3] = 1;
+    estr[0] = 1; estr[1] = (cuuint32_t)g.sw; estr[2] = (cuuint32_t)g.sh; estr[3] = 1;
+  }
+  const CUresult rc = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)src, gdim, gstr, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CRV_CHECK(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)rc);
+  CRV_CUDA(cudaFuncSetAttribute(syrk_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NH_SMEM_BYTES));
+  syrk_nhwc_kernel<<<pl.pairs * p.splits, NH_THREADS, NH_SMEM_BYTES, s>>>(p, map);
+  CRV_CUDA(cudaGetLastError());
+  TcParams rp;                         // the fixed-order reduction only needs the tile / permutation fields
+  memset(&rp, 0, sizeof(rp));
+  rp.g = g;
+  rp.divC = p.divC;
+  rp.T = p.T; rp.pairs = pl.pairs; rp.splits = p.splits;
+  rp.KK = p.KK;
+  rp.ws = p.ws;
+  syrk_tc_reduce_kernel<<<pl.pairs * 64, 256, 0, s>>>(rp, alpha, F);
   CRV_CUDA(cudaGetLastError());
   return 0;
 }

@@ -81,6 +81,14 @@ def _grad_of(p: Tensor, what: str) -> Tensor:
     return g if g.is_contiguous() else g.contiguous()
 
 
+class _DenseTarget:
+    """Stands in for a parameter whose storage is not row-major: `.data` is a dense buffer of the same shape."""
+
+    def __init__(self, data: Tensor):
+        self.data = data
+        self.shape = data.shape
+
+
 class Curvature(ABC):
     """Base class of all approximations (reference: curvatures.py:17-129)."""
 
@@ -186,7 +194,14 @@ class Curvature(ABC):
                 mean_w = self.model_state[names[id(weight)]]
                 mean_b = self.model_state[names[id(bias)]] if bias is not None else None
                 z = None if noise is None else noise[key]
-                self._sample_into(key, weight, bias, mean_w, mean_b, z)
+                if weight.is_contiguous():
+                    self._sample_into(key, weight, bias, mean_w, mean_b, z)
+                else:
+                    # e.g. a channels-last convolution weight: the kernel writes the logical (M, K0) row-major
+                    # matrix, so sample into a dense buffer and let copy_ apply the parameter's strides
+                    dense_w = torch.empty(weight.shape, dtype=weight.dtype, device=weight.device)
+                    self._sample_into(key, _DenseTarget(dense_w), bias, mean_w.contiguous(), mean_b, z)
+                    weight.data.copy_(dense_w)
                 written.add(names[id(weight)])
                 if bias is not None:
                     written.add(names[id(bias)])
@@ -334,12 +349,8 @@ class KFAC(Curvature):
                     if forward is None or backward is None:
                         raise RuntimeError("KFAC.update: no recorded input / output gradient for "
                                            f"{module_class}; run a forward and backward pass first")
-                    x = forward.detach()
-                    g = backward.detach()
-                    if not x.is_contiguous():
-                        x = x.contiguous()
-                    if not g.is_contiguous():
-                        g = g.contiguous()
+                    x = forward.detach()     # any dense layout: the binding picks the NCHW or the
+                    g = backward.detach()    # channels-last kernel (and copies only if neither applies)
                     if layer not in self.state:
                         self.state[layer] = self._views[layer]
                     first, second = self.state[layer]

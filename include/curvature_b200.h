@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CRV_ABI_VERSION 1
+#define CRV_ABI_VERSION 2
 
 typedef void* crv_stream_t; /* cudaStream_t */
 
@@ -46,7 +46,9 @@ enum crv_op {
   CRV_OP_SYRK_ROWS   = 1, /* dims = {N,M,L,has_bias,precision}                     */
   CRV_OP_EFB_PROJECT = 2, /* dims = {M,K}                                          */
   CRV_OP_CHOL_INV    = 3, /* dims = {count, d_0, ..., d_{count-1}}                 */
-  CRV_OP_SAMPLE_MN   = 4  /* dims = {M,K}                                          */
+  CRV_OP_SAMPLE_MN   = 4, /* dims = {M,K}                                          */
+  CRV_OP_SYRK_CONV_NHWC = 5, /* dims as CRV_OP_SYRK_CONV; 0 if the geometry is unsupported */
+  CRV_OP_SYRK_ROWS_NHWC = 6  /* dims as CRV_OP_SYRK_ROWS; 0 if the geometry is unsupported */
 };
 
 int         crv_abi_version(void);
@@ -72,6 +74,22 @@ int crv_syrk_conv_accum(const float* x, int N, int C, int H, int W,
  * (curvatures.py:332-336).  F is (D,D), D = M + has_bias. */
 int crv_syrk_rows_accum(const float* g, int N, int M, int L, int has_bias, float alpha, float* F,
                         void* ws, size_t ws_bytes, int precision, crv_stream_t stream);
+
+/* K1c / K1d -- the same two contractions for CHANNELS-LAST operands: x is the (N,C,H,W) activation stored as
+ * [N][H][W][C] (torch.channels_last), g the (N,M,L) operand stored as [N][L][M] (for Linear layers, L = 1, both
+ * layouts coincide).  The logical tensor, the row order of the factor and the result are exactly those of K1a /
+ * K1b; only the memory layout of the input differs.  This is the TMA-fed path: every filter tap is a shifted box
+ * of cp.async.bulk.tensor (zero fill = padding), operands reach tcgen05.mma in MN-major form, no thread touches
+ * them.  Tensor-core tiers only (CRV_PREC_TF32: round-to-nearest TF32 copy made by a pre-pass into ws;
+ * CRV_PREC_TF32_TMA: the fp32 words are fed as they are, i.e. TF32 truncation).  Requirements: has_bias == 0,
+ * C >= 32, C % 4 == 0, and C % 32 == 0 when kh*kw > 1; crv_workspace_bytes() returns 0 for an unsupported
+ * geometry and the call itself returns an error (callers then use K1a / K1b on an NCHW copy). */
+int crv_syrk_conv_accum_nhwc(const float* x, int N, int C, int H, int W,
+                             int kh, int kw, int sh, int sw, int ph, int pw,
+                             int has_bias, float alpha, float* A,
+                             void* ws, size_t ws_bytes, int precision, crv_stream_t stream);
+int crv_syrk_rows_accum_nhwc(const float* g, int N, int M, int L, int has_bias, float alpha, float* F,
+                             void* ws, size_t ws_bytes, int precision, crv_stream_t stream);
 
 /* K2 -- squared-gradient accumulation (Diagonal.update, curvatures.py:151-158; the `diags`
  * part of EFB.update, curvatures.py:431-434):

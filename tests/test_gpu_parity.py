@@ -415,3 +415,127 @@ def test_gemm_entry_point():
     C = torch.ones(70, 129, device=DEV)
     nat.gemm(A, B, alpha=2.0, beta=3.0, out=C)
     assert rel_fro(C, 2 * (A.double() @ B.double()) + 3) <= 1e-6
+
+
+# ---- channels-last (NHWC) operands: the TMA-fed MN-major tcgen05 kernel ---------------------------------------
+TC_TIERS = [nat.PREC_TF32, nat.PREC_TF32_TMA]
+
+NHWC_GEOMS = [
+    # N, C, H, W, kernel, stride, padding
+    (2, 32, 8, 8, (3, 3), (1, 1), (1, 1)),       # 8x8 grid: boxes of 8x4
+    (3, 64, 14, 14, (3, 3), (1, 1), (1, 1)),     # 14x14: boxes of 14x2 + 4 zero rows
+    (2, 64, 7, 7, (3, 3), (1, 1), (1, 1)),       # 7x7: boxes of 7x1 + 1 zero row
+    (2, 32, 28, 28, (3, 3), (2, 2), (1, 1)),     # stride 2: elementStrides in the tensor map
+    (2, 96, 12, 16, (3, 3), (1, 1), (1, 1)),     # K = 864: three full 256-row blocks + 96 rows
+    (2, 64, 12, 10, (3, 5), (1, 2), (1, 2)),     # non-square kernel, mixed stride / padding
+    (2, 128, 9, 9, (1, 1), (2, 2), (0, 0)),      # 1x1 stride 2 (ResNet downsample)
+    (4, 40, 6, 6, (1, 1), (1, 1), (0, 0)),       # flat, C % 32 != 0: channel tail by out-of-bounds fill
+    (3, 288, 5, 5, (1, 1), (1, 1), (0, 0)),      # flat, two blocks, R = 75 (ragged last box)
+    (70, 32, 6, 6, (3, 3), (1, 1), (1, 1)),      # many boxes: several contraction splits
+    (2, 32, 6, 6, (5, 5), (1, 1), (2, 2)),       # 25 taps
+    (1, 64, 4, 4, (3, 3), (1, 1), (0, 0)),       # no padding: 2x2 output grid
+]
+
+
+@pytest.mark.parametrize("geom", NHWC_GEOMS)
+@pytest.mark.parametrize("prec", TC_TIERS)
+def test_nhwc_implicit_im2col_syrk_bit_exact_on_integers(geom, prec):
+    """Same gate as the NCHW test, for channels-last activations: tap shifts are TMA box coordinates, padding is
+    the out-of-bounds fill, strides are elementStrides; any indexing error is an exact mismatch."""
+    N, C, H, W, k, s, p = geom
+    gen = torch.Generator().manual_seed(hash(geom) % (2 ** 31))
+    x = torch.randint(-2, 3, (N, C, H, W), generator=gen).float()
+    want, R = oracle_A(x, k, s, p, False)
+    K = want.shape[0]
+    out = torch.zeros(K, K, device=DEV)
+    xc = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    assert nat._is_channels_last(xc) or C == 1
+    before = nat.launch_calls
+    nat.syrk_conv_accum(xc, k, s, p, False, 1.0, out, prec)
+    assert nat.workspace_bytes(nat.OP_SYRK_CONV_NHWC, [N, C, H, W, *k, *s, *p, 0, prec]) > 0   # took the TMA path
+    assert nat.launch_calls - before == 2 + int(prec == nat.PREC_TF32)
+    assert torch.equal(out.cpu().double(), want), f"max diff {(out.cpu().double() - want).abs().max()}"
+    nat.syrk_conv_accum(xc, k, s, p, False, 2.0, out, prec)
+    assert torch.equal(out.cpu().double(), 3 * want)
+
+
+@pytest.mark.parametrize("shape", [(256, 1000), (5, 64), (3, 48, 5, 5), (2, 256, 14, 14), (300, 36, 2, 2), (7, 2048, 1, 1)])
+@pytest.mark.parametrize("prec", TC_TIERS)
+def test_nhwc_rows_syrk_bit_exact_on_integers(shape, prec):
+    gen = torch.Generator().manual_seed(len(shape) * 1000 + shape[1])
+    g = torch.randint(-3, 4, shape, generator=gen).float()
+    M = shape[1]
+    X = g.reshape(shape[0], M, -1).permute(1, 0, 2).reshape(M, -1).double()
+    want = X @ X.t()
+    gd = g.to(DEV)
+    if gd.dim() == 4:
+        gd = gd.contiguous(memory_format=torch.channels_last)
+    out = torch.zeros(M, M, device=DEV)
+    nat.syrk_rows_accum(gd, False, 1.0, out, prec)
+    assert torch.equal(out.cpu().double(), want)
+
+
+@pytest.mark.parametrize("layer", RESNET_LAYERS[1:], ids=[l[0] for l in RESNET_LAYERS[1:]])
+@pytest.mark.parametrize("prec", TC_TIERS)
+def test_nhwc_resnet_shaped_factors_against_fp64(layer, prec):
+    name, N, C, H, W, k, s, p = layer
+    torch.manual_seed(1)
+    x = torch.relu(torch.randn(N, C, H, W, device=DEV)).contiguous(memory_format=torch.channels_last)
+    cols = F.unfold(x.double(), k, padding=p, stride=s)
+    X = cols.permute(1, 0, 2).reshape(cols.shape[1], -1)
+    want = (X @ X.t()) / X.shape[1]
+    out = torch.zeros_like(want, dtype=torch.float32)
+    nat.syrk_conv_accum(x, (k, k), (s, s), (p, p), False, 1.0 / X.shape[1], out, prec)
+    err = rel_fro(out, want)
+    # round-to-nearest TF32 operands stay inside the fp32 bar on these distributions; fed as raw fp32 words the
+    # tensor core truncates them (stated 1e-3 tier)
+    assert err <= (1e-5 if prec == nat.PREC_TF32 else 1e-3), (name, err)
+    assert torch.equal(out, out.t())
+    OH = (H + 2 * p - k) // s + 1
+    gten = (torch.randn(N, min(C, 256), OH, OH, device=DEV) * 1e-3).contiguous(memory_format=torch.channels_last)
+    Xg = gten.double().permute(1, 0, 2, 3).reshape(gten.shape[1], -1)
+    wantg = (Xg @ Xg.t()) * (N * N / Xg.shape[1])
+    outg = torch.zeros_like(wantg, dtype=torch.float32)
+    nat.syrk_rows_accum(gten, False, N * N / Xg.shape[1], outg, prec)
+    assert rel_fro(outg, wantg) <= (1e-5 if prec == nat.PREC_TF32 else 1e-3), (name, rel_fro(outg, wantg))
+
+
+def test_kfac_channels_last_model_matches_nchw_model():
+    """The same network run in torch.channels_last memory format records channels-last activations / gradients;
+    the factors, the inverse factors and a posterior sample (same noise) must agree with the NCHW fp32 path."""
+    torch.manual_seed(3)
+
+    def make():
+        return torch.nn.Sequential(
+            torch.nn.Conv2d(3, 32, 3, padding=1, bias=False), torch.nn.ReLU(),
+            torch.nn.Conv2d(32, 64, 3, stride=2, padding=1, bias=False), torch.nn.ReLU(),
+            torch.nn.Conv2d(64, 64, 1, bias=False), torch.nn.ReLU(),
+            torch.nn.Conv2d(64, 32, 3, padding=1, bias=True), torch.nn.ReLU(),
+            torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(), torch.nn.Linear(32, 10))
+    ref_model = make().to(DEV)
+    cl_model = make().to(DEV)
+    cl_model.load_state_dict(ref_model.state_dict())
+    cl_model = cl_model.to(memory_format=torch.channels_last)
+    x = torch.randn(8, 3, 16, 16, device=DEV)
+    labels = torch.randint(0, 10, (8,), device=DEV)
+    ref, cl = cb.KFAC(ref_model, precision="fp32"), cb.KFAC(cl_model, precision="tf32")
+    for model, est, inp in ((ref_model, ref, x), (cl_model, cl, x.contiguous(memory_format=torch.channels_last))):
+        for _ in range(2):
+            model.zero_grad()
+            torch.nn.functional.cross_entropy(model(inp), labels).backward()
+            est.update(8)
+    n_tma = 0
+    for lr, lc in zip(ref.state, cl.state):
+        xr = cl.record[lc][0]
+        n_tma += int(xr.dim() == 4 and nat._is_channels_last(xr))
+        for f in range(2):
+            assert rel_fro(cl.state[lc][f], ref.state[lr][f]) <= 2e-5, (lc, f, rel_fro(cl.state[lc][f], ref.state[lr][f]))
+    assert n_tma >= 3          # the inner convolutions really saw channels-last activations
+    ref.invert(0.5, 10.0)
+    cl.invert(0.5, 10.0)
+    noise_r = {l: torch.randn(ref.inv_state[l][0].shape[0], ref.inv_state[l][1].shape[0], device=DEV) for l in ref.state}
+    noise_c = {lc: noise_r[lr] for lr, lc in zip(ref.state, cl.state)}
+    ref.sample_and_replace(noise_r)
+    cl.sample_and_replace(noise_c)
+    for (k1, v1), (k2, v2) in zip(ref_model.state_dict().items(), cl_model.state_dict().items()):
+        assert v1.shape == v2.shape and rel_fro(v2, v1) <= 1e-3, (k1, rel_fro(v2, v1))
