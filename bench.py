@@ -261,7 +261,7 @@ def main():
         table = []
         for layer, K, M, R, f in rows:
             x, g = kfac.record[layer]
-            xs, gs = x.detach().contiguous(), g.detach().contiguous()
+            xs, gs = x.detach(), g.detach()
             first, second = kfac.state[layer]
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             bias = layer.bias is not None
@@ -283,7 +283,9 @@ def main():
             a_ms, g_ms = statistics.median(ta), statistics.median(tg)
             table.append({"layer": str(layer), "K": K, "M": M, "R": R, "A_ms": a_ms, "G_ms": g_ms,
                           "A_tflops": R * K * (K + 1) / a_ms / 1e9, "G_tflops": R * M * (M + 1) / g_ms / 1e9,
-                          "A_gbs": 4 * x.numel() / a_ms / 1e6, "G_gbs": 4 * g.numel() / g_ms / 1e6})
+                          "A_gbs": 4 * x.numel() / a_ms / 1e6, "G_gbs": 4 * g.numel() / g_ms / 1e6,
+                          "x_channels_last": bool(x.dim() == 4 and nat._is_channels_last(x)),
+                          "g_channels_last": bool(g.dim() == 4 and nat._is_channels_last(g))})
         os.makedirs(os.path.dirname(os.path.abspath(args.per_layer)), exist_ok=True)
         json.dump(table, open(args.per_layer, "w"), indent=1)
 

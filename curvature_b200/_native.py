@@ -149,7 +149,7 @@ def _is_channels_last(t):
 
 
 def _tensor_core(precision):
-    return precision in (PREC_TF32, PREC_TF32_TMA)
+    return precision in (PREC_TF32, PREC_TF32_TMA, PREC_BF16)
 
 
 def syrk_conv_accum(x, kernel_size, stride, padding, has_bias, alpha, out, precision=PREC_FP32):
@@ -171,13 +171,16 @@ def syrk_conv_accum(x, kernel_size, stride, padding, has_bias, alpha, out, preci
         nb = workspace_bytes(OP_SYRK_CONV_NHWC, dims)
         if nb and x.data_ptr() % 16 == 0:
             ws = workspace(nb, x.device)
-            launch_calls += 2 + int(precision == PREC_TF32)
+            launch_calls += 2 + int(precision in (PREC_TF32, PREC_BF16))
             _check(_syrk_conv_nhwc(_dense(x, "activation"), N, C, H, W, kh, kw, sh, sw, ph, pw, 0, float(alpha),
                                    _dev(out, "factor"), ws.data_ptr(), ws.numel(), precision, _stream(x)),
                    "crv_syrk_conv_accum_nhwc")
             return
     if not x.is_contiguous():
         x = x.contiguous()
+    if precision == PREC_BF16:        # operands the channels-last kernel cannot take: thread-staged TF32 kernel
+        precision = PREC_TF32
+        dims[-1] = precision
     nb = workspace_bytes(OP_SYRK_CONV, dims)
     ws = workspace(nb, x.device)
     launch_calls += 1 if precision == PREC_FP32 else 2
@@ -205,12 +208,14 @@ def syrk_rows_accum(g, has_bias, alpha, out, precision=PREC_FP32):
         nb = workspace_bytes(OP_SYRK_ROWS_NHWC, [N, M, L, 0, precision])
         if nb and g.data_ptr() % 16 == 0:
             ws = workspace(nb, g.device)
-            launch_calls += 2 + int(precision == PREC_TF32)
+            launch_calls += 2 + int(precision in (PREC_TF32, PREC_BF16))
             _check(_syrk_rows_nhwc(_dense(g, "operand"), N, M, L, 0, float(alpha), _dev(out, "factor"),
                                    ws.data_ptr(), ws.numel(), precision, _stream(g)), "crv_syrk_rows_accum_nhwc")
             return
     if not g.is_contiguous():
         g = g.contiguous()
+    if precision == PREC_BF16:
+        precision = PREC_TF32
     nb = workspace_bytes(OP_SYRK_ROWS, [N, M, L, int(bool(has_bias)), precision])
     ws = workspace(nb, g.device)
     launch_calls += 1 if precision == PREC_FP32 else 2

@@ -752,7 +752,7 @@ EncodeTiledFn tensor_map_encoder() {
 // ---- channels-last (NHWC) operands: MN-major, TMA-fed kernel -------------------------------------------
 // When the recorded tensor is channels-last -- [N][H][W][C] for activations / output gradients, [N][F] for
 // Linear operands -- the channel axis is contiguous, so for a fixed position the 32 channels of a chunk are one
-// 128-byte run: exactly one row of the MN-major SWIZZLE_128B operand layout of tcgen05 (rows = contraction
+// 128-byte run: exactly one row of the MN-major operand layout of tcgen05 (rows = contraction
 // index = position, 128 bytes = 32 consecutive operand rows).  A filter tap is then a shift of the box
 // COORDINATES in the W / H dimensions (never of the innermost dimension), which TMA handles at any alignment,
 // with out-of-bounds zero fill supplying the convolution padding and elementStrides supplying the stride.
@@ -782,19 +782,47 @@ struct NhParams {
   float* ws;
 };
 
-// MN-major SWIZZLE_128B descriptor: 128-byte rows (32 fp32 along M/N), 8 consecutive rows (contraction) per
-// 1024-byte atom; leading byte offset = distance between 32-row chunks along M/N; stride byte offset = distance
-// between 8-position groups (unused by a K = 8 instruction but kept consistent).
+// MN-major descriptor for 32-bit operands.  tcgen05 accepts exactly one shared-memory layout for MN-major TF32
+// (measured with scripts/experiments/mn_major_probe.cu; CUTLASS calls it SW128_32B): 128-byte rows (32 fp32 along
+// M/N) whose 32-byte quarters are XOR-swizzled with (row & 3) -- what TMA writes in CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+// mode -- in atoms of 4 consecutive rows (contraction index).  Layout type 1 in bits [61,64); stride byte offset =
+// 512 B between the two 4-row atoms a K = 8 instruction reads; leading byte offset = distance between 32-row
+// chunks along M/N.  (The plain SWIZZLE_128B layout, type 2, silently yields an all-zero product.)
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 __device__ __forceinline__ uint32_t umma_idesc_mn(uint32_t M, uint32_t N) {
   return umma_idesc(M, N) | (1u << 15) | (1u << 16);   // A and B both MN-major
 }
+// 16-bit operands (bf16): the ordinary SWIZZLE_128B MN-major layout -- 128-byte rows (64 bf16 along M/N), 16-byte
+// chunks XOR-swizzled with (row & 7), atoms of 8 rows; a K = 16 instruction reads two atoms, 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_mn16(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// D = fp32, A = B = BF16 (format 1), both MN-major
+__device__ __forceinline__ uint32_t umma_idesc_mn16(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
+// BF16 = false: fp32 words read as TF32, 32 channels per 128-byte row, 8 positions per MMA.
+// BF16 = true : bf16 copy of the operand (made by the cast pre-pass), 64 channels per row, 16 positions per MMA:
+//               half the bytes per operand element through L2 -> SM, twice the MMA rate.
+template <bool BF16>
 __global__ void __launch_bounds__(NH_THREADS, 1)
 syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int CH = BF16 ? 64 : 32;        // operand rows (channels) per chunk = per 128-byte smem row
+  constexpr int KPOS = BF16 ? 16 : 8;       // contraction positions per MMA instruction
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -812,8 +840,8 @@ syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
   const int rowsA = min(TB, p.D - I * TB);
   const int mh = (rowsA + 127) >> 7;
   const int ncols = diag ? ((rowsA + 15) & ~15) : TB;
-  const int nchA = (rowsA + 31) >> 5, nchB = diag ? 0 : TB / 32;
-  const int slotsA = mh * 4, nslots = slotsA + nchB, loaded = nchA + nchB;
+  const int nchA = (rowsA + CH - 1) / CH, nchB = diag ? 0 : TB / CH;
+  const int slotsA = mh * (128 / CH), nslots = slotsA + nchB, loaded = nchA + nchB;
   const int NB = diag ? p.NBdiag : p.NBoff;
   const uint32_t chunk_bytes = (uint32_t)(NB * p.PB) * 128u;
   const uint32_t stage_bytes = (uint32_t)nslots * chunk_bytes;
@@ -832,7 +860,7 @@ syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
   }
   if (warp == 0 && lane < loaded) {
     const bool isB = lane >= nchA;
-    const int kp = isB ? J * TB + (lane - nchA) * 32 : I * TB + lane * 32;
+    const int kp = isB ? J * TB + (lane - nchA) * CH : I * TB + lane * CH;
     const int tap = (int)fdiv((uint32_t)kp, p.divC);
     const int ti = (int)fdiv((uint32_t)tap, p.divKW);
     tab[lane] = make_int4(kp - tap * p.C, p.flat ? 0 : (tap - ti * p.kw) - p.pw, p.flat ? 0 : ti - p.ph,
@@ -892,7 +920,7 @@ syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_mn(128, (uint32_t)ncols);
+      const uint32_t idesc = BF16 ? umma_idesc_mn16(128, (uint32_t)ncols) : umma_idesc_mn(128, (uint32_t)ncols);
       uint32_t acc = 0;
       for (int it = 0; it < nit; ++it) {
         const int s = it % nstage;
@@ -902,12 +930,19 @@ syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
         const uint32_t st = sbase + (uint32_t)s * stage_bytes;
         const uint32_t bst = diag ? st : st + (uint32_t)slotsA * chunk_bytes;
         const int nv = min(NB, b_end - (b_begin + it * NB));
-        const int nkg = nv * (p.PB >> 3);
+        const int nkg = nv * (p.PB / KPOS);
         for (int kg = 0; kg < nkg; ++kg) {
-          const uint64_t bdesc = umma_desc_mn(bst + (uint32_t)kg * 1024u, chunk_bytes);
-          for (int h = 0; h < mh; ++h) {
-            const uint64_t adesc = umma_desc_mn(st + (uint32_t)(h * 4) * chunk_bytes + (uint32_t)kg * 1024u, chunk_bytes);
-            tc_mma_tf32(tmem + (uint32_t)h * 256u, adesc, bdesc, idesc, acc);
+          const uint32_t koff = (uint32_t)kg * (uint32_t)(KPOS * 128);
+          if (BF16) {
+            const uint64_t bdesc = umma_desc_mn16(bst + koff, chunk_bytes);
+            for (int h = 0; h < mh; ++h)
+              tc_mma_bf16(tmem + (uint32_t)h * 256u, umma_desc_mn16(st + (uint32_t)(h * 2) * chunk_bytes + koff, chunk_bytes),
+                          bdesc, idesc, acc);
+          } else {
+            const uint64_t bdesc = umma_desc_mn(bst + koff, chunk_bytes);
+            for (int h = 0; h < mh; ++h)
+              tc_mma_tf32(tmem + (uint32_t)h * 256u, umma_desc_mn(st + (uint32_t)(h * 4) * chunk_bytes + koff, chunk_bytes),
+                          bdesc, idesc, acc);
           }
           acc = 1;
         }
@@ -940,9 +975,21 @@ __global__ void __launch_bounds__(256) round_tf32_kernel(const float4* __restric
   }
 }
 
+// out[i] = bf16(in[i]) (round to nearest even, layout preserved): the pre-pass of the `bf16` tier.
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+    const float4 v = __ldg(in + i);
+    uint2 o;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(v.y), "f"(v.x));   // low half = first element
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(v.w), "f"(v.z));
+    out[i] = o;
+  }
+}
+
 struct NhPlan {
   NhParams p;
   int pairs;
+  int bf16;                      // operands go through the bf16 copy
   size_t partial_bytes, copy_bytes;
 };
 
@@ -959,17 +1006,23 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
   p.divKW = make_fastdiv((uint32_t)g.kw);
   p.T = (g.D + TB - 1) / TB;
   pl.pairs = p.T * (p.T + 1) / 2;
+  // The bf16 copy costs one extra pass over the tensor (read 4 B, write 2 B per element): it pays when every
+  // element then travels L2 -> SM several times -- k x k convolutions (each element feeds kh*kw operand rows) and
+  // factors of three or more row blocks.  Single-tile, read-once operands are HBM-bound and stay on the direct path.
+  pl.bf16 = (precision == CRV_PREC_BF16 && (KK > 1 || p.T >= 3) && g.C >= 64 && (g.C & 7) == 0 &&
+             (KK == 1 || (g.C & 63) == 0)) ? 1 : 0;
+  const int CH = pl.bf16 ? 64 : 32, gran = pl.bf16 ? 16 : 8;
   p.sh = g.sh; p.sw = g.sw; p.ph = g.ph; p.pw = g.pw;
   p.flat = (KK == 1 && g.sh == 1 && g.sw == 1 && g.ph == 0 && g.pw == 0) ? 1 : 0;
   // chunk slots per stage of the two item kinds
   const int mhd = ((p.T > 1 ? TB : g.D) + 127) >> 7;
-  const int slots_diag = mhd * 4, slots_off = 8 + 8;
+  const int slots_diag = mhd * (128 / CH), slots_off = 2 * (TB / CH);
   const int slots_max = p.T > 1 ? slots_off : slots_diag;
   const int pcap = NH_STAGE_TARGET / (slots_max * 128);       // positions per stage at the target stage size
   if (p.flat) {
     long long pb = pcap < 256 ? pcap : 256;
-    const long long r8 = (g.R + 7) & ~7LL;
-    if (pb > r8) pb = r8;
+    const long long rr = (g.R + gran - 1) / gran * gran;
+    if (pb > rr) pb = rr;
     p.PB = p.PBv = (int)pb;
     p.bw = (int)pb; p.bh = 1; p.pcw = 1; p.ppi = 1;
     p.nbox = (int)((g.R + pb - 1) / pb);
@@ -980,7 +1033,7 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
       if (g.OW % bw || bw * g.sw > 256) continue;
       for (int bh = 1; bh <= g.OH; ++bh) {
         if (g.OH % bh || bh * g.sh > 256) continue;
-        const int pbv = bw * bh, pb = (pbv + 7) & ~7;
+        const int pbv = bw * bh, pb = (pbv + gran - 1) / gran * gran;
         if (pb > pcap) continue;
         const double eff = (double)pbv / pb;
         const bool better = eff > best_eff + 1e-9 ||
@@ -1024,7 +1077,9 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
   p.bps = bps;
   p.splits = (p.nbox + bps - 1) / bps;
   pl.partial_bytes = (size_t)pl.pairs * p.splits * TILE_ELEMS * sizeof(float);
-  pl.copy_bytes = precision == CRV_PREC_TF32 ? (((size_t)g.N * g.C * g.H * g.W * sizeof(float) + 1023) & ~(size_t)1023) : 0;
+  const size_t numel = (size_t)g.N * g.C * g.H * g.W;
+  pl.copy_bytes = pl.bf16 ? ((numel * 2 + 1023) & ~(size_t)1023)
+                          : (precision == CRV_PREC_TF32 ? ((numel * 4 + 1023) & ~(size_t)1023) : 0);
   return true;
 }
 
@@ -1096,7 +1151,7 @@ int syrk_tc_launch(const ConvGeom& g, float alpha, float* F, int precision, void
 
 // ---- channels-last entry points ----------------------------------------------------------------------
 bool syrk_nhwc_supported(const ConvGeom& g, int precision) {
-  if (precision != CRV_PREC_TF32 && precision != CRV_PREC_TF32_TMA) return false;
+  if (precision != CRV_PREC_TF32 && precision != CRV_PREC_TF32_TMA && precision != CRV_PREC_BF16) return false;
   NhPlan pl;
   return nhwc_plan(g, precision, 148, pl);
 }
@@ -1109,8 +1164,8 @@ size_t syrk_nhwc_workspace(const ConvGeom& g, int precision) {
 
 int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,
                      cudaStream_t s) {
-  CRV_CHECK(precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32_TMA,
-            "channels-last SYRK: tier %d is not built (available: tf32, tf32_tma)", precision);
+  CRV_CHECK(precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32_TMA || precision == CRV_PREC_BF16,
+            "channels-last SYRK: tier %d is not built (available: tf32, tf32_tma, bf16)", precision);
   CRV_CHECK(F != nullptr, "null factor pointer");
   const int sms = device_sm_count();
   CRV_CHECK(sms > 0, "no CUDA device");
@@ -1120,38 +1175,47 @@ int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, vo
   CRV_CHECK(tensor_map_encoder() != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
   const size_t need = pl.partial_bytes + 1024 + pl.copy_bytes;
   CRV_CHECK(ws != nullptr && ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
-  CRV_CHECK(((uintptr_t)ws & 1023) == 0, "workspace must be 1024-byte aligned");
+  CRV_CHECK(((uintptr_t)ws & 15) == 0, "workspace must be 16-byte aligned");
   NhParams& p = pl.p;
   p.ws = (float*)ws;
   const float* src = g.x;
-  if (precision == CRV_PREC_TF32) {   // rounding pre-pass: TF32 round-to-nearest copy, same layout
-    float* copy = (float*)((char*)ws + ((pl.partial_bytes + 1023) & ~(size_t)1023));
+  if (pl.copy_bytes) {   // pre-pass: bf16 copy (tier bf16) or TF32 round-to-nearest copy (tier tf32), same layout
+    float* copy = (float*)((((uintptr_t)ws + pl.partial_bytes) + 1023) & ~(uintptr_t)1023);
     const size_t n4 = (size_t)g.N * g.C * g.H * g.W / 4;
     const unsigned blocks = (unsigned)((n4 + 255) / 256 < (size_t)sms * 16 ? (n4 + 255) / 256 : (size_t)sms * 16);
-    round_tf32_kernel<<<blocks, 256, 0, s>>>((const float4*)g.x, (float4*)copy, n4);
+    if (pl.bf16) cast_bf16_kernel<<<blocks, 256, 0, s>>>((const float4*)g.x, (uint2*)copy, n4);
+    else round_tf32_kernel<<<blocks, 256, 0, s>>>((const float4*)g.x, (float4*)copy, n4);
     CRV_CUDA(cudaGetLastError());
     src = copy;
   }
+  const cuuint64_t esz = pl.bf16 ? 2 : 4;
+  const cuuint32_t chbox = pl.bf16 ? 64 : 32;
   CUtensorMap map;
   cuuint64_t gdim[4], gstr[3];
   cuuint32_t box[4], estr[4];
   if (p.flat) {
     gdim[0] = (cuuint64_t)g.C; gdim[1] = (cuuint64_t)g.R; gdim[2] = 1; gdim[3] = 1;
-    gstr[0] = (cuuint64_t)g.C * 4; gstr[1] = (cuuint64_t)g.R * g.C * 4; gstr[2] = gstr[1];
-    box[0] = 32; box[1] = (cuuint32_t)p.PB; box[2] = 1; box[3] = 1;
+    gstr[0] = (cuuint64_t)g.C * esz; gstr[1] = (cuuint64_t)g.R * g.C * esz; gstr[2] = gstr[1];
+    box[0] = chbox; box[1] = (cuuint32_t)p.PB; box[2] = 1; box[3] = 1;
     estr[0] = estr[1] = estr[2] = estr[3] = 1;
   } else {
     gdim[0] = (cuuint64_t)g.C; gdim[1] = (cuuint64_t)g.W; gdim[2] = (cuuint64_t)g.H; gdim[3] = (cuuint64_t)g.N;
-    gstr[0] = (cuuint64_t)g.C * 4; gstr[1] = (cuuint64_t)g.W * g.C * 4; gstr[2] = (cuuint64_t)g.H * g.W * g.C * 4;
-    box[0] = 32; box[1] = (cuuint32_t)(p.bw * g.sw); box[2] = (cuuint32_t)(p.bh * g.sh); box[3] = 1;
+    gstr[0] = (cuuint64_t)g.C * esz; gstr[1] = (cuuint64_t)g.W * g.C * esz; gstr[2] = (cuuint64_t)g.H * g.W * g.C * esz;
+    box[0] = chbox; box[1] = (cuuint32_t)(p.bw * g.sw); box[2] = (cuuint32_t)(p.bh * g.sh); box[3] = 1;
     estr[0] = 1; estr[1] = (cuuint32_t)g.sw; estr[2] = (cuuint32_t)g.sh; estr[3] = 1;
   }
-  const CUresult rc = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)src, gdim, gstr, box, estr,
-                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  const CUresult rc = tensor_map_encoder()(&map, pl.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                           4, (void*)src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           pl.bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CRV_CHECK(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)rc);
-  CRV_CUDA(cudaFuncSetAttribute(syrk_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NH_SMEM_BYTES));
-  syrk_nhwc_kernel<<<pl.pairs * p.splits, NH_THREADS, NH_SMEM_BYTES, s>>>(p, map);
+  if (pl.bf16) {
+    CRV_CUDA(cudaFuncSetAttribute(syrk_nhwc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NH_SMEM_BYTES));
+    syrk_nhwc_kernel<true><<<pl.pairs * p.splits, NH_THREADS, NH_SMEM_BYTES, s>>>(p, map);
+  } else {
+    CRV_CUDA(cudaFuncSetAttribute(syrk_nhwc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NH_SMEM_BYTES));
+    syrk_nhwc_kernel<false><<<pl.pairs * p.splits, NH_THREADS, NH_SMEM_BYTES, s>>>(p, map);
+  }
   CRV_CUDA(cudaGetLastError());
   TcParams rp;                         // the fixed-order reduction only needs the tile / permutation fields
   memset(&rp, 0, sizeof(rp));

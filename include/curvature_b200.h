@@ -35,7 +35,8 @@ enum crv_precision {
   CRV_PREC_FP32   = 0, /* CUDA-core fp32 FMA (exact fp32 products); parity tier 1e-5            */
   CRV_PREC_TF32   = 1, /* tcgen05 kind::tf32, operands rounded to nearest (cvt.rna), fp32 accum  */
   CRV_PREC_TF32X3 = 2, /* tcgen05 3xTF32 error-compensated split (hi*hi + hi*lo + lo*hi)          */
-  CRV_PREC_BF16   = 3, /* tcgen05 kind::f16 with bf16 operands, fp32 accum; parity tier 1e-3      */
+  CRV_PREC_BF16   = 3, /* tcgen05 kind::f16 on a bf16 copy of the operand (cast pre-pass), fp32 accum; parity tier
+                          1e-3.  Channels-last entry points only; read-once operands stay on the TF32 path    */
   CRV_PREC_TF32_TMA = 4 /* tcgen05 kind::tf32 fed by TMA where the geometry allows (hardware TF32
                            truncation of the fp32 operands; parity tier 1e-3), else as CRV_PREC_TF32 */
 };
@@ -81,7 +82,8 @@ int crv_syrk_rows_accum(const float* g, int N, int M, int L, int has_bias, float
  * K1b; only the memory layout of the input differs.  This is the TMA-fed path: every filter tap is a shifted box
  * of cp.async.bulk.tensor (zero fill = padding), operands reach tcgen05.mma in MN-major form, no thread touches
  * them.  Tensor-core tiers only (CRV_PREC_TF32: round-to-nearest TF32 copy made by a pre-pass into ws;
- * CRV_PREC_TF32_TMA: the fp32 words are fed as they are, i.e. TF32 truncation).  Requirements: has_bias == 0,
+ * CRV_PREC_TF32_TMA: the fp32 words are fed as they are, i.e. TF32 truncation; CRV_PREC_BF16: bf16 copy made by
+ * a pre-pass for operands that are re-read -- k x k convolutions and factors of >= 3 row blocks --, else as TF32_TMA).  Requirements: has_bias == 0,
  * C >= 32, C % 4 == 0, and C % 32 == 0 when kh*kw > 1; crv_workspace_bytes() returns 0 for an unsupported
  * geometry and the call itself returns an error (callers then use K1a / K1b on an NCHW copy). */
 int crv_syrk_conv_accum_nhwc(const float* x, int N, int C, int H, int W,
