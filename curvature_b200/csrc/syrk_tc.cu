@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "../../include/curvature_b200.h"
 #include <math.h>
+#include <stdlib.h>
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace crv {
@@ -135,6 +136,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
       : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in bits
@@ -614,10 +621,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) syrk_tc_kernel(const TcParams p) 
 }
 
 // ---- fixed-order reduction of the S partial tiles into the factor ------------------------------
-// One CTA per 32x32 sub-tile of a block pair.  A lane owns one column and sums the S partials in split
-// order (deterministic, 8 loads in flight); the direct block is added row-wise and the mirror image is
-// added through a shared-memory transpose, so both read-modify-writes of the factor are coalesced.
-__global__ void __launch_bounds__(256) syrk_tc_reduce_kernel(const TcParams p, const float alpha, float* __restrict__ F) {
+// One CTA of 1024 threads per 32x32 sub-tile of a block pair, one element per thread.  Every thread sums its S
+// partials in split order (deterministic) with 16 independent loads in flight -- the partials were just written
+// and sit in L2, so the kernel is a latency chain of S/16 round trips, not a bandwidth problem.  The direct block
+// is added row-wise and the mirror image through a shared-memory transpose, so both read-modify-writes of the
+// factor are coalesced along the tap-major index.
+__global__ void __launch_bounds__(1024) syrk_tc_reduce_kernel(const TcParams p, const float alpha, float* __restrict__ F) {
   __shared__ float tile[32][33];
   const int pair = blockIdx.x >> 6, sub = blockIdx.x & 63;
   const int br = sub >> 3, bc = sub & 7;
@@ -637,34 +646,32 @@ __global__ void __launch_bounds__(256) syrk_tc_reduce_kernel(const TcParams p, c
     return c * p.KK + t;
   };
   const float* __restrict__ base = p.ws + (size_t)pair * p.splits * TILE_ELEMS;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int row = br * 32 + w * 4 + q, col = bc * 32 + lane;
+  {
+    const int row = br * 32 + w, col = bc * 32 + lane;
     const bool valid = row < rowsA && col < colsB;
     float v = 0.f;
     if (valid) {
       const float* __restrict__ b = base + row * TB + col;
       float sum = 0.f;
       int s = 0;
-      for (; s + 8 <= p.splits; s += 8) {
-        float t[8];
+      for (; s + 16 <= p.splits; s += 16) {
+        float t[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) t[u] = b[(size_t)(s + u) * TILE_ELEMS];
+        for (int u = 0; u < 16; ++u) t[u] = __ldcg(b + (size_t)(s + u) * TILE_ELEMS);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) sum += t[u];
+        for (int u = 0; u < 16; ++u) sum += t[u];
       }
-      for (; s < p.splits; ++s) sum += b[(size_t)s * TILE_ELEMS];
+      for (; s < p.splits; ++s) sum += __ldcg(b + (size_t)s * TILE_ELEMS);
       v = alpha * sum;
       if (!(diag && col > row)) F[(size_t)perm(I * TB + row) * g.D + perm(J * TB + col)] += v;
     }
-    tile[w * 4 + q][lane] = v;
+    tile[w][lane] = v;
   }
   __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {           // mirror image: lanes run along the original rows
-    const int col = bc * 32 + w * 4 + q, row = br * 32 + lane;
+  {                                       // mirror image: lanes run along the original rows
+    const int col = bc * 32 + w, row = br * 32 + lane;
     if (row < rowsA && col < colsB && !(diag && col >= row))
-      F[(size_t)perm(J * TB + col) * g.D + perm(I * TB + row)] += tile[lane][w * 4 + q];
+      F[(size_t)perm(J * TB + col) * g.D + perm(I * TB + row)] += tile[lane][w];
   }
 }
 
@@ -763,8 +770,9 @@ EncodeTiledFn tensor_map_encoder() {
 // Positions of a box that do not exist are never loaded: box extents divide the output grid (bw | OW, bh | OH),
 // and where bw*bh is not a multiple of 8 (the contraction depth of one tf32 MMA) the remaining rows of the
 // box's shared-memory slot are zeroed once at kernel start -- TMA never writes them.
-constexpr int NH_THREADS = 6 * 32;
+constexpr int NH_THREADS = 9 * 32;             // warp 0: TMA; 1: MMA + TMEM owner; 2-5: TMA + epilogue; 6-8: TMA
 constexpr int NH_MAXSTAGE = 8;
+constexpr int NH_NPROD = 8;                   // TMA-issuing threads (lane 0 of every warp but the MMA warp)
 constexpr int NH_DATA_BYTES = 216 * 1024;
 constexpr int NH_SMEM_BYTES = NH_DATA_BYTES + 1024 /*barriers, chunk table*/ + 1024 /*alignment slack*/;
 constexpr int NH_STAGE_TARGET = 64 * 1024;
@@ -779,6 +787,7 @@ struct NhParams {
   FastDiv divPPI, divPCW;
   int ppi, pcw, bw, bh;      // boxes per image, boxes per box-row, box extent in output positions
   int sh, sw, ph, pw, flat;
+  int pfd;                   // L2 prefetch distance in ring revolutions (0 = off)
   float* ws;
 };
 
@@ -841,17 +850,21 @@ syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
   const int mh = (rowsA + 127) >> 7;
   const int ncols = diag ? ((rowsA + 15) & ~15) : TB;
   const int nchA = (rowsA + CH - 1) / CH, nchB = diag ? 0 : TB / CH;
-  const int slotsA = mh * (128 / CH), nslots = slotsA + nchB, loaded = nchA + nchB;
+  // A stage holds only the chunks that are really loaded: A chunks first, then B chunks.  An M = 128 descriptor
+  // always spans 128 / CH chunks, so for a short A block it reads on into the B chunks (or, for a diagonal item,
+  // past the stage into the next one / the ring's tail pad): those are accumulator rows >= rowsA, never stored.
+  const int slotsA = mh * (128 / CH), nslots = nchA + nchB, loaded = nslots;
   const int NB = diag ? p.NBdiag : p.NBoff;
   const uint32_t chunk_bytes = (uint32_t)(NB * p.PB) * 128u;
   const uint32_t stage_bytes = (uint32_t)nslots * chunk_bytes;
-  const int nstage = min(NH_MAXSTAGE, (int)(NH_DATA_BYTES / stage_bytes));
+  const uint32_t tail_pad = diag ? (uint32_t)(slotsA - nchA) * chunk_bytes : 0u;
+  const int nstage = min(NH_MAXSTAGE, (int)((NH_DATA_BYTES - tail_pad) / stage_bytes));
   const int b_begin = split * p.bps, b_end = min(p.nbox, b_begin + p.bps);
   const int nit = (b_end - b_begin + NB - 1) / NB;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NH_MAXSTAGE; ++s) {
-      mbar_init(bars + 8 * s, 1);
+      mbar_init(bars + 8 * s, NH_NPROD);
       mbar_init(bars + 8 * (NH_MAXSTAGE + s), 1);
     }
     mbar_init(bar_tmem_full, 1);
@@ -864,7 +877,7 @@ syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
     const int tap = (int)fdiv((uint32_t)kp, p.divC);
     const int ti = (int)fdiv((uint32_t)tap, p.divKW);
     tab[lane] = make_int4(kp - tap * p.C, p.flat ? 0 : (tap - ti * p.kw) - p.pw, p.flat ? 0 : ti - p.ph,
-                          isB ? slotsA + (lane - nchA) : lane);
+                          lane);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
@@ -886,18 +899,28 @@ syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp != 1) {
+    // TMA issue is spread over NH_NPROD threads in different warps.  Measured (scripts/experiments/tma_rate_probe.cu):
+    // one thread sustains one cp.async.bulk.tensor per ~150 cycles whatever the box size -- 35 B/cycle/SM with the
+    // 8 KB boxes of a 3x3 layer, 18 B/cycle with 3.5 KB boxes -- while 4-8 issuing warps reach the TMA unit's
+    // ~66 B/cycle/SM with any of them.  Each issuer arms the stage barrier with its own bytes.
     if (lane == 0) {
+      const int me = warp == 0 ? 0 : warp - 1;                 // 0 .. NH_NPROD-1
       const uint32_t box_bytes = (uint32_t)p.PBv * 128u;
+      const int PFD = p.pfd > 0 ? p.pfd * nstage : (1 << 30);    // prefetch distance in pipeline iterations
       for (int it = 0; it < nit; ++it) {
         const int s = it % nstage;
         const uint32_t ph = (uint32_t)(it / nstage) & 1u;
-        mbar_wait(bars + 8 * (NH_MAXSTAGE + s), ph ^ 1u);
         const int b0 = b_begin + it * NB;
         const int nv = min(NB, b_end - b0);
-        mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)(nv * loaded) * box_bytes);
+        const int total = nv * loaded;                          // TMA instructions of this stage
+        const int mine = total > me ? (total - me + NH_NPROD - 1) / NH_NPROD : 0;
+        mbar_wait(bars + 8 * (NH_MAXSTAGE + s), ph ^ 1u);
+        if (mine) mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)mine * box_bytes);
+        else mbar_arrive(bars + 8 * s);
         const uint32_t st = sbase + (uint32_t)s * stage_bytes;
-        for (int j = 0; j < nv; ++j) {
+        for (int e = me; e < total; e += NH_NPROD) {
+          const int j = e / loaded, q = e - j * loaded;
           const uint32_t b = (uint32_t)(b0 + j);
           int X0, Y0, Nn;
           if (p.flat) {
@@ -909,15 +932,43 @@ syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
             const uint32_t pc = rem - pr * (uint32_t)p.pcw;
             X0 = (int)pc * p.bw * p.sw; Y0 = (int)pr * p.bh * p.sh; Nn = (int)n;
           }
-          const uint32_t dstj = st + (uint32_t)(j * p.PB) * 128u;
-          for (int q = 0; q < loaded; ++q) {
-            const int4 e = tab[q];
-            tma_load_4d(dstj + (uint32_t)e.w * chunk_bytes, &tmap, e.x, X0 + e.y, Y0 + e.z, Nn, bars + 8 * s);
+          const int4 t4 = tab[q];
+          tma_load_4d(st + (uint32_t)(j * p.PB) * 128u + (uint32_t)t4.w * chunk_bytes, &tmap, t4.x, X0 + t4.y, Y0 + t4.z, Nn,
+                      bars + 8 * s);
+        }
+        // L2 prefetch, PFD iterations ahead, issued by the DIAGONAL item of each row block only: it loads one block
+        // where an off-diagonal item loads two, so it has TMA bandwidth to spare, and the off-diagonal items of the
+        // same contraction split -- which walk the same boxes at the same time -- then find block I in L2 instead of
+        // waiting for the slowest first-touch HBM miss of every stage (the ring holds only ~2 stages in flight).
+        if (diag && it + PFD < nit) {
+          const int pb0 = b_begin + (it + PFD) * NB;
+          const int pnv = min(NB, b_end - pb0);
+          const int ptotal = pnv * loaded;
+          for (int e = me; e < ptotal; e += NH_NPROD) {
+            const int j = e / loaded, q = e - j * loaded;
+            const uint32_t b = (uint32_t)(pb0 + j);
+            int X0, Y0, Nn;
+            if (p.flat) {
+              X0 = (int)b * p.PB; Y0 = 0; Nn = 0;
+            } else {
+              const uint32_t n = fdiv(b, p.divPPI);
+              const uint32_t rem = b - n * (uint32_t)p.ppi;
+              const uint32_t pr = fdiv(rem, p.divPCW);
+              const uint32_t pc = rem - pr * (uint32_t)p.pcw;
+              X0 = (int)pc * p.bw * p.sw; Y0 = (int)pr * p.bh * p.sh; Nn = (int)n;
+            }
+            const int4 t4 = tab[q];
+            tma_prefetch_4d(&tmap, t4.x, X0 + t4.y, Y0 + t4.z, Nn);
           }
         }
       }
     }
     __syncwarp();
+    if (warp >= 2 && warp < 6) {
+      ItemShape t;
+      t.mh = mh; t.ncols = ncols; t.rowsA = rowsA;
+      epilogue_store(t, bar_tmem_full, tmem, p.ws + (size_t)blockIdx.x * TILE_ELEMS, warp & 3, lane);
+    }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = BF16 ? umma_idesc_mn16(128, (uint32_t)ncols) : umma_idesc_mn(128, (uint32_t)ncols);
@@ -928,7 +979,7 @@ syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
         mbar_wait(bars + 8 * s, ph);
         tc_fence_after();
         const uint32_t st = sbase + (uint32_t)s * stage_bytes;
-        const uint32_t bst = diag ? st : st + (uint32_t)slotsA * chunk_bytes;
+        const uint32_t bst = diag ? st : st + (uint32_t)nchA * chunk_bytes;
         const int nv = min(NB, b_end - (b_begin + it * NB));
         const int nkg = nv * (p.PB / KPOS);
         for (int kg = 0; kg < nkg; ++kg) {
@@ -951,10 +1002,6 @@ syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
       tc_commit(bar_tmem_full);
     }
     __syncwarp();
-  } else {
-    ItemShape t;
-    t.mh = mh; t.ncols = ncols; t.rowsA = rowsA;
-    epilogue_store(t, bar_tmem_full, tmem, p.ws + (size_t)blockIdx.x * TILE_ELEMS, warp & 3, lane);
   }
 
   tc_fence_before();
@@ -1014,11 +1061,16 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
   const int CH = pl.bf16 ? 64 : 32, gran = pl.bf16 ? 16 : 8;
   p.sh = g.sh; p.sw = g.sw; p.ph = g.ph; p.pw = g.pw;
   p.flat = (KK == 1 && g.sh == 1 && g.sw == 1 && g.ph == 0 && g.pw == 0) ? 1 : 0;
+  {
+    const char* e = getenv("CURVATURE_B200_PFD");
+    p.pfd = e ? atoi(e) : 0;   // measured on ResNet-50: 14.5k img/s without, 14.2k / 14.0k / 13.7k at 1 / 2 / 4 revolutions
+  }
   // chunk slots per stage of the two item kinds
-  const int mhd = ((p.T > 1 ? TB : g.D) + 127) >> 7;
-  const int slots_diag = mhd * (128 / CH), slots_off = 2 * (TB / CH);
+  const int slots_diag = ((p.T > 1 ? TB : g.D) + CH - 1) / CH, slots_off = 2 * (TB / CH);   // chunks loaded per box
   const int slots_max = p.T > 1 ? slots_off : slots_diag;
-  const int pcap = NH_STAGE_TARGET / (slots_max * 128);       // positions per stage at the target stage size
+  // positions per stage at the target stage size (single-tile factors stream from HBM: smaller stages, more of them)
+  const int stage_target = p.T > 1 ? NH_STAGE_TARGET : NH_STAGE_TARGET / 2;   // single-tile factors stream from HBM
+  const int pcap = stage_target / (slots_max * 128);
   if (p.flat) {
     long long pb = pcap < 256 ? pcap : 256;
     const long long rr = (g.R + gran - 1) / gran * gran;
@@ -1027,6 +1079,9 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
     p.bw = (int)pb; p.bh = 1; p.pcw = 1; p.ppi = 1;
     p.nbox = (int)((g.R + pb - 1) / pb);
   } else {
+    // box = bw x bh output positions, bw | OW, bh | OH (no box overhangs the grid), padded to `gran` rows.
+    // Highest fill efficiency first; among equals a box that fits the target stage (largest such), else the smallest.
+    const int pcap_hi = pcap;
     int best_bw = 0, best_bh = 0, best_pb = 0;
     double best_eff = -1.0;
     for (int bw = 1; bw <= g.OW; ++bw) {
@@ -1034,10 +1089,17 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
       for (int bh = 1; bh <= g.OH; ++bh) {
         if (g.OH % bh || bh * g.sh > 256) continue;
         const int pbv = bw * bh, pb = (pbv + gran - 1) / gran * gran;
-        if (pb > pcap) continue;
+        if (pb > pcap_hi) continue;
         const double eff = (double)pbv / pb;
-        const bool better = eff > best_eff + 1e-9 ||
-                            (eff > best_eff - 1e-9 && (pb > best_pb || (pb == best_pb && bw > best_bw)));
+        bool better;
+        if (eff > best_eff + 1e-9) better = true;
+        else if (eff < best_eff - 1e-9) better = false;
+        else {
+          const bool fit = pb <= pcap, best_fit = best_pb <= pcap;
+          if (fit != best_fit) better = fit;
+          else if (fit) better = pb > best_pb || (pb == best_pb && bw > best_bw);
+          else better = pb < best_pb || (pb == best_pb && bw > best_bw);
+        }
         if (better) { best_eff = eff; best_bw = bw; best_bh = bh; best_pb = pb; }
       }
     }
@@ -1052,14 +1114,14 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
   p.divPPI = make_fastdiv((uint32_t)p.ppi);
   p.divPCW = make_fastdiv((uint32_t)p.pcw);
   auto boxes_per_stage = [&](int slots) {
-    int nb = NH_STAGE_TARGET / (slots * p.PB * 128);
+    int nb = stage_target / (slots * p.PB * 128);
     return nb < 1 ? 1 : nb;
   };
   p.NBoff = boxes_per_stage(slots_off);
   p.NBdiag = boxes_per_stage(slots_diag);
   if (p.T > 1) p.NBdiag = p.NBoff * (p.NBdiag / p.NBoff > 0 ? p.NBdiag / p.NBoff : 1);
   if (slots_max * p.NBoff * p.PB * 128 * 2 > NH_DATA_BYTES && p.T > 1) return false;   // needs >= 2 stages
-  if (slots_diag * p.NBdiag * p.PB * 128 * 2 > NH_DATA_BYTES) return false;
+  if ((slots_diag * 2 + 3) * p.NBdiag * p.PB * 128 > NH_DATA_BYTES) return false;      // (+ tail pad)
   // contraction splits: same makespan model as the staged kernel, in units of 32 positions
   const double units = (double)p.nbox * p.PB / 32.0;
   const int maxS = (int)(units / 16) > 0 ? (int)(units / 16) : 1;
@@ -1143,7 +1205,7 @@ int syrk_tc_launch(const ConvGeom& g, float alpha, float* F, int precision, void
     syrk_tc_kernel<<<pl.pairs * pl.splits, NTHREADS, SMEM_BYTES, s>>>(p);
   }
   CRV_CUDA(cudaGetLastError());
-  syrk_tc_reduce_kernel<<<pl.pairs * 64, 256, 0, s>>>(p, alpha, F);
+  syrk_tc_reduce_kernel<<<pl.pairs * 64, 1024, 0, s>>>(p, alpha, F);
   CRV_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1224,7 +1286,7 @@ int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, vo
   rp.T = p.T; rp.pairs = pl.pairs; rp.splits = p.splits;
   rp.KK = p.KK;
   rp.ws = p.ws;
-  syrk_tc_reduce_kernel<<<pl.pairs * 64, 256, 0, s>>>(rp, alpha, F);
+  syrk_tc_reduce_kernel<<<pl.pairs * 64, 1024, 0, s>>>(rp, alpha, F);
   CRV_CUDA(cudaGetLastError());
   return 0;
 }

@@ -35,6 +35,7 @@ def main():
     ap.add_argument("names")
     ap.add_argument("--prec", default="tf32")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--layout", default="channels_last", choices=["channels_last", "nchw"])
     args = ap.parse_args()
     prec = nat.PRECISION_NAMES[args.prec]
     dev = "cuda:0"
@@ -42,6 +43,8 @@ def main():
         kind, N, C, H, W, k, s, p = LAYERS[name]
         torch.manual_seed(0)
         x = torch.relu(torch.randn(N, C, H, W, device=dev))
+        if args.layout == "channels_last":
+            x = x.contiguous(memory_format=torch.channels_last)
         if kind == "A":
             K = C * k * k
             OH = (H + 2 * p - k) // s + 1
