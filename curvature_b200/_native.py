@@ -38,6 +38,9 @@ def _sig(name, restype, *argtypes):
 _abi_version = _sig("crv_abi_version", c_int)
 _last_error = _sig("crv_last_error", c_char_p)
 _sm_count = _sig("crv_device_sm_count", c_int)
+_profile_enable = _sig("crv_profile_enable", c_int, c_int)
+_profile_collect = _sig("crv_profile_collect", c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double),
+                       POINTER(ctypes.c_double), POINTER(ctypes.c_longlong), c_int)
 _workspace_bytes = _sig("crv_workspace_bytes", c_size_t, c_int, POINTER(c_int64), c_int)
 _syrk_conv = _sig("crv_syrk_conv_accum", c_int, _f32p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                   c_int, c_int, c_int, c_float, _f32p, c_void_p, c_size_t, c_int, c_void_p)
@@ -62,7 +65,8 @@ _gemm = _sig("crv_gemm", c_int, _f32p, c_int, c_int, _f32p, c_int, c_int, _f32p,
 
 ABI_VERSION = _abi_version()
 EXPORTED_SYMBOLS = (
-    "crv_abi_version", "crv_last_error", "crv_device_sm_count", "crv_workspace_bytes",
+    "crv_abi_version", "crv_last_error", "crv_device_sm_count", "crv_workspace_bytes", "crv_profile_enable",
+    "crv_profile_collect",
     "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc",
     "crv_diag_accum", "crv_efb_project_accum",
     "crv_chol_inv_batched", "crv_sample_matrix_normal", "crv_elementwise_inv_sqrt", "crv_diag_sample",
@@ -131,6 +135,25 @@ def workspace_bytes(op, dims):
 
 def sm_count():
     return _sm_count()
+
+
+KERNEL_CLASSES = ("syrk_nhwc_bf16", "syrk_nhwc_tf32", "syrk_staged_nchw", "syrk_split_reduce", "cast_prepass", "syrk_simt_fp32")
+
+
+def profile_enable(on=True):
+    """Bracket every SYRK-family kernel launch with a CUDA event pair on its stream (bench.py's roofline)."""
+    _check(_profile_enable(int(bool(on))), "crv_profile_enable")
+
+
+def profile_collect():
+    """{kernel class: {ms, flops, bytes, launches}} of the launches recorded since the last collect."""
+    n = len(KERNEL_CLASSES)
+    ms = (ctypes.c_double * n)()
+    fl = (ctypes.c_double * n)()
+    by = (ctypes.c_double * n)()
+    la = (ctypes.c_longlong * n)()
+    _check(_profile_collect(ms, fl, by, la, n), "crv_profile_collect")
+    return {k: {"ms": ms[i], "flops": fl[i], "bytes": by[i], "launches": int(la[i])} for i, k in enumerate(KERNEL_CLASSES)}
 
 
 def _dense(t, what):

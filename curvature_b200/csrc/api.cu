@@ -2,6 +2,8 @@
 #include "../../include/curvature_b200.h"
 #include "common.cuh"
 #include <stdarg.h>
+#include <vector>
+#include <utility>
 
 namespace crv {
 
@@ -31,6 +33,28 @@ int device_sm_count() {
   return cached_sms;
 }
 
+// ---- per-kernel event timing --------------------------------------------------------------------
+namespace {
+struct ProfRec { cudaEvent_t e0, e1; int kclass; double flops, bytes; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+}  // namespace
+
+void profile_begin(int kclass, double flops, double bytes, cudaStream_t s) {
+  if (!g_prof_on) return;
+  ProfRec r;
+  if (!g_prof_pool.empty()) { r.e0 = g_prof_pool.back().first; r.e1 = g_prof_pool.back().second; g_prof_pool.pop_back(); }
+  else { cudaEventCreate(&r.e0); cudaEventCreate(&r.e1); }
+  r.kclass = kclass; r.flops = flops; r.bytes = bytes;
+  cudaEventRecord(r.e0, s);
+  g_prof.push_back(r);
+}
+void profile_end(cudaStream_t s) {
+  if (!g_prof_on || g_prof.empty()) return;
+  cudaEventRecord(g_prof.back().e1, s);
+}
+
 static int syrk_dispatch(const ConvGeom& g, float alpha, float* F, void* ws, size_t ws_bytes, int precision,
                          cudaStream_t s) {
   if (precision == CRV_PREC_FP32) return syrk_simt_launch(g, alpha, F, s);
@@ -50,6 +74,25 @@ extern "C" {
 int crv_abi_version(void) { return CRV_ABI_VERSION; }
 const char* crv_last_error(void) { return last_error(); }
 int crv_device_sm_count(void) { return device_sm_count(); }
+
+int crv_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return 0;
+}
+
+int crv_profile_collect(double* ms, double* flops, double* bytes, long long* launches, int nclasses) {
+  CRV_CHECK(ms && flops && bytes && launches && nclasses >= KC_COUNT, "crv_profile_collect: need %d classes", (int)KC_COUNT);
+  for (int i = 0; i < nclasses; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+  for (auto& r : g_prof) {
+    CRV_CUDA(cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    CRV_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms[r.kclass] += t; flops[r.kclass] += r.flops; bytes[r.kclass] += r.bytes; launches[r.kclass] += 1;
+    g_prof_pool.push_back(std::make_pair(r.e0, r.e1));
+  }
+  g_prof.clear();
+  return 0;
+}
 
 size_t crv_workspace_bytes(int op, const int64_t* dims, int ndims) {
   switch (op) {

@@ -67,6 +67,20 @@ inline int make_geom(ConvGeom& g, const float* x, int N, int C, int H, int W, in
 
 int device_sm_count();
 
+// ---- optional per-kernel CUDA-event timing (crv_profile_*): a scope records one event pair on the launching stream
+// around one kernel launch when profiling is enabled, and costs one predictable branch when it is not.
+enum KernelClass {
+  KC_SYRK_NHWC_BF16 = 0,   // syrk_nhwc_kernel<true>   (TMA-fed MN-major, bf16 operands)
+  KC_SYRK_NHWC_TF32 = 1,   // syrk_nhwc_kernel<false>  (TMA-fed MN-major, TF32 operands)
+  KC_SYRK_STAGED    = 2,   // syrk_tc_kernel / syrk_tc_tma_kernel (NCHW operands)
+  KC_SYRK_REDUCE    = 3,   // syrk_tc_reduce_kernel
+  KC_PREPASS        = 4,   // cast_bf16_kernel / round_tf32_kernel
+  KC_SYRK_SIMT      = 5,   // syrk_simt_kernel (fp32 tier)
+  KC_COUNT          = 6
+};
+void profile_begin(int kclass, double flops, double bytes, cudaStream_t s);
+void profile_end(cudaStream_t s);
+
 // ---- kernel launchers (one per .cu file) -------------------------------------------------
 int syrk_simt_launch(const ConvGeom& g, float alpha, float* F, cudaStream_t s);
 int syrk_tc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,

@@ -169,7 +169,9 @@ int syrk_simt_launch(const ConvGeom& g, float alpha, float* F, cudaStream_t s) {
   splits = (chunks + cps - 1) / cps;
   CRV_CHECK(pairs < (1LL << 31), "factor too large");
   dim3 grid((unsigned)pairs, (unsigned)splits, 1);
+  profile_begin(KC_SYRK_SIMT, (double)g.R * g.D * (g.D + 1), 4.0 * g.N * g.C * g.H * g.W, s);
   syrk_simt_kernel<<<grid, NT, 0, s>>>(g, alpha, F, (int)cps);
+  profile_end(s);
   CRV_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1199,13 +1199,19 @@ int syrk_tc_launch(const ConvGeom& g, float alpha, float* F, int precision, void
                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CRV_CHECK(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)rc);
     CRV_CUDA(cudaFuncSetAttribute(syrk_tc_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    profile_begin(KC_SYRK_STAGED, (double)g.R * g.D * (g.D + 1), 4.0 * g.N * g.C * g.H * g.W, s);
     syrk_tc_tma_kernel<<<pl.pairs * pl.splits, TMA_THREADS, SMEM_BYTES, s>>>(p, tg, map);
+    profile_end(s);
   } else {
     CRV_CUDA(cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    profile_begin(KC_SYRK_STAGED, (double)g.R * g.D * (g.D + 1), 4.0 * g.N * g.C * g.H * g.W, s);
     syrk_tc_kernel<<<pl.pairs * pl.splits, NTHREADS, SMEM_BYTES, s>>>(p);
+    profile_end(s);
   }
   CRV_CUDA(cudaGetLastError());
+  profile_begin(KC_SYRK_REDUCE, 0.0, (double)pl.ws_bytes + 8.0 * g.D * g.D, s);
   syrk_tc_reduce_kernel<<<pl.pairs * 64, 1024, 0, s>>>(p, alpha, F);
+  profile_end(s);
   CRV_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1245,8 +1251,10 @@ int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, vo
     float* copy = (float*)((((uintptr_t)ws + pl.partial_bytes) + 1023) & ~(uintptr_t)1023);
     const size_t n4 = (size_t)g.N * g.C * g.H * g.W / 4;
     const unsigned blocks = (unsigned)((n4 + 255) / 256 < (size_t)sms * 16 ? (n4 + 255) / 256 : (size_t)sms * 16);
+    profile_begin(KC_PREPASS, 0.0, (pl.bf16 ? 6.0 : 8.0) * (double)n4 * 4.0, s);
     if (pl.bf16) cast_bf16_kernel<<<blocks, 256, 0, s>>>((const float4*)g.x, (uint2*)copy, n4);
     else round_tf32_kernel<<<blocks, 256, 0, s>>>((const float4*)g.x, (float4*)copy, n4);
+    profile_end(s);
     CRV_CUDA(cudaGetLastError());
     src = copy;
   }
@@ -1273,10 +1281,14 @@ int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, vo
   CRV_CHECK(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)rc);
   if (pl.bf16) {
     CRV_CUDA(cudaFuncSetAttribute(syrk_nhwc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NH_SMEM_BYTES));
+    profile_begin(KC_SYRK_NHWC_BF16, (double)g.R * g.D * (g.D + 1), 2.0 * g.N * g.C * g.H * g.W, s);
     syrk_nhwc_kernel<true><<<pl.pairs * p.splits, NH_THREADS, NH_SMEM_BYTES, s>>>(p, map);
+    profile_end(s);
   } else {
     CRV_CUDA(cudaFuncSetAttribute(syrk_nhwc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NH_SMEM_BYTES));
+    profile_begin(KC_SYRK_NHWC_TF32, (double)g.R * g.D * (g.D + 1), 4.0 * g.N * g.C * g.H * g.W, s);
     syrk_nhwc_kernel<false><<<pl.pairs * p.splits, NH_THREADS, NH_SMEM_BYTES, s>>>(p, map);
+    profile_end(s);
   }
   CRV_CUDA(cudaGetLastError());
   TcParams rp;                         // the fixed-order reduction only needs the tile / permutation fields
@@ -1286,7 +1298,9 @@ int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, vo
   rp.T = p.T; rp.pairs = pl.pairs; rp.splits = p.splits;
   rp.KK = p.KK;
   rp.ws = p.ws;
+  profile_begin(KC_SYRK_REDUCE, 0.0, (double)pl.partial_bytes + 8.0 * g.D * g.D, s);
   syrk_tc_reduce_kernel<<<pl.pairs * 64, 1024, 0, s>>>(rp, alpha, F);
+  profile_end(s);
   CRV_CUDA(cudaGetLastError());
   return 0;
 }

@@ -58,6 +58,15 @@ const char* crv_last_error(void);
 int         crv_device_sm_count(void);
 size_t      crv_workspace_bytes(int op, const int64_t* dims, int ndims);
 
+/* Measurement aid (bench.py's roofline): when enabled, every SYRK-family kernel launch is bracketed by a CUDA event
+ * pair recorded on the launching stream.  crv_profile_collect() waits for the recorded events, returns per kernel
+ * class the summed device time (ms), the algorithmic flops and bytes of those launches and their number, and
+ * clears the records.  Classes: 0 channels-last SYRK bf16, 1 channels-last SYRK tf32, 2 NCHW staged SYRK,
+ * 3 split reduction, 4 cast / rounding pre-pass, 5 fp32 SIMT SYRK.  Not thread-safe; off by default. */
+#define CRV_KERNEL_CLASSES 6
+int         crv_profile_enable(int on);
+int         crv_profile_collect(double* ms, double* flops, double* bytes, long long* launches, int nclasses);
+
 /* K1a -- first Kronecker factor of a Conv2d layer, fused implicit im2col + SYRK + running sum:
  *   A[k1,k2] += alpha * sum_r X[k1,r] X[k2,r],   X = unfold(x) in the reference's row order
  *   k = c*kh*kw + i*kw + j, r = n*OH*OW + oh*OW + ow, zero padding, dilation 1, groups 1,
