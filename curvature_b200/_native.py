@@ -57,6 +57,7 @@ _chol_inv = _sig("crv_chol_inv_batched", c_int, POINTER(c_void_p), POINTER(c_int
                  POINTER(c_float), POINTER(c_void_p), c_void_p, c_void_p, c_size_t, c_void_p)
 _sample_mn = _sig("crv_sample_matrix_normal", c_int, _f32p, _f32p, _f32p, _f32p, c_int, c_int, c_int, _f32p,
                   _f32p, _f32p, _f32p, _f32p, c_void_p, c_size_t, c_int, c_void_p)
+_round_tf32 = _sig("crv_round_tf32", c_int, _f32p, _f32p, c_size_t, c_void_p)
 _inv_sqrt = _sig("crv_elementwise_inv_sqrt", c_int, _f32p, c_float, c_float, _f32p, c_size_t, c_void_p)
 _diag_sample = _sig("crv_diag_sample", c_int, _f32p, _f32p, c_int, c_int, c_int, _f32p, _f32p, _f32p, _f32p,
                     _f32p, c_void_p)
@@ -69,7 +70,7 @@ EXPORTED_SYMBOLS = (
     "crv_profile_collect",
     "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc",
     "crv_diag_accum", "crv_efb_project_accum",
-    "crv_chol_inv_batched", "crv_sample_matrix_normal", "crv_elementwise_inv_sqrt", "crv_diag_sample",
+    "crv_chol_inv_batched", "crv_sample_matrix_normal", "crv_round_tf32", "crv_elementwise_inv_sqrt", "crv_diag_sample",
     "crv_gemm")
 
 # counts kernel-launching C-ABI calls (bench.py reports launches from it)
@@ -304,6 +305,16 @@ def sample_matrix_normal(LG, LA, z, has_bias, row_scale=None, mu_w=None, mu_b=No
                       int(bool(has_bias)), _opt(mu_w, "mu_w"), _opt(mu_b, "mu_b"), _opt(w_out, "weight"),
                       _opt(b_out, "bias"), _opt(s_out, "sample"), ws.data_ptr(), ws.numel(), precision,
                       _stream(LG)), "crv_sample_matrix_normal")
+
+
+def round_tf32(t, out=None):
+    """Round a dense fp32 tensor to the nearest TF32 values (into `out`, default a new tensor; `out=t` rounds in place)."""
+    global launch_calls
+    if out is None:
+        out = torch.empty_like(t)
+    launch_calls += 1
+    _check(_round_tf32(_dev(t, "tensor"), _dev(out, "out"), t.numel(), _stream(t)), "crv_round_tf32")
+    return out
 
 
 def elementwise_inv_sqrt(v, add, mul, out):

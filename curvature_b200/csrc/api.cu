@@ -55,6 +55,18 @@ void profile_end(cudaStream_t s) {
   cudaEventRecord(g_prof.back().e1, s);
 }
 
+// GEMM dispatch: tensor-core tiers use the tcgen05 kernel and fall back to the CUDA-core kernel only when TMA cannot
+// address the operands (leading dimension not a multiple of 4 floats, e.g. the 2049-wide fc factor with its bias column)
+static int gemm_dispatch(int precision, const float* A, long long sa_m, long long sa_k, const float* B, long long sb_k,
+                         long long sb_n, float* C, int ldc, int m, int n, int k, float alpha, float beta, int epilogue,
+                         const SampleEpilogue* sample, int round_out, cudaStream_t s) {
+  if (precision != CRV_PREC_FP32) {
+    const int rc = gemm_tc_launch(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, m, n, k, alpha, beta, epilogue, sample, round_out, s);
+    if (rc >= 0) return rc;
+  }
+  return gemm_simt_launch(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, m, n, k, alpha, beta, epilogue, sample, s);
+}
+
 static int syrk_dispatch(const ConvGeom& g, float alpha, float* F, void* ws, size_t ws_bytes, int precision,
                          cudaStream_t s) {
   if (precision == CRV_PREC_FP32) return syrk_simt_launch(g, alpha, F, s);
@@ -187,27 +199,25 @@ int crv_diag_accum(const float* wgrad, const float* bgrad, int M, int K0, float 
 
 int crv_gemm(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc,
              int m, int n, int k, float alpha, float beta, int precision, crv_stream_t stream) {
-  CRV_CHECK(precision == CRV_PREC_FP32, "crv_gemm: only the fp32 tier is built");
   // op(A)(i,kk): A[i*lda + kk] or, transposed, A[kk*lda + i]
   const long long sa_m = transA ? 1 : lda, sa_k = transA ? lda : 1;
   const long long sb_k = transB ? 1 : ldb, sb_n = transB ? ldb : 1;
-  return gemm_simt_launch(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, m, n, k, alpha, beta, EPI_STORE, nullptr,
-                          (cudaStream_t)stream);
+  return gemm_dispatch(precision, A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, m, n, k, alpha, beta, EPI_STORE, nullptr, 0,
+                       (cudaStream_t)stream);
 }
 
 int crv_efb_project_accum(const float* QG, const float* QA, const float* G, int M, int K, float* lambdas,
                           void* ws, size_t ws_bytes, int precision, crv_stream_t stream) {
-  CRV_CHECK(precision == CRV_PREC_FP32, "crv_efb_project_accum: only the fp32 tier is built");
   CRV_CHECK(QG && QA && G && lambdas, "null pointer");
   CRV_CHECK(ws && ws_bytes >= (size_t)M * K * sizeof(float), "workspace too small");
   float* T = (float*)ws;
   // T = QG^T * G        (M x M)^T (M x K)
-  if (int rc = gemm_simt_launch(QG, 1, M, G, K, 1, T, K, M, K, M, 1.f, 0.f, EPI_STORE, nullptr,
-                                (cudaStream_t)stream))
+  if (int rc = gemm_dispatch(precision, QG, 1, M, G, K, 1, T, K, M, K, M, 1.f, 0.f, EPI_STORE, nullptr,
+                             precision != CRV_PREC_FP32, (cudaStream_t)stream))
     return rc;
   // lambdas += (T * QA)^2   (M x K)(K x K)
-  return gemm_simt_launch(T, K, 1, QA, K, 1, lambdas, K, M, K, K, 1.f, 0.f, EPI_SQUARE_ACCUM, nullptr,
-                          (cudaStream_t)stream);
+  return gemm_dispatch(precision, T, K, 1, QA, K, 1, lambdas, K, M, K, K, 1.f, 0.f, EPI_SQUARE_ACCUM, nullptr, 0,
+                       (cudaStream_t)stream);
 }
 
 int crv_chol_inv_batched(const float* const* F, const int* dims, int count, const float* add,
@@ -220,7 +230,6 @@ int crv_sample_matrix_normal(const float* LG, const float* LA, const float* z, c
                              int K0, int has_bias, const float* mu_w, const float* mu_b, float* w_out,
                              float* b_out, float* s_out, void* ws, size_t ws_bytes, int precision,
                              crv_stream_t stream) {
-  CRV_CHECK(precision == CRV_PREC_FP32, "crv_sample_matrix_normal: only the fp32 tier is built");
   CRV_CHECK(LG && LA && z, "null pointer");
   CRV_CHECK(M > 0 && K0 > 0, "bad shape");
   CRV_CHECK(!w_out || mu_w, "w_out needs mu_w");
@@ -237,12 +246,18 @@ int crv_sample_matrix_normal(const float* LG, const float* LA, const float* z, c
     zz = Z2;
   }
   // T = LG * z^T : A = LG (M x M), B(kk, n) = z[n, kk]  -> sb_k = 1, sb_n = M
-  if (int rc = gemm_simt_launch(LG, M, 1, zz, 1, M, T, K, M, K, M, 1.f, 0.f, EPI_STORE, nullptr, s)) return rc;
+  if (int rc = gemm_dispatch(precision, LG, M, 1, zz, 1, M, T, K, M, K, M, 1.f, 0.f, EPI_STORE, nullptr,
+                             precision != CRV_PREC_FP32, s))
+    return rc;
   // S = T * LA^T : B(kk, n) = LA[n, kk] -> sb_k = 1, sb_n = K
   SampleEpilogue se;
   se.mu_w = mu_w; se.mu_b = mu_b; se.w_out = w_out; se.b_out = b_out; se.s_out = s_out;
   se.K0 = K0; se.has_bias = has_bias ? 1 : 0;
-  return gemm_simt_launch(T, K, 1, LA, 1, K, nullptr, K, M, K, K, 1.f, 0.f, 2, &se, s);
+  return gemm_dispatch(precision, T, K, 1, LA, 1, K, nullptr, K, M, K, K, 1.f, 0.f, 2, &se, 0, s);
+}
+
+int crv_round_tf32(const float* in, float* out, size_t n, crv_stream_t stream) {
+  return round_tf32_launch(in, out, n, (cudaStream_t)stream);
 }
 
 int crv_elementwise_inv_sqrt(const float* v, float add, float mul, float* out, size_t n, crv_stream_t stream) {

@@ -103,6 +103,12 @@ int gemm_simt_launch(const float* A, long long sa_m, long long sa_k, const float
                      long long sb_n, float* C, int ldc, int m, int n, int k, float alpha, float beta,
                      int epilogue, const SampleEpilogue* sample, cudaStream_t s);
 
+// tensor-core (TF32) GEMM with the same epilogues; returns -1 when the operands cannot be fed by TMA
+int gemm_tc_launch(const float* A, long long sa_m, long long sa_k, const float* B, long long sb_k,
+                   long long sb_n, float* C, int ldc, int m, int n, int k, float alpha, float beta,
+                   int epilogue, const SampleEpilogue* sample, int round_out, cudaStream_t s);
+int round_tf32_launch(const float* in, float* out, size_t n, cudaStream_t s);
+
 int diag_accum_launch(const float* wgrad, const float* bgrad, int M, int K0, float scale, float* state,
                       float* grads_out, cudaStream_t s);
 int inv_sqrt_launch(const float* v, float add, float mul, float* out, size_t n, cudaStream_t s);

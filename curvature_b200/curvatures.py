@@ -81,6 +81,20 @@ def _grad_of(p: Tensor, what: str) -> Tensor:
     return g if g.is_contiguous() else g.contiguous()
 
 
+def _gemm_tier(precision: int) -> int:
+    """Tier of the chained GEMMs (K3 / K5): fp32 stays on the CUDA cores, every tensor-core tier uses the TF32 GEMM."""
+    return nat.PREC_FP32 if precision == nat.PREC_FP32 else nat.PREC_TF32
+
+
+def _rounded(cache: dict, key, tensors):
+    """TF32-rounded copies of operands that stay constant over many GEMM calls (made once, cached)."""
+    hit = cache.get(key)
+    if hit is None or any(h[0] is not t for h, t in zip(hit, tensors)):
+        hit = [(t, nat.round_tf32(t if t.is_contiguous() else t.contiguous())) for t in tensors]
+        cache[key] = hit
+    return [h[1] for h in hit]
+
+
 class _DenseTarget:
     """Stands in for a parameter whose storage is not row-major: `.data` is a dense buffer of the same shape."""
 
@@ -411,16 +425,27 @@ class KFAC(Curvature):
         first, second = self.inv_state[layer]
         z = self._noise(first, second, noise)
         out = torch.empty(second.size(0), first.size(0), device=first.device, dtype=first.dtype)
-        nat.sample_matrix_normal(second, first, z, False, s_out=out, precision=nat.PREC_FP32)
+        tier, first, second, z = self._gemm_operands(layer, first, second, z, noise is not None)
+        nat.sample_matrix_normal(second, first, z, False, s_out=out, precision=tier)
         return out
+
+    def _gemm_operands(self, key, first, second, z, z_is_callers):
+        """Operands of the two-GEMM draw for this estimator's tier: tensor-core tiers get the inverse factors rounded
+        to TF32 once per `invert` (cached) and the noise rounded (a copy if the caller owns it)."""
+        tier = _gemm_tier(self.precision)
+        if tier != nat.PREC_FP32:
+            first, second = _rounded(self.__dict__.setdefault('_inv_tf32', {}), key, (first, second))
+            z = nat.round_tf32(z, out=None if z_is_callers else z)
+        return tier, first, second, z
 
     def _sample_into(self, key, weight, bias, mean_w, mean_b, noise):
         assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
         first, second = self.inv_state[key]
         z = self._noise(first, second, noise)
+        tier, first, second, z = self._gemm_operands(key, first, second, z, noise is not None)
         nat.sample_matrix_normal(second, first, z, bias is not None, mu_w=mean_w, mu_b=mean_b,
                                  w_out=weight.data, b_out=None if bias is None else bias.data,
-                                 precision=nat.PREC_FP32)
+                                 precision=tier)
 
 
 class EFB(Curvature):
@@ -461,7 +486,11 @@ class EFB(Curvature):
                 grads = torch.empty_like(self.state[layer])
                 nat.diag_accum(wg, bg, batch_size, state=self.diags[layer], grads_out=grads)
                 qa, qg = self.eigvecs[layer]
-                nat.efb_project_accum(qg, qa, grads, self.state[layer], nat.PREC_FP32)
+                tier = _gemm_tier(self.precision)
+                if tier != nat.PREC_FP32:      # eigenbases rounded to TF32 once, the gradient copy in place
+                    qa, qg = _rounded(self.__dict__.setdefault('_eig_tf32', {}), layer, (qa, qg))
+                    nat.round_tf32(grads, out=grads)
+                nat.efb_project_accum(qg, qa, grads, self.state[layer], tier)
             elif name == 'MultiheadAttention':
                 raise NotImplementedError
 
@@ -489,16 +518,22 @@ class EFB(Curvature):
         first, second = self.eigvecs[layer]
         z = self._noise(first, second, noise)
         out = torch.empty(second.size(0), first.size(0), device=first.device, dtype=first.dtype)
-        nat.sample_matrix_normal(second, first, z, False, row_scale=self.inv_state[layer], s_out=out)
+        tier = _gemm_tier(self.precision)
+        if tier != nat.PREC_FP32:
+            first, second = _rounded(self.__dict__.setdefault('_eig_tf32', {}), layer, (first, second))
+        nat.sample_matrix_normal(second, first, z, False, row_scale=self.inv_state[layer], s_out=out, precision=tier)
         return out
 
     def _sample_into(self, key, weight, bias, mean_w, mean_b, noise):
         assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
         first, second = self.eigvecs[key]
         z = self._noise(first, second, noise)
+        tier = _gemm_tier(self.precision)
+        if tier != nat.PREC_FP32:
+            first, second = _rounded(self.__dict__.setdefault('_eig_tf32', {}), key, (first, second))
         nat.sample_matrix_normal(second, first, z, bias is not None, row_scale=self.inv_state[key],
                                  mu_w=mean_w, mu_b=mean_b, w_out=weight.data,
-                                 b_out=None if bias is None else bias.data)
+                                 b_out=None if bias is None else bias.data, precision=tier)
 
 
 class INF(Curvature):

@@ -112,7 +112,9 @@ int crv_diag_accum(const float* wgrad, const float* bgrad, int M, int K0, float 
 
 /* K3 -- EFB eigenbasis projection (curvatures.py:427-433):
  *   lambdas[m,k] += ((QG^T * G * QA)[m,k])^2,   QG (M,M), G (M,K), QA (K,K).
- * ws holds the (M,K) intermediate. */
+ * ws holds the (M,K) intermediate.  precision: CRV_PREC_FP32 = CUDA-core fp32 GEMMs; any tensor-core tier = two
+ * tcgen05 TF32 GEMM launches (gemm_tc.cu; the intermediate is rounded to nearest TF32 in the first epilogue, the square
+ * is fused into the second), CUDA-core fallback only if K or M is not a multiple of 4. */
 int crv_efb_project_accum(const float* QG, const float* QA, const float* G, int M, int K,
                           float* lambdas, void* ws, size_t ws_bytes, int precision,
                           crv_stream_t stream);
@@ -135,12 +137,18 @@ int crv_chol_inv_batched(const float* const* F, const int* dims, int count,
  * z is (K, M) exactly as the reference draws it, LA (K,K), LG (M,M), K = K0 + has_bias.
  * If row_scale != NULL (EFB.sample, curvatures.py:458-460) z is first multiplied elementwise
  * by row_scale^T where row_scale is (M,K).  s_out (M,K), if non-NULL, receives S itself
- * (KFAC.sample's return value); w_out / b_out / mu_* may be NULL when only S is wanted. */
+ * (KFAC.sample's return value); w_out / b_out / mu_* may be NULL when only S is wanted.
+ * precision as for crv_efb_project_accum. */
 int crv_sample_matrix_normal(const float* LG, const float* LA, const float* z, const float* row_scale,
                              int M, int K0, int has_bias,
                              const float* mu_w, const float* mu_b, float* w_out, float* b_out,
                              float* s_out, void* ws, size_t ws_bytes, int precision,
                              crv_stream_t stream);
+
+/* out[i] = in[i] rounded to the nearest TF32 value (in place if out == in).  The tensor-core GEMMs of K3 / K5 read fp32
+ * words as TF32 (truncation); operands that stay constant over many calls (EFB eigenbases, inverse factors) are rounded
+ * once with this call so that the products carry round-to-nearest instead of truncation error. */
+int crv_round_tf32(const float* in, float* out, size_t n, crv_stream_t stream);
 
 /* out[i] = sqrt(1 / (mul * v[i] + add))  (Diagonal.invert :188, EFB.invert :450, INF :526). */
 int crv_elementwise_inv_sqrt(const float* v, float add, float mul, float* out, size_t n,
