@@ -50,6 +50,8 @@ _syrk_conv_nhwc = _sig("crv_syrk_conv_accum_nhwc", c_int, _f32p, c_int, c_int, c
                        c_int, c_int, c_int, c_int, c_float, _f32p, c_void_p, c_size_t, c_int, c_void_p)
 _syrk_rows_nhwc = _sig("crv_syrk_rows_accum_nhwc", c_int, _f32p, c_int, c_int, c_int, c_int, c_float, _f32p,
                        c_void_p, c_size_t, c_int, c_void_p)
+_stream_join = _sig("crv_stream_join", c_int, c_void_p)
+_stream_fork = _sig("crv_stream_fork", c_int, c_void_p)
 _diag_accum = _sig("crv_diag_accum", c_int, _f32p, _f32p, c_int, c_int, c_float, _f32p, _f32p, c_void_p)
 _efb_project = _sig("crv_efb_project_accum", c_int, _f32p, _f32p, _f32p, c_int, c_int, _f32p, c_void_p,
                     c_size_t, c_int, c_void_p)
@@ -68,7 +70,7 @@ ABI_VERSION = _abi_version()
 EXPORTED_SYMBOLS = (
     "crv_abi_version", "crv_last_error", "crv_device_sm_count", "crv_workspace_bytes", "crv_profile_enable",
     "crv_profile_collect",
-    "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc",
+    "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc", "crv_stream_join", "crv_stream_fork",
     "crv_diag_accum", "crv_efb_project_accum",
     "crv_chol_inv_batched", "crv_sample_matrix_normal", "crv_round_tf32", "crv_elementwise_inv_sqrt", "crv_diag_sample",
     "crv_gemm")
@@ -120,13 +122,31 @@ _workspaces = {}
 
 
 def workspace(nbytes, device):
-    """Grow-only scratch buffer per device (kernels never allocate)."""
+    """Grow-only scratch buffer per device (kernels never allocate).  Growing it drains the device first: a split
+    reduction on the library's side stream may still be reading the old buffer."""
     nbytes = max(int(nbytes), 256)
     buf = _workspaces.get(device)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        if buf is not None:
+            torch.cuda.synchronize(device)
+        buf = torch.empty(nbytes + nbytes // 4, dtype=torch.uint8, device=device)
         _workspaces[device] = buf
     return buf
+
+
+def stream_fork(device=None):
+    """Tell the library that every tensor the following SYRK calls read is complete on torch's current stream now."""
+    if device is not None and torch.device(device).type != "cuda":
+        raise RuntimeError("curvature_b200: the model must live on a CUDA device "
+                           "(there is no CPU fallback; the CUDA kernels are the only implementation)")
+    with torch.cuda.device(device):
+        _check(_stream_fork(torch.cuda.current_stream().cuda_stream), "crv_stream_fork")
+
+
+def stream_join(device=None):
+    """Make torch's current stream wait for the split reductions still running on the library's side stream."""
+    with torch.cuda.device(device):
+        _check(_stream_join(torch.cuda.current_stream().cuda_stream), "crv_stream_join")
 
 
 def workspace_bytes(op, dims):
@@ -176,7 +196,7 @@ def _tensor_core(precision):
     return precision in (PREC_TF32, PREC_TF32_TMA, PREC_BF16)
 
 
-def syrk_conv_accum(x, kernel_size, stride, padding, has_bias, alpha, out, precision=PREC_FP32):
+def syrk_conv_accum(x, kernel_size, stride, padding, has_bias, alpha, out, precision=PREC_FP32, join=True):
     """out (K,K) += alpha * unfold(x) unfold(x)^T  with the optional ones row (K1a / K1c).
 
     x is the logical (N,C,H,W) activation.  A channels-last tensor goes to the TMA-fed MN-major kernel
@@ -199,6 +219,8 @@ def syrk_conv_accum(x, kernel_size, stride, padding, has_bias, alpha, out, preci
             _check(_syrk_conv_nhwc(_dense(x, "activation"), N, C, H, W, kh, kw, sh, sw, ph, pw, 0, float(alpha),
                                    _dev(out, "factor"), ws.data_ptr(), ws.numel(), precision, _stream(x)),
                    "crv_syrk_conv_accum_nhwc")
+            if join:
+                _check(_stream_join(_stream(x)), "crv_stream_join")
             return
     if not x.is_contiguous():
         x = x.contiguous()
@@ -213,7 +235,7 @@ def syrk_conv_accum(x, kernel_size, stride, padding, has_bias, alpha, out, preci
            "crv_syrk_conv_accum")
 
 
-def syrk_rows_accum(g, has_bias, alpha, out, precision=PREC_FP32):
+def syrk_rows_accum(g, has_bias, alpha, out, precision=PREC_FP32, join=True):
     """out (D,D) += alpha * sum_{n,l} g[n,:,l] g[n,:,l]^T for g viewed as (N, M, L) (K1b / K1d).
 
     Channels-last 4-D operands and 2-D (Linear) operands are [R][M] matrices in memory: they go to the TMA-fed
@@ -235,6 +257,8 @@ def syrk_rows_accum(g, has_bias, alpha, out, precision=PREC_FP32):
             launch_calls += 2 + int(precision in (PREC_TF32, PREC_BF16))
             _check(_syrk_rows_nhwc(_dense(g, "operand"), N, M, L, 0, float(alpha), _dev(out, "factor"),
                                    ws.data_ptr(), ws.numel(), precision, _stream(g)), "crv_syrk_rows_accum_nhwc")
+            if join:
+                _check(_stream_join(_stream(g)), "crv_stream_join")
             return
     if not g.is_contiguous():
         g = g.contiguous()

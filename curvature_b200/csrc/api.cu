@@ -192,6 +192,9 @@ int crv_syrk_rows_accum_nhwc(const float* gptr, int N, int M, int L, int has_bia
   return syrk_nhwc_launch(g, alpha, F, precision, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+int crv_stream_join(crv_stream_t stream) { return syrk_stream_join((cudaStream_t)stream); }
+int crv_stream_fork(crv_stream_t stream) { return syrk_stream_fork((cudaStream_t)stream); }
+
 int crv_diag_accum(const float* wgrad, const float* bgrad, int M, int K0, float scale, float* state,
                    float* grads_out, crv_stream_t stream) {
   return diag_accum_launch(wgrad, bgrad, M, K0, scale, state, grads_out, (cudaStream_t)stream);

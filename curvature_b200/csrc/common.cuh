@@ -87,6 +87,8 @@ int syrk_tc_launch(const ConvGeom& g, float alpha, float* F, int precision, void
                    cudaStream_t s);
 size_t syrk_tc_workspace(const ConvGeom& g, int precision);
 // channels-last operands (g.x is [N][H][W][C]); tensor-core tiers only
+int syrk_stream_join(cudaStream_t s);
+int syrk_stream_fork(cudaStream_t s);
 bool syrk_nhwc_supported(const ConvGeom& g, int precision);
 size_t syrk_nhwc_workspace(const ConvGeom& g, int precision);
 int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,

@@ -1056,7 +1056,8 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
   // The bf16 copy costs one extra pass over the tensor (read 4 B, write 2 B per element): it pays when every
   // element then travels L2 -> SM several times -- k x k convolutions (each element feeds kh*kw operand rows) and
   // factors of three or more row blocks.  Single-tile, read-once operands are HBM-bound and stay on the direct path.
-  pl.bf16 = (precision == CRV_PREC_BF16 && (KK > 1 || p.T >= 3) && g.C >= 64 && (g.C & 7) == 0 &&
+  static const int bf16_min_t = getenv("CURVATURE_B200_BF16_MIN_T") ? atoi(getenv("CURVATURE_B200_BF16_MIN_T")) : 3;
+  pl.bf16 = (precision == CRV_PREC_BF16 && (KK > 1 || p.T >= bf16_min_t) && g.C >= 64 && (g.C & 7) == 0 &&
              (KK == 1 || (g.C & 63) == 0)) ? 1 : 0;
   const int CH = pl.bf16 ? 64 : 32, gran = pl.bf16 ? 16 : 8;
   p.sh = g.sh; p.sw = g.sw; p.ph = g.ph; p.pw = g.pw;
@@ -1169,6 +1170,7 @@ int syrk_tc_launch(const ConvGeom& g, float alpha, float* F, int precision, void
   const int sms = device_sm_count();
   CRV_CHECK(sms > 0, "no CUDA device");
   CRV_CHECK(g.R < (1LL << 31) - 64, "contraction length too large");
+  if (int rc = syrk_stream_join(s)) return rc;   // this path's workspace overlaps both halves of the channels-last one
   TmaGeom tg;
   int tma_chunks = 0;
   const bool use_tma = precision == CRV_PREC_TF32_TMA && tma_geometry(g, tg, tma_chunks) && tensor_map_encoder();
@@ -1217,6 +1219,73 @@ int syrk_tc_launch(const ConvGeom& g, float alpha, float* F, int precision, void
 }
 
 
+// ---- split reduction on a side stream --------------------------------------------------------------------
+// The fixed-order reduction of a factor's partial tiles depends only on that factor's main kernel, and the next
+// factor's main kernel depends on neither (different factor, and the workspace is double-buffered): so the reduction
+// is enqueued on an internal side stream behind an event, where it overlaps the next main kernel (it needs 1024
+// threads and 4 KB of shared memory per CTA and fits beside the resident SYRK CTA).  crv_stream_join() makes the
+// caller's stream wait for the outstanding reductions; the host classes call it at the end of update().
+namespace {
+struct SideState {
+  cudaStream_t side = nullptr;       // split reductions
+  cudaStream_t cast = nullptr;       // cast / rounding pre-passes (only between crv_stream_fork and crv_stream_join)
+  cudaEvent_t ev_main[2] = {nullptr, nullptr}, ev_red[2] = {nullptr, nullptr}, ev_cast[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr;
+  bool red_pending[2] = {false, false}, main_pending[2] = {false, false};
+  bool forked = false;
+  int toggle = 0;
+  bool enabled = true, init = false;
+};
+SideState g_side_state[16];
+
+SideState* side_state() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) { cudaGetLastError(); return nullptr; }
+  SideState& st = g_side_state[dev];
+  if (!st.init) {
+    st.init = true;
+    const char* e = getenv("CURVATURE_B200_SIDE_STREAM");
+    st.enabled = !(e && atoi(e) == 0);
+    if (st.enabled) {
+      bool ok = cudaStreamCreateWithFlags(&st.side, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&st.cast, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaEventCreateWithFlags(&st.ev_fork, cudaEventDisableTiming) == cudaSuccess;
+      for (int i = 0; i < 2 && ok; ++i)
+        ok = cudaEventCreateWithFlags(&st.ev_main[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&st.ev_red[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&st.ev_cast[i], cudaEventDisableTiming) == cudaSuccess;
+      if (!ok) { cudaGetLastError(); st.enabled = false; }
+    }
+  }
+  return &st;
+}
+}  // namespace
+
+// Make `s` wait for every reduction still outstanding on the side stream (no host synchronisation); ends a fork.
+int syrk_stream_join(cudaStream_t s) {
+  SideState* st = side_state();
+  if (!st || !st->enabled) return 0;
+  for (int b = 0; b < 2; ++b)
+    if (st->red_pending[b]) {
+      CRV_CUDA(cudaStreamWaitEvent(s, st->ev_red[b], 0));
+      st->red_pending[b] = false;
+    }
+  st->forked = false;
+  return 0;
+}
+
+// Declare that every operand tensor of the SYRK calls that follow (until the next join) is complete on `s` NOW: the
+// cast / rounding pre-pass of call i may then run on a side stream, concurrently with the main kernel of call i-1
+// (an HBM-bound copy beside an L2/TMA-bound contraction), instead of in order behind it.
+int syrk_stream_fork(cudaStream_t s) {
+  SideState* st = side_state();
+  if (!st || !st->enabled) return 0;
+  CRV_CUDA(cudaEventRecord(st->ev_fork, s));
+  CRV_CUDA(cudaStreamWaitEvent(st->cast, st->ev_fork, 0));
+  st->forked = true;
+  return 0;
+}
+
 // ---- channels-last entry points ----------------------------------------------------------------------
 bool syrk_nhwc_supported(const ConvGeom& g, int precision) {
   if (precision != CRV_PREC_TF32 && precision != CRV_PREC_TF32_TMA && precision != CRV_PREC_BF16) return false;
@@ -1227,7 +1296,7 @@ bool syrk_nhwc_supported(const ConvGeom& g, int precision) {
 size_t syrk_nhwc_workspace(const ConvGeom& g, int precision) {
   NhPlan pl;
   if (!nhwc_plan(g, precision, device_sm_count(), pl)) return 0;
-  return pl.partial_bytes + 1024 + pl.copy_bytes;
+  return 2 * (pl.partial_bytes + 4096 + pl.copy_bytes);    // two halves: main kernel i+1 writes one while reduction i reads the other
 }
 
 int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,
@@ -1241,21 +1310,42 @@ int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, vo
   CRV_CHECK(nhwc_plan(g, precision, sms, pl),
             "channels-last SYRK: unsupported geometry (needs no bias row, C %% 4 == 0, C >= 32, C %% 32 == 0 for k x k)");
   CRV_CHECK(tensor_map_encoder() != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
-  const size_t need = pl.partial_bytes + 1024 + pl.copy_bytes;
+  const size_t need = 2 * (pl.partial_bytes + 4096 + pl.copy_bytes);
   CRV_CHECK(ws != nullptr && ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
   CRV_CHECK(((uintptr_t)ws & 15) == 0, "workspace must be 16-byte aligned");
+  // workspace half for this call; the main stream first waits for the reduction that last read it (two calls ago)
+  SideState* st = side_state();
+  const bool use_side = st && st->enabled;
+  int buf = 0;
+  if (use_side) {
+    buf = st->toggle;
+    st->toggle ^= 1;
+    if (st->red_pending[buf]) CRV_CUDA(cudaStreamWaitEvent(s, st->ev_red[buf], 0));
+  }
+  const size_t half = (ws_bytes / 2) & ~(size_t)1023;
+  char* wsb = (char*)((((uintptr_t)ws + 1023) & ~(uintptr_t)1023) + (size_t)buf * (half - 1024));
   NhParams& p = pl.p;
-  p.ws = (float*)ws;
+  p.ws = (float*)wsb;
   const float* src = g.x;
   if (pl.copy_bytes) {   // pre-pass: bf16 copy (tier bf16) or TF32 round-to-nearest copy (tier tf32), same layout
-    float* copy = (float*)((((uintptr_t)ws + pl.partial_bytes) + 1023) & ~(uintptr_t)1023);
+    float* copy = (float*)((((uintptr_t)wsb + pl.partial_bytes) + 1023) & ~(uintptr_t)1023);
     const size_t n4 = (size_t)g.N * g.C * g.H * g.W / 4;
     const unsigned blocks = (unsigned)((n4 + 255) / 256 < (size_t)sms * 16 ? (n4 + 255) / 256 : (size_t)sms * 16);
-    profile_begin(KC_PREPASS, 0.0, (pl.bf16 ? 6.0 : 8.0) * (double)n4 * 4.0, s);
-    if (pl.bf16) cast_bf16_kernel<<<blocks, 256, 0, s>>>((const float4*)g.x, (uint2*)copy, n4);
-    else round_tf32_kernel<<<blocks, 256, 0, s>>>((const float4*)g.x, (float4*)copy, n4);
-    profile_end(s);
+    cudaStream_t cs = s;
+    const bool side_cast = use_side && st->forked;
+    if (side_cast) {      // wait only for the main kernel that last read this half's copy region (two calls ago)
+      cs = st->cast;
+      if (st->main_pending[buf]) CRV_CUDA(cudaStreamWaitEvent(cs, st->ev_main[buf], 0));
+    }
+    profile_begin(KC_PREPASS, 0.0, (pl.bf16 ? 6.0 : 8.0) * (double)n4 * 4.0, cs);
+    if (pl.bf16) cast_bf16_kernel<<<blocks, 256, 0, cs>>>((const float4*)g.x, (uint2*)copy, n4);
+    else round_tf32_kernel<<<blocks, 256, 0, cs>>>((const float4*)g.x, (float4*)copy, n4);
+    profile_end(cs);
     CRV_CUDA(cudaGetLastError());
+    if (side_cast) {
+      CRV_CUDA(cudaEventRecord(st->ev_cast[buf], cs));
+      CRV_CUDA(cudaStreamWaitEvent(s, st->ev_cast[buf], 0));
+    }
     src = copy;
   }
   const cuuint64_t esz = pl.bf16 ? 2 : 4;
@@ -1298,10 +1388,30 @@ int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, vo
   rp.T = p.T; rp.pairs = pl.pairs; rp.splits = p.splits;
   rp.KK = p.KK;
   rp.ws = p.ws;
-  profile_begin(KC_SYRK_REDUCE, 0.0, (double)pl.partial_bytes + 8.0 * g.D * g.D, s);
-  syrk_tc_reduce_kernel<<<pl.pairs * 64, 1024, 0, s>>>(rp, alpha, F);
-  profile_end(s);
+  cudaStream_t rs = s;
+  if (use_side) {
+    CRV_CUDA(cudaEventRecord(st->ev_main[buf], s));
+    st->main_pending[buf] = true;
+    CRV_CUDA(cudaStreamWaitEvent(st->side, st->ev_main[buf], 0));
+    rs = st->side;
+  }
+  {
+    // same shared-memory carve-out as the SYRK kernel, or the two cannot be resident on one SM at the same time
+    static bool carveout_set = false;
+    if (!carveout_set) {
+      carveout_set = true;
+      cudaFuncSetAttribute(syrk_tc_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaGetLastError();
+    }
+  }
+  profile_begin(KC_SYRK_REDUCE, 0.0, (double)pl.partial_bytes + 8.0 * g.D * g.D, rs);
+  syrk_tc_reduce_kernel<<<pl.pairs * 64, 1024, 0, rs>>>(rp, alpha, F);
+  profile_end(rs);
   CRV_CUDA(cudaGetLastError());
+  if (use_side) {
+    CRV_CUDA(cudaEventRecord(st->ev_red[buf], st->side));
+    st->red_pending[buf] = true;
+  }
   return 0;
 }
 

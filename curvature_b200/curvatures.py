@@ -355,6 +355,8 @@ class KFAC(Curvature):
         `batch_size` is accepted for API compatibility; like the reference the factors are normalised by the
         recorded tensors' own shapes."""
         self._ensure_arena()
+        if self.record:      # every recorded tensor is complete on the current stream: pre-passes may run ahead
+            nat.stream_fork(next(iter(self.record)).weight.device)
         for layer in self.model.modules():
             module_class = layer.__class__.__name__
             if module_class in self.layer_types:
@@ -377,17 +379,20 @@ class KFAC(Curvature):
                         ph, pw = _pair(layer.padding)
                         r_x = N * ((H + 2 * ph - kh) // sh + 1) * ((W + 2 * pw - kw) // sw + 1)
                         nat.syrk_conv_accum(x, (kh, kw), (sh, sw), (ph, pw), has_bias, 1.0 / r_x, first,
-                                            self.precision)
+                                            self.precision, join=False)
                         r_g = n_g * g.shape[2] * g.shape[3]
                     else:
                         if x.dim() != 2:
                             raise NotImplementedError("KFAC supports 2-D Linear inputs only (as the reference)")
-                        nat.syrk_rows_accum(x, has_bias, 1.0 / x.size(0), first, self.precision)
+                        nat.syrk_rows_accum(x, has_bias, 1.0 / x.size(0), first, self.precision, join=False)
                         r_g = n_g
                     # reference: (g * N)(g * N)^T / R  ==  g g^T * N^2 / R
-                    nat.syrk_rows_accum(g, False, float(n_g) * float(n_g) / float(r_g), second, self.precision)
+                    nat.syrk_rows_accum(g, False, float(n_g) * float(n_g) / float(r_g), second, self.precision,
+                                        join=False)
                 elif module_class == 'MultiheadAttention':
                     raise NotImplementedError
+        # the split reductions run on the library's side stream: order the caller's stream after them
+        nat.stream_join(next(iter(self.record)).weight.device)
 
     def invert(self,
                add: Union[float, list, tuple] = 0.,

@@ -102,6 +102,17 @@ int crv_syrk_conv_accum_nhwc(const float* x, int N, int C, int H, int W,
 int crv_syrk_rows_accum_nhwc(const float* g, int N, int M, int L, int has_bias, float alpha, float* F,
                              void* ws, size_t ws_bytes, int precision, crv_stream_t stream);
 
+/* The channels-last SYRK calls enqueue their split reduction (the kernel that adds the result into the factor) on an
+ * internal side stream, so that it overlaps the next call's main kernel.  crv_stream_join() makes `stream` wait (on the
+ * device, no host synchronisation) for every reduction still outstanding; call it after the last SYRK call of an
+ * estimation step and before anything else reads or writes the factors.  CURVATURE_B200_SIDE_STREAM=0 disables the side
+ * stream (everything then runs in order on the caller's stream and the join is a no-op). */
+int crv_stream_join(crv_stream_t stream);
+/* Optional: declares that every operand tensor of the SYRK calls that follow, up to the next crv_stream_join(), is
+ * complete on `stream` at this point.  The cast / rounding pre-pass of call i may then run on a second side stream,
+ * concurrently with the main kernel of call i-1.  Without a fork the pre-pass runs in order on the caller's stream. */
+int crv_stream_fork(crv_stream_t stream);
+
 /* K2 -- squared-gradient accumulation (Diagonal.update, curvatures.py:151-158; the `diags`
  * part of EFB.update, curvatures.py:431-434):
  *   state[m, k] += scale * G[m,k]^2,  G = [wgrad.view(M,K0) | bgrad]  (bias column last).
