@@ -109,6 +109,33 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// Warp-uniform value -> uniform register (REDUX writes a UR): lets ptxas keep everything derived from it uniform.
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+// tcgen05.mma with the two shared-memory descriptors given as (low word, common high word): the low word holds the
+// start-address and leading-byte-offset fields, so stepping through a stage is one 32-bit add per operand.
+__device__ __forceinline__ void tc_mma_lohi(bool bf16, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  if (bf16)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 1 in exactly one (elected) lane of a fully converged warp
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
@@ -775,7 +802,7 @@ constexpr int NH_MAXSTAGE = 8;
 constexpr int NH_NPROD = 8;                   // TMA-issuing threads (lane 0 of every warp but the MMA warp)
 constexpr int NH_DATA_BYTES = 216 * 1024;
 constexpr int NH_SMEM_BYTES = NH_DATA_BYTES + 1024 /*barriers, chunk table*/ + 1024 /*alignment slack*/;
-constexpr int NH_STAGE_TARGET = 64 * 1024;
+static const int NH_STAGE_TARGET = getenv("CURVATURE_B200_STAGE_KB") ? atoi(getenv("CURVATURE_B200_STAGE_KB")) * 1024 : 64 * 1024;
 
 struct NhParams {
   int D, C, KK, kw;
@@ -788,6 +815,7 @@ struct NhParams {
   int ppi, pcw, bw, bh;      // boxes per image, boxes per box-row, box extent in output positions
   int sh, sw, ph, pw, flat;
   int pfd;                   // L2 prefetch distance in ring revolutions (0 = off)
+  int dbg;                   // ablation switches for profiling (bit 0: no TMA loads, bit 1: no MMAs); 0 in production
   float* ws;
 };
 
@@ -916,8 +944,9 @@ syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
         const int total = nv * loaded;                          // TMA instructions of this stage
         const int mine = total > me ? (total - me + NH_NPROD - 1) / NH_NPROD : 0;
         mbar_wait(bars + 8 * (NH_MAXSTAGE + s), ph ^ 1u);
-        if (mine) mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)mine * box_bytes);
+        if (mine && !(p.dbg & 1)) mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)mine * box_bytes);
         else mbar_arrive(bars + 8 * s);
+        if (p.dbg & 1) continue;
         const uint32_t st = sbase + (uint32_t)s * stage_bytes;
         for (int e = me; e < total; e += NH_NPROD) {
           const int j = e / loaded, q = e - j * loaded;
@@ -970,37 +999,51 @@ syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
       epilogue_store(t, bar_tmem_full, tmem, p.ws + (size_t)blockIdx.x * TILE_ELEMS, warp & 3, lane);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = BF16 ? umma_idesc_mn16(128, (uint32_t)ncols) : umma_idesc_mn(128, (uint32_t)ncols);
-      uint32_t acc = 0;
-      for (int it = 0; it < nit; ++it) {
-        const int s = it % nstage;
-        const uint32_t ph = (uint32_t)(it / nstage) & 1u;
-        mbar_wait(bars + 8 * s, ph);
-        tc_fence_after();
-        const uint32_t st = sbase + (uint32_t)s * stage_bytes;
-        const uint32_t bst = diag ? st : st + (uint32_t)nchA * chunk_bytes;
-        const int nv = min(NB, b_end - (b_begin + it * NB));
-        const int nkg = nv * (p.PB / KPOS);
+    // The WHOLE warp runs this loop in uniform control flow and only the tcgen05 instructions themselves are
+    // predicated on one elected lane: ptxas then keeps descriptors, addresses and the predicate in uniform registers
+    // and the loop body is UIADD3 + UTCHMMA.  With `if (lane == 0) { loop }` it emitted an R2UR / ELECT waterfall per
+    // instruction that took ~224 cycles per MMA against the tensor pipe's 128 (scripts/experiments/mma_rate_probe.cu).
+    // Per-CTA quantities come out of decode_pair / runtime divisions in vector registers; a warp reduction (REDUX
+    // writes a uniform register) moves each of them to the uniform datapath once, outside the loop.
+    const uint32_t leader = elect_one();
+    const uint32_t u_chunk = uni(chunk_bytes), u_stage = uni(stage_bytes), u_tmem = uni(tmem);
+    const int u_nstage = (int)uni((uint32_t)nstage), u_nit = (int)uni((uint32_t)nit), u_NB = (int)uni((uint32_t)NB);
+    const int u_bbeg = (int)uni((uint32_t)b_begin), u_bend = (int)uni((uint32_t)b_end);
+    const uint32_t idesc = uni(BF16 ? umma_idesc_mn16(128, (uint32_t)ncols) : umma_idesc_mn(128, (uint32_t)ncols));
+    // descriptor fields other than the start address (leading byte offset = chunk stride)
+    const uint64_t dfull = (BF16 ? umma_desc_mn16(0u, u_chunk) : umma_desc_mn(0u, u_chunk));
+    const uint32_t dlo = (uint32_t)dfull, dhi32 = (uint32_t)(dfull >> 32);
+    constexpr uint32_t KSTEP = (uint32_t)((KPOS * 128) >> 4);             // one MMA's positions, in 16-byte units
+    const uint32_t hstep = (uint32_t)(128 / CH) * u_chunk;                // second 128-row half of the A block
+    const uint32_t boff = uni(diag ? 0u : (uint32_t)nchA * chunk_bytes);
+    const int kpb = p.PB / KPOS;
+    const bool two = uni((uint32_t)mh) == 2u;
+    const bool run = !(p.dbg & 2);
+    uint32_t acc = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < u_nit; ++it) {
+      mbar_wait(bars + 8 * s, ph);
+      tc_fence_after();
+      const uint32_t st = sbase + (uint32_t)s * u_stage;
+      const int nv = min(u_NB, u_bend - (u_bbeg + it * u_NB));
+      const int nkg = run ? nv * kpb : 0;
+      const uint32_t a0 = dlo | ((st >> 4) & 0x3FFFu);
+      const uint32_t a1 = dlo | (((st + hstep) >> 4) & 0x3FFFu);
+      const uint32_t b0 = dlo | (((st + boff) >> 4) & 0x3FFFu);
+      if (leader) {
         for (int kg = 0; kg < nkg; ++kg) {
-          const uint32_t koff = (uint32_t)kg * (uint32_t)(KPOS * 128);
-          if (BF16) {
-            const uint64_t bdesc = umma_desc_mn16(bst + koff, chunk_bytes);
-            for (int h = 0; h < mh; ++h)
-              tc_mma_bf16(tmem + (uint32_t)h * 256u, umma_desc_mn16(st + (uint32_t)(h * 2) * chunk_bytes + koff, chunk_bytes),
-                          bdesc, idesc, acc);
-          } else {
-            const uint64_t bdesc = umma_desc_mn(bst + koff, chunk_bytes);
-            for (int h = 0; h < mh; ++h)
-              tc_mma_tf32(tmem + (uint32_t)h * 256u, umma_desc_mn(st + (uint32_t)(h * 4) * chunk_bytes + koff, chunk_bytes),
-                          bdesc, idesc, acc);
-          }
+          const uint32_t ko = (uint32_t)kg * KSTEP;
+          tc_mma_lohi(BF16, u_tmem, a0 + ko, b0 + ko, dhi32, idesc, acc);
+          if (two) tc_mma_lohi(BF16, u_tmem + 256u, a1 + ko, b0 + ko, dhi32, idesc, acc);
           acc = 1;
         }
-        tc_commit(bars + 8 * (NH_MAXSTAGE + s));
       }
-      tc_commit(bar_tmem_full);
+      if (nkg > 0) acc = 1;
+      if (leader) tc_commit(bars + 8 * (NH_MAXSTAGE + s));
+      if (++s == u_nstage) { s = 0; ph ^= 1u; }
     }
+    if (leader) tc_commit(bar_tmem_full);
     __syncwarp();
   }
 
@@ -1064,6 +1107,8 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
   p.flat = (KK == 1 && g.sh == 1 && g.sw == 1 && g.ph == 0 && g.pw == 0) ? 1 : 0;
   {
     const char* e = getenv("CURVATURE_B200_PFD");
+    const char* d = getenv("CURVATURE_B200_DBG");
+    p.dbg = d ? atoi(d) : 0;
     p.pfd = e ? atoi(e) : 0;   // measured on ResNet-50: 14.5k img/s without, 14.2k / 14.0k / 13.7k at 1 / 2 / 4 revolutions
   }
   // chunk slots per stage of the two item kinds

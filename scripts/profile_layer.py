@@ -27,6 +27,13 @@ LAYERS = {
     "g256": ("G", 256, 256, 56, 56, 1, 1, 0),
     "g1024": ("G", 256, 1024, 14, 14, 1, 1, 0),
     "g2048": ("G", 256, 2048, 7, 7, 1, 1, 0),
+    "g256s": ("G", 256, 256, 14, 14, 1, 1, 0),
+    "g128": ("G", 256, 128, 28, 28, 1, 1, 0),
+    "g512": ("G", 256, 512, 28, 28, 1, 1, 0),
+    "a512": ("A", 256, 512, 28, 28, 1, 1, 0),
+    "a128": ("A", 256, 128, 28, 28, 1, 1, 0),
+    "a2048": ("A", 256, 2048, 7, 7, 1, 1, 0),
+    "a1152s2": ("A", 256, 128, 56, 56, 3, 2, 1),
 }
 
 
@@ -57,6 +64,16 @@ def main():
             out = torch.zeros(K, K, device=dev)
             fn = lambda: nat.syrk_rows_accum(x, False, 1.0 / R, out, prec)  # noqa: E731
         times = []
+        fn()
+        torch.cuda.synchronize()
+        nat.profile_enable(True)
+        nat.profile_collect()
+        for _ in range(max(args.reps, 1)):
+            fn()
+        torch.cuda.synchronize()
+        prof = nat.profile_collect()
+        nat.profile_enable(False)
+        kms = "  ".join(f"{k.replace('syrk_', '')}={v['ms'] / v['launches'] * 1e3:.1f}us" for k, v in prof.items() if v["launches"])
         for _ in range(args.reps + 1):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -64,9 +81,9 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
-        ms = statistics.median(times[1:])
+        ms = statistics.median(times[1:] or times)
         print(f"{name:6s} K={K:5d} R={R:8d}  {ms:8.3f} ms  {R * K * (K + 1) / ms / 1e9:7.1f} TFLOP/s (algorithmic)  "
-              f"{4 * x.numel() / ms / 1e6:7.0f} GB/s (input once)")
+              f"{4 * x.numel() / ms / 1e6:7.0f} GB/s (input once)  | {kms}")
 
 
 if __name__ == "__main__":
