@@ -342,9 +342,13 @@ def main():
     peak_src = "of measured (MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "of fallback (1.4 PFLOP/s sustained bf16"
     tier = args.precision
     step_ms = statistics.mean(update_ms)
-    # dominant kernel = the kernel class with the largest share of the step's device time
+    # dominant kernel = the contraction kernel class with the largest share of the step's device time.  The split
+    # reduction and the cast pre-pass run on side streams: their event brackets include the time they wait for an SM
+    # next to the resident SYRK CTAs, so they are reported in step_breakdown but not ranked here (the serialised ncu
+    # launch list under profiles/ gives their true share).
     busy = {k: v for k, v in kernels.items() if v["launches"]}
-    dom = max(busy, key=lambda k: busy[k]["ms"]) if busy else None
+    ranked = {k: v for k, v in busy.items() if v["flops"]} or busy
+    dom = max(ranked, key=lambda k: ranked[k]["ms"]) if ranked else None
     kern_total_ms = sum(v["ms"] for v in busy.values())
     roofline = None
     if dom is not None:

@@ -39,6 +39,7 @@ _abi_version = _sig("crv_abi_version", c_int)
 _last_error = _sig("crv_last_error", c_char_p)
 _sm_count = _sig("crv_device_sm_count", c_int)
 _profile_enable = _sig("crv_profile_enable", c_int, c_int)
+_debug_timeline = _sig("crv_debug_timeline", c_int, ctypes.c_void_p)
 _profile_collect = _sig("crv_profile_collect", c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double),
                        POINTER(ctypes.c_double), POINTER(ctypes.c_longlong), c_int)
 _workspace_bytes = _sig("crv_workspace_bytes", c_size_t, c_int, POINTER(c_int64), c_int)
@@ -69,7 +70,7 @@ _gemm = _sig("crv_gemm", c_int, _f32p, c_int, c_int, _f32p, c_int, c_int, _f32p,
 ABI_VERSION = _abi_version()
 EXPORTED_SYMBOLS = (
     "crv_abi_version", "crv_last_error", "crv_device_sm_count", "crv_workspace_bytes", "crv_profile_enable",
-    "crv_profile_collect",
+    "crv_profile_collect", "crv_debug_timeline",
     "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc", "crv_stream_join", "crv_stream_fork",
     "crv_diag_accum", "crv_efb_project_accum",
     "crv_chol_inv_batched", "crv_sample_matrix_normal", "crv_round_tf32", "crv_elementwise_inv_sqrt", "crv_diag_sample",
@@ -164,6 +165,11 @@ KERNEL_CLASSES = ("syrk_nhwc_bf16", "syrk_nhwc_tf32", "syrk_staged_nchw", "syrk_
 def profile_enable(on=True):
     """Bracket every SYRK-family kernel launch with a CUDA event pair on its stream (bench.py's roofline)."""
     _check(_profile_enable(int(bool(on))), "crv_profile_enable")
+
+
+def debug_timeline(buf=None):
+    """Profiling aid: per-CTA time stamps of the channels-last SYRK kernel into `buf` (int64 CUDA tensor, >= 1280)."""
+    _check(_debug_timeline(None if buf is None else buf.data_ptr()), "crv_debug_timeline")
 
 
 def profile_collect():

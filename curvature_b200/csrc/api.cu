@@ -41,6 +41,9 @@ std::vector<ProfRec> g_prof;
 std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
 }  // namespace
 
+static long long* g_timeline = nullptr;
+long long* debug_timeline_buffer() { return g_timeline; }
+
 void profile_begin(int kclass, double flops, double bytes, cudaStream_t s) {
   if (!g_prof_on) return;
   ProfRec r;
@@ -86,6 +89,8 @@ extern "C" {
 int crv_abi_version(void) { return CRV_ABI_VERSION; }
 const char* crv_last_error(void) { return last_error(); }
 int crv_device_sm_count(void) { return device_sm_count(); }
+
+int crv_debug_timeline(long long* buf) { g_timeline = buf; return 0; }
 
 int crv_profile_enable(int on) {
   g_prof_on = on != 0;

@@ -78,6 +78,7 @@ enum KernelClass {
   KC_SYRK_SIMT      = 5,   // syrk_simt_kernel (fp32 tier)
   KC_COUNT          = 6
 };
+long long* debug_timeline_buffer();
 void profile_begin(int kclass, double flops, double bytes, cudaStream_t s);
 void profile_end(cudaStream_t s);
 

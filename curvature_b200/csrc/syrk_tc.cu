@@ -24,6 +24,10 @@
 #include <math.h>
 #include <stdlib.h>
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+#include <vector>
+#include <algorithm>
+#include <cmath>
+#include <utility>
 
 namespace crv {
 namespace {
@@ -130,6 +134,12 @@ __device__ __forceinline__ void tc_mma_lohi(bool bf16, uint32_t tmem_d, uint32_t
         ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ long long nv_kg(int NB, int left, int kpb) { return (long long)min(NB, left) * kpb; }
 // 1 in exactly one (elected) lane of a fully converged warp
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
@@ -249,9 +259,9 @@ __device__ __forceinline__ void mma_issue_all(const ItemShape& t, uint32_t sbase
 }
 
 // One warp (TMEM lane quadrant `quad`): accumulator -> registers -> partial tile in the workspace.
-__device__ __forceinline__ void epilogue_store(const ItemShape& t, uint32_t bar_tmem_full, uint32_t tmem,
+__device__ __forceinline__ void epilogue_store(const ItemShape& t, uint32_t bar_tmem_full, uint32_t parity, uint32_t tmem,
                                                float* __restrict__ wsp, int quad, int lane) {
-  mbar_wait(bar_tmem_full, 0);
+  mbar_wait(bar_tmem_full, parity);
   tc_fence_after();
   for (int h = 0; h < t.mh; ++h) {
     const int row = h * 128 + quad * 32 + lane;
@@ -357,7 +367,7 @@ syrk_tc_tma_kernel(const TcParams p, const TmaGeom tg, const __grid_constant__ C
     if (lane == 0) mma_issue_all(t, sbase, bars, bar_tmem_full, tmem);
     __syncwarp();
   } else {
-    epilogue_store(t, bar_tmem_full, tmem, p.ws + (size_t)blockIdx.x * TILE_ELEMS, warp & 3, lane);
+    epilogue_store(t, bar_tmem_full, 0u, tmem, p.ws + (size_t)blockIdx.x * TILE_ELEMS, warp & 3, lane);
   }
 
   tc_fence_before();
@@ -797,9 +807,9 @@ EncodeTiledFn tensor_map_encoder() {
 // Positions of a box that do not exist are never loaded: box extents divide the output grid (bw | OW, bh | OH),
 // and where bw*bh is not a multiple of 8 (the contraction depth of one tf32 MMA) the remaining rows of the
 // box's shared-memory slot are zeroed once at kernel start -- TMA never writes them.
-constexpr int NH_THREADS = 9 * 32;             // warp 0: TMA; 1: MMA + TMEM owner; 2-5: TMA + epilogue; 6-8: TMA
+constexpr int NH_THREADS = 13 * 32;            // warp 0: TMA; 1: MMA + TMEM owner; 2-5: epilogue; 6-12: TMA
 constexpr int NH_MAXSTAGE = 8;
-constexpr int NH_NPROD = 8;                   // TMA-issuing threads (lane 0 of every warp but the MMA warp)
+constexpr int NH_NPROD = 8;                   // TMA-issuing warps (one elected lane each)
 constexpr int NH_DATA_BYTES = 216 * 1024;
 constexpr int NH_SMEM_BYTES = NH_DATA_BYTES + 1024 /*barriers, chunk table*/ + 1024 /*alignment slack*/;
 static const int NH_STAGE_TARGET = getenv("CURVATURE_B200_STAGE_KB") ? atoi(getenv("CURVATURE_B200_STAGE_KB")) * 1024 : 64 * 1024;
@@ -812,9 +822,10 @@ struct NhParams {
   int PB, PBv;               // rows per box slot (multiple of 8) / rows a box really holds
   int NBoff, NBdiag;         // boxes per pipeline stage for off-diagonal / diagonal items
   FastDiv divPPI, divPCW;
-  int ppi, pcw, bw, bh;      // boxes per image, boxes per box-row, box extent in output positions
+  int ppi, pcw, bw, bh, bn;  // boxes per image group, boxes per box-row, box extent in output positions / images
   int sh, sw, ph, pw, flat;
   int pfd;                   // L2 prefetch distance in ring revolutions (0 = off)
+  long long* tl;             // per-CTA timeline (profiling aid, see crv_debug_timeline); null in production
   int dbg;                   // ablation switches for profiling (bit 0: no TMA loads, bit 1: no MMAs); 0 in production
   float* ws;
 };
@@ -852,43 +863,78 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       : "memory");
 }
 
+// ---- stream-K work partition -----------------------------------------------------------------------------
+// The work of one factor is the list of (block pair q, box b) units in pair-major order.  Pairs differ in cost
+// (a diagonal pair loads one block, the last row block may be short: one MMA per k-group instead of two), and
+// pairs * splits rarely equals the SM count, so instead of "every pair is cut into the same number of equal splits"
+// the host cuts the COST axis into G equal ranges, one per CTA (boundaries rounded to whole pipeline stages).  A CTA
+// walks its range pair by pair; every (CTA, pair) segment accumulates in TMEM and is flushed to its own partial tile
+// (slot = CTA + pair, unique), which the fixed-order reduction sums per pair in CTA order: still bit-reproducible.
+constexpr int SK_MAXG = 160;
+struct SkTable {
+  int G;                      // CTAs
+  uint16_t q[SK_MAXG + 1];    // boundary c = (pair q[c], box b[c]); strictly increasing; q[G] = pairs, b[G] = 0
+  uint32_t b[SK_MAXG + 1];
+};
+
+struct SegGeom {
+  int I, J, rowsA, mh, ncols, nchA, nchB, nslots, NB, nstage;
+  bool diag;
+  uint32_t chunk_bytes, stage_bytes;
+};
+template <int CH>
+__device__ __forceinline__ SegGeom seg_geom(const NhParams& p, int q) {
+  SegGeom t;
+  decode_pair(q, p.T, t.I, t.J);
+  t.diag = (t.I == t.J);
+  t.rowsA = min(TB, p.D - t.I * TB);
+  t.mh = (t.rowsA + 127) >> 7;
+  t.ncols = t.diag ? ((t.rowsA + 15) & ~15) : TB;
+  t.nchA = (t.rowsA + CH - 1) / CH;
+  t.nchB = t.diag ? 0 : TB / CH;
+  // A stage holds only the chunks that are really loaded: A chunks first, then B chunks.  An M = 128 descriptor
+  // always spans 128 / CH chunks, so for a short A block it reads on into the B chunks (or, for a diagonal item,
+  // past the stage into the next one / the ring's tail pad): those are accumulator rows >= rowsA, never stored.
+  const int slotsA = t.mh * (128 / CH);
+  t.nslots = t.nchA + t.nchB;
+  t.NB = t.diag ? p.NBdiag : p.NBoff;
+  t.chunk_bytes = (uint32_t)(t.NB * p.PB) * 128u;
+  t.stage_bytes = (uint32_t)t.nslots * t.chunk_bytes;
+  const uint32_t tail_pad = t.diag ? (uint32_t)(slotsA - t.nchA) * t.chunk_bytes : 0u;
+  t.nstage = min(NH_MAXSTAGE, (int)((NH_DATA_BYTES - tail_pad) / t.stage_bytes));
+  return t;
+}
+
 // BF16 = false: fp32 words read as TF32, 32 channels per 128-byte row, 8 positions per MMA.
 // BF16 = true : bf16 copy of the operand (made by the cast pre-pass), 64 channels per row, 16 positions per MMA:
 //               half the bytes per operand element through L2 -> SM, twice the MMA rate.
+// Warps: 0 and 6..12 issue TMA (8 issuers), 1 issues the MMAs and owns TMEM, 2..5 drain the accumulator.
 template <bool BF16>
 __global__ void __launch_bounds__(NH_THREADS, 1)
-syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
+syrk_nhwc_kernel(const __grid_constant__ NhParams p, const __grid_constant__ SkTable sk,
+                 const __grid_constant__ CUtensorMap tmap) {
   constexpr int CH = BF16 ? 64 : 32;        // operand rows (channels) per chunk = per 128-byte smem row
   constexpr int KPOS = BF16 ? 16 : 8;       // contraction positions per MMA instruction
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;
-  const uint32_t bars = sbase + NH_DATA_BYTES;                 // full[8] | empty[8] | tmem_full
+  const uint32_t bars = sbase + NH_DATA_BYTES;                 // full[8] | empty[8] | tmem_full | tmem_empty
   const uint32_t bar_tmem_full = bars + 8 * (2 * NH_MAXSTAGE);
+  const uint32_t bar_tmem_empty = bar_tmem_full + 8;
   uint8_t* aux = smem_raw + (sbase - raw) + NH_DATA_BYTES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 8 * (2 * NH_MAXSTAGE + 1));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 8 * (2 * NH_MAXSTAGE + 2));
   int4* tab = reinterpret_cast<int4*>(aux + 256);              // per loaded chunk: {c0, dx, dy, slot}
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int pair = blockIdx.x / p.splits, split = blockIdx.x - pair * p.splits;
-  int I, J;
-  decode_pair(pair, p.T, I, J);
-  const bool diag = (I == J);
-  const int rowsA = min(TB, p.D - I * TB);
-  const int mh = (rowsA + 127) >> 7;
-  const int ncols = diag ? ((rowsA + 15) & ~15) : TB;
-  const int nchA = (rowsA + CH - 1) / CH, nchB = diag ? 0 : TB / CH;
-  // A stage holds only the chunks that are really loaded: A chunks first, then B chunks.  An M = 128 descriptor
-  // always spans 128 / CH chunks, so for a short A block it reads on into the B chunks (or, for a diagonal item,
-  // past the stage into the next one / the ring's tail pad): those are accumulator rows >= rowsA, never stored.
-  const int slotsA = mh * (128 / CH), nslots = nchA + nchB, loaded = nslots;
-  const int NB = diag ? p.NBdiag : p.NBoff;
-  const uint32_t chunk_bytes = (uint32_t)(NB * p.PB) * 128u;
-  const uint32_t stage_bytes = (uint32_t)nslots * chunk_bytes;
-  const uint32_t tail_pad = diag ? (uint32_t)(slotsA - nchA) * chunk_bytes : 0u;
-  const int nstage = min(NH_MAXSTAGE, (int)((NH_DATA_BYTES - tail_pad) / stage_bytes));
-  const int b_begin = split * p.bps, b_end = min(p.nbox, b_begin + p.bps);
-  const int nit = (b_end - b_begin + NB - 1) / NB;
+  long long* tl = p.tl ? p.tl + 8 * (size_t)blockIdx.x : nullptr;
+  if (tl && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tl[0] = (long long)gtimer(); tl[7] = smid;
+  }
+  // this CTA's range of the work list
+  const int q0 = (int)sk.q[blockIdx.x], q1 = (int)sk.q[blockIdx.x + 1];
+  const int bq0 = (int)sk.b[blockIdx.x], bq1 = (int)sk.b[blockIdx.x + 1];
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NH_MAXSTAGE; ++s) {
@@ -896,86 +942,80 @@ syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
       mbar_init(bars + 8 * (NH_MAXSTAGE + s), 1);
     }
     mbar_init(bar_tmem_full, 1);
+    mbar_init(bar_tmem_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
-  }
-  if (warp == 0 && lane < loaded) {
-    const bool isB = lane >= nchA;
-    const int kp = isB ? J * TB + (lane - nchA) * CH : I * TB + lane * CH;
-    const int tap = (int)fdiv((uint32_t)kp, p.divC);
-    const int ti = (int)fdiv((uint32_t)tap, p.divKW);
-    tab[lane] = make_int4(kp - tap * p.C, p.flat ? 0 : (tap - ti * p.kw) - p.pw, p.flat ? 0 : ti - p.ph,
-                          lane);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (p.PB > p.PBv) {   // zero the rows of every box slot that no box ever writes
-    const int pad16 = (p.PB - p.PBv) * 8;                       // 16-byte words per box slot
-    const int total = nstage * nslots * NB * pad16;
-    for (int e = threadIdx.x; e < total; e += NH_THREADS) {
-      const int slot = e / pad16, w = e - slot * pad16;
-      const uint32_t a = sbase + (uint32_t)slot * (uint32_t)p.PB * 128u + (uint32_t)p.PBv * 128u + (uint32_t)w * 16u;
-      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0) : "memory");
-    }
-    fence_proxy_async();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (tl && threadIdx.x == 0) tl[1] = (long long)gtimer();
 
-  if (warp != 1) {
-    // TMA issue is spread over NH_NPROD threads in different warps.  Measured (scripts/experiments/tma_rate_probe.cu):
-    // one thread sustains one cp.async.bulk.tensor per ~150 cycles whatever the box size -- 35 B/cycle/SM with the
-    // 8 KB boxes of a 3x3 layer, 18 B/cycle with 3.5 KB boxes -- while 4-8 issuing warps reach the TMA unit's
-    // ~66 B/cycle/SM with any of them.  Each issuer arms the stage barrier with its own bytes.
-    if (lane == 0) {
-      const int me = warp == 0 ? 0 : warp - 1;                 // 0 .. NH_NPROD-1
-      const uint32_t box_bytes = (uint32_t)p.PBv * 128u;
-      const int PFD = p.pfd > 0 ? p.pfd * nstage : (1 << 30);    // prefetch distance in pipeline iterations
-      for (int it = 0; it < nit; ++it) {
-        const int s = it % nstage;
-        const uint32_t ph = (uint32_t)(it / nstage) & 1u;
-        const int b0 = b_begin + it * NB;
-        const int nv = min(NB, b_end - b0);
-        const int total = nv * loaded;                          // TMA instructions of this stage
-        const int mine = total > me ? (total - me + NH_NPROD - 1) / NH_NPROD : 0;
-        mbar_wait(bars + 8 * (NH_MAXSTAGE + s), ph ^ 1u);
-        if (mine && !(p.dbg & 1)) mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)mine * box_bytes);
-        else mbar_arrive(bars + 8 * s);
-        if (p.dbg & 1) continue;
-        const uint32_t st = sbase + (uint32_t)s * stage_bytes;
-        for (int e = me; e < total; e += NH_NPROD) {
-          const int j = e / loaded, q = e - j * loaded;
-          const uint32_t b = (uint32_t)(b0 + j);
-          int X0, Y0, Nn;
-          if (p.flat) {
-            X0 = (int)b * p.PB; Y0 = 0; Nn = 0;
-          } else {
-            const uint32_t n = fdiv(b, p.divPPI);
-            const uint32_t rem = b - n * (uint32_t)p.ppi;
-            const uint32_t pr = fdiv(rem, p.divPCW);
-            const uint32_t pc = rem - pr * (uint32_t)p.pcw;
-            X0 = (int)pc * p.bw * p.sw; Y0 = (int)pr * p.bh * p.sh; Nn = (int)n;
-          }
-          const int4 t4 = tab[q];
-          tma_load_4d(st + (uint32_t)(j * p.PB) * 128u + (uint32_t)t4.w * chunk_bytes, &tmap, t4.x, X0 + t4.y, Y0 + t4.z, Nn,
-                      bars + 8 * s);
+  if (warp == 0 || warp >= 6) {
+    // ---- TMA producers.  Issue is spread over NH_NPROD warps (scripts/experiments/tma_rate_probe.cu: one issuer
+    // sustains one cp.async.bulk.tensor per ~150 cycles whatever the box size; 4-8 issuers reach the TMA unit's
+    // ~66 B/cycle/SM).  Each issuer arms the stage barrier with its own bytes.  The loop runs warp-uniformly, only
+    // the mbarrier / TMA instructions are predicated on one elected lane.
+    const uint32_t leader = elect_one();
+    const int me = (int)uni((uint32_t)(warp == 0 ? 0 : warp - 5));     // 0 .. NH_NPROD-1
+    const uint32_t box_bytes = (uint32_t)p.PBv * 128u;
+    const int ptid = me * 32 + lane;
+    uint32_t pph = 0;                                                   // per-stage parity of the empty barriers
+    int nseg = 0;
+    for (int q = q0; q <= q1; ++q) {
+      const int b_begin = q == q0 ? bq0 : 0, b_end = q == q1 ? bq1 : p.nbox;
+      if (b_begin >= b_end) continue;
+      const SegGeom t = seg_geom<CH>(p, q);
+      // the previous segment's MMAs have all retired (its accumulator is complete): every stage is free, whatever
+      // the stage geometry of this segment is
+      if (nseg > 0) mbar_wait(bar_tmem_full, (uint32_t)(nseg - 1) & 1u);
+      asm volatile("bar.sync 1, %0;" ::"r"(NH_NPROD * 32) : "memory");  // nobody still reads the old chunk table
+      const int loaded = t.nslots;
+      if (me == 0 && lane < loaded) {
+        const bool isB = lane >= t.nchA;
+        const int kp = isB ? t.J * TB + (lane - t.nchA) * CH : t.I * TB + lane * CH;
+        const int tap = (int)fdiv((uint32_t)kp, p.divC);
+        const int ti = (int)fdiv((uint32_t)tap, p.divKW);
+        tab[lane] = make_int4(kp - tap * p.C, p.flat ? 0 : (tap - ti * p.kw) - p.pw, p.flat ? 0 : ti - p.ph, lane);
+      }
+      if (p.PB > p.PBv) {   // zero the rows of every box slot that no box ever writes (TMA never touches them)
+        const int pad16 = (p.PB - p.PBv) * 8;                       // 16-byte words per box slot
+        const int total = t.nstage * t.nslots * t.NB * pad16;
+        for (int e = ptid; e < total; e += NH_NPROD * 32) {
+          const int slot = e / pad16, w = e - slot * pad16;
+          const uint32_t a = sbase + (uint32_t)slot * (uint32_t)p.PB * 128u + (uint32_t)p.PBv * 128u + (uint32_t)w * 16u;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0) : "memory");
         }
-        // L2 prefetch, PFD iterations ahead, issued by the DIAGONAL item of each row block only: it loads one block
-        // where an off-diagonal item loads two, so it has TMA bandwidth to spare, and the off-diagonal items of the
-        // same contraction split -- which walk the same boxes at the same time -- then find block I in L2 instead of
-        // waiting for the slowest first-touch HBM miss of every stage (the ring holds only ~2 stages in flight).
-        if (diag && it + PFD < nit) {
-          const int pb0 = b_begin + (it + PFD) * NB;
-          const int pnv = min(NB, b_end - pb0);
-          const int ptotal = pnv * loaded;
-          for (int e = me; e < ptotal; e += NH_NPROD) {
-            const int j = e / loaded, q = e - j * loaded;
-            const uint32_t b = (uint32_t)(pb0 + j);
+        fence_proxy_async();
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(NH_NPROD * 32) : "memory");
+      const int NB = (int)uni((uint32_t)t.NB), nstage = (int)uni((uint32_t)t.nstage), nld = (int)uni((uint32_t)loaded);
+      const uint32_t stage_bytes = uni(t.stage_bytes), chunk_bytes = uni(t.chunk_bytes);
+      const int ub = (int)uni((uint32_t)b_begin), ue = (int)uni((uint32_t)b_end);
+      const int nit = (ue - ub + NB - 1) / NB;
+      int s = 0;
+      for (int it = 0; it < nit; ++it) {
+        const int b0 = ub + it * NB;
+        const int nv = min(NB, ue - b0);
+        const int total = nv * nld;                             // TMA instructions of this stage
+        const int mine = total > me ? (total - me + NH_NPROD - 1) / NH_NPROD : 0;
+        mbar_wait(bars + 8 * (NH_MAXSTAGE + s), ((pph >> s) & 1u) ^ 1u);
+        pph ^= 1u << s;
+        const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+        if (leader) {
+          if (mine && !(p.dbg & 1)) mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)mine * box_bytes);
+          else mbar_arrive(bars + 8 * s);
+        }
+        if (!(p.dbg & 1)) {
+          for (int e = me; e < total; e += NH_NPROD) {
+            const int j = e / nld, qq = e - j * nld;
+            const uint32_t b = (uint32_t)(b0 + j);
             int X0, Y0, Nn;
             if (p.flat) {
               X0 = (int)b * p.PB; Y0 = 0; Nn = 0;
@@ -984,73 +1024,167 @@ syrk_nhwc_kernel(const NhParams p, const __grid_constant__ CUtensorMap tmap) {
               const uint32_t rem = b - n * (uint32_t)p.ppi;
               const uint32_t pr = fdiv(rem, p.divPCW);
               const uint32_t pc = rem - pr * (uint32_t)p.pcw;
-              X0 = (int)pc * p.bw * p.sw; Y0 = (int)pr * p.bh * p.sh; Nn = (int)n;
+              X0 = (int)pc * p.bw * p.sw; Y0 = (int)pr * p.bh * p.sh; Nn = (int)n * p.bn;
             }
-            const int4 t4 = tab[q];
-            tma_prefetch_4d(&tmap, t4.x, X0 + t4.y, Y0 + t4.z, Nn);
+            const int4 t4 = tab[qq];
+            if (leader)
+              tma_load_4d(st + (uint32_t)(j * p.PB) * 128u + (uint32_t)t4.w * chunk_bytes, &tmap, t4.x, X0 + t4.y, Y0 + t4.z,
+                          Nn, bars + 8 * s);
           }
         }
+        if (++s == nstage) s = 0;
       }
-    }
-    __syncwarp();
-    if (warp >= 2 && warp < 6) {
-      ItemShape t;
-      t.mh = mh; t.ncols = ncols; t.rowsA = rowsA;
-      epilogue_store(t, bar_tmem_full, tmem, p.ws + (size_t)blockIdx.x * TILE_ELEMS, warp & 3, lane);
+      ++nseg;
     }
   } else if (warp == 1) {
-    // The WHOLE warp runs this loop in uniform control flow and only the tcgen05 instructions themselves are
-    // predicated on one elected lane: ptxas then keeps descriptors, addresses and the predicate in uniform registers
-    // and the loop body is UIADD3 + UTCHMMA.  With `if (lane == 0) { loop }` it emitted an R2UR / ELECT waterfall per
-    // instruction that took ~224 cycles per MMA against the tensor pipe's 128 (scripts/experiments/mma_rate_probe.cu).
-    // Per-CTA quantities come out of decode_pair / runtime divisions in vector registers; a warp reduction (REDUX
-    // writes a uniform register) moves each of them to the uniform datapath once, outside the loop.
+    // ---- MMA issuer.  The WHOLE warp runs this loop in uniform control flow and only the tcgen05 instructions
+    // themselves are predicated on one elected lane: ptxas then keeps descriptors, addresses and the predicate in
+    // uniform registers and the loop body is UIADD3 + UTCHMMA.  With `if (lane == 0) { loop }` it emitted an R2UR /
+    // ELECT waterfall per instruction that took ~224 cycles per MMA against the tensor pipe's 128
+    // (scripts/experiments/mma_rate_probe.cu).  Per-segment quantities come out of decode_pair / runtime divisions
+    // in vector registers; a warp reduction (REDUX writes a uniform register) moves them to the uniform datapath.
     const uint32_t leader = elect_one();
-    const uint32_t u_chunk = uni(chunk_bytes), u_stage = uni(stage_bytes), u_tmem = uni(tmem);
-    const int u_nstage = (int)uni((uint32_t)nstage), u_nit = (int)uni((uint32_t)nit), u_NB = (int)uni((uint32_t)NB);
-    const int u_bbeg = (int)uni((uint32_t)b_begin), u_bend = (int)uni((uint32_t)b_end);
-    const uint32_t idesc = uni(BF16 ? umma_idesc_mn16(128, (uint32_t)ncols) : umma_idesc_mn(128, (uint32_t)ncols));
-    // descriptor fields other than the start address (leading byte offset = chunk stride)
-    const uint64_t dfull = (BF16 ? umma_desc_mn16(0u, u_chunk) : umma_desc_mn(0u, u_chunk));
-    const uint32_t dlo = (uint32_t)dfull, dhi32 = (uint32_t)(dfull >> 32);
+    const uint32_t u_tmem = uni(tmem);
     constexpr uint32_t KSTEP = (uint32_t)((KPOS * 128) >> 4);             // one MMA's positions, in 16-byte units
-    const uint32_t hstep = (uint32_t)(128 / CH) * u_chunk;                // second 128-row half of the A block
-    const uint32_t boff = uni(diag ? 0u : (uint32_t)nchA * chunk_bytes);
     const int kpb = p.PB / KPOS;
-    const bool two = uni((uint32_t)mh) == 2u;
     const bool run = !(p.dbg & 2);
-    uint32_t acc = 0;
-    int s = 0;
-    uint32_t ph = 0;
-    for (int it = 0; it < u_nit; ++it) {
-      mbar_wait(bars + 8 * s, ph);
-      tc_fence_after();
-      const uint32_t st = sbase + (uint32_t)s * u_stage;
-      const int nv = min(u_NB, u_bend - (u_bbeg + it * u_NB));
-      const int nkg = run ? nv * kpb : 0;
-      const uint32_t a0 = dlo | ((st >> 4) & 0x3FFFu);
-      const uint32_t a1 = dlo | (((st + hstep) >> 4) & 0x3FFFu);
-      const uint32_t b0 = dlo | (((st + boff) >> 4) & 0x3FFFu);
-      if (leader) {
-        for (int kg = 0; kg < nkg; ++kg) {
-          const uint32_t ko = (uint32_t)kg * KSTEP;
-          tc_mma_lohi(BF16, u_tmem, a0 + ko, b0 + ko, dhi32, idesc, acc);
-          if (two) tc_mma_lohi(BF16, u_tmem + 256u, a1 + ko, b0 + ko, dhi32, idesc, acc);
-          acc = 1;
-        }
+    uint32_t cph = 0;                                                     // per-stage parity of the full barriers
+    int nseg = 0;
+    for (int q = q0; q <= q1; ++q) {
+      const int b_begin = q == q0 ? bq0 : 0, b_end = q == q1 ? bq1 : p.nbox;
+      if (b_begin >= b_end) continue;
+      const SegGeom t = seg_geom<CH>(p, q);
+      const uint32_t u_chunk = uni(t.chunk_bytes), u_stage = uni(t.stage_bytes);
+      const int u_nstage = (int)uni((uint32_t)t.nstage), u_NB = (int)uni((uint32_t)t.NB);
+      const int ub = (int)uni((uint32_t)b_begin), ue = (int)uni((uint32_t)b_end);
+      const int u_nit = (ue - ub + u_NB - 1) / u_NB;
+      const uint32_t idesc = uni(BF16 ? umma_idesc_mn16(128, (uint32_t)t.ncols) : umma_idesc_mn(128, (uint32_t)t.ncols));
+      const uint64_t dfull = (BF16 ? umma_desc_mn16(0u, u_chunk) : umma_desc_mn(0u, u_chunk));
+      const uint32_t dlo = (uint32_t)dfull, dhi32 = (uint32_t)(dfull >> 32);
+      const uint32_t hstep = (uint32_t)(128 / CH) * u_chunk;              // second 128-row half of the A block
+      const uint32_t boff = uni(t.diag ? 0u : (uint32_t)t.nchA * t.chunk_bytes);
+      const bool two = uni((uint32_t)t.mh) == 2u;
+      if (nseg > 0) {                                                     // accumulator drained by the epilogue warps
+        mbar_wait(bar_tmem_empty, (uint32_t)(nseg - 1) & 1u);
+        tc_fence_after();
       }
-      if (nkg > 0) acc = 1;
-      if (leader) tc_commit(bars + 8 * (NH_MAXSTAGE + s));
-      if (++s == u_nstage) { s = 0; ph ^= 1u; }
+      uint32_t acc = 0;
+      int s = 0;
+      for (int it = 0; it < u_nit; ++it) {
+        mbar_wait(bars + 8 * s, (cph >> s) & 1u);
+        cph ^= 1u << s;
+        tc_fence_after();
+        if (tl && nseg == 0 && it == 0 && lane == 0) tl[2] = (long long)gtimer();
+        if (tl && lane == 0) tl[6] += nv_kg(u_NB, ue - (ub + it * u_NB), kpb);
+        const uint32_t st = sbase + (uint32_t)s * u_stage;
+        const int nv = min(u_NB, ue - (ub + it * u_NB));
+        const int nkg = run ? nv * kpb : 0;
+        const uint32_t a0 = dlo | ((st >> 4) & 0x3FFFu);
+        const uint32_t a1 = dlo | (((st + hstep) >> 4) & 0x3FFFu);
+        const uint32_t b0 = dlo | (((st + boff) >> 4) & 0x3FFFu);
+        if (leader) {
+          for (int kg = 0; kg < nkg; ++kg) {
+            const uint32_t ko = (uint32_t)kg * KSTEP;
+            tc_mma_lohi(BF16, u_tmem, a0 + ko, b0 + ko, dhi32, idesc, acc);
+            if (two) tc_mma_lohi(BF16, u_tmem + 256u, a1 + ko, b0 + ko, dhi32, idesc, acc);
+            acc = 1;
+          }
+        }
+        if (nkg > 0) acc = 1;
+        if (leader) tc_commit(bars + 8 * (NH_MAXSTAGE + s));
+        if (++s == u_nstage) s = 0;
+      }
+      if (leader) tc_commit(bar_tmem_full);
+      ++nseg;
+      if (tl && lane == 0) { tl[3] = (long long)gtimer(); tl[5] = nseg; }
     }
-    if (leader) tc_commit(bar_tmem_full);
     __syncwarp();
+  } else {
+    // ---- epilogue warps 2..5 (TMEM lane quadrant = warp & 3): accumulator -> registers -> partial tile `CTA + pair`
+    int nseg = 0;
+    for (int q = q0; q <= q1; ++q) {
+      const int b_begin = q == q0 ? bq0 : 0, b_end = q == q1 ? bq1 : p.nbox;
+      if (b_begin >= b_end) continue;
+      const SegGeom g = seg_geom<CH>(p, q);
+      ItemShape t;
+      t.mh = g.mh; t.ncols = g.ncols; t.rowsA = g.rowsA;
+      epilogue_store(t, bar_tmem_full, (uint32_t)nseg & 1u, tmem, p.ws + (size_t)(blockIdx.x + q) * TILE_ELEMS, warp & 3, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tmem_empty);
+      ++nseg;
+      if (tl && warp == 2 && lane == 0) tl[4] = (long long)gtimer();
+    }
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// Fixed-order reduction for the stream-K partition: the partial tiles of pair q are slots (c + q) for the CTAs
+// c_lo..c_hi whose ranges intersect the pair, found from the boundary table; summed in CTA order.
+__global__ void __launch_bounds__(1024) syrk_sk_reduce_kernel(const __grid_constant__ TcParams p, const __grid_constant__ SkTable sk,
+                                                              const float alpha, float* __restrict__ F) {
+  __shared__ float tile[32][33];
+  __shared__ int s_lo, s_hi;
+  const int pair = blockIdx.x >> 6, sub = blockIdx.x & 63;
+  const int br = sub >> 3, bc = sub & 7;
+  int I, J;
+  decode_pair(pair, p.T, I, J);
+  const bool diag = (I == J);
+  if (diag && bc > br) return;            // diagonal blocks: lower triangle only, mirrored below (exact symmetry)
+  const ConvGeom& g = p.g;
+  const int rowsA = min(TB, g.D - I * TB);
+  const int colsB = diag ? rowsA : TB;
+  if (br * 32 >= rowsA || bc * 32 >= colsB) return;
+  if (threadIdx.x == 0) { s_lo = 0; s_hi = 0; }
+  __syncthreads();
+  if ((int)threadIdx.x < sk.G) {
+    const int c = threadIdx.x;
+    const int cq = (int)sk.q[c];
+    const uint32_t cb = sk.b[c];
+    if (cq < pair || (cq == pair && cb == 0)) atomicMax(&s_lo, c);        // boundary(c) <= (pair, 0)
+    if (cq <= pair) atomicMax(&s_hi, c);                                  // boundary(c) <  (pair + 1, 0)
+  }
+  __syncthreads();
+  const int c_lo = s_lo, nsl = s_hi - s_lo + 1;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  auto perm = [&](int kp) -> int {        // tap-major k' -> the reference's row index c*kh*kw + tap
+    if (kp >= g.K0) return kp;
+    const int t = (int)fdiv((uint32_t)kp, p.divC);
+    const int c = kp - t * g.C;
+    return c * p.KK + t;
+  };
+  const float* __restrict__ base = p.ws + (size_t)(c_lo + pair) * TILE_ELEMS;
+  {
+    const int row = br * 32 + w, col = bc * 32 + lane;
+    const bool valid = row < rowsA && col < colsB;
+    float v = 0.f;
+    if (valid) {
+      const float* __restrict__ b = base + row * TB + col;
+      float sum = 0.f;
+      int s = 0;
+      for (; s + 16 <= nsl; s += 16) {
+        float t[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t[u] = __ldcg(b + (size_t)(s + u) * TILE_ELEMS);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) sum += t[u];
+      }
+      for (; s < nsl; ++s) sum += __ldcg(b + (size_t)s * TILE_ELEMS);
+      v = alpha * sum;
+      if (!(diag && col > row)) F[(size_t)perm(I * TB + row) * g.D + perm(J * TB + col)] += v;
+    }
+    tile[w][lane] = v;
+  }
+  __syncthreads();
+  {                                       // mirror image: lanes run along the original rows
+    const int col = bc * 32 + w, row = br * 32 + lane;
+    if (row < rowsA && col < colsB && !(diag && col >= row))
+      F[(size_t)perm(J * TB + col) * g.D + perm(I * TB + row)] += tile[lane][w];
   }
 }
 
@@ -1107,6 +1241,7 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
   p.flat = (KK == 1 && g.sh == 1 && g.sw == 1 && g.ph == 0 && g.pw == 0) ? 1 : 0;
   {
     const char* e = getenv("CURVATURE_B200_PFD");
+    p.tl = debug_timeline_buffer();
     const char* d = getenv("CURVATURE_B200_DBG");
     p.dbg = d ? atoi(d) : 0;
     p.pfd = e ? atoi(e) : 0;   // measured on ResNet-50: 14.5k img/s without, 14.2k / 14.0k / 13.7k at 1 / 2 / 4 revolutions
@@ -1122,38 +1257,40 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
     const long long rr = (g.R + gran - 1) / gran * gran;
     if (pb > rr) pb = rr;
     p.PB = p.PBv = (int)pb;
-    p.bw = (int)pb; p.bh = 1; p.pcw = 1; p.ppi = 1;
+    p.bw = (int)pb; p.bh = 1; p.bn = 1; p.pcw = 1; p.ppi = 1;
     p.nbox = (int)((g.R + pb - 1) / pb);
   } else {
-    // box = bw x bh output positions, bw | OW, bh | OH (no box overhangs the grid), padded to `gran` rows.
-    // Highest fill efficiency first; among equals a box that fits the target stage (largest such), else the smallest.
+    // box = bw x bh output positions of bn consecutive images, bw | OW, bh | OH (no box overhangs the output grid: an
+    // overhanging position would read real pixels through a negative tap shift; an overhanging IMAGE is all zero
+    // fill and harmless), padded to `gran` rows.  The image extent is what makes 14x14 / 7x7 / 28x28 maps fill
+    // whole MMA k-groups (2x2x16, 1x1x64, 4x4x4 positions) with boxes of several KB instead of 87 % / 77 % fill or
+    // 2 KB boxes.  Highest fill efficiency first; among equals the largest box that fits the target stage.
     const int pcap_hi = pcap;
-    int best_bw = 0, best_bh = 0, best_pb = 0;
+    int best_bw = 0, best_bh = 0, best_bn = 1, best_pb = 0;
     double best_eff = -1.0;
-    for (int bw = 1; bw <= g.OW; ++bw) {
-      if (g.OW % bw || bw * g.sw > 256) continue;
-      for (int bh = 1; bh <= g.OH; ++bh) {
-        if (g.OH % bh || bh * g.sh > 256) continue;
-        const int pbv = bw * bh, pb = (pbv + gran - 1) / gran * gran;
-        if (pb > pcap_hi) continue;
-        const double eff = (double)pbv / pb;
-        bool better;
-        if (eff > best_eff + 1e-9) better = true;
-        else if (eff < best_eff - 1e-9) better = false;
-        else {
-          const bool fit = pb <= pcap, best_fit = best_pb <= pcap;
-          if (fit != best_fit) better = fit;
-          else if (fit) better = pb > best_pb || (pb == best_pb && bw > best_bw);
-          else better = pb < best_pb || (pb == best_pb && bw > best_bw);
+    for (int bn = 1; bn <= 64; bn *= 2) {
+      if (bn > 1 && bn > g.N) break;
+      const double effn = (double)g.N / (double)((g.N + bn - 1) / bn * bn);
+      for (int bw = 1; bw <= g.OW; ++bw) {
+        if (g.OW % bw || bw * g.sw > 256) continue;
+        for (int bh = 1; bh <= g.OH; ++bh) {
+          if (g.OH % bh || bh * g.sh > 256) continue;
+          const int pbv = bw * bh * bn, pb = (pbv + gran - 1) / gran * gran;
+          if (pb > pcap_hi) continue;
+          const double eff = (double)pbv / pb * effn;
+          bool better;
+          if (eff > best_eff + 1e-9) better = true;
+          else if (eff < best_eff - 1e-9) better = false;
+          else better = pb > best_pb || (pb == best_pb && (bn < best_bn || (bn == best_bn && bw > best_bw)));
+          if (better) { best_eff = eff; best_bw = bw; best_bh = bh; best_bn = bn; best_pb = pb; }
         }
-        if (better) { best_eff = eff; best_bw = bw; best_bh = bh; best_pb = pb; }
       }
     }
     if (best_bw == 0) return false;
-    p.bw = best_bw; p.bh = best_bh; p.PBv = best_bw * best_bh; p.PB = best_pb;
+    p.bw = best_bw; p.bh = best_bh; p.bn = best_bn; p.PBv = best_bw * best_bh * best_bn; p.PB = best_pb;
     p.pcw = g.OW / best_bw;
     p.ppi = p.pcw * (g.OH / best_bh);
-    const long long nb = (long long)g.N * p.ppi;
+    const long long nb = (long long)((g.N + best_bn - 1) / best_bn) * p.ppi;
     if (nb >= (1LL << 30)) return false;
     p.nbox = (int)nb;
   }
@@ -1168,27 +1305,75 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
   if (p.T > 1) p.NBdiag = p.NBoff * (p.NBdiag / p.NBoff > 0 ? p.NBdiag / p.NBoff : 1);
   if (slots_max * p.NBoff * p.PB * 128 * 2 > NH_DATA_BYTES && p.T > 1) return false;   // needs >= 2 stages
   if ((slots_diag * 2 + 3) * p.NBdiag * p.PB * 128 > NH_DATA_BYTES) return false;      // (+ tail pad)
-  // contraction splits: same makespan model as the staged kernel, in units of 32 positions
-  const double units = (double)p.nbox * p.PB / 32.0;
-  const int maxS = (int)(units / 16) > 0 ? (int)(units / 16) : 1;
-  double best = 1e300;
-  int bestS = 1;
-  for (int S = 1; S <= maxS && S <= 8 * sms; ++S) {
-    const long long items = (long long)pl.pairs * S;
-    const long long waves = (items + sms - 1) / sms;
-    const double est = (double)waves * (units / S + 10.0) + 0.14 * (double)items;
-    if (est < best * 0.999) { best = est; bestS = S; }
-  }
-  const int nbmax = p.NBdiag > p.NBoff ? p.NBdiag : p.NBoff;
-  int bps = (p.nbox + bestS - 1) / bestS;
-  bps = (bps + nbmax - 1) / nbmax * nbmax;
-  p.bps = bps;
-  p.splits = (p.nbox + bps - 1) / bps;
-  pl.partial_bytes = (size_t)pl.pairs * p.splits * TILE_ELEMS * sizeof(float);
+  p.bps = 0; p.splits = 0;                                   // (stream-K: the partition lives in the SkTable)
+  pl.partial_bytes = (size_t)(sms + pl.pairs) * TILE_ELEMS * sizeof(float);
   const size_t numel = (size_t)g.N * g.C * g.H * g.W;
   pl.copy_bytes = pl.bf16 ? ((numel * 2 + 1023) & ~(size_t)1023)
                           : (precision == CRV_PREC_TF32 ? ((numel * 4 + 1023) & ~(size_t)1023) : 0);
   return true;
+}
+
+void host_decode_pair(int pair, int T, int& I, int& J) {   // mirror of decode_pair
+  const int noff = T * (T - 1) / 2;
+  if (pair < noff) {
+    int i = 1;
+    while ((i + 1) * i / 2 <= pair) ++i;
+    I = i; J = pair - i * (i - 1) / 2;
+  } else {
+    I = J = pair - noff;
+  }
+}
+
+// Cut the cost axis of one factor into at most `sms` equal ranges (see SkTable).  Cost of one k-group of a pair =
+// max(MMA issue/pipe time, operand bytes / beta) in ns; beta = L2 -> SM bytes per cycle per SM (the TMA side delivers
+// ~14 TB/s = 50 B/cycle/SM with boxes of >= 8 KB, so with the default the MMA term decides).
+void build_sk(const NhPlan& pl, int sms, SkTable& sk) {
+  const NhParams& p = pl.p;
+  const int CH = pl.bf16 ? 64 : 32, KPOS = pl.bf16 ? 16 : 8;
+  static const double beta = getenv("CURVATURE_B200_SK_BETA") ? atof(getenv("CURVATURE_B200_SK_BETA")) : 64.0;
+  const int P = pl.pairs;
+  std::vector<long long> w(P), nbq(P), pre(P + 1, 0);
+  long long iters = 0;
+  for (int q = 0; q < P; ++q) {
+    int I, J;
+    host_decode_pair(q, p.T, I, J);
+    const bool diag = I == J;
+    const int rowsA = std::min(TB, p.D - I * TB);
+    const int mh = (rowsA + 127) >> 7;
+    const int ncols = diag ? ((rowsA + 15) & ~15) : TB;
+    const int nslots = (rowsA + CH - 1) / CH + (diag ? 0 : TB / CH);
+    // measured with the per-CTA timeline (crv_debug_timeline), ns per k-group at ~1.85 GHz: two MMAs of N = 256: 150;
+    // one MMA: 100 / 80 / 67 at N = 256 / 128 / 64 (a single instruction per k-group is issue-bound, not pipe-bound)
+    const double mma = mh == 2 ? 150.0 * std::max(ncols / 256.0, 0.5) : 56.0 + 0.17 * ncols;
+    const double byt = (double)nslots * KPOS * 128 / beta / 1.85;
+    w[q] = (long long)std::llround(std::max(mma, byt));
+    nbq[q] = diag ? p.NBdiag : p.NBoff;
+    pre[q + 1] = pre[q] + w[q];
+    iters += (p.nbox + nbq[q] - 1) / nbq[q];
+  }
+  int G = sms < SK_MAXG ? sms : SK_MAXG;
+  if ((long long)G > iters) G = (int)iters;
+  if (G < 1) G = 1;
+  const double Wt = (double)p.nbox * (double)pre[P];
+  std::vector<std::pair<int, long long>> bd;
+  bd.push_back({0, 0});
+  for (int c = 1; c < G; ++c) {
+    const double x = Wt * c / G;
+    int q = 0;
+    while (q + 1 < P && (double)p.nbox * (double)pre[q + 1] <= x) ++q;
+    const double box = (x - (double)p.nbox * (double)pre[q]) / (double)w[q];
+    const long long nb = nbq[q];
+    long long b = (long long)std::llround(box / nb) * nb;
+    // a sliver at either end of a pair costs a pipeline ramp and an accumulator flush: snap it to the pair boundary
+    const long long its = (p.nbox + nb - 1) / nb, snap = std::min<long long>(8, its / 4) * nb;
+    if (b < snap) b = 0;
+    if (b > (long long)p.nbox - snap || b >= p.nbox) { ++q; b = 0; }
+    if (q > bd.back().first || (q == bd.back().first && b > bd.back().second)) bd.push_back({q, b});
+  }
+  if (bd.back().first >= P) bd.pop_back();
+  sk.G = (int)bd.size();
+  for (int c = 0; c < sk.G; ++c) { sk.q[c] = (uint16_t)bd[c].first; sk.b[c] = (uint32_t)bd[c].second; }
+  sk.q[sk.G] = (uint16_t)P; sk.b[sk.G] = 0;
 }
 
 }  // namespace
@@ -1406,7 +1591,7 @@ int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, vo
   } else {
     gdim[0] = (cuuint64_t)g.C; gdim[1] = (cuuint64_t)g.W; gdim[2] = (cuuint64_t)g.H; gdim[3] = (cuuint64_t)g.N;
     gstr[0] = (cuuint64_t)g.C * esz; gstr[1] = (cuuint64_t)g.W * g.C * esz; gstr[2] = (cuuint64_t)g.H * g.W * g.C * esz;
-    box[0] = chbox; box[1] = (cuuint32_t)(p.bw * g.sw); box[2] = (cuuint32_t)(p.bh * g.sh); box[3] = 1;
+    box[0] = chbox; box[1] = (cuuint32_t)(p.bw * g.sw); box[2] = (cuuint32_t)(p.bh * g.sh); box[3] = (cuuint32_t)p.bn;
     estr[0] = 1; estr[1] = (cuuint32_t)g.sw; estr[2] = (cuuint32_t)g.sh; estr[3] = 1;
   }
   const CUresult rc = tensor_map_encoder()(&map, pl.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
@@ -1414,15 +1599,17 @@ int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, vo
                                            pl.bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CRV_CHECK(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)rc);
+  SkTable sk;
+  build_sk(pl, sms, sk);
   if (pl.bf16) {
     CRV_CUDA(cudaFuncSetAttribute(syrk_nhwc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NH_SMEM_BYTES));
     profile_begin(KC_SYRK_NHWC_BF16, (double)g.R * g.D * (g.D + 1), 2.0 * g.N * g.C * g.H * g.W, s);
-    syrk_nhwc_kernel<true><<<pl.pairs * p.splits, NH_THREADS, NH_SMEM_BYTES, s>>>(p, map);
+    syrk_nhwc_kernel<true><<<sk.G, NH_THREADS, NH_SMEM_BYTES, s>>>(p, sk, map);
     profile_end(s);
   } else {
     CRV_CUDA(cudaFuncSetAttribute(syrk_nhwc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NH_SMEM_BYTES));
     profile_begin(KC_SYRK_NHWC_TF32, (double)g.R * g.D * (g.D + 1), 4.0 * g.N * g.C * g.H * g.W, s);
-    syrk_nhwc_kernel<false><<<pl.pairs * p.splits, NH_THREADS, NH_SMEM_BYTES, s>>>(p, map);
+    syrk_nhwc_kernel<false><<<sk.G, NH_THREADS, NH_SMEM_BYTES, s>>>(p, sk, map);
     profile_end(s);
   }
   CRV_CUDA(cudaGetLastError());
@@ -1430,7 +1617,7 @@ int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, vo
   memset(&rp, 0, sizeof(rp));
   rp.g = g;
   rp.divC = p.divC;
-  rp.T = p.T; rp.pairs = pl.pairs; rp.splits = p.splits;
+  rp.T = p.T; rp.pairs = pl.pairs; rp.splits = 0;
   rp.KK = p.KK;
   rp.ws = p.ws;
   cudaStream_t rs = s;
@@ -1445,12 +1632,12 @@ int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, vo
     static bool carveout_set = false;
     if (!carveout_set) {
       carveout_set = true;
-      cudaFuncSetAttribute(syrk_tc_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(syrk_sk_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       cudaGetLastError();
     }
   }
-  profile_begin(KC_SYRK_REDUCE, 0.0, (double)pl.partial_bytes + 8.0 * g.D * g.D, rs);
-  syrk_tc_reduce_kernel<<<pl.pairs * 64, 1024, 0, rs>>>(rp, alpha, F);
+  profile_begin(KC_SYRK_REDUCE, 0.0, (double)(sk.G + pl.pairs) * TILE_ELEMS * 4.0 + 8.0 * g.D * g.D, rs);
+  syrk_sk_reduce_kernel<<<pl.pairs * 64, 1024, 0, rs>>>(rp, sk, alpha, F);
   profile_end(rs);
   CRV_CUDA(cudaGetLastError());
   if (use_side) {

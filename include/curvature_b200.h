@@ -66,6 +66,11 @@ size_t      crv_workspace_bytes(int op, const int64_t* dims, int ndims);
 #define CRV_KERNEL_CLASSES 6
 int         crv_profile_enable(int on);
 int         crv_profile_collect(double* ms, double* flops, double* bytes, long long* launches, int nclasses);
+/* Profiling aid: when `buf` (device memory, >= 160 * 8 int64) is non-null, every CTA of the channels-last SYRK kernel
+ * launched afterwards writes 8 words at buf[8 * cta]: globaltimer ns at entry / after the prologue / at the first
+ * operand arrival / when the last MMA was issued / when the accumulator was drained, the number of (CTA, pair)
+ * segments, MMA k-groups issued, SM id.  Pass null to switch it off (the default). */
+int         crv_debug_timeline(long long* buf);
 
 /* K1a -- first Kronecker factor of a Conv2d layer, fused implicit im2col + SYRK + running sum:
  *   A[k1,k2] += alpha * sum_r X[k1,r] X[k2,r],   X = unfold(x) in the reference's row order

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--prec", default="tf32")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--layout", default="channels_last", choices=["channels_last", "nchw"])
+    ap.add_argument("--timeline", action="store_true", help="print the per-CTA timeline of one launch")
     args = ap.parse_args()
     prec = nat.PRECISION_NAMES[args.prec]
     dev = "cuda:0"
@@ -82,6 +83,26 @@ def main():
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
         ms = statistics.median(times[1:] or times)
+        if args.timeline:
+            tl = torch.zeros(160 * 8, dtype=torch.int64, device=dev)
+            nat.debug_timeline(tl)
+            fn()
+            torch.cuda.synchronize()
+            nat.debug_timeline(None)
+            t = tl.view(160, 8).cpu()
+            t = t[t[:, 0] > 0]
+            t0 = int(t[:, 0].min())
+            import numpy as np
+            a = t.numpy().astype(np.int64)
+            rel = lambda c: (a[:, c] - t0) / 1e3
+            print(f"   timeline ({len(a)} CTAs, us from first CTA start): start max {rel(0).max():.1f} | prologue {np.median(rel(1) - rel(0)):.1f} | "
+                  f"first data {np.median(rel(2) - rel(1)):.1f} | last MMA issued min/med/max {rel(3).min():.1f}/{np.median(rel(3)):.1f}/{rel(3).max():.1f} | "
+                  f"drained min/med/max {rel(4).min():.1f}/{np.median(rel(4)):.1f}/{rel(4).max():.1f} | segments max {a[:, 5].max()} | "
+                  f"k-groups min/med/max {a[:, 6].min()}/{int(np.median(a[:, 6]))}/{a[:, 6].max()}")
+            dur = rel(3) - rel(2)
+            rate = dur * 1e3 / np.maximum(a[:, 6], 1)
+            print(f"   ns per k-group min/med/max {rate.min():.1f}/{np.median(rate):.1f}/{rate.max():.1f}; by segments: " +
+                  ", ".join(f"{k} seg: {int((a[:, 5] == k).sum())} CTAs, MMA phase {np.median(dur[a[:, 5] == k]):.1f} us" for k in sorted(set(a[:, 5]))))
         print(f"{name:6s} K={K:5d} R={R:8d}  {ms:8.3f} ms  {R * K * (K + 1) / ms / 1e9:7.1f} TFLOP/s (algorithmic)  "
               f"{4 * x.numel() / ms / 1e6:7.0f} GB/s (input once)  | {kms}")
 
