@@ -67,11 +67,23 @@ _diag_sample = _sig("crv_diag_sample", c_int, _f32p, _f32p, c_int, c_int, c_int,
 _gemm = _sig("crv_gemm", c_int, _f32p, c_int, c_int, _f32p, c_int, c_int, _f32p, c_int, c_int, c_int, c_int,
              c_float, c_float, c_int, c_void_p)
 
+
+
+class SyrkItem(ctypes.Structure):
+    """crv_syrk_item (include/curvature_b200.h)"""
+    _fields_ = [("x", c_void_p), ("N", c_int), ("C", c_int), ("H", c_int), ("W", c_int), ("kh", c_int), ("kw", c_int),
+                ("sh", c_int), ("sw", c_int), ("ph", c_int), ("pw", c_int), ("alpha", c_float), ("F", c_void_p),
+                ("nchw", c_int)]
+
+
+_syrk_batch_ws = _sig("crv_syrk_batch_nhwc_workspace", c_size_t, POINTER(SyrkItem), c_int, c_int)
+_syrk_batch = _sig("crv_syrk_batch_nhwc", c_int, POINTER(SyrkItem), c_int, c_void_p, c_size_t, c_int, c_void_p)
+
 ABI_VERSION = _abi_version()
 EXPORTED_SYMBOLS = (
     "crv_abi_version", "crv_last_error", "crv_device_sm_count", "crv_workspace_bytes", "crv_profile_enable",
     "crv_profile_collect", "crv_debug_timeline",
-    "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc", "crv_stream_join", "crv_stream_fork",
+    "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc", "crv_syrk_batch_nhwc", "crv_syrk_batch_nhwc_workspace", "crv_stream_join", "crv_stream_fork",
     "crv_diag_accum", "crv_efb_project_accum",
     "crv_chol_inv_batched", "crv_sample_matrix_normal", "crv_round_tf32", "crv_elementwise_inv_sqrt", "crv_diag_sample",
     "crv_gemm")
@@ -275,6 +287,60 @@ def syrk_rows_accum(g, has_bias, alpha, out, precision=PREC_FP32, join=True):
     launch_calls += 1 if precision == PREC_FP32 else 2
     _check(_syrk_rows(_dev(g, "operand"), N, M, L, int(bool(has_bias)), float(alpha), _dev(out, "factor"),
                       ws.data_ptr(), ws.numel(), precision, _stream(g)), "crv_syrk_rows_accum")
+
+
+def nhwc_item(t, kernel_size, stride, padding, has_bias, alpha, out, precision):
+    """The crv_syrk_item of `out += alpha * X X^T` if the channels-last kernel can take the operand, else None.
+    `t` is a conv input (N,C,H,W) with the layer's geometry, or -- kernel_size None -- a rows operand (N,M,...)."""
+    if not _tensor_core(precision) or has_bias or t.data_ptr() % 16:
+        return None
+    if kernel_size is None:
+        N, M = t.shape[0], t.shape[1]
+        L = 1
+        for s in t.shape[2:]:
+            L *= s
+        rows_major = _is_channels_last(t) or (t.dim() == 2 and t.is_contiguous()) or \
+            (t.dim() == 4 and L == 1 and t.is_contiguous())
+        if not rows_major or tuple(out.shape) != (M, M):
+            return None
+        if not workspace_bytes(OP_SYRK_ROWS_NHWC, [N, M, L, 0, precision]):
+            return None
+        return SyrkItem(_dense(t, "operand"), N, M, 1, L, 1, 1, 1, 1, 0, 0, float(alpha), _dev(out, "factor"), 0)
+    N, C, H, W = t.shape
+    kh, kw = kernel_size
+    sh, sw = stride
+    ph, pw = padding
+    K = C * kh * kw
+    if tuple(out.shape) != (K, K):
+        return None
+    if _is_channels_last(t):
+        nchw = 0
+    elif t.is_contiguous() and C <= 4:       # the packed small-C path also takes NCHW-dense inputs
+        nchw = 1
+    else:
+        return None
+    item = SyrkItem(_dense(t, "activation"), N, C, H, W, kh, kw, sh, sw, ph, pw, float(alpha), _dev(out, "factor"), nchw)
+    if not _syrk_batch_ws(ctypes.byref(item), 1, precision):
+        return None
+    return item
+
+
+def syrk_batch_nhwc(items, precision, device, join=True):
+    """One C-ABI call for a list of crv_syrk_items (K1e): read-once factors share stream-K launches."""
+    global launch_calls
+    if not items:
+        return
+    arr = (SyrkItem * len(items))(*items)
+    nb = _syrk_batch_ws(arr, len(items), precision)
+    if not nb:
+        raise RuntimeError("crv_syrk_batch_nhwc_workspace: " + (_last_error() or b"unsupported item").decode())
+    ws = workspace(nb, device)
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream().cuda_stream
+        launch_calls += 2 * len(items)
+        _check(_syrk_batch(arr, len(items), ws.data_ptr(), ws.numel(), precision, stream), "crv_syrk_batch_nhwc")
+        if join:
+            _check(_stream_join(stream), "crv_stream_join")
 
 
 def diag_accum(wgrad, bgrad, scale, state=None, grads_out=None):

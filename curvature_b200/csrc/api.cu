@@ -197,6 +197,37 @@ int crv_syrk_rows_accum_nhwc(const float* gptr, int N, int M, int L, int has_bia
   return syrk_nhwc_launch(g, alpha, F, precision, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+static int batch_geoms(const crv_syrk_item* items, int n, std::vector<ConvGeom>& gs, std::vector<float>& alphas,
+                       std::vector<float*>& Fs) {
+  CRV_CHECK(items != nullptr && n > 0, "empty batch");
+  gs.resize(n); alphas.resize(n); Fs.resize(n);
+  for (int i = 0; i < n; ++i) {
+    const crv_syrk_item& it = items[i];
+    if (int rc = make_geom(gs[i], it.x, it.N, it.C, it.H, it.W, it.kh, it.kw, it.sh, it.sw, it.ph, it.pw, 0)) return rc;
+    gs[i].x_nchw = it.nchw ? 1 : 0;
+    alphas[i] = it.alpha;
+    Fs[i] = it.F;
+  }
+  return 0;
+}
+
+size_t crv_syrk_batch_nhwc_workspace(const crv_syrk_item* items, int n, int precision) {
+  std::vector<ConvGeom> gs;
+  std::vector<float> alphas;
+  std::vector<float*> Fs;
+  if (batch_geoms(items, n, gs, alphas, Fs)) return 0;
+  return syrk_nhwc_batch_workspace(gs.data(), n, precision);
+}
+
+int crv_syrk_batch_nhwc(const crv_syrk_item* items, int n, void* ws, size_t ws_bytes, int precision,
+                        crv_stream_t stream) {
+  std::vector<ConvGeom> gs;
+  std::vector<float> alphas;
+  std::vector<float*> Fs;
+  if (int rc = batch_geoms(items, n, gs, alphas, Fs)) return rc;
+  return syrk_nhwc_batch_launch(gs.data(), alphas.data(), Fs.data(), n, precision, ws, ws_bytes, (cudaStream_t)stream);
+}
+
 int crv_stream_join(crv_stream_t stream) { return syrk_stream_join((cudaStream_t)stream); }
 int crv_stream_fork(crv_stream_t stream) { return syrk_stream_fork((cudaStream_t)stream); }
 

@@ -43,6 +43,7 @@ struct ConvGeom {
   int D;         // K0 + has_bias
   int has_bias;
   long long R;   // N*L
+  int x_nchw;    // channels-last entry points only: 1 = x is NCHW-dense (accepted for the packed small-C path)
 };
 
 inline int make_geom(ConvGeom& g, const float* x, int N, int C, int H, int W, int kh, int kw, int sh,
@@ -61,6 +62,7 @@ inline int make_geom(ConvGeom& g, const float* x, int N, int C, int H, int W, in
   g.has_bias = has_bias ? 1 : 0;
   g.D = g.K0 + g.has_bias;
   g.R = (long long)N * g.L;
+  g.x_nchw = 0;
   CRV_CHECK((long long)N * C * H * W < (1LL << 31), "input tensor too large for 32-bit indexing");
   return 0;
 }
@@ -92,6 +94,9 @@ int syrk_stream_join(cudaStream_t s);
 int syrk_stream_fork(cudaStream_t s);
 bool syrk_nhwc_supported(const ConvGeom& g, int precision);
 size_t syrk_nhwc_workspace(const ConvGeom& g, int precision);
+size_t syrk_nhwc_batch_workspace(const ConvGeom* gs, int n, int precision);
+int syrk_nhwc_batch_launch(const ConvGeom* gs, const float* alphas, float* const* Fs, int n, int precision, void* ws,
+                           size_t ws_bytes, cudaStream_t s);
 int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,
                      cudaStream_t s);
 

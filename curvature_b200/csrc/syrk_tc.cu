@@ -825,10 +825,28 @@ struct NhParams {
   int ppi, pcw, bw, bh, bn;  // boxes per image group, boxes per box-row, box extent in output positions / images
   int sh, sw, ph, pw, flat;
   int pfd;                   // L2 prefetch distance in ring revolutions (0 = off)
-  long long* tl;             // per-CTA timeline (profiling aid, see crv_debug_timeline); null in production
-  int dbg;                   // ablation switches for profiling (bit 0: no TMA loads, bit 1: no MMAs); 0 in production
-  float* ws;
+  int K0;                    // rows that are tap-major permuted (the reduction undoes it)
+  int ldF;                   // order of the factor F (= D except on the packed path, where D counts padding rows)
+  int pk_kh, pk_kw, pk_c;    // packed small-C path: the original filter and channel count (pk_c = 0: not packed)
+  float alpha;
+  float* F;                  // the factor this item accumulates into
 };
+
+// One launch works on a GROUP of factors: the work list is the concatenation of their pair lists (global pair index
+// q; factor i owns q in [qbeg[i], qbeg[i+1])).  Read-once, HBM-bound factors of many layers share one launch (their
+// fixed costs -- launch, pipeline ramp, accumulator flush, reduction -- are paid once per CTA instead of once per
+// factor per CTA); a factor whose operand is re-read many times from L2 is a group of one, so that all SMs walk the
+// same tensor at the same time.
+constexpr int GRP_MAXF = 48;
+struct GroupParams {
+  int nf;
+  int dbg;                   // ablation switches for profiling (bit 0: no TMA loads, bit 1: no MMAs); 0 in production
+  long long* tl;             // per-CTA timeline (profiling aid, see crv_debug_timeline); null in production
+  float* ws;                 // partial tiles, slot = CTA + q
+  int qbeg[GRP_MAXF + 1];
+  NhParams f[GRP_MAXF];
+};
+struct alignas(64) GroupMaps { CUtensorMap m[GRP_MAXF]; };
 
 // MN-major descriptor for 32-bit operands.  tcgen05 accepts exactly one shared-memory layout for MN-major TF32
 // (measured with scripts/experiments/mn_major_probe.cu; CUTLASS calls it SW128_32B): 128-byte rows (32 fp32 along
@@ -911,8 +929,8 @@ __device__ __forceinline__ SegGeom seg_geom(const NhParams& p, int q) {
 // Warps: 0 and 6..12 issue TMA (8 issuers), 1 issues the MMAs and owns TMEM, 2..5 drain the accumulator.
 template <bool BF16>
 __global__ void __launch_bounds__(NH_THREADS, 1)
-syrk_nhwc_kernel(const __grid_constant__ NhParams p, const __grid_constant__ SkTable sk,
-                 const __grid_constant__ CUtensorMap tmap) {
+syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ SkTable sk,
+                 const __grid_constant__ GroupMaps maps) {
   constexpr int CH = BF16 ? 64 : 32;        // operand rows (channels) per chunk = per 128-byte smem row
   constexpr int KPOS = BF16 ? 16 : 8;       // contraction positions per MMA instruction
   extern __shared__ uint8_t smem_raw[];
@@ -926,7 +944,7 @@ syrk_nhwc_kernel(const __grid_constant__ NhParams p, const __grid_constant__ SkT
   int4* tab = reinterpret_cast<int4*>(aux + 256);              // per loaded chunk: {c0, dx, dy, slot}
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  long long* tl = p.tl ? p.tl + 8 * (size_t)blockIdx.x : nullptr;
+  long long* tl = gp.tl ? gp.tl + 8 * (size_t)blockIdx.x : nullptr;
   if (tl && threadIdx.x == 0) {
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -944,7 +962,6 @@ syrk_nhwc_kernel(const __grid_constant__ NhParams p, const __grid_constant__ SkT
     mbar_init(bar_tmem_full, 1);
     mbar_init(bar_tmem_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
@@ -956,6 +973,12 @@ syrk_nhwc_kernel(const __grid_constant__ NhParams p, const __grid_constant__ SkT
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (tl && threadIdx.x == 0) tl[1] = (long long)gtimer();
+  // factor of a global pair index (q0 <= q <= q1; factors are few: linear scan)
+  auto factor_of = [&](int q) -> int {
+    int f = 0;
+    while (f + 1 < gp.nf && q >= gp.qbeg[f + 1]) ++f;
+    return f;
+  };
 
   if (warp == 0 || warp >= 6) {
     // ---- TMA producers.  Issue is spread over NH_NPROD warps (scripts/experiments/tma_rate_probe.cu: one issuer
@@ -964,14 +987,18 @@ syrk_nhwc_kernel(const __grid_constant__ NhParams p, const __grid_constant__ SkT
     // the mbarrier / TMA instructions are predicated on one elected lane.
     const uint32_t leader = elect_one();
     const int me = (int)uni((uint32_t)(warp == 0 ? 0 : warp - 5));     // 0 .. NH_NPROD-1
-    const uint32_t box_bytes = (uint32_t)p.PBv * 128u;
     const int ptid = me * 32 + lane;
     uint32_t pph = 0;                                                   // per-stage parity of the empty barriers
     int nseg = 0;
-    for (int q = q0; q <= q1; ++q) {
+    for (int q = q0; q <= q1 && q < gp.qbeg[gp.nf]; ++q) {
+      const int fi = factor_of(q);
+      const NhParams& p = gp.f[fi];
+      const CUtensorMap* tmap = &maps.m[fi];
       const int b_begin = q == q0 ? bq0 : 0, b_end = q == q1 ? bq1 : p.nbox;
       if (b_begin >= b_end) continue;
-      const SegGeom t = seg_geom<CH>(p, q);
+      const SegGeom t = seg_geom<CH>(p, q - gp.qbeg[fi]);
+      const uint32_t box_bytes = (uint32_t)p.PBv * 128u;
+      if (leader) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
       // the previous segment's MMAs have all retired (its accumulator is complete): every stage is free, whatever
       // the stage geometry of this segment is
       if (nseg > 0) mbar_wait(bar_tmem_full, (uint32_t)(nseg - 1) & 1u);
@@ -1009,10 +1036,10 @@ syrk_nhwc_kernel(const __grid_constant__ NhParams p, const __grid_constant__ SkT
         pph ^= 1u << s;
         const uint32_t st = sbase + (uint32_t)s * stage_bytes;
         if (leader) {
-          if (mine && !(p.dbg & 1)) mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)mine * box_bytes);
+          if (mine && !(gp.dbg & 1)) mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)mine * box_bytes);
           else mbar_arrive(bars + 8 * s);
         }
-        if (!(p.dbg & 1)) {
+        if (!(gp.dbg & 1)) {
           for (int e = me; e < total; e += NH_NPROD) {
             const int j = e / nld, qq = e - j * nld;
             const uint32_t b = (uint32_t)(b0 + j);
@@ -1028,7 +1055,7 @@ syrk_nhwc_kernel(const __grid_constant__ NhParams p, const __grid_constant__ SkT
             }
             const int4 t4 = tab[qq];
             if (leader)
-              tma_load_4d(st + (uint32_t)(j * p.PB) * 128u + (uint32_t)t4.w * chunk_bytes, &tmap, t4.x, X0 + t4.y, Y0 + t4.z,
+              tma_load_4d(st + (uint32_t)(j * p.PB) * 128u + (uint32_t)t4.w * chunk_bytes, tmap, t4.x, X0 + t4.y, Y0 + t4.z,
                           Nn, bars + 8 * s);
           }
         }
@@ -1046,14 +1073,16 @@ syrk_nhwc_kernel(const __grid_constant__ NhParams p, const __grid_constant__ SkT
     const uint32_t leader = elect_one();
     const uint32_t u_tmem = uni(tmem);
     constexpr uint32_t KSTEP = (uint32_t)((KPOS * 128) >> 4);             // one MMA's positions, in 16-byte units
-    const int kpb = p.PB / KPOS;
-    const bool run = !(p.dbg & 2);
+    const bool run = !(gp.dbg & 2);
     uint32_t cph = 0;                                                     // per-stage parity of the full barriers
     int nseg = 0;
-    for (int q = q0; q <= q1; ++q) {
+    for (int q = q0; q <= q1 && q < gp.qbeg[gp.nf]; ++q) {
+      const int fi = factor_of(q);
+      const NhParams& p = gp.f[fi];
       const int b_begin = q == q0 ? bq0 : 0, b_end = q == q1 ? bq1 : p.nbox;
       if (b_begin >= b_end) continue;
-      const SegGeom t = seg_geom<CH>(p, q);
+      const SegGeom t = seg_geom<CH>(p, q - gp.qbeg[fi]);
+      const int kpb = (int)uni((uint32_t)(p.PB / KPOS));
       const uint32_t u_chunk = uni(t.chunk_bytes), u_stage = uni(t.stage_bytes);
       const int u_nstage = (int)uni((uint32_t)t.nstage), u_NB = (int)uni((uint32_t)t.NB);
       const int ub = (int)uni((uint32_t)b_begin), ue = (int)uni((uint32_t)b_end);
@@ -1102,13 +1131,15 @@ syrk_nhwc_kernel(const __grid_constant__ NhParams p, const __grid_constant__ SkT
   } else {
     // ---- epilogue warps 2..5 (TMEM lane quadrant = warp & 3): accumulator -> registers -> partial tile `CTA + pair`
     int nseg = 0;
-    for (int q = q0; q <= q1; ++q) {
+    for (int q = q0; q <= q1 && q < gp.qbeg[gp.nf]; ++q) {
+      const int fi = factor_of(q);
+      const NhParams& p = gp.f[fi];
       const int b_begin = q == q0 ? bq0 : 0, b_end = q == q1 ? bq1 : p.nbox;
       if (b_begin >= b_end) continue;
-      const SegGeom g = seg_geom<CH>(p, q);
+      const SegGeom g = seg_geom<CH>(p, q - gp.qbeg[fi]);
       ItemShape t;
       t.mh = g.mh; t.ncols = g.ncols; t.rowsA = g.rowsA;
-      epilogue_store(t, bar_tmem_full, (uint32_t)nseg & 1u, tmem, p.ws + (size_t)(blockIdx.x + q) * TILE_ELEMS, warp & 3, lane);
+      epilogue_store(t, bar_tmem_full, (uint32_t)nseg & 1u, tmem, gp.ws + (size_t)(blockIdx.x + q) * TILE_ELEMS, warp & 3, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tmem_empty);
@@ -1124,20 +1155,23 @@ syrk_nhwc_kernel(const __grid_constant__ NhParams p, const __grid_constant__ SkT
   }
 }
 
-// Fixed-order reduction for the stream-K partition: the partial tiles of pair q are slots (c + q) for the CTAs
-// c_lo..c_hi whose ranges intersect the pair, found from the boundary table; summed in CTA order.
-__global__ void __launch_bounds__(1024) syrk_sk_reduce_kernel(const __grid_constant__ TcParams p, const __grid_constant__ SkTable sk,
-                                                              const float alpha, float* __restrict__ F) {
+// Fixed-order reduction for the stream-K partition: the partial tiles of global pair q are slots (c + q) for the
+// CTAs c_lo..c_hi whose ranges intersect the pair, found from the boundary table; summed in CTA order, scaled,
+// un-permuted and added (tile + mirror image) into the pair's factor.  One launch reduces every factor of a group.
+__global__ void __launch_bounds__(1024) syrk_sk_reduce_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ SkTable sk) {
   __shared__ float tile[32][33];
   __shared__ int s_lo, s_hi;
-  const int pair = blockIdx.x >> 6, sub = blockIdx.x & 63;
+  const int q = blockIdx.x >> 6, sub = blockIdx.x & 63;
+  int fi = 0;
+  while (fi + 1 < gp.nf && q >= gp.qbeg[fi + 1]) ++fi;
+  const NhParams& p = gp.f[fi];
+  const int pair = q - gp.qbeg[fi];
   const int br = sub >> 3, bc = sub & 7;
   int I, J;
   decode_pair(pair, p.T, I, J);
   const bool diag = (I == J);
   if (diag && bc > br) return;            // diagonal blocks: lower triangle only, mirrored below (exact symmetry)
-  const ConvGeom& g = p.g;
-  const int rowsA = min(TB, g.D - I * TB);
+  const int rowsA = min(TB, p.D - I * TB);
   const int colsB = diag ? rowsA : TB;
   if (br * 32 >= rowsA || bc * 32 >= colsB) return;
   if (threadIdx.x == 0) { s_lo = 0; s_hi = 0; }
@@ -1146,19 +1180,27 @@ __global__ void __launch_bounds__(1024) syrk_sk_reduce_kernel(const __grid_const
     const int c = threadIdx.x;
     const int cq = (int)sk.q[c];
     const uint32_t cb = sk.b[c];
-    if (cq < pair || (cq == pair && cb == 0)) atomicMax(&s_lo, c);        // boundary(c) <= (pair, 0)
-    if (cq <= pair) atomicMax(&s_hi, c);                                  // boundary(c) <  (pair + 1, 0)
+    if (cq < q || (cq == q && cb == 0)) atomicMax(&s_lo, c);              // boundary(c) <= (q, 0)
+    if (cq <= q) atomicMax(&s_hi, c);                                     // boundary(c) <  (q + 1, 0)
   }
   __syncthreads();
   const int c_lo = s_lo, nsl = s_hi - s_lo + 1;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  auto perm = [&](int kp) -> int {        // tap-major k' -> the reference's row index c*kh*kw + tap
-    if (kp >= g.K0) return kp;
+  const int D = p.ldF, K0 = p.K0, C = p.C, KK = p.KK;
+  float* __restrict__ F = p.F;
+  const float alpha = p.alpha;
+  const int pk_c = p.pk_c, pk_kh = p.pk_kh, pk_kw = p.pk_kw;
+  auto perm = [&](int kp) -> int {        // tap-major k' -> the reference's row index c*kh*kw + tap (-1: padding row)
+    if (pk_c) {                           // packed path: k' = ip*64 + i2*32 + j*4 + c, filter row i = 2*ip + i2
+      const int i = 2 * (kp >> 6) + ((kp >> 5) & 1), j = (kp >> 2) & 7, c = kp & 3;
+      return (i < pk_kh && j < pk_kw && c < pk_c) ? (c * pk_kh + i) * pk_kw + j : -1;
+    }
+    if (kp >= K0) return kp;
     const int t = (int)fdiv((uint32_t)kp, p.divC);
-    const int c = kp - t * g.C;
-    return c * p.KK + t;
+    const int c = kp - t * C;
+    return c * KK + t;
   };
-  const float* __restrict__ base = p.ws + (size_t)(c_lo + pair) * TILE_ELEMS;
+  const float* __restrict__ base = gp.ws + (size_t)(c_lo + q) * TILE_ELEMS;
   {
     const int row = br * 32 + w, col = bc * 32 + lane;
     const bool valid = row < rowsA && col < colsB;
@@ -1176,15 +1218,58 @@ __global__ void __launch_bounds__(1024) syrk_sk_reduce_kernel(const __grid_const
       }
       for (; s < nsl; ++s) sum += __ldcg(b + (size_t)s * TILE_ELEMS);
       v = alpha * sum;
-      if (!(diag && col > row)) F[(size_t)perm(I * TB + row) * g.D + perm(J * TB + col)] += v;
+      const int pr = perm(I * TB + row), pc = perm(J * TB + col);
+      if (!(diag && col > row) && pr >= 0 && pc >= 0) F[(size_t)pr * D + pc] += v;
     }
     tile[w][lane] = v;
   }
   __syncthreads();
   {                                       // mirror image: lanes run along the original rows
     const int col = bc * 32 + w, row = br * 32 + lane;
-    if (row < rowsA && col < colsB && !(diag && col >= row))
-      F[(size_t)perm(J * TB + col) * g.D + perm(I * TB + row)] += tile[lane][w];
+    if (row < rowsA && col < colsB && !(diag && col >= row)) {
+      const int pr = perm(J * TB + col), pc = perm(I * TB + row);
+      if (pr >= 0 && pc >= 0) F[(size_t)pr * D + pc] += tile[lane][w];
+    }
+  }
+}
+
+// Pack pre-pass of the small-C path: Q[n][r][ow][i2*32 + j*4 + c] = bf16(x[n][c][2r + i2 - ph][ow*sw + j - pw]) (0 outside
+// the image, for j >= kw and for c >= C).  One thread writes the 64 bytes of one (n, r, ow, i2); x is addressed through
+// element strides, so NCHW-dense and channels-last inputs both work.
+__global__ void __launch_bounds__(256) pack_smallc_kernel(const float* __restrict__ x, uint4* __restrict__ Q, int N, int C, int H, int W,
+                                                          long long sN, long long sC, long long sH, long long sW, int Hq, int OW,
+                                                          int kw, int sw, int ph, int pw) {
+  const long long total = (long long)N * Hq * OW * 2;
+  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+    const int i2 = (int)(t & 1);
+    long long u = t >> 1;
+    const int ow = (int)(u % OW); u /= OW;
+    const int r = (int)(u % Hq);
+    const int n = (int)(u / Hq);
+    const int h = 2 * r + i2 - ph;
+    uint32_t o[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) o[k] = 0u;
+    if (h >= 0 && h < H) {
+      const float* __restrict__ row = x + n * sN + h * sH;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int w = ow * sw + j - pw;
+        if (j < kw && w >= 0 && w < W) {
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < C) v[c] = __ldg(row + c * sC + w * sW);
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o[2 * j]) : "f"(v[1]), "f"(v[0]));
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o[2 * j + 1]) : "f"(v[3]), "f"(v[2]));
+        }
+      }
+    }
+    uint4* dst = Q + t * 4;
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
   }
 }
 
@@ -1214,18 +1299,46 @@ struct NhPlan {
   NhParams p;
   int pairs;
   int bf16;                      // operands go through the bf16 copy
+  int pack;                      // packed small-C path: the operand the kernel sees is Q (geometry gq), made by the pack pre-pass
+  ConvGeom gq;
   size_t partial_bytes, copy_bytes;
 };
 
-bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
+bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl, bool src_is_bf16 = false);
+
+// Small-C convolutions (the ResNet stem): see the header, "packed small-C path".
+bool packable(const ConvGeom& g, int precision) {
+  return precision == CRV_PREC_BF16 && !g.has_bias && g.C <= 4 && g.kw <= 8 && g.sh == 2 && g.kh >= 2 && g.kh <= 16 &&
+         g.sw <= 8 && g.R < (1LL << 31) - 512;
+}
+bool pack_plan(const ConvGeom& g, int sms, NhPlan& pl) {
+  const int nip = (g.kh + 1) / 2;
+  ConvGeom gq;
+  static const float dummy = 0.f;
+  if (make_geom(gq, &dummy, g.N, 64, g.OH + nip - 1, g.OW, nip, 1, 1, 1, 0, 0, 0)) return false;
+  gq.x = nullptr;
+  if (!nhwc_plan(gq, CRV_PREC_BF16, sms, pl, true) || !pl.bf16) return false;
+  pl.pack = 1;
+  pl.gq = gq;
+  pl.p.ldF = g.D;
+  pl.p.pk_kh = g.kh; pl.p.pk_kw = g.kw; pl.p.pk_c = g.C;
+  pl.copy_bytes = ((size_t)gq.N * gq.H * gq.W * 64 * 2 + 1023) & ~(size_t)1023;
+  return true;
+}
+
+bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl, bool src_is_bf16) {
   const int KK = g.kh * g.kw;
+  pl.pack = 0;
+  if (!src_is_bf16 && packable(g, precision)) return pack_plan(g, sms, pl);
+  if (g.x_nchw) return false;
   if (g.has_bias || g.C < 32 || (g.C & 3) != 0) return false;
   if (KK > 1 && (g.C & 31) != 0) return false;
   if (((uintptr_t)g.x & 15) != 0) return false;
   if (g.sh > 8 || g.sw > 8) return false;
   if (g.R >= (1LL << 31) - 512) return false;
   NhParams& p = pl.p;
-  p.D = g.D; p.C = g.C; p.KK = KK; p.kw = g.kw;
+  p.D = g.D; p.C = g.C; p.KK = KK; p.kw = g.kw; p.K0 = g.K0; p.alpha = 0.f; p.F = nullptr;
+  p.ldF = g.D; p.pk_kh = p.pk_kw = p.pk_c = 0;
   p.divC = make_fastdiv((uint32_t)g.C);
   p.divKW = make_fastdiv((uint32_t)g.kw);
   p.T = (g.D + TB - 1) / TB;
@@ -1234,16 +1347,13 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
   // element then travels L2 -> SM several times -- k x k convolutions (each element feeds kh*kw operand rows) and
   // factors of three or more row blocks.  Single-tile, read-once operands are HBM-bound and stay on the direct path.
   static const int bf16_min_t = getenv("CURVATURE_B200_BF16_MIN_T") ? atoi(getenv("CURVATURE_B200_BF16_MIN_T")) : 3;
-  pl.bf16 = (precision == CRV_PREC_BF16 && (KK > 1 || p.T >= bf16_min_t) && g.C >= 64 && (g.C & 7) == 0 &&
-             (KK == 1 || (g.C & 63) == 0)) ? 1 : 0;
+  pl.bf16 = (src_is_bf16 || (precision == CRV_PREC_BF16 && (KK > 1 || p.T >= bf16_min_t) && g.C >= 64 && (g.C & 7) == 0 &&
+                             (KK == 1 || (g.C & 63) == 0))) ? 1 : 0;
   const int CH = pl.bf16 ? 64 : 32, gran = pl.bf16 ? 16 : 8;
   p.sh = g.sh; p.sw = g.sw; p.ph = g.ph; p.pw = g.pw;
   p.flat = (KK == 1 && g.sh == 1 && g.sw == 1 && g.ph == 0 && g.pw == 0) ? 1 : 0;
   {
     const char* e = getenv("CURVATURE_B200_PFD");
-    p.tl = debug_timeline_buffer();
-    const char* d = getenv("CURVATURE_B200_DBG");
-    p.dbg = d ? atoi(d) : 0;
     p.pfd = e ? atoi(e) : 0;   // measured on ResNet-50: 14.5k img/s without, 14.2k / 14.0k / 13.7k at 1 / 2 / 4 revolutions
   }
   // chunk slots per stage of the two item kinds
@@ -1253,7 +1363,8 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
   const int stage_target = p.T > 1 ? NH_STAGE_TARGET : NH_STAGE_TARGET / 2;   // single-tile factors stream from HBM
   const int pcap = stage_target / (slots_max * 128);
   if (p.flat) {
-    long long pb = pcap < 256 ? pcap : 256;
+    long long pb = (pcap < 256 ? pcap : 256) / gran * gran;     // whole MMA k-groups
+    if (pb < gran) return false;
     const long long rr = (g.R + gran - 1) / gran * gran;
     if (pb > rr) pb = rr;
     p.PB = p.PBv = (int)pb;
@@ -1306,7 +1417,7 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
   if (slots_max * p.NBoff * p.PB * 128 * 2 > NH_DATA_BYTES && p.T > 1) return false;   // needs >= 2 stages
   if ((slots_diag * 2 + 3) * p.NBdiag * p.PB * 128 > NH_DATA_BYTES) return false;      // (+ tail pad)
   p.bps = 0; p.splits = 0;                                   // (stream-K: the partition lives in the SkTable)
-  pl.partial_bytes = (size_t)(sms + pl.pairs) * TILE_ELEMS * sizeof(float);
+  pl.partial_bytes = (size_t)(SK_MAXG + pl.pairs) * TILE_ELEMS * sizeof(float);
   const size_t numel = (size_t)g.N * g.C * g.H * g.W;
   pl.copy_bytes = pl.bf16 ? ((numel * 2 + 1023) & ~(size_t)1023)
                           : (precision == CRV_PREC_TF32 ? ((numel * 4 + 1023) & ~(size_t)1023) : 0);
@@ -1324,51 +1435,64 @@ void host_decode_pair(int pair, int T, int& I, int& J) {   // mirror of decode_p
   }
 }
 
-// Cut the cost axis of one factor into at most `sms` equal ranges (see SkTable).  Cost of one k-group of a pair =
-// max(MMA issue/pipe time, operand bytes / beta) in ns; beta = L2 -> SM bytes per cycle per SM (the TMA side delivers
-// ~14 TB/s = 50 B/cycle/SM with boxes of >= 8 KB, so with the default the MMA term decides).
-void build_sk(const NhPlan& pl, int sms, SkTable& sk) {
-  const NhParams& p = pl.p;
-  const int CH = pl.bf16 ? 64 : 32, KPOS = pl.bf16 ? 16 : 8;
+// Cut the cost axis of a group of factors into at most `sms` equal ranges (see SkTable).  Cost of one k-group of a
+// pair, in ns = max(MMA issue/pipe time, operand bytes / beta, and -- for single-pair factors, which are read exactly
+// once -- operand bytes / the HBM share of one SM); beta = L2 -> SM bytes per cycle per SM (the TMA side delivers
+// ~14 TB/s = 50 B/cycle/SM with boxes of >= 8 KB, so with the default the MMA term decides for re-read operands).
+void build_sk(const std::vector<const NhPlan*>& pls, int sms, GroupParams& gp, SkTable& sk) {
   static const double beta = getenv("CURVATURE_B200_SK_BETA") ? atof(getenv("CURVATURE_B200_SK_BETA")) : 64.0;
-  const int P = pl.pairs;
-  std::vector<long long> w(P), nbq(P), pre(P + 1, 0);
+  static const double hbm = getenv("CURVATURE_B200_SK_HBM") ? atof(getenv("CURVATURE_B200_SK_HBM")) : 42.0;   // B/ns per SM
+  std::vector<double> cbox;          // cost of one box of global pair q
+  std::vector<long long> nbq, nboxq;
   long long iters = 0;
-  for (int q = 0; q < P; ++q) {
-    int I, J;
-    host_decode_pair(q, p.T, I, J);
-    const bool diag = I == J;
-    const int rowsA = std::min(TB, p.D - I * TB);
-    const int mh = (rowsA + 127) >> 7;
-    const int ncols = diag ? ((rowsA + 15) & ~15) : TB;
-    const int nslots = (rowsA + CH - 1) / CH + (diag ? 0 : TB / CH);
-    // measured with the per-CTA timeline (crv_debug_timeline), ns per k-group at ~1.85 GHz: two MMAs of N = 256: 150;
-    // one MMA: 100 / 80 / 67 at N = 256 / 128 / 64 (a single instruction per k-group is issue-bound, not pipe-bound)
-    const double mma = mh == 2 ? 150.0 * std::max(ncols / 256.0, 0.5) : 56.0 + 0.17 * ncols;
-    const double byt = (double)nslots * KPOS * 128 / beta / 1.85;
-    w[q] = (long long)std::llround(std::max(mma, byt));
-    nbq[q] = diag ? p.NBdiag : p.NBoff;
-    pre[q + 1] = pre[q] + w[q];
-    iters += (p.nbox + nbq[q] - 1) / nbq[q];
+  gp.qbeg[0] = 0;
+  for (size_t f = 0; f < pls.size(); ++f) {
+    const NhPlan& pl = *pls[f];
+    const NhParams& p = pl.p;
+    const int CH = pl.bf16 ? 64 : 32, KPOS = pl.bf16 ? 16 : 8;
+    for (int q = 0; q < pl.pairs; ++q) {
+      int I, J;
+      host_decode_pair(q, p.T, I, J);
+      const bool diag = I == J;
+      const int rowsA = std::min(TB, p.D - I * TB);
+      const int mh = (rowsA + 127) >> 7;
+      const int ncols = diag ? ((rowsA + 15) & ~15) : TB;
+      const int nslots = (rowsA + CH - 1) / CH + (diag ? 0 : TB / CH);
+      // measured with the per-CTA timeline (crv_debug_timeline), ns per k-group at ~1.85 GHz: two MMAs of N = 256:
+      // 150; one MMA: 100 / 80 / 67 at N = 256 / 128 / 64 (one instruction per k-group is issue-bound, not pipe-bound)
+      const double mma = mh == 2 ? 150.0 * std::max(ncols / 256.0, 0.5) : 56.0 + 0.17 * ncols;
+      const double bytes = (double)nslots * KPOS * 128;
+      double c = std::max(mma, bytes / beta / 1.85);
+      if (pls.size() > 1 || p.T == 1) c = std::max(c, bytes / hbm);   // nobody else walks this operand at the same time
+      cbox.push_back(c * (p.PB / KPOS));
+      nbq.push_back(diag ? p.NBdiag : p.NBoff);
+      nboxq.push_back(p.nbox);
+      iters += (p.nbox + nbq.back() - 1) / nbq.back();
+    }
+    gp.qbeg[f + 1] = gp.qbeg[f] + pl.pairs;
   }
+  const int P = (int)cbox.size();
+  std::vector<double> pre(P + 1, 0.0);
+  for (int q = 0; q < P; ++q) pre[q + 1] = pre[q] + cbox[q] * (double)nboxq[q];
   int G = sms < SK_MAXG ? sms : SK_MAXG;
   if ((long long)G > iters) G = (int)iters;
   if (G < 1) G = 1;
-  const double Wt = (double)p.nbox * (double)pre[P];
+  const double Wt = pre[P];
   std::vector<std::pair<int, long long>> bd;
   bd.push_back({0, 0});
+  int q = 0;
   for (int c = 1; c < G; ++c) {
     const double x = Wt * c / G;
-    int q = 0;
-    while (q + 1 < P && (double)p.nbox * (double)pre[q + 1] <= x) ++q;
-    const double box = (x - (double)p.nbox * (double)pre[q]) / (double)w[q];
-    const long long nb = nbq[q];
+    while (q + 1 < P && pre[q + 1] <= x) ++q;
+    int qq = q;
+    const double box = (x - pre[qq]) / cbox[qq];
+    const long long nb = nbq[qq], nbox = nboxq[qq];
     long long b = (long long)std::llround(box / nb) * nb;
     // a sliver at either end of a pair costs a pipeline ramp and an accumulator flush: snap it to the pair boundary
-    const long long its = (p.nbox + nb - 1) / nb, snap = std::min<long long>(8, its / 4) * nb;
+    const long long its = (nbox + nb - 1) / nb, snap = std::min<long long>(8, its / 4) * nb;
     if (b < snap) b = 0;
-    if (b > (long long)p.nbox - snap || b >= p.nbox) { ++q; b = 0; }
-    if (q > bd.back().first || (q == bd.back().first && b > bd.back().second)) bd.push_back({q, b});
+    if (b > nbox - snap || b >= nbox) { ++qq; b = 0; }
+    if (qq > bd.back().first || (qq == bd.back().first && b > bd.back().second)) bd.push_back({qq, b});
   }
   if (bd.back().first >= P) bd.pop_back();
   sk.G = (int)bd.size();
@@ -1523,64 +1647,23 @@ bool syrk_nhwc_supported(const ConvGeom& g, int precision) {
   return nhwc_plan(g, precision, 148, pl);
 }
 
-size_t syrk_nhwc_workspace(const ConvGeom& g, int precision) {
-  NhPlan pl;
-  if (!nhwc_plan(g, precision, device_sm_count(), pl)) return 0;
-  return 2 * (pl.partial_bytes + 4096 + pl.copy_bytes);    // two halves: main kernel i+1 writes one while reduction i reads the other
+namespace {
+// which launch a factor goes into: re-read operands (bf16 copy, or several block pairs) get a launch of their own;
+// single-pair, read-once operands share launches of up to GRP_MAXF factors
+int group_max_t() {
+  static const int t = getenv("CURVATURE_B200_GROUP_T") ? atoi(getenv("CURVATURE_B200_GROUP_T")) : 2;
+  return t;
+}
+bool rides_in_group(const NhPlan& pl) { return !pl.bf16 && pl.p.T <= group_max_t() && pl.copy_bytes == 0; }
+
+size_t launch_need(size_t pairs, size_t copy_bytes) {
+  return (size_t)(SK_MAXG + pairs) * TILE_ELEMS * sizeof(float) + 4096 + copy_bytes;
 }
 
-int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,
-                     cudaStream_t s) {
-  CRV_CHECK(precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32_TMA || precision == CRV_PREC_BF16,
-            "channels-last SYRK: tier %d is not built (available: tf32, tf32_tma, bf16)", precision);
-  CRV_CHECK(F != nullptr, "null factor pointer");
-  const int sms = device_sm_count();
-  CRV_CHECK(sms > 0, "no CUDA device");
-  NhPlan pl;
-  CRV_CHECK(nhwc_plan(g, precision, sms, pl),
-            "channels-last SYRK: unsupported geometry (needs no bias row, C %% 4 == 0, C >= 32, C %% 32 == 0 for k x k)");
-  CRV_CHECK(tensor_map_encoder() != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
-  const size_t need = 2 * (pl.partial_bytes + 4096 + pl.copy_bytes);
-  CRV_CHECK(ws != nullptr && ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
-  CRV_CHECK(((uintptr_t)ws & 15) == 0, "workspace must be 16-byte aligned");
-  // workspace half for this call; the main stream first waits for the reduction that last read it (two calls ago)
-  SideState* st = side_state();
-  const bool use_side = st && st->enabled;
-  int buf = 0;
-  if (use_side) {
-    buf = st->toggle;
-    st->toggle ^= 1;
-    if (st->red_pending[buf]) CRV_CUDA(cudaStreamWaitEvent(s, st->ev_red[buf], 0));
-  }
-  const size_t half = (ws_bytes / 2) & ~(size_t)1023;
-  char* wsb = (char*)((((uintptr_t)ws + 1023) & ~(uintptr_t)1023) + (size_t)buf * (half - 1024));
-  NhParams& p = pl.p;
-  p.ws = (float*)wsb;
-  const float* src = g.x;
-  if (pl.copy_bytes) {   // pre-pass: bf16 copy (tier bf16) or TF32 round-to-nearest copy (tier tf32), same layout
-    float* copy = (float*)((((uintptr_t)wsb + pl.partial_bytes) + 1023) & ~(uintptr_t)1023);
-    const size_t n4 = (size_t)g.N * g.C * g.H * g.W / 4;
-    const unsigned blocks = (unsigned)((n4 + 255) / 256 < (size_t)sms * 16 ? (n4 + 255) / 256 : (size_t)sms * 16);
-    cudaStream_t cs = s;
-    const bool side_cast = use_side && st->forked;
-    if (side_cast) {      // wait only for the main kernel that last read this half's copy region (two calls ago)
-      cs = st->cast;
-      if (st->main_pending[buf]) CRV_CUDA(cudaStreamWaitEvent(cs, st->ev_main[buf], 0));
-    }
-    profile_begin(KC_PREPASS, 0.0, (pl.bf16 ? 6.0 : 8.0) * (double)n4 * 4.0, cs);
-    if (pl.bf16) cast_bf16_kernel<<<blocks, 256, 0, cs>>>((const float4*)g.x, (uint2*)copy, n4);
-    else round_tf32_kernel<<<blocks, 256, 0, cs>>>((const float4*)g.x, (float4*)copy, n4);
-    profile_end(cs);
-    CRV_CUDA(cudaGetLastError());
-    if (side_cast) {
-      CRV_CUDA(cudaEventRecord(st->ev_cast[buf], cs));
-      CRV_CUDA(cudaStreamWaitEvent(s, st->ev_cast[buf], 0));
-    }
-    src = copy;
-  }
+int make_tensor_map(const ConvGeom& g, const NhPlan& pl, const void* src, CUtensorMap* map) {
+  const NhParams& p = pl.p;
   const cuuint64_t esz = pl.bf16 ? 2 : 4;
   const cuuint32_t chbox = pl.bf16 ? 64 : 32;
-  CUtensorMap map;
   cuuint64_t gdim[4], gstr[3];
   cuuint32_t box[4], estr[4];
   if (p.flat) {
@@ -1594,32 +1677,110 @@ int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, vo
     box[0] = chbox; box[1] = (cuuint32_t)(p.bw * g.sw); box[2] = (cuuint32_t)(p.bh * g.sh); box[3] = (cuuint32_t)p.bn;
     estr[0] = 1; estr[1] = (cuuint32_t)g.sw; estr[2] = (cuuint32_t)g.sh; estr[3] = 1;
   }
-  const CUresult rc = tensor_map_encoder()(&map, pl.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+  const CUresult rc = tensor_map_encoder()(map, pl.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                                            4, (void*)src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                            pl.bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CRV_CHECK(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)rc);
-  SkTable sk;
-  build_sk(pl, sms, sk);
-  if (pl.bf16) {
-    CRV_CUDA(cudaFuncSetAttribute(syrk_nhwc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NH_SMEM_BYTES));
-    profile_begin(KC_SYRK_NHWC_BF16, (double)g.R * g.D * (g.D + 1), 2.0 * g.N * g.C * g.H * g.W, s);
-    syrk_nhwc_kernel<true><<<sk.G, NH_THREADS, NH_SMEM_BYTES, s>>>(p, sk, map);
-    profile_end(s);
-  } else {
-    CRV_CUDA(cudaFuncSetAttribute(syrk_nhwc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NH_SMEM_BYTES));
-    profile_begin(KC_SYRK_NHWC_TF32, (double)g.R * g.D * (g.D + 1), 4.0 * g.N * g.C * g.H * g.W, s);
-    syrk_nhwc_kernel<false><<<sk.G, NH_THREADS, NH_SMEM_BYTES, s>>>(p, sk, map);
-    profile_end(s);
+  return 0;
+}
+
+// One launch of the stream-K kernel (+ its reduction) over the factors idx[0..cnt) -- all of the same operand type.
+int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, const std::vector<NhPlan>& plans,
+                 const int* idx, int cnt, void* ws, size_t ws_bytes, cudaStream_t s) {
+  const int sms = device_sm_count();
+  const bool bf16 = plans[idx[0]].bf16 != 0;
+  size_t pairs = 0, copy_bytes = 0;
+  for (int k = 0; k < cnt; ++k) { pairs += plans[idx[k]].pairs; copy_bytes += plans[idx[k]].copy_bytes; }
+  CRV_CHECK(cnt == 1 || copy_bytes == 0, "internal: operands with a pre-pass copy are launched one by one");
+  const size_t partial_bytes = (size_t)(SK_MAXG + pairs) * TILE_ELEMS * sizeof(float);
+  const size_t need = 2 * launch_need(pairs, copy_bytes);
+  CRV_CHECK(ws != nullptr && ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
+  CRV_CHECK(((uintptr_t)ws & 15) == 0, "workspace must be 16-byte aligned");
+  // workspace half for this call; the main stream first waits for the reduction that last read it (two calls ago)
+  SideState* st = side_state();
+  const bool use_side = st && st->enabled;
+  int buf = 0;
+  if (use_side) {
+    buf = st->toggle;
+    st->toggle ^= 1;
+    if (st->red_pending[buf]) CRV_CUDA(cudaStreamWaitEvent(s, st->ev_red[buf], 0));
   }
+  const size_t half = (ws_bytes / 2) & ~(size_t)1023;
+  char* wsb = (char*)((((uintptr_t)ws + 1023) & ~(uintptr_t)1023) + (size_t)buf * (half - 1024));
+  static GroupParams gp;       // (8 KB: kept off the stack; the library is not re-entrant, see the header)
+  static GroupMaps maps;
+  static SkTable sk;
+  gp.nf = cnt;
+  gp.ws = (float*)wsb;
+  gp.tl = debug_timeline_buffer();
+  {
+    const char* d = getenv("CURVATURE_B200_DBG");
+    gp.dbg = d ? atoi(d) : 0;
+  }
+  double flops = 0.0, bytes = 0.0, fbytes = 0.0;
+  std::vector<const NhPlan*> pls(cnt);
+  for (int k = 0; k < cnt; ++k) {
+    const ConvGeom& g = gs[idx[k]];
+    const NhPlan& pl = plans[idx[k]];
+    pls[k] = &pl;
+    gp.f[k] = pl.p;
+    gp.f[k].alpha = alphas[idx[k]];
+    gp.f[k].F = Fs[idx[k]];
+    const float* src = g.x;
+    if (pl.copy_bytes) {   // pre-pass: bf16 copy (tier bf16) / TF32 round-to-nearest copy (tier tf32), same layout; or pack
+      float* copy = (float*)((((uintptr_t)wsb + partial_bytes) + 1023) & ~(uintptr_t)1023);
+      const size_t n4 = (size_t)g.N * g.C * g.H * g.W / 4;
+      cudaStream_t cs = s;
+      const bool side_cast = use_side && st->forked;
+      if (side_cast) {      // wait only for the main kernel that last read this half's copy region (two calls ago)
+        cs = st->cast;
+        if (st->main_pending[buf]) CRV_CUDA(cudaStreamWaitEvent(cs, st->ev_main[buf], 0));
+      }
+      if (pl.pack) {
+        const ConvGeom& q = pl.gq;
+        const long long nt = (long long)q.N * q.H * q.W * 2;
+        const unsigned blocks = (unsigned)std::min<long long>((nt + 255) / 256, (long long)sms * 32);
+        long long sN, sC, sH, sW;
+        if (g.x_nchw) { sW = 1; sH = g.W; sC = (long long)g.H * g.W; sN = sC * g.C; }
+        else { sC = 1; sW = g.C; sH = (long long)g.W * g.C; sN = sH * g.H; }
+        profile_begin(KC_PREPASS, 0.0, 4.0 * g.N * g.C * g.H * g.W + (double)nt * 64.0, cs);
+        pack_smallc_kernel<<<blocks, 256, 0, cs>>>(g.x, (uint4*)copy, g.N, g.C, g.H, g.W, sN, sC, sH, sW, q.H, q.W, g.kw,
+                                                   g.sw, g.ph, g.pw);
+      } else {
+        const unsigned blocks = (unsigned)((n4 + 255) / 256 < (size_t)sms * 16 ? (n4 + 255) / 256 : (size_t)sms * 16);
+        profile_begin(KC_PREPASS, 0.0, (pl.bf16 ? 6.0 : 8.0) * (double)n4 * 4.0, cs);
+        if (pl.bf16) cast_bf16_kernel<<<blocks, 256, 0, cs>>>((const float4*)g.x, (uint2*)copy, n4);
+        else round_tf32_kernel<<<blocks, 256, 0, cs>>>((const float4*)g.x, (float4*)copy, n4);
+      }
+      profile_end(cs);
+      CRV_CUDA(cudaGetLastError());
+      if (side_cast) {
+        CRV_CUDA(cudaEventRecord(st->ev_cast[buf], cs));
+        CRV_CUDA(cudaStreamWaitEvent(s, st->ev_cast[buf], 0));
+      }
+      src = copy;
+    }
+    if (int rc = make_tensor_map(pl.pack ? pl.gq : g, pl, src, &maps.m[k])) return rc;
+    flops += (double)g.R * g.D * (g.D + 1);
+    bytes += pl.pack ? 2.0 * pl.gq.N * pl.gq.C * pl.gq.H * pl.gq.W : (pl.bf16 ? 2.0 : 4.0) * g.N * g.C * g.H * g.W;
+    fbytes += 8.0 * g.D * g.D;
+  }
+  build_sk(pls, sms, gp, sk);
+  static bool attr_set = false;
+  if (!attr_set) {
+    attr_set = true;
+    CRV_CUDA(cudaFuncSetAttribute(syrk_nhwc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NH_SMEM_BYTES));
+    CRV_CUDA(cudaFuncSetAttribute(syrk_nhwc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NH_SMEM_BYTES));
+    // same shared-memory carve-out as the SYRK kernel, or the two can never be resident on one SM at the same time
+    cudaFuncSetAttribute(syrk_sk_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaGetLastError();
+  }
+  profile_begin(bf16 ? KC_SYRK_NHWC_BF16 : KC_SYRK_NHWC_TF32, flops, bytes, s);
+  if (bf16) syrk_nhwc_kernel<true><<<sk.G, NH_THREADS, NH_SMEM_BYTES, s>>>(gp, sk, maps);
+  else syrk_nhwc_kernel<false><<<sk.G, NH_THREADS, NH_SMEM_BYTES, s>>>(gp, sk, maps);
+  profile_end(s);
   CRV_CUDA(cudaGetLastError());
-  TcParams rp;                         // the fixed-order reduction only needs the tile / permutation fields
-  memset(&rp, 0, sizeof(rp));
-  rp.g = g;
-  rp.divC = p.divC;
-  rp.T = p.T; rp.pairs = pl.pairs; rp.splits = 0;
-  rp.KK = p.KK;
-  rp.ws = p.ws;
   cudaStream_t rs = s;
   if (use_side) {
     CRV_CUDA(cudaEventRecord(st->ev_main[buf], s));
@@ -1627,17 +1788,8 @@ int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, vo
     CRV_CUDA(cudaStreamWaitEvent(st->side, st->ev_main[buf], 0));
     rs = st->side;
   }
-  {
-    // same shared-memory carve-out as the SYRK kernel, or the two cannot be resident on one SM at the same time
-    static bool carveout_set = false;
-    if (!carveout_set) {
-      carveout_set = true;
-      cudaFuncSetAttribute(syrk_sk_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      cudaGetLastError();
-    }
-  }
-  profile_begin(KC_SYRK_REDUCE, 0.0, (double)(sk.G + pl.pairs) * TILE_ELEMS * 4.0 + 8.0 * g.D * g.D, rs);
-  syrk_sk_reduce_kernel<<<pl.pairs * 64, 1024, 0, rs>>>(rp, sk, alpha, F);
+  profile_begin(KC_SYRK_REDUCE, 0.0, (double)(sk.G + pairs) * TILE_ELEMS * 4.0 + fbytes, rs);
+  syrk_sk_reduce_kernel<<<(unsigned)pairs * 64, 1024, 0, rs>>>(gp, sk);
   profile_end(rs);
   CRV_CUDA(cudaGetLastError());
   if (use_side) {
@@ -1645,6 +1797,64 @@ int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, vo
     st->red_pending[buf] = true;
   }
   return 0;
+}
+
+// plan every factor of a batch and cut the batch into launches (lists of indices into the batch)
+int plan_batch(const ConvGeom* gs, int n, int precision, std::vector<NhPlan>& plans, std::vector<std::vector<int>>& launches) {
+  CRV_CHECK(precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32_TMA || precision == CRV_PREC_BF16,
+            "channels-last SYRK: tier %d is not built (available: tf32, tf32_tma, bf16)", precision);
+  const int sms = device_sm_count();
+  CRV_CHECK(sms > 0, "no CUDA device");
+  plans.resize(n);
+  std::vector<int> grp;
+  static const int grp_max = getenv("CURVATURE_B200_GROUP") ? std::max(1, std::min(GRP_MAXF, atoi(getenv("CURVATURE_B200_GROUP")))) : GRP_MAXF;
+  for (int i = 0; i < n; ++i) {
+    CRV_CHECK(nhwc_plan(gs[i], precision, sms, plans[i]),
+              "channels-last SYRK: unsupported geometry (needs no bias row, C %% 4 == 0, C >= 32, C %% 32 == 0 for k x k)");
+    if (rides_in_group(plans[i])) {
+      grp.push_back(i);
+      if ((int)grp.size() == grp_max) { launches.push_back(grp); grp.clear(); }
+    } else {
+      launches.push_back(std::vector<int>(1, i));
+    }
+  }
+  if (!grp.empty()) launches.push_back(grp);
+  return 0;
+}
+}  // namespace
+
+size_t syrk_nhwc_batch_workspace(const ConvGeom* gs, int n, int precision) {
+  std::vector<NhPlan> plans;
+  std::vector<std::vector<int>> launches;
+  if (n <= 0 || plan_batch(gs, n, precision, plans, launches)) return 0;
+  size_t need = 0;
+  for (const auto& l : launches) {
+    size_t pairs = 0, copy = 0;
+    for (int i : l) { pairs += plans[i].pairs; copy += plans[i].copy_bytes; }
+    need = std::max(need, launch_need(pairs, copy));
+  }
+  return 2 * need;    // two halves: main kernel i+1 writes one while reduction i reads the other
+}
+
+// F_i += alpha_i * X_i X_i^T for a batch of channels-last operands.
+int syrk_nhwc_batch_launch(const ConvGeom* gs, const float* alphas, float* const* Fs, int n, int precision, void* ws,
+                           size_t ws_bytes, cudaStream_t s) {
+  CRV_CHECK(n > 0, "empty batch");
+  for (int i = 0; i < n; ++i) CRV_CHECK(Fs[i] != nullptr, "null factor pointer");
+  CRV_CHECK(tensor_map_encoder() != nullptr, "cuTensorMapEncodeTiled is not available in this driver");
+  std::vector<NhPlan> plans;
+  std::vector<std::vector<int>> launches;
+  if (int rc = plan_batch(gs, n, precision, plans, launches)) return rc;
+  for (const auto& l : launches)
+    if (int rc = launch_group(gs, alphas, Fs, plans, l.data(), (int)l.size(), ws, ws_bytes, s)) return rc;
+  return 0;
+}
+
+size_t syrk_nhwc_workspace(const ConvGeom& g, int precision) { return syrk_nhwc_batch_workspace(&g, 1, precision); }
+
+int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,
+                     cudaStream_t s) {
+  return syrk_nhwc_batch_launch(&g, &alpha, &F, 1, precision, ws, ws_bytes, s);
 }
 
 }  // namespace crv

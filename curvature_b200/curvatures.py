@@ -355,8 +355,11 @@ class KFAC(Curvature):
         `batch_size` is accepted for API compatibility; like the reference the factors are normalised by the
         recorded tensors' own shapes."""
         self._ensure_arena()
+        device = None
         if self.record:      # every recorded tensor is complete on the current stream: pre-passes may run ahead
-            nat.stream_fork(next(iter(self.record)).weight.device)
+            device = next(iter(self.record)).weight.device
+            nat.stream_fork(device)
+        batch = []           # channels-last operands: one C-ABI call for the whole step (crv_syrk_batch_nhwc)
         for layer in self.model.modules():
             module_class = layer.__class__.__name__
             if module_class in self.layer_types:
@@ -378,21 +381,36 @@ class KFAC(Curvature):
                         sh, sw = _pair(layer.stride)
                         ph, pw = _pair(layer.padding)
                         r_x = N * ((H + 2 * ph - kh) // sh + 1) * ((W + 2 * pw - kw) // sw + 1)
-                        nat.syrk_conv_accum(x, (kh, kw), (sh, sw), (ph, pw), has_bias, 1.0 / r_x, first,
-                                            self.precision, join=False)
+                        item = nat.nhwc_item(x, (kh, kw), (sh, sw), (ph, pw), has_bias, 1.0 / r_x, first, self.precision)
+                        if item is not None:
+                            batch.append(item)
+                        else:
+                            nat.syrk_conv_accum(x, (kh, kw), (sh, sw), (ph, pw), has_bias, 1.0 / r_x, first,
+                                                self.precision, join=False)
                         r_g = n_g * g.shape[2] * g.shape[3]
                     else:
                         if x.dim() != 2:
                             raise NotImplementedError("KFAC supports 2-D Linear inputs only (as the reference)")
-                        nat.syrk_rows_accum(x, has_bias, 1.0 / x.size(0), first, self.precision, join=False)
+                        item = nat.nhwc_item(x, None, None, None, has_bias, 1.0 / x.size(0), first, self.precision)
+                        if item is not None:
+                            batch.append(item)
+                        else:
+                            nat.syrk_rows_accum(x, has_bias, 1.0 / x.size(0), first, self.precision, join=False)
                         r_g = n_g
                     # reference: (g * N)(g * N)^T / R  ==  g g^T * N^2 / R
-                    nat.syrk_rows_accum(g, False, float(n_g) * float(n_g) / float(r_g), second, self.precision,
-                                        join=False)
+                    alpha_g = float(n_g) * float(n_g) / float(r_g)
+                    item = nat.nhwc_item(g, None, None, None, False, alpha_g, second, self.precision)
+                    if item is not None:
+                        batch.append(item)
+                    else:
+                        nat.syrk_rows_accum(g, False, alpha_g, second, self.precision, join=False)
                 elif module_class == 'MultiheadAttention':
                     raise NotImplementedError
+        if batch:
+            nat.syrk_batch_nhwc(batch, self.precision, device, join=False)
         # the split reductions run on the library's side stream: order the caller's stream after them
-        nat.stream_join(next(iter(self.record)).weight.device)
+        if device is not None:
+            nat.stream_join(device)
 
     def invert(self,
                add: Union[float, list, tuple] = 0.,

@@ -107,6 +107,30 @@ int crv_syrk_conv_accum_nhwc(const float* x, int N, int C, int H, int W,
 int crv_syrk_rows_accum_nhwc(const float* g, int N, int M, int L, int has_bias, float alpha, float* F,
                              void* ws, size_t ws_bytes, int precision, crv_stream_t stream);
 
+/* K1e -- a whole estimation step's factors in one call: F_i += alpha_i * X_i X_i^T for i < n, every operand
+ * channels-last as in K1c / K1d (a rows operand (N, M, L) is the item C = M, H = 1, W = L, 1x1 kernel).  This is what
+ * KFAC.update (curvature/curvatures.py:312-350, the loop over layers) maps to: read-once, HBM-bound factors of many
+ * layers share kernel launches (one stream-K work list over all of them), re-read operands get a launch each.  Same
+ * requirements, tiers and results as K1c / K1d called item by item (the partition of the work differs, every sum is
+ * still reduced in a fixed order).  crv_syrk_batch_nhwc_workspace() returns the bytes `ws` must have (0 if any item's
+ * geometry is unsupported).
+ * Packed small-C path (the ResNet stem, 3 -> 64 channels, 7x7, stride 2): a convolution with C <= 4, kw <= 8 and
+ * vertical stride 2 is first packed by a pre-pass into a bf16 tensor Q[N][OH + ceil(kh/2) - 1][OW][64] whose 64
+ * "channels" are (input row parity, 8 horizontal taps, 4 channels) -- a kw-fold, not a kh*kw-fold expansion, in ws --
+ * which turns it into a ceil(kh/2) x 1 convolution over 64 channels that the TMA-fed kernel takes; the reduction drops
+ * the padding rows and writes the factor in the reference's row order.  x may be NCHW-dense (nchw = 1) there. */
+typedef struct {
+  const float* x;
+  int N, C, H, W;
+  int kh, kw, sh, sw, ph, pw;
+  float alpha;
+  float* F;
+  int nchw;          /* 1: x is NCHW-dense instead of channels-last; accepted only for the packed small-C path below */
+} crv_syrk_item;
+size_t crv_syrk_batch_nhwc_workspace(const crv_syrk_item* items, int n, int precision);
+int crv_syrk_batch_nhwc(const crv_syrk_item* items, int n, void* ws, size_t ws_bytes, int precision,
+                        crv_stream_t stream);
+
 /* The channels-last SYRK calls enqueue their split reduction (the kernel that adds the result into the factor) on an
  * internal side stream, so that it overlaps the next call's main kernel.  crv_stream_join() makes `stream` wait (on the
  * device, no host synchronisation) for every reduction still outstanding; call it after the last SYRK call of an

@@ -589,3 +589,90 @@ def test_kfac_channels_last_model_matches_nchw_model():
     cl.sample_and_replace(noise_c)
     for (k1, v1), (k2, v2) in zip(ref_model.state_dict().items(), cl_model.state_dict().items()):
         assert v1.shape == v2.shape and rel_fro(v2, v1) <= 1e-3, (k1, rel_fro(v2, v1))
+
+
+# ---- K1e: batch call (stream-K groups) and the packed small-C path -------------------------------------------------
+PACK_GEOMS = [
+    # N, C, H, W, kernel, stride, padding      (vertical stride 2, C <= 4, kw <= 8)
+    (2, 3, 32, 32, (7, 7), (2, 2), (3, 3)),      # the ResNet stem's geometry on a small image
+    (3, 3, 17, 23, (7, 7), (2, 2), (3, 3)),      # odd sizes: ragged last rows / columns
+    (2, 1, 12, 12, (5, 5), (2, 2), (2, 2)),      # one channel
+    (2, 4, 10, 14, (3, 8), (2, 1), (1, 4)),      # C = 4, widest filter, horizontal stride 1
+    (5, 2, 9, 9, (2, 3), (2, 3), (0, 0)),        # kh = 2 (one row pair), no padding, horizontal stride 3
+]
+
+
+@pytest.mark.parametrize("geom", PACK_GEOMS)
+@pytest.mark.parametrize("nchw", [False, True])
+def test_packed_small_c_conv_bit_exact_on_integers(geom, nchw):
+    """Small-C convolutions go through the pack pre-pass (row-parity x 8 taps x 4 channels = 64 packed channels) and the
+    TMA-fed kernel as a ceil(kh/2) x 1 convolution; the reduction drops the padding rows.  Integer inputs: exact."""
+    N, C, H, W, k, s, p = geom
+    gen = torch.Generator().manual_seed(hash(geom) % (2 ** 31))
+    x = torch.randint(-2, 3, (N, C, H, W), generator=gen).float()
+    want, R = oracle_A(x, k, s, p, False)
+    K = want.shape[0]
+    out = torch.zeros(K, K, device=DEV)
+    xd = x.to(DEV)
+    if not nchw:
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    item = nat.nhwc_item(xd, k, s, p, False, 1.0, out, nat.PREC_BF16)
+    assert item is not None and item.nchw == int(nchw or C == 1)
+    nat.syrk_batch_nhwc([item], nat.PREC_BF16, xd.device)
+    assert torch.equal(out.cpu().double(), want), f"max diff {(out.cpu().double() - want).abs().max()}"
+    nat.syrk_batch_nhwc([nat.nhwc_item(xd, k, s, p, False, 2.0, out, nat.PREC_BF16)], nat.PREC_BF16, xd.device)
+    assert torch.equal(out.cpu().double(), 3 * want)
+
+
+@pytest.mark.parametrize("prec", TC_TIERS)
+def test_batch_call_equals_item_by_item_calls(prec):
+    """crv_syrk_batch_nhwc over a mixed bag of operands (grouped read-once factors, multi-block factors with their own
+    launch, more items than one group holds) gives exactly the per-item results on integer inputs."""
+    gen = torch.Generator().manual_seed(11)
+    specs = [(2, 32, 8, 8, (3, 3), (1, 1), (1, 1)), (2, 64, 7, 7, (1, 1), (1, 1), (0, 0)), (3, 288, 5, 5, (1, 1), (1, 1), (0, 0)),
+             (2, 128, 9, 9, (1, 1), (2, 2), (0, 0)), (2, 96, 12, 16, (3, 3), (1, 1), (1, 1)), (4, 40, 6, 6, (1, 1), (1, 1), (0, 0)),
+             (2, 512, 4, 4, (1, 1), (1, 1), (0, 0))]
+    specs = specs + [(3, 64 + 32 * (i % 5), 5, 6, (1, 1), (1, 1), (0, 0)) for i in range(60)]    # > GRP_MAXF grouped items
+    items, outs, wants, keep = [], [], [], []
+    for (N, C, H, W, k, s, p) in specs:
+        x = torch.randint(-2, 3, (N, C, H, W), generator=gen).float()
+        want, _ = oracle_A(x, k, s, p, False)
+        out = torch.zeros(want.shape[0], want.shape[0], device=DEV)
+        xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
+        item = nat.nhwc_item(xd, k, s, p, False, 1.0, out, prec)
+        assert item is not None
+        items.append(item); outs.append(out); wants.append(want); keep.append(xd)
+    for shape in [(5, 64), (300, 36, 2, 2), (7, 1000, 1, 1)]:
+        g = torch.randint(-3, 4, shape, generator=gen).float()
+        M = shape[1]
+        X = g.reshape(shape[0], M, -1).permute(1, 0, 2).reshape(M, -1).double()
+        gd = g.to(DEV)
+        if gd.dim() == 4:
+            gd = gd.contiguous(memory_format=torch.channels_last)
+        out = torch.zeros(M, M, device=DEV)
+        item = nat.nhwc_item(gd, None, None, None, False, 1.0, out, prec)
+        assert item is not None
+        items.append(item); outs.append(out); wants.append(X @ X.t()); keep.append(gd)
+    nat.syrk_batch_nhwc(items, prec, DEV)
+    for i, (out, want) in enumerate(zip(outs, wants)):
+        assert torch.equal(out.cpu().double(), want), f"item {i}: max diff {(out.cpu().double() - want).abs().max()}"
+    nat.syrk_batch_nhwc(items, prec, DEV)       # accumulates
+    for out, want in zip(outs, wants):
+        assert torch.equal(out.cpu().double(), 2 * want)
+
+
+def test_resnet_stem_factor_against_fp64():
+    """The 3 -> 64, 7x7, stride-2 stem at 224^2 through the packed path (bf16 operands, stated 1e-3 tier)."""
+    torch.manual_seed(5)
+    x = torch.randn(8, 3, 224, 224, device=DEV)
+    cols = F.unfold(x.double(), 7, padding=3, stride=2)
+    X = cols.permute(1, 0, 2).reshape(cols.shape[1], -1)
+    want = (X @ X.t()) / X.shape[1]
+    for xd in (x, x.contiguous(memory_format=torch.channels_last)):
+        out = torch.zeros(147, 147, device=DEV)
+        item = nat.nhwc_item(xd, (7, 7), (2, 2), (3, 3), False, 1.0 / X.shape[1], out, nat.PREC_BF16)
+        assert item is not None
+        nat.syrk_batch_nhwc([item], nat.PREC_BF16, xd.device)
+        err = rel_fro(out, want)
+        assert err <= FACTOR_TOL[nat.PREC_BF16], err
+        assert torch.equal(out, out.t())
