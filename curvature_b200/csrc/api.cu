@@ -41,6 +41,7 @@ std::vector<ProfRec> g_prof;
 std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
 }  // namespace
 
+bool profile_on() { return g_prof_on; }
 static long long* g_timeline = nullptr;
 long long* debug_timeline_buffer() { return g_timeline; }
 

@@ -81,6 +81,7 @@ enum KernelClass {
   KC_COUNT          = 6
 };
 long long* debug_timeline_buffer();
+bool profile_on();
 void profile_begin(int kclass, double flops, double bytes, cudaStream_t s);
 void profile_end(cudaStream_t s);
 

@@ -286,6 +286,51 @@ __device__ __forceinline__ void epilogue_store(const ItemShape& t, uint32_t bar_
   }
 }
 
+// Same, with coalesced stores: a lane holds 32 columns of ITS row, so a direct store instruction touches 32 rows
+// (32 sectors for 512 bytes).  Each warp instead passes its 32 x 32 block through a private 4 KB shared-memory tile
+// (16-byte chunks XOR-swizzled with the row, conflict-free both ways) and writes four whole 128-byte row segments per
+// instruction: 16x fewer memory transactions, the accumulator drains in ~1/3 of the time.
+__device__ __forceinline__ void epilogue_store_coalesced(const ItemShape& t, uint32_t bar_tmem_full, uint32_t parity, uint32_t tmem,
+                                                         float* __restrict__ wsp, int quad, int lane, uint32_t stg) {
+  mbar_wait(bar_tmem_full, parity);
+  tc_fence_after();
+  const int sub = lane >> 3, ch = lane & 7;             // read-back role: row within a group of 4, 16-byte chunk
+  for (int h = 0; h < t.mh; ++h) {
+    const int row0 = h * 128 + quad * 32;
+    for (int cc = 0; cc < t.ncols; cc += 32) {
+      uint32_t a[32];
+      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * 256 + cc);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+            "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]),
+            "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]),
+            "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      __syncwarp();                                     // the previous block has been read back
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((k ^ (lane & 7)) * 16);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a[4 * k]), "r"(a[4 * k + 1]),
+                     "r"(a[4 * k + 2]), "r"(a[4 * k + 3]) : "memory");
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r4 = 0; r4 < 8; ++r4) {
+        const int r = r4 * 4 + sub;
+        uint32_t v0, v1, v2, v3;
+        const uint32_t addr = stg + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) * 16);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr) : "memory");
+        if (row0 + r < t.rowsA && cc + ch * 4 < t.ncols)
+          *reinterpret_cast<uint4*>(wsp + (size_t)(row0 + r) * TB + cc + ch * 4) = make_uint4(v0, v1, v2, v3);
+      }
+    }
+  }
+}
+
 // ---- TMA-fed kernel ---------------------------------------------------------------------------------
 // Same tiles, same MMA loop, same epilogue; the operands are fetched by the TMA unit instead of by threads:
 // one cp.async.bulk.tensor.4d per (filter tap, channel segment) box of [channels][bh x bw positions] lands
@@ -810,8 +855,9 @@ EncodeTiledFn tensor_map_encoder() {
 constexpr int NH_THREADS = 13 * 32;            // warp 0: TMA; 1: MMA + TMEM owner; 2-5: epilogue; 6-12: TMA
 constexpr int NH_MAXSTAGE = 8;
 constexpr int NH_NPROD = 8;                   // TMA-issuing warps (one elected lane each)
-constexpr int NH_DATA_BYTES = 216 * 1024;
-constexpr int NH_SMEM_BYTES = NH_DATA_BYTES + 1024 /*barriers, chunk table*/ + 1024 /*alignment slack*/;
+constexpr int NH_DATA_BYTES = 200 * 1024;     // operand stage ring
+constexpr int NH_EPI_BYTES = 16 * 1024;       // epilogue staging: 4 warps x (32 rows x 128 B)
+constexpr int NH_SMEM_BYTES = NH_DATA_BYTES + NH_EPI_BYTES + 1024 /*barriers, chunk table*/ + 1024 /*alignment slack*/;
 static const int NH_STAGE_TARGET = getenv("CURVATURE_B200_STAGE_KB") ? atoi(getenv("CURVATURE_B200_STAGE_KB")) * 1024 : 64 * 1024;
 
 struct NhParams {
@@ -936,10 +982,11 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;
-  const uint32_t bars = sbase + NH_DATA_BYTES;                 // full[8] | empty[8] | tmem_full | tmem_empty
+  const uint32_t epi = sbase + NH_DATA_BYTES;                  // epilogue staging
+  const uint32_t bars = epi + NH_EPI_BYTES;                    // full[8] | empty[8] | tmem_full | tmem_empty
   const uint32_t bar_tmem_full = bars + 8 * (2 * NH_MAXSTAGE);
   const uint32_t bar_tmem_empty = bar_tmem_full + 8;
-  uint8_t* aux = smem_raw + (sbase - raw) + NH_DATA_BYTES;
+  uint8_t* aux = smem_raw + (sbase - raw) + NH_DATA_BYTES + NH_EPI_BYTES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 8 * (2 * NH_MAXSTAGE + 2));
   int4* tab = reinterpret_cast<int4*>(aux + 256);              // per loaded chunk: {c0, dx, dy, slot}
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1139,7 +1186,8 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       const SegGeom g = seg_geom<CH>(p, q - gp.qbeg[fi]);
       ItemShape t;
       t.mh = g.mh; t.ncols = g.ncols; t.rowsA = g.rowsA;
-      epilogue_store(t, bar_tmem_full, (uint32_t)nseg & 1u, tmem, gp.ws + (size_t)(blockIdx.x + q) * TILE_ELEMS, warp & 3, lane);
+      epilogue_store_coalesced(t, bar_tmem_full, (uint32_t)nseg & 1u, tmem, gp.ws + (size_t)(blockIdx.x + q) * TILE_ELEMS,
+                               warp & 3, lane, epi + (uint32_t)(warp & 3) * 4096u);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tmem_empty);
@@ -1231,6 +1279,78 @@ __global__ void __launch_bounds__(1024) syrk_sk_reduce_kernel(const __grid_const
       if (pr >= 0 && pc >= 0) F[(size_t)pr * D + pc] += tile[lane][w];
     }
   }
+}
+
+// Reduction for k x k convolution factors (KK = kh*kw taps, 2 <= KK <= 9, one factor per launch).  The generic kernel
+// above scatters every element of a tile to F[c1*KK + t1][c2*KK + t2] -- KK floats apart in both directions, one 32-byte
+// sector per 4-byte element, which made the 4608^2 factor's reduction cost as much as its contraction.  Here one CTA
+// owns the F rows (32 channels c1, one tap t1) x the 32*KK CONTIGUOUS columns of 32 channels c2 and all taps t2: it
+// gathers the KK sub-tiles (one per t2, each from its own block pair, transposed where only the mirror pair was
+// computed), sums their partial tiles in the same fixed CTA order, interleaves them in shared memory and adds whole
+// 32*KK-float row segments to F.  Same sums, same order, same (exactly symmetric) result.
+__global__ void __launch_bounds__(1024) syrk_sk_reduce_taps_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ SkTable sk) {
+  extern __shared__ float outbuf[];                  // [32][KK*32 + 1]
+  __shared__ int s_lo[9], s_hi[9];
+  const NhParams& p = gp.f[0];
+  const int C = p.C, KK = p.KK, T = p.T, D = p.ldF;
+  const int ncb = C >> 5;
+  const int cb2 = blockIdx.x % ncb;
+  const int t1 = (blockIdx.x / ncb) % KK;
+  const int cb1 = blockIdx.x / (ncb * KK);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int pitch = KK * 32 + 1;
+  const int noff = T * (T - 1) / 2;
+  const int k1 = t1 * C + cb1 * 32;
+  const int I1 = k1 >> 8, r1 = k1 & 255;
+  auto pair_of = [&](int t2, int& transposed, int& rr, int& cc) -> int {
+    const int k2 = t2 * C + cb2 * 32;
+    const int I2 = k2 >> 8, r2 = k2 & 255;
+    if (I1 > I2 || (I1 == I2 && r1 >= r2)) { transposed = 0; rr = r1; cc = r2; return I1 == I2 ? noff + I1 : I1 * (I1 - 1) / 2 + I2; }
+    transposed = 1; rr = r2; cc = r1;
+    return I1 == I2 ? noff + I1 : I2 * (I2 - 1) / 2 + I1;
+  };
+  if (threadIdx.x < 9) { s_lo[threadIdx.x] = 0; s_hi[threadIdx.x] = 0; }
+  __syncthreads();
+  for (int t2 = w; t2 < KK; t2 += 32) {              // one warp per tap: slots of its pair from the boundary table
+    int tr, rr, cc;
+    const int q = pair_of(t2, tr, rr, cc);
+    int lo = 0, hi = 0;
+    for (int c = lane; c < sk.G; c += 32) {
+      const int cq = (int)sk.q[c];
+      if (cq < q || (cq == q && sk.b[c] == 0)) lo = c;
+      if (cq <= q) hi = c;
+    }
+    lo = __reduce_max_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane == 0) { s_lo[t2] = lo; s_hi[t2] = hi; }
+  }
+  __syncthreads();
+  for (int t2 = 0; t2 < KK; ++t2) {
+    int tr, rr, cc;
+    const int q = pair_of(t2, tr, rr, cc);
+    const bool dsub = (k1 >> 5) == ((t2 * C + cb2 * 32) >> 5);        // the sub-tile on the factor's diagonal
+    if (dsub && lane > w) continue;                                   // lower triangle only, mirrored below
+    const int c_lo = s_lo[t2], nsl = s_hi[t2] - c_lo + 1;
+    const float* __restrict__ b = gp.ws + (size_t)(c_lo + q) * TILE_ELEMS + (rr + w) * TB + (cc + lane);
+    float sum = 0.f;
+    int sl = 0;
+    for (; sl + 16 <= nsl; sl += 16) {
+      float t[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) t[u] = __ldcg(b + (size_t)(sl + u) * TILE_ELEMS);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) sum += t[u];
+    }
+    for (; sl < nsl; ++sl) sum += __ldcg(b + (size_t)sl * TILE_ELEMS);
+    // (w, lane) is (row, column) of the stored sub-tile; in F it is (c1, c2) = (w, lane), or (lane, w) if transposed
+    if (!tr) outbuf[w * pitch + lane * KK + t2] = sum;
+    else outbuf[lane * pitch + w * KK + t2] = sum;
+    if (dsub && lane != w) outbuf[lane * pitch + w * KK + t2] = sum;
+  }
+  __syncthreads();
+  const float alpha = p.alpha;
+  float* __restrict__ Frow = p.F + (size_t)((cb1 * 32 + w) * KK + t1) * D + (size_t)cb2 * 32 * KK;
+  for (int k = lane; k < KK * 32; k += 32) Frow[k] += alpha * outbuf[w * pitch + k];
 }
 
 // Pack pre-pass of the small-C path: Q[n][r][ow][i2*32 + j*4 + c] = bf16(x[n][c][2r + i2 - ph][ow*sw + j - pw]) (0 outside
@@ -1699,7 +1819,9 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
   CRV_CHECK(((uintptr_t)ws & 15) == 0, "workspace must be 16-byte aligned");
   // workspace half for this call; the main stream first waits for the reduction that last read it (two calls ago)
   SideState* st = side_state();
-  const bool use_side = st && st->enabled;
+  // (while per-kernel event timing is on, everything runs in order on the caller's stream: an event bracket then
+  // times the kernel alone, not the kernel plus whatever shares the SMs with it)
+  const bool use_side = st && st->enabled && !profile_on();
   int buf = 0;
   if (use_side) {
     buf = st->toggle;
@@ -1789,7 +1911,19 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
     rs = st->side;
   }
   profile_begin(KC_SYRK_REDUCE, 0.0, (double)(sk.G + pairs) * TILE_ELEMS * 4.0 + fbytes, rs);
-  syrk_sk_reduce_kernel<<<(unsigned)pairs * 64, 1024, 0, rs>>>(gp, sk);
+  static const bool taps_reduce = !(getenv("CURVATURE_B200_TAPS_REDUCE") && atoi(getenv("CURVATURE_B200_TAPS_REDUCE")) == 0);
+  if (taps_reduce && cnt == 1 && !plans[idx[0]].pack && gp.f[0].KK >= 2 && gp.f[0].KK <= 9 && (gp.f[0].C & 31) == 0) {
+    const int KK = gp.f[0].KK, ncb = gp.f[0].C / 32;
+    const size_t sm = (size_t)32 * (KK * 32 + 1) * sizeof(float);
+    static bool attr2 = false;
+    if (!attr2) {
+      attr2 = true;
+      CRV_CUDA(cudaFuncSetAttribute(syrk_sk_reduce_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * (9 * 32 + 1) * 4));
+    }
+    syrk_sk_reduce_taps_kernel<<<(unsigned)(ncb * KK * ncb), 1024, sm, rs>>>(gp, sk);
+  } else {
+    syrk_sk_reduce_kernel<<<(unsigned)pairs * 64, 1024, 0, rs>>>(gp, sk);
+  }
   profile_end(rs);
   CRV_CUDA(cudaGetLastError());
   if (use_side) {

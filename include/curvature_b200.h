@@ -62,7 +62,9 @@ size_t      crv_workspace_bytes(int op, const int64_t* dims, int ndims);
  * pair recorded on the launching stream.  crv_profile_collect() waits for the recorded events, returns per kernel
  * class the summed device time (ms), the algorithmic flops and bytes of those launches and their number, and
  * clears the records.  Classes: 0 channels-last SYRK bf16, 1 channels-last SYRK tf32, 2 NCHW staged SYRK,
- * 3 split reduction, 4 cast / rounding pre-pass, 5 fp32 SIMT SYRK.  Not thread-safe; off by default. */
+ * 3 split reduction, 4 cast / rounding pre-pass, 5 fp32 SIMT SYRK.  While it is enabled the library does not use its
+ * internal side streams (reductions and pre-passes run in order on the caller's stream), so that every bracket times
+ * its kernel alone.  Not thread-safe; off by default. */
 #define CRV_KERNEL_CLASSES 6
 int         crv_profile_enable(int on);
 int         crv_profile_collect(double* ms, double* flops, double* bytes, long long* launches, int nclasses);
