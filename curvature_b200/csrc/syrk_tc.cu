@@ -852,10 +852,13 @@ EncodeTiledFn tensor_map_encoder() {
 // Positions of a box that do not exist are never loaded: box extents divide the output grid (bw | OW, bh | OH),
 // and where bw*bh is not a multiple of 8 (the contraction depth of one tf32 MMA) the remaining rows of the
 // box's shared-memory slot are zeroed once at kernel start -- TMA never writes them.
-constexpr int NH_THREADS = 13 * 32;            // warp 0: TMA; 1: MMA + TMEM owner; 2-5: epilogue; 6-12: TMA
+constexpr int NH_THREADS = 13 * 32;            // warp 0: TMA; 1: MMA + TMEM owner; 2-5: epilogue; 6-12: TMA.  Registers are
+                                               // allocated in groups of 4 warps: the kernel is capped at 96 registers (16 warps x
+                                               // 96 x 32 = 48 K) so that a reduction / pre-pass CTA fits beside it on the SM
 constexpr int NH_MAXSTAGE = 8;
 constexpr int NH_NPROD = 8;                   // TMA-issuing warps (one elected lane each)
-constexpr int NH_DATA_BYTES = 200 * 1024;     // operand stage ring
+constexpr int NH_DATA_BYTES = 192 * 1024;     // operand stage ring (3 x 64 KB / 6 x 32 KB); the CTA leaves ~16 KB of the SM's
+                                              // shared memory free so that reduction / pre-pass CTAs can be co-resident
 constexpr int NH_EPI_BYTES = 16 * 1024;       // epilogue staging: 4 warps x (32 rows x 128 B)
 constexpr int NH_SMEM_BYTES = NH_DATA_BYTES + NH_EPI_BYTES + 1024 /*barriers, chunk table*/ + 1024 /*alignment slack*/;
 static const int NH_STAGE_TARGET = getenv("CURVATURE_B200_STAGE_KB") ? atoi(getenv("CURVATURE_B200_STAGE_KB")) * 1024 : 64 * 1024;
@@ -974,7 +977,7 @@ __device__ __forceinline__ SegGeom seg_geom(const NhParams& p, int q) {
 //               half the bytes per operand element through L2 -> SM, twice the MMA rate.
 // Warps: 0 and 6..12 issue TMA (8 issuers), 1 issues the MMAs and owns TMEM, 2..5 drain the accumulator.
 template <bool BF16>
-__global__ void __launch_bounds__(NH_THREADS, 1)
+__global__ void __maxnreg__(96)
 syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ SkTable sk,
                  const __grid_constant__ GroupMaps maps) {
   constexpr int CH = BF16 ? 64 : 32;        // operand rows (channels) per chunk = per 128-byte smem row
@@ -1206,7 +1209,9 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
 // Fixed-order reduction for the stream-K partition: the partial tiles of global pair q are slots (c + q) for the
 // CTAs c_lo..c_hi whose ranges intersect the pair, found from the boundary table; summed in CTA order, scaled,
 // un-permuted and added (tile + mirror image) into the pair's factor.  One launch reduces every factor of a group.
-__global__ void __launch_bounds__(1024) syrk_sk_reduce_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ SkTable sk) {
+__global__ void __launch_bounds__(256) syrk_sk_reduce_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ SkTable sk) {
+  // 256 threads / 4 KB of shared memory per CTA: small enough to be co-resident with a SYRK CTA of the next launch
+  // (416 threads, ~211 KB), so that on the side stream the reduction really overlaps it.
   __shared__ float tile[32][33];
   __shared__ int s_lo, s_hi;
   const int q = blockIdx.x >> 6, sub = blockIdx.x & 63;
@@ -1233,7 +1238,7 @@ __global__ void __launch_bounds__(1024) syrk_sk_reduce_kernel(const __grid_const
   }
   __syncthreads();
   const int c_lo = s_lo, nsl = s_hi - s_lo + 1;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, w0 = threadIdx.x >> 5;
   const int D = p.ldF, K0 = p.K0, C = p.C, KK = p.KK;
   float* __restrict__ F = p.F;
   const float alpha = p.alpha;
@@ -1249,33 +1254,39 @@ __global__ void __launch_bounds__(1024) syrk_sk_reduce_kernel(const __grid_const
     return c * KK + t;
   };
   const float* __restrict__ base = gp.ws + (size_t)(c_lo + q) * TILE_ELEMS;
-  {
-    const int row = br * 32 + w, col = bc * 32 + lane;
+  const int col = bc * 32 + lane;
+  const int pcol = col < colsB ? perm(J * TB + col) : -1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int w = w0 + 8 * k;
+    const int row = br * 32 + w;
     const bool valid = row < rowsA && col < colsB;
     float v = 0.f;
     if (valid) {
       const float* __restrict__ b = base + row * TB + col;
       float sum = 0.f;
       int s = 0;
-      for (; s + 16 <= nsl; s += 16) {
-        float t[16];
+      for (; s + 8 <= nsl; s += 8) {
+        float t[8];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) t[u] = __ldcg(b + (size_t)(s + u) * TILE_ELEMS);
+        for (int u = 0; u < 8; ++u) t[u] = __ldcg(b + (size_t)(s + u) * TILE_ELEMS);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) sum += t[u];
+        for (int u = 0; u < 8; ++u) sum += t[u];
       }
       for (; s < nsl; ++s) sum += __ldcg(b + (size_t)s * TILE_ELEMS);
       v = alpha * sum;
-      const int pr = perm(I * TB + row), pc = perm(J * TB + col);
-      if (!(diag && col > row) && pr >= 0 && pc >= 0) F[(size_t)pr * D + pc] += v;
+      const int pr = perm(I * TB + row);
+      if (!(diag && col > row) && pr >= 0 && pcol >= 0) F[(size_t)pr * D + pcol] += v;
     }
     tile[w][lane] = v;
   }
   __syncthreads();
-  {                                       // mirror image: lanes run along the original rows
-    const int col = bc * 32 + w, row = br * 32 + lane;
-    if (row < rowsA && col < colsB && !(diag && col >= row)) {
-      const int pr = perm(J * TB + col), pc = perm(I * TB + row);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {           // mirror image: lanes run along the original rows
+    const int w = w0 + 8 * k;
+    const int colm = bc * 32 + w, rowm = br * 32 + lane;
+    if (rowm < rowsA && colm < colsB && !(diag && colm >= rowm)) {
+      const int pr = perm(J * TB + colm), pc = perm(I * TB + rowm);
       if (pr >= 0 && pc >= 0) F[(size_t)pr * D + pc] += tile[lane][w];
     }
   }
@@ -1288,32 +1299,31 @@ __global__ void __launch_bounds__(1024) syrk_sk_reduce_kernel(const __grid_const
 // gathers the KK sub-tiles (one per t2, each from its own block pair, transposed where only the mirror pair was
 // computed), sums their partial tiles in the same fixed CTA order, interleaves them in shared memory and adds whole
 // 32*KK-float row segments to F.  Same sums, same order, same (exactly symmetric) result.
-__global__ void __launch_bounds__(1024) syrk_sk_reduce_taps_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ SkTable sk) {
-  extern __shared__ float outbuf[];                  // [32][KK*32 + 1]
+__global__ void __launch_bounds__(256) syrk_sk_reduce_taps_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ SkTable sk) {
+  extern __shared__ float outbuf[];                  // [8][KK*32 + 1]
   __shared__ int s_lo[9], s_hi[9];
   const NhParams& p = gp.f[0];
   const int C = p.C, KK = p.KK, T = p.T, D = p.ldF;
   const int ncb = C >> 5;
-  const int cb2 = blockIdx.x % ncb;
+  const int cb2 = blockIdx.x % ncb;                  // 32 channels c2 (columns)
   const int t1 = (blockIdx.x / ncb) % KK;
-  const int cb1 = blockIdx.x / (ncb * KK);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int rb = blockIdx.x / (ncb * KK);            // 8 channels c1 (rows)
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int pitch = KK * 32 + 1;
   const int noff = T * (T - 1) / 2;
-  const int k1 = t1 * C + cb1 * 32;
+  const int k1 = t1 * C + rb * 8;
   const int I1 = k1 >> 8, r1 = k1 & 255;
-  auto pair_of = [&](int t2, int& transposed, int& rr, int& cc) -> int {
+  auto pair_of = [&](int t2, int& I2, int& r2) -> int {
     const int k2 = t2 * C + cb2 * 32;
-    const int I2 = k2 >> 8, r2 = k2 & 255;
-    if (I1 > I2 || (I1 == I2 && r1 >= r2)) { transposed = 0; rr = r1; cc = r2; return I1 == I2 ? noff + I1 : I1 * (I1 - 1) / 2 + I2; }
-    transposed = 1; rr = r2; cc = r1;
-    return I1 == I2 ? noff + I1 : I2 * (I2 - 1) / 2 + I1;
+    I2 = k2 >> 8; r2 = k2 & 255;
+    const int hi = max(I1, I2), lo = min(I1, I2);
+    return hi == lo ? noff + hi : hi * (hi - 1) / 2 + lo;
   };
-  if (threadIdx.x < 9) { s_lo[threadIdx.x] = 0; s_hi[threadIdx.x] = 0; }
+  if (tid < 9) { s_lo[tid] = 0; s_hi[tid] = 0; }
   __syncthreads();
-  for (int t2 = w; t2 < KK; t2 += 32) {              // one warp per tap: slots of its pair from the boundary table
-    int tr, rr, cc;
-    const int q = pair_of(t2, tr, rr, cc);
+  for (int t2 = w; t2 < KK; t2 += 8) {               // one warp per tap: slots of its pair from the boundary table
+    int I2, r2;
+    const int q = pair_of(t2, I2, r2);
     int lo = 0, hi = 0;
     for (int c = lane; c < sk.G; c += 32) {
       const int cq = (int)sk.q[c];
@@ -1326,30 +1336,35 @@ __global__ void __launch_bounds__(1024) syrk_sk_reduce_taps_kernel(const __grid_
   }
   __syncthreads();
   for (int t2 = 0; t2 < KK; ++t2) {
-    int tr, rr, cc;
-    const int q = pair_of(t2, tr, rr, cc);
-    const bool dsub = (k1 >> 5) == ((t2 * C + cb2 * 32) >> 5);        // the sub-tile on the factor's diagonal
-    if (dsub && lane > w) continue;                                   // lower triangle only, mirrored below
+    int I2, r2;
+    const int q = pair_of(t2, I2, r2);
+    // (a, b) = (c1, c2) offsets of this thread's element; the stored element is [max][min] of the two k' indices
+    // (block-wise, then within the diagonal block), read along the stored rows so that the loads coalesce
+    int a, b, sr, sc;
+    if (I1 > I2 || (I1 == I2 && r1 >= r2 + 32)) { a = tid >> 5; b = tid & 31; sr = r1 + a; sc = r2 + b; }
+    else if (I1 < I2 || r1 + 8 <= r2) { b = tid >> 3; a = tid & 7; sr = r2 + b; sc = r1 + a; }
+    else {
+      a = tid >> 5; b = tid & 31;
+      const int ka = r1 + a, kb = r2 + b;
+      sr = max(ka, kb); sc = min(ka, kb);
+    }
     const int c_lo = s_lo[t2], nsl = s_hi[t2] - c_lo + 1;
-    const float* __restrict__ b = gp.ws + (size_t)(c_lo + q) * TILE_ELEMS + (rr + w) * TB + (cc + lane);
+    const float* __restrict__ src = gp.ws + (size_t)(c_lo + q) * TILE_ELEMS + sr * TB + sc;
     float sum = 0.f;
     int sl = 0;
-    for (; sl + 16 <= nsl; sl += 16) {
-      float t[16];
+    for (; sl + 8 <= nsl; sl += 8) {
+      float t[8];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) t[u] = __ldcg(b + (size_t)(sl + u) * TILE_ELEMS);
+      for (int u = 0; u < 8; ++u) t[u] = __ldcg(src + (size_t)(sl + u) * TILE_ELEMS);
 #pragma unroll
-      for (int u = 0; u < 16; ++u) sum += t[u];
+      for (int u = 0; u < 8; ++u) sum += t[u];
     }
-    for (; sl < nsl; ++sl) sum += __ldcg(b + (size_t)sl * TILE_ELEMS);
-    // (w, lane) is (row, column) of the stored sub-tile; in F it is (c1, c2) = (w, lane), or (lane, w) if transposed
-    if (!tr) outbuf[w * pitch + lane * KK + t2] = sum;
-    else outbuf[lane * pitch + w * KK + t2] = sum;
-    if (dsub && lane != w) outbuf[lane * pitch + w * KK + t2] = sum;
+    for (; sl < nsl; ++sl) sum += __ldcg(src + (size_t)sl * TILE_ELEMS);
+    outbuf[a * pitch + b * KK + t2] = sum;
   }
   __syncthreads();
   const float alpha = p.alpha;
-  float* __restrict__ Frow = p.F + (size_t)((cb1 * 32 + w) * KK + t1) * D + (size_t)cb2 * 32 * KK;
+  float* __restrict__ Frow = p.F + (size_t)((rb * 8 + w) * KK + t1) * D + (size_t)cb2 * 32 * KK;
   for (int k = lane; k < KK * 32; k += 32) Frow[k] += alpha * outbuf[w * pitch + k];
 }
 
@@ -1703,6 +1718,10 @@ namespace {
 struct SideState {
   cudaStream_t side = nullptr;       // split reductions
   cudaStream_t cast = nullptr;       // cast / rounding pre-passes (only between crv_stream_fork and crv_stream_join)
+  cudaStream_t hp = nullptr;         // contraction kernels between fork and join: highest priority, so that the block
+                                     // scheduler places a SYRK CTA on every SM first and fills the rest of the SM with
+                                     // reduction / pre-pass CTAs (queued earlier, they would otherwise crowd it out)
+  cudaEvent_t ev_hp = nullptr;
   cudaEvent_t ev_main[2] = {nullptr, nullptr}, ev_red[2] = {nullptr, nullptr}, ev_cast[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
   bool red_pending[2] = {false, false}, main_pending[2] = {false, false};
@@ -1721,8 +1740,12 @@ SideState* side_state() {
     const char* e = getenv("CURVATURE_B200_SIDE_STREAM");
     st.enabled = !(e && atoi(e) == 0);
     if (st.enabled) {
-      bool ok = cudaStreamCreateWithFlags(&st.side, cudaStreamNonBlocking) == cudaSuccess &&
-                cudaStreamCreateWithFlags(&st.cast, cudaStreamNonBlocking) == cudaSuccess &&
+      int least = 0, greatest = 0;
+      if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); least = greatest = 0; }
+      bool ok = cudaStreamCreateWithPriority(&st.side, cudaStreamNonBlocking, least) == cudaSuccess &&
+                cudaStreamCreateWithPriority(&st.cast, cudaStreamNonBlocking, least) == cudaSuccess &&
+                cudaStreamCreateWithPriority(&st.hp, cudaStreamNonBlocking, greatest) == cudaSuccess &&
+                cudaEventCreateWithFlags(&st.ev_hp, cudaEventDisableTiming) == cudaSuccess &&
                 cudaEventCreateWithFlags(&st.ev_fork, cudaEventDisableTiming) == cudaSuccess;
       for (int i = 0; i < 2 && ok; ++i)
         ok = cudaEventCreateWithFlags(&st.ev_main[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -1744,6 +1767,10 @@ int syrk_stream_join(cudaStream_t s) {
       CRV_CUDA(cudaStreamWaitEvent(s, st->ev_red[b], 0));
       st->red_pending[b] = false;
     }
+  if (st->forked) {          // the contraction kernels of the fork ran on the internal high-priority stream
+    CRV_CUDA(cudaEventRecord(st->ev_hp, st->hp));
+    CRV_CUDA(cudaStreamWaitEvent(s, st->ev_hp, 0));
+  }
   st->forked = false;
   return 0;
 }
@@ -1756,6 +1783,7 @@ int syrk_stream_fork(cudaStream_t s) {
   if (!st || !st->enabled) return 0;
   CRV_CUDA(cudaEventRecord(st->ev_fork, s));
   CRV_CUDA(cudaStreamWaitEvent(st->cast, st->ev_fork, 0));
+  CRV_CUDA(cudaStreamWaitEvent(st->hp, st->ev_fork, 0));
   st->forked = true;
   return 0;
 }
@@ -1807,7 +1835,7 @@ int make_tensor_map(const ConvGeom& g, const NhPlan& pl, const void* src, CUtens
 
 // One launch of the stream-K kernel (+ its reduction) over the factors idx[0..cnt) -- all of the same operand type.
 int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, const std::vector<NhPlan>& plans,
-                 const int* idx, int cnt, void* ws, size_t ws_bytes, cudaStream_t s) {
+                 const int* idx, int cnt, void* ws, size_t ws_bytes, cudaStream_t caller) {
   const int sms = device_sm_count();
   const bool bf16 = plans[idx[0]].bf16 != 0;
   size_t pairs = 0, copy_bytes = 0;
@@ -1822,6 +1850,8 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
   // (while per-kernel event timing is on, everything runs in order on the caller's stream: an event bracket then
   // times the kernel alone, not the kernel plus whatever shares the SMs with it)
   const bool use_side = st && st->enabled && !profile_on();
+  // between fork and join the contraction kernels run on the internal high-priority stream (see SideState::hp)
+  cudaStream_t s = (use_side && st->forked) ? st->hp : caller;
   int buf = 0;
   if (use_side) {
     buf = st->toggle;
@@ -1896,6 +1926,8 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
     CRV_CUDA(cudaFuncSetAttribute(syrk_nhwc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NH_SMEM_BYTES));
     // same shared-memory carve-out as the SYRK kernel, or the two can never be resident on one SM at the same time
     cudaFuncSetAttribute(syrk_sk_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(syrk_sk_reduce_taps_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(cast_bf16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaGetLastError();
   }
   profile_begin(bf16 ? KC_SYRK_NHWC_BF16 : KC_SYRK_NHWC_TF32, flops, bytes, s);
@@ -1913,16 +1945,11 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
   profile_begin(KC_SYRK_REDUCE, 0.0, (double)(sk.G + pairs) * TILE_ELEMS * 4.0 + fbytes, rs);
   static const bool taps_reduce = !(getenv("CURVATURE_B200_TAPS_REDUCE") && atoi(getenv("CURVATURE_B200_TAPS_REDUCE")) == 0);
   if (taps_reduce && cnt == 1 && !plans[idx[0]].pack && gp.f[0].KK >= 2 && gp.f[0].KK <= 9 && (gp.f[0].C & 31) == 0) {
-    const int KK = gp.f[0].KK, ncb = gp.f[0].C / 32;
-    const size_t sm = (size_t)32 * (KK * 32 + 1) * sizeof(float);
-    static bool attr2 = false;
-    if (!attr2) {
-      attr2 = true;
-      CRV_CUDA(cudaFuncSetAttribute(syrk_sk_reduce_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * (9 * 32 + 1) * 4));
-    }
-    syrk_sk_reduce_taps_kernel<<<(unsigned)(ncb * KK * ncb), 1024, sm, rs>>>(gp, sk);
+    const int KK = gp.f[0].KK, C = gp.f[0].C;
+    const size_t sm = (size_t)8 * (KK * 32 + 1) * sizeof(float);
+    syrk_sk_reduce_taps_kernel<<<(unsigned)((C / 8) * KK * (C / 32)), 256, sm, rs>>>(gp, sk);
   } else {
-    syrk_sk_reduce_kernel<<<(unsigned)pairs * 64, 1024, 0, rs>>>(gp, sk);
+    syrk_sk_reduce_kernel<<<(unsigned)pairs * 64, 256, 0, rs>>>(gp, sk);
   }
   profile_end(rs);
   CRV_CUDA(cudaGetLastError());

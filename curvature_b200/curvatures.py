@@ -356,9 +356,8 @@ class KFAC(Curvature):
         recorded tensors' own shapes."""
         self._ensure_arena()
         device = None
-        if self.record:      # every recorded tensor is complete on the current stream: pre-passes may run ahead
+        if self.record:
             device = next(iter(self.record)).weight.device
-            nat.stream_fork(device)
         batch = []           # channels-last operands: one C-ABI call for the whole step (crv_syrk_batch_nhwc)
         for layer in self.model.modules():
             module_class = layer.__class__.__name__
@@ -407,6 +406,9 @@ class KFAC(Curvature):
                 elif module_class == 'MultiheadAttention':
                     raise NotImplementedError
         if batch:
+            # every recorded tensor is complete on the current stream: between this fork and the join below the library
+            # runs pre-passes, contractions and reductions on its own prioritised streams
+            nat.stream_fork(device)
             nat.syrk_batch_nhwc(batch, self.precision, device, join=False)
         # the split reductions run on the library's side stream: order the caller's stream after them
         if device is not None:
