@@ -170,6 +170,9 @@ def cpu_reference_run(args, steps, warmup, model_name, batch):
 
 def main():
     args = parse()
+    # the model's own forward / backward (torch + cuDNN, not this repo's code) is part of `e2e` only; let cuDNN pick
+    # its fastest algorithms for the fixed shapes
+    torch.backends.cudnn.benchmark = os.environ.get("CRV_BENCH_CUDNN_BENCHMARK", "1") != "0"
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))

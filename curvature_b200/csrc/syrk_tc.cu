@@ -938,10 +938,14 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
 // walks its range pair by pair; every (CTA, pair) segment accumulates in TMEM and is flushed to its own partial tile
 // (slot = CTA + pair, unique), which the fixed-order reduction sums per pair in CTA order: still bit-reproducible.
 constexpr int SK_MAXG = 160;
+constexpr int SK_MAXP = 1024;
 struct SkTable {
   int G;                      // CTAs
+  int have_slots;             // plo / pn are filled (the launch has <= SK_MAXP pairs); else the reduction scans q / b
   uint16_t q[SK_MAXG + 1];    // boundary c = (pair q[c], box b[c]); strictly increasing; q[G] = pairs, b[G] = 0
   uint32_t b[SK_MAXG + 1];
+  uint16_t plo[SK_MAXP];      // per pair: first CTA whose range intersects it ...
+  uint16_t pn[SK_MAXP];       // ... and how many do (its partial tiles are slots plo + q .. plo + q + pn - 1)
 };
 
 struct SegGeom {
@@ -1227,17 +1231,22 @@ __global__ void __launch_bounds__(256) syrk_sk_reduce_kernel(const __grid_consta
   const int rowsA = min(TB, p.D - I * TB);
   const int colsB = diag ? rowsA : TB;
   if (br * 32 >= rowsA || bc * 32 >= colsB) return;
-  if (threadIdx.x == 0) { s_lo = 0; s_hi = 0; }
-  __syncthreads();
-  if ((int)threadIdx.x < sk.G) {
-    const int c = threadIdx.x;
-    const int cq = (int)sk.q[c];
-    const uint32_t cb = sk.b[c];
-    if (cq < q || (cq == q && cb == 0)) atomicMax(&s_lo, c);              // boundary(c) <= (q, 0)
-    if (cq <= q) atomicMax(&s_hi, c);                                     // boundary(c) <  (q + 1, 0)
+  int c_lo, nsl;
+  if (sk.have_slots) {
+    c_lo = (int)sk.plo[q]; nsl = (int)sk.pn[q];
+  } else {
+    if (threadIdx.x == 0) { s_lo = 0; s_hi = 0; }
+    __syncthreads();
+    if ((int)threadIdx.x < sk.G) {
+      const int c = threadIdx.x;
+      const int cq = (int)sk.q[c];
+      const uint32_t cb = sk.b[c];
+      if (cq < q || (cq == q && cb == 0)) atomicMax(&s_lo, c);            // boundary(c) <= (q, 0)
+      if (cq <= q) atomicMax(&s_hi, c);                                   // boundary(c) <  (q + 1, 0)
+    }
+    __syncthreads();
+    c_lo = s_lo; nsl = s_hi - s_lo + 1;
   }
-  __syncthreads();
-  const int c_lo = s_lo, nsl = s_hi - s_lo + 1;
   const int lane = threadIdx.x & 31, w0 = threadIdx.x >> 5;
   const int D = p.ldF, K0 = p.K0, C = p.C, KK = p.KK;
   float* __restrict__ F = p.F;
@@ -1299,7 +1308,7 @@ __global__ void __launch_bounds__(256) syrk_sk_reduce_kernel(const __grid_consta
 // gathers the KK sub-tiles (one per t2, each from its own block pair, transposed where only the mirror pair was
 // computed), sums their partial tiles in the same fixed CTA order, interleaves them in shared memory and adds whole
 // 32*KK-float row segments to F.  Same sums, same order, same (exactly symmetric) result.
-__global__ void __launch_bounds__(256) syrk_sk_reduce_taps_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ SkTable sk) {
+__global__ void __launch_bounds__(256, 4) syrk_sk_reduce_taps_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ SkTable sk) {
   extern __shared__ float outbuf[];                  // [8][KK*32 + 1]
   __shared__ int s_lo[9], s_hi[9];
   const NhParams& p = gp.f[0];
@@ -1319,49 +1328,65 @@ __global__ void __launch_bounds__(256) syrk_sk_reduce_taps_kernel(const __grid_c
     const int hi = max(I1, I2), lo = min(I1, I2);
     return hi == lo ? noff + hi : hi * (hi - 1) / 2 + lo;
   };
-  if (tid < 9) { s_lo[tid] = 0; s_hi[tid] = 0; }
-  __syncthreads();
-  for (int t2 = w; t2 < KK; t2 += 8) {               // one warp per tap: slots of its pair from the boundary table
-    int I2, r2;
-    const int q = pair_of(t2, I2, r2);
-    int lo = 0, hi = 0;
-    for (int c = lane; c < sk.G; c += 32) {
-      const int cq = (int)sk.q[c];
-      if (cq < q || (cq == q && sk.b[c] == 0)) lo = c;
-      if (cq <= q) hi = c;
+  if (!sk.have_slots) {
+    if (tid < 9) { s_lo[tid] = 0; s_hi[tid] = 0; }
+    __syncthreads();
+    for (int t2 = w; t2 < KK; t2 += 8) {             // one warp per tap: slots of its pair from the boundary table
+      int I2, r2;
+      const int q = pair_of(t2, I2, r2);
+      int lo = 0, hi = 0;
+      for (int c = lane; c < sk.G; c += 32) {
+        const int cq = (int)sk.q[c];
+        if (cq < q || (cq == q && sk.b[c] == 0)) lo = c;
+        if (cq <= q) hi = c;
+      }
+      lo = __reduce_max_sync(0xffffffffu, lo);
+      hi = __reduce_max_sync(0xffffffffu, hi);
+      if (lane == 0) { s_lo[t2] = lo; s_hi[t2] = hi; }
     }
-    lo = __reduce_max_sync(0xffffffffu, lo);
-    hi = __reduce_max_sync(0xffffffffu, hi);
-    if (lane == 0) { s_lo[t2] = lo; s_hi[t2] = hi; }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int t2 = 0; t2 < KK; ++t2) {
-    int I2, r2;
-    const int q = pair_of(t2, I2, r2);
-    // (a, b) = (c1, c2) offsets of this thread's element; the stored element is [max][min] of the two k' indices
-    // (block-wise, then within the diagonal block), read along the stored rows so that the loads coalesce
-    int a, b, sr, sc;
-    if (I1 > I2 || (I1 == I2 && r1 >= r2 + 32)) { a = tid >> 5; b = tid & 31; sr = r1 + a; sc = r2 + b; }
-    else if (I1 < I2 || r1 + 8 <= r2) { b = tid >> 3; a = tid & 7; sr = r2 + b; sc = r1 + a; }
-    else {
-      a = tid >> 5; b = tid & 31;
-      const int ka = r1 + a, kb = r2 + b;
-      sr = max(ka, kb); sc = min(ka, kb);
-    }
-    const int c_lo = s_lo[t2], nsl = s_hi[t2] - c_lo + 1;
-    const float* __restrict__ src = gp.ws + (size_t)(c_lo + q) * TILE_ELEMS + sr * TB + sc;
-    float sum = 0.f;
-    int sl = 0;
-    for (; sl + 8 <= nsl; sl += 8) {
-      float t[8];
+  // per tap: where this thread's element lives and how many partial tiles it has; then all taps' loads of one slot
+  // index are issued together (KK independent loads in flight per round instead of a chain of KK * nsl round trips)
+  const float* src[9];
+  int nsl[9], oidx[9];
+  int nmax = 0;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) t[u] = __ldcg(src + (size_t)(sl + u) * TILE_ELEMS);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) sum += t[u];
+  for (int t2 = 0; t2 < 9; ++t2) {
+    src[t2] = gp.ws; nsl[t2] = 0; oidx[t2] = 0;
+    if (t2 < KK) {
+      int I2, r2;
+      const int q = pair_of(t2, I2, r2);
+      // (a, b) = (c1, c2) offsets of this thread's element; the stored element is [max][min] of the two k' indices
+      // (block-wise, then within the diagonal block), read along the stored rows so that the loads coalesce
+      int a, b, sr, sc;
+      if (I1 > I2 || (I1 == I2 && r1 >= r2 + 32)) { a = tid >> 5; b = tid & 31; sr = r1 + a; sc = r2 + b; }
+      else if (I1 < I2 || r1 + 8 <= r2) { b = tid >> 3; a = tid & 7; sr = r2 + b; sc = r1 + a; }
+      else {
+        a = tid >> 5; b = tid & 31;
+        const int ka = r1 + a, kb = r2 + b;
+        sr = max(ka, kb); sc = min(ka, kb);
+      }
+      const int c_lo = sk.have_slots ? (int)sk.plo[q] : s_lo[t2];
+      nsl[t2] = sk.have_slots ? (int)sk.pn[q] : s_hi[t2] - c_lo + 1;
+      nmax = max(nmax, nsl[t2]);
+      src[t2] = gp.ws + (size_t)(c_lo + q) * TILE_ELEMS + sr * TB + sc;
+      oidx[t2] = a * pitch + b * KK + t2;
     }
-    for (; sl < nsl; ++sl) sum += __ldcg(src + (size_t)sl * TILE_ELEMS);
-    outbuf[a * pitch + b * KK + t2] = sum;
   }
+  float sum[9];
+#pragma unroll
+  for (int t2 = 0; t2 < 9; ++t2) sum[t2] = 0.f;
+  for (int sl = 0; sl < nmax; ++sl) {
+    float v[9];
+#pragma unroll
+    for (int t2 = 0; t2 < 9; ++t2) v[t2] = sl < nsl[t2] ? __ldcg(src[t2] + (size_t)sl * TILE_ELEMS) : 0.f;
+#pragma unroll
+    for (int t2 = 0; t2 < 9; ++t2) sum[t2] += v[t2];          // (+0 for taps that have fewer partial tiles: exact)
+  }
+#pragma unroll
+  for (int t2 = 0; t2 < 9; ++t2)
+    if (t2 < KK) outbuf[oidx[t2]] = sum[t2];
   __syncthreads();
   const float alpha = p.alpha;
   float* __restrict__ Frow = p.F + (size_t)((rb * 8 + w) * KK + t1) * D + (size_t)cb2 * 32 * KK;
@@ -1633,6 +1658,17 @@ void build_sk(const std::vector<const NhPlan*>& pls, int sms, GroupParams& gp, S
   sk.G = (int)bd.size();
   for (int c = 0; c < sk.G; ++c) { sk.q[c] = (uint16_t)bd[c].first; sk.b[c] = (uint32_t)bd[c].second; }
   sk.q[sk.G] = (uint16_t)P; sk.b[sk.G] = 0;
+  sk.have_slots = P <= SK_MAXP ? 1 : 0;
+  if (sk.have_slots) {
+    int lo = 0, hi = 0;
+    for (int qq = 0; qq < P; ++qq) {
+      while (lo + 1 < sk.G && ((int)sk.q[lo + 1] < qq || ((int)sk.q[lo + 1] == qq && sk.b[lo + 1] == 0))) ++lo;   // last boundary <= (qq, 0)
+      if (hi < lo) hi = lo;
+      while (hi + 1 < sk.G && (int)sk.q[hi + 1] <= qq) ++hi;                                                     // last boundary < (qq + 1, 0)
+      sk.plo[qq] = (uint16_t)lo;
+      sk.pn[qq] = (uint16_t)(hi - lo + 1);
+    }
+  }
 }
 
 }  // namespace
@@ -1944,7 +1980,9 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
   }
   profile_begin(KC_SYRK_REDUCE, 0.0, (double)(sk.G + pairs) * TILE_ELEMS * 4.0 + fbytes, rs);
   static const bool taps_reduce = !(getenv("CURVATURE_B200_TAPS_REDUCE") && atoi(getenv("CURVATURE_B200_TAPS_REDUCE")) == 0);
-  if (taps_reduce && cnt == 1 && !plans[idx[0]].pack && gp.f[0].KK >= 2 && gp.f[0].KK <= 9 && (gp.f[0].C & 31) == 0) {
+  // (worth it when a pair has few partial tiles: with few pairs the generic kernel's 16-deep load batches win)
+  if (taps_reduce && cnt == 1 && !plans[idx[0]].pack && gp.f[0].KK >= 2 && gp.f[0].KK <= 9 && (gp.f[0].C & 31) == 0 &&
+      gp.f[0].T >= 8) {
     const int KK = gp.f[0].KK, C = gp.f[0].C;
     const size_t sm = (size_t)8 * (KK * 32 + 1) * sizeof(float);
     syrk_sk_reduce_taps_kernel<<<(unsigned)((C / 8) * KK * (C / 32)), 256, sm, rs>>>(gp, sk);

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CRV_ABI_VERSION 2
+#define CRV_ABI_VERSION 3
 
 typedef void* crv_stream_t; /* cudaStream_t */
 
