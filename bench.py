@@ -232,6 +232,10 @@ def main():
     # ---------------- update-only (inputs resident in HBM) ----------------
     for _ in range(args.warmup):
         kfac.update(batch)
+    if world > 1:                         # warm NCCL up on a scratch buffer of the arena's size (channels, NVLS setup)
+        scratch = torch.zeros_like(kfac.arena.flat)
+        dist.all_reduce(scratch)
+        del scratch
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = nat.launch_calls

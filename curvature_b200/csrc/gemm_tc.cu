@@ -167,29 +167,42 @@ gemm_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap ta, const _
       }
     }
   } else {
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
-                             ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
-      uint32_t acc = 0;
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % G_NSTAGE;
-        const uint32_t ph = (uint32_t)(it / G_NSTAGE) & 1u;
-        bar_wait(bars + 8 * s, ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = sbase + (uint32_t)s * G_STAGE, sb = sa + 16384u;
+    // MMA issuer: the whole warp runs the loop in uniform control flow, only the tcgen05 instructions are predicated on
+    // one elected lane, so that ptxas keeps descriptors and addresses in uniform registers (see syrk_tc.cu: an
+    // `if (lane == 0)` loop costs ~224 cycles per instruction against 64 for the N = 128 MMA itself).
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(leader));
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
+                           ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+    const uint32_t u_tmem = __reduce_max_sync(0xffffffffu, tmem);
+    // descriptor = (low word: start address + leading byte offset, constant high word); one k-step = +1024 B (MN) / +32 B (K)
+    const uint64_t da = p.a_mn ? desc_mn(0u, 4096u) : desc_k(0u), db = p.b_mn ? desc_mn(0u, 4096u) : desc_k(0u);
+    const uint32_t a_lo = (uint32_t)da, a_hi = (uint32_t)(da >> 32), b_lo = (uint32_t)db, b_hi = (uint32_t)(db >> 32);
+    const uint32_t a_step = p.a_mn ? (1024u >> 4) : (32u >> 4), b_step = p.b_mn ? (1024u >> 4) : (32u >> 4);
+    uint32_t acc = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nk; ++it) {
+      bar_wait(bars + 8 * s, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = sbase + (uint32_t)s * G_STAGE, sb = sa + 16384u;
+      const uint32_t a0 = a_lo | ((sa >> 4) & 0x3FFFu), b0 = b_lo | ((sb >> 4) & 0x3FFFu);
+      if (leader) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t ad = p.a_mn ? desc_mn(sa + (uint32_t)ks * 1024u, 4096u) : desc_k(sa + (uint32_t)ks * 32u);
-          const uint64_t bd = p.b_mn ? desc_mn(sb + (uint32_t)ks * 1024u, 4096u) : desc_k(sb + (uint32_t)ks * 32u);
-          asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
-                       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, q;\n\t}"
-                       ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
-          acc = 1;
+          asm volatile("{\n\t.reg .pred q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+                       "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                       "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, q;\n\t}"
+                       ::"r"(u_tmem), "r"(a0 + (uint32_t)ks * a_step), "r"(a_hi), "r"(b0 + (uint32_t)ks * b_step), "r"(b_hi),
+                         "r"(idesc), "r"(ks == 0 ? acc : 1u) : "memory");
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bars + 8 * (G_NSTAGE + s)) : "memory");
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_done) : "memory");
+      acc = 1;
+      if (++s == G_NSTAGE) { s = 0; ph ^= 1u; }
     }
+    if (leader)
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_done) : "memory");
     __syncwarp();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
