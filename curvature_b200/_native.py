@@ -76,6 +76,13 @@ class SyrkItem(ctypes.Structure):
                 ("nchw", c_int)]
 
 
+class DiagItem(ctypes.Structure):
+    """crv_diag_item (include/curvature_b200.h)"""
+    _fields_ = [("wgrad", c_void_p), ("bgrad", c_void_p), ("M", c_int), ("K0", c_int), ("state", c_void_p),
+                ("grads_out", c_void_p)]
+
+
+_diag_batch = _sig("crv_diag_accum_batch", c_int, POINTER(DiagItem), c_int, c_float, c_void_p)
 _syrk_batch_ws = _sig("crv_syrk_batch_nhwc_workspace", c_size_t, POINTER(SyrkItem), c_int, c_int)
 _syrk_batch = _sig("crv_syrk_batch_nhwc", c_int, POINTER(SyrkItem), c_int, c_void_p, c_size_t, c_int, c_void_p)
 
@@ -84,7 +91,7 @@ EXPORTED_SYMBOLS = (
     "crv_abi_version", "crv_last_error", "crv_device_sm_count", "crv_workspace_bytes", "crv_profile_enable",
     "crv_profile_collect", "crv_debug_timeline",
     "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc", "crv_syrk_batch_nhwc", "crv_syrk_batch_nhwc_workspace", "crv_stream_join", "crv_stream_fork",
-    "crv_diag_accum", "crv_efb_project_accum",
+    "crv_diag_accum", "crv_diag_accum_batch", "crv_efb_project_accum",
     "crv_chol_inv_batched", "crv_sample_matrix_normal", "crv_round_tf32", "crv_elementwise_inv_sqrt", "crv_diag_sample",
     "crv_gemm")
 
@@ -351,6 +358,21 @@ def diag_accum(wgrad, bgrad, scale, state=None, grads_out=None):
     launch_calls += 1
     _check(_diag_accum(_dev(wgrad, "weight.grad"), _opt(bgrad, "bias.grad"), M, K0, float(scale),
                        _opt(state, "state"), _opt(grads_out, "grads_out"), _stream(wgrad)), "crv_diag_accum")
+
+
+def diag_accum_batch(entries, scale):
+    """One launch for a list of (wgrad, bgrad or None, state or None, grads_out or None) (K2b)."""
+    global launch_calls
+    if not entries:
+        return
+    items = []
+    for wgrad, bgrad, state, grads_out in entries:
+        M = wgrad.shape[0]
+        items.append(DiagItem(_dev(wgrad, "weight.grad"), _opt(bgrad, "bias.grad"), M, wgrad.numel() // M,
+                              _opt(state, "state"), _opt(grads_out, "grads_out")))
+    arr = (DiagItem * len(items))(*items)
+    launch_calls += 1
+    _check(_diag_batch(arr, len(items), float(scale), _stream(entries[0][0])), "crv_diag_accum_batch")
 
 
 def efb_project_accum(QG, QA, G, lambdas, precision=PREC_FP32):

@@ -237,6 +237,18 @@ int crv_diag_accum(const float* wgrad, const float* bgrad, int M, int K0, float 
   return diag_accum_launch(wgrad, bgrad, M, K0, scale, state, grads_out, (cudaStream_t)stream);
 }
 
+int crv_diag_accum_batch(const crv_diag_item* items, int n, float scale, crv_stream_t stream) {
+  CRV_CHECK(items != nullptr && n > 0, "empty batch");
+  std::vector<const float*> w(n), b(n);
+  std::vector<float*> st(n), go(n);
+  std::vector<int> M(n), K0(n);
+  for (int i = 0; i < n; ++i) {
+    w[i] = items[i].wgrad; b[i] = items[i].bgrad; st[i] = items[i].state; go[i] = items[i].grads_out;
+    M[i] = items[i].M; K0[i] = items[i].K0;
+  }
+  return diag_accum_batch_launch(w.data(), b.data(), M.data(), K0.data(), scale, st.data(), go.data(), n, (cudaStream_t)stream);
+}
+
 int crv_gemm(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc,
              int m, int n, int k, float alpha, float beta, int precision, crv_stream_t stream) {
   // op(A)(i,kk): A[i*lda + kk] or, transposed, A[kk*lda + i]

@@ -118,6 +118,8 @@ int gemm_tc_launch(const float* A, long long sa_m, long long sa_k, const float* 
                    int epilogue, const SampleEpilogue* sample, int round_out, cudaStream_t s);
 int round_tf32_launch(const float* in, float* out, size_t n, cudaStream_t s);
 
+int diag_accum_batch_launch(const float* const* wgrad, const float* const* bgrad, const int* M, const int* K0, float scale,
+                            float* const* state, float* const* grads_out, int n, cudaStream_t s);
 int diag_accum_launch(const float* wgrad, const float* bgrad, int M, int K0, float scale, float* state,
                       float* grads_out, cudaStream_t s);
 int inv_sqrt_launch(const float* v, float add, float mul, float* out, size_t n, cudaStream_t s);

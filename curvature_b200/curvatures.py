@@ -249,12 +249,14 @@ class Diagonal(Curvature):
                batch_size: int):
         """Accumulates the squared gradients of all selected layers (call after `backward`)."""
         self._ensure_arena()
+        entries = []
         for key, weight, bias in self._entries():
             wg = _grad_of(weight, 'weight')
             bg = _grad_of(bias, 'bias') if bias is not None else None
             if key not in self.state:
                 self.state[key] = self._views[key]
-            nat.diag_accum(wg, bg, batch_size, state=self.state[key])
+            entries.append((wg, bg, self.state[key], None))
+        nat.diag_accum_batch(entries, batch_size)      # one launch for the whole model (crv_diag_accum_batch)
 
     def invert(self,
                add: Union[float, list, tuple] = 0.,
@@ -502,6 +504,7 @@ class EFB(Curvature):
     def update(self,
                batch_size: int):
         self._ensure_arena()
+        entries, work = [], []
         for name, layer in self._selected():
             if name in ['Linear', 'Conv2d']:
                 wg = _grad_of(layer.weight, 'weight')
@@ -509,15 +512,19 @@ class EFB(Curvature):
                 if layer not in self.state:
                     self.state[layer], self.diags[layer] = self._views[layer]
                 grads = torch.empty_like(self.state[layer])
-                nat.diag_accum(wg, bg, batch_size, state=self.diags[layer], grads_out=grads)
-                qa, qg = self.eigvecs[layer]
-                tier = _gemm_tier(self.precision)
-                if tier != nat.PREC_FP32:      # eigenbases rounded to TF32 once, the gradient copy in place
-                    qa, qg = _rounded(self.__dict__.setdefault('_eig_tf32', {}), layer, (qa, qg))
-                    nat.round_tf32(grads, out=grads)
-                nat.efb_project_accum(qg, qa, grads, self.state[layer], tier)
+                entries.append((wg, bg, self.diags[layer], grads))
+                work.append((layer, grads))
             elif name == 'MultiheadAttention':
                 raise NotImplementedError
+        # diags += batch_size * g^2 and the concatenated gradient copies, one launch for the whole model
+        nat.diag_accum_batch(entries, batch_size)
+        tier = _gemm_tier(self.precision)
+        for layer, grads in work:
+            qa, qg = self.eigvecs[layer]
+            if tier != nat.PREC_FP32:      # eigenbases rounded to TF32 once, the gradient copy in place
+                qa, qg = _rounded(self.__dict__.setdefault('_eig_tf32', {}), layer, (qa, qg))
+                nat.round_tf32(grads, out=grads)
+            nat.efb_project_accum(qg, qa, grads, self.state[layer], tier)
 
     def invert(self,
                add: Union[float, list, tuple] = 0.,

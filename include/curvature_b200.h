@@ -152,6 +152,17 @@ int crv_stream_fork(crv_stream_t stream);
 int crv_diag_accum(const float* wgrad, const float* bgrad, int M, int K0, float scale,
                    float* state, float* grads_out, crv_stream_t stream);
 
+/* K2b -- the same for every parameter group of the model in ONE launch (what Diagonal.update, curvatures.py:141-158,
+ * and the diags half of EFB.update, :431-434, loop over): per-layer launches are latency-bound at a few MB each. */
+typedef struct {
+  const float* wgrad;   /* (M, K0) */
+  const float* bgrad;   /* (M) or null */
+  int M, K0;
+  float* state;         /* (M, K0 + has_bias) running sum, or null */
+  float* grads_out;     /* optional copy of [wgrad | bgrad], or null */
+} crv_diag_item;
+int crv_diag_accum_batch(const crv_diag_item* items, int n, float scale, crv_stream_t stream);
+
 /* K3 -- EFB eigenbasis projection (curvatures.py:427-433):
  *   lambdas[m,k] += ((QG^T * G * QA)[m,k])^2,   QG (M,M), G (M,K), QA (K,K).
  * ws holds the (M,K) intermediate.  precision: CRV_PREC_FP32 = CUDA-core fp32 GEMMs; any tensor-core tier = two

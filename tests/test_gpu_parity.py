@@ -676,3 +676,30 @@ def test_resnet_stem_factor_against_fp64():
         err = rel_fro(out, want)
         assert err <= FACTOR_TOL[nat.PREC_BF16], err
         assert torch.equal(out, out.t())
+
+
+def test_diag_accum_batch_matches_per_layer_calls():
+    """crv_diag_accum_batch (one launch for all parameter groups) == crv_diag_accum layer by layer, bit for bit."""
+    torch.manual_seed(9)
+    shapes = [(6, 25, True), (16, 150, True), (7, 64, False), (1000, 2048, True), (3, 1, True), (64, 147, False), (512, 4608, False),
+              (5, 3, False), (2048, 512, False)]
+    entries, wants_s, wants_g = [], [], []
+    for M, K0, bias in shapes:
+        wg = torch.randn(M, K0, device=DEV)
+        bg = torch.randn(M, device=DEV) if bias else None
+        K = K0 + int(bias)
+        s0 = torch.rand(M, K, device=DEV)
+        s_ref, g_ref = s0.clone(), torch.empty(M, K, device=DEV)
+        nat.diag_accum(wg, bg, 37.0, state=s_ref, grads_out=g_ref)
+        s_new, g_new = s0.clone(), torch.empty(M, K, device=DEV)
+        entries.append((wg, bg, s_new, g_new))
+        wants_s.append(s_ref); wants_g.append(g_ref)
+    nat.diag_accum_batch(entries, 37.0)
+    for (wg, bg, s_new, g_new), s_ref, g_ref in zip(entries, wants_s, wants_g):
+        assert torch.equal(s_new, s_ref) and torch.equal(g_new, g_ref)
+    # state only / grads only
+    wg = torch.randn(40, 9, device=DEV)
+    s1, s2 = torch.zeros(40, 9, device=DEV), torch.zeros(40, 9, device=DEV)
+    g2 = torch.empty(40, 9, device=DEV)
+    nat.diag_accum_batch([(wg, None, s1, None), (wg, None, None, g2)], 2.0)
+    assert torch.equal(s1, 2.0 * wg * wg) and torch.equal(g2, wg)
