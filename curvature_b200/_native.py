@@ -76,6 +76,25 @@ class SyrkItem(ctypes.Structure):
                 ("nchw", c_int)]
 
 
+class EfbItem(ctypes.Structure):
+    """crv_efb_item (include/curvature_b200.h)"""
+    _fields_ = [("QG", c_void_p), ("QA", c_void_p), ("G", c_void_p), ("M", c_int), ("K", c_int), ("lambdas", c_void_p),
+                ("round_g", c_int)]
+
+
+class SampleItem(ctypes.Structure):
+    """crv_sample_item (include/curvature_b200.h)"""
+    _fields_ = [("LG", c_void_p), ("LA", c_void_p), ("z", c_void_p), ("row_scale", c_void_p), ("M", c_int), ("K0", c_int),
+                ("has_bias", c_int), ("mu_w", c_void_p), ("mu_b", c_void_p), ("w_out", c_void_p), ("b_out", c_void_p),
+                ("s_out", c_void_p)]
+
+
+_efb_batch_ws = _sig("crv_efb_project_batch_workspace", c_size_t, POINTER(EfbItem), c_int)
+_efb_batch = _sig("crv_efb_project_batch", c_int, POINTER(EfbItem), c_int, c_void_p, c_size_t, c_int, c_void_p)
+_sample_batch_ws = _sig("crv_sample_matrix_normal_batch_workspace", c_size_t, POINTER(SampleItem), c_int)
+_sample_batch = _sig("crv_sample_matrix_normal_batch", c_int, POINTER(SampleItem), c_int, c_void_p, c_size_t, c_int, c_void_p)
+
+
 class DiagItem(ctypes.Structure):
     """crv_diag_item (include/curvature_b200.h)"""
     _fields_ = [("wgrad", c_void_p), ("bgrad", c_void_p), ("M", c_int), ("K0", c_int), ("state", c_void_p),
@@ -91,7 +110,8 @@ EXPORTED_SYMBOLS = (
     "crv_abi_version", "crv_last_error", "crv_device_sm_count", "crv_workspace_bytes", "crv_profile_enable",
     "crv_profile_collect", "crv_debug_timeline",
     "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc", "crv_syrk_batch_nhwc", "crv_syrk_batch_nhwc_workspace", "crv_stream_join", "crv_stream_fork",
-    "crv_diag_accum", "crv_diag_accum_batch", "crv_efb_project_accum",
+    "crv_diag_accum", "crv_diag_accum_batch", "crv_efb_project_accum", "crv_efb_project_batch",
+    "crv_efb_project_batch_workspace", "crv_sample_matrix_normal_batch", "crv_sample_matrix_normal_batch_workspace",
     "crv_chol_inv_batched", "crv_sample_matrix_normal", "crv_round_tf32", "crv_elementwise_inv_sqrt", "crv_diag_sample",
     "crv_gemm")
 
@@ -383,6 +403,44 @@ def efb_project_accum(QG, QA, G, lambdas, precision=PREC_FP32):
     launch_calls += 2
     _check(_efb_project(_dev(QG, "QG"), _dev(QA, "QA"), _dev(G, "grads"), M, K, _dev(lambdas, "lambdas"),
                         ws.data_ptr(), ws.numel(), precision, _stream(G)), "crv_efb_project_accum")
+
+
+def efb_project_batch(entries, precision, round_g):
+    """One call for a list of (QG, QA, G, lambdas) (K3b): lambdas += (QG^T G QA)^2 per entry."""
+    global launch_calls
+    if not entries:
+        return
+    items = [EfbItem(_dev(QG, "QG"), _dev(QA, "QA"), _dev(G, "grads"), G.shape[0], G.shape[1], _dev(lam, "lambdas"),
+                     int(bool(round_g))) for QG, QA, G, lam in entries]
+    arr = (EfbItem * len(items))(*items)
+    dev = entries[0][2].device
+    ws = workspace(_efb_batch_ws(arr, len(items)), dev)
+    launch_calls += 2 * len(items)
+    _check(_efb_batch(arr, len(items), ws.data_ptr(), ws.numel(), precision, _stream(entries[0][2])),
+           "crv_efb_project_batch")
+
+
+def sample_matrix_normal_batch(entries, precision):
+    """One call for a list of dicts with the arguments of sample_matrix_normal (K5b)."""
+    global launch_calls
+    if not entries:
+        return
+    items = []
+    for e in entries:
+        LG, LA, z = e["LG"], e["LA"], e["z"]
+        M, K = LG.shape[0], LA.shape[0]
+        has_bias = int(bool(e["has_bias"]))
+        if tuple(z.shape) != (K, M):
+            raise ValueError(f"noise has shape {tuple(z.shape)}, expected {(K, M)}")
+        items.append(SampleItem(_dev(LG, "LG"), _dev(LA, "LA"), _dev(z, "noise"), _opt(e.get("row_scale"), "row_scale"), M,
+                                K - has_bias, has_bias, _opt(e.get("mu_w"), "mu_w"), _opt(e.get("mu_b"), "mu_b"),
+                                _opt(e.get("w_out"), "weight"), _opt(e.get("b_out"), "bias"), _opt(e.get("s_out"), "sample")))
+    arr = (SampleItem * len(items))(*items)
+    dev = entries[0]["LG"].device
+    ws = workspace(_sample_batch_ws(arr, len(items)), dev)
+    launch_calls += 2 * len(items)
+    _check(_sample_batch(arr, len(items), ws.data_ptr(), ws.numel(), precision, _stream(entries[0]["LG"])),
+           "crv_sample_matrix_normal_batch")
 
 
 def chol_inv_batched(factors, adds, muls, outs):

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <vector>
+#include <algorithm>
 #include <utility>
 
 namespace crv {
@@ -258,11 +259,145 @@ int crv_gemm(const float* A, int lda, int transA, const float* B, int ldb, int t
                        (cudaStream_t)stream);
 }
 
+// ---- stream pool for the batched K3 / K5 calls: the per-layer GEMM chains of a model are independent and mostly
+// small (a 64 x 576 layer is a handful of CTAs), so they are spread over a few internal streams and overlap; the
+// caller's stream forks into the pool and joins it again (device-side dependencies only).
+namespace {
+constexpr int POOL = 4;
+struct StreamPool {
+  cudaStream_t s[POOL] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t done[POOL] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr;
+  bool init = false, ok = false;
+};
+StreamPool g_pool[16];
+StreamPool* stream_pool() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) { cudaGetLastError(); return nullptr; }
+  StreamPool& p = g_pool[dev];
+  if (!p.init) {
+    p.init = true;
+    p.ok = cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < POOL && p.ok; ++i)
+      p.ok = cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!p.ok) cudaGetLastError();
+  }
+  return p.ok ? &p : nullptr;
+}
+// greedy longest-processing-time assignment of items (cost[i]) to POOL lanes; returns the lane of each item
+std::vector<int> lanes_by_cost(const std::vector<double>& cost) {
+  std::vector<int> order(cost.size()), lane(cost.size());
+  for (size_t i = 0; i < cost.size(); ++i) order[i] = (int)i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  double load[POOL] = {0, 0, 0, 0};
+  for (int i : order) {
+    int best = 0;
+    for (int l = 1; l < POOL; ++l) if (load[l] < load[best]) best = l;
+    lane[i] = best;
+    load[best] += cost[i];
+  }
+  return lane;
+}
+}  // namespace
+
+static int efb_project_one(const float* QG, const float* QA, const float* G, int M, int K, float* lambdas, float* T,
+                           int precision, cudaStream_t stream);
+static int sample_mn_one(const float* LG, const float* LA, const float* z, const float* row_scale, int M, int K0,
+                         int has_bias, const float* mu_w, const float* mu_b, float* w_out, float* b_out, float* s_out,
+                         float* T, int precision, cudaStream_t s);
+
+size_t crv_efb_project_batch_workspace(const crv_efb_item* items, int n) {
+  size_t mx = 0;
+  for (int i = 0; items && i < n; ++i) mx = std::max(mx, (size_t)items[i].M * (size_t)items[i].K);
+  return (size_t)POOL * ((mx * sizeof(float) + 255) & ~(size_t)255);
+}
+
+int crv_efb_project_batch(const crv_efb_item* items, int n, void* ws, size_t ws_bytes, int precision,
+                          crv_stream_t stream) {
+  CRV_CHECK(items != nullptr && n > 0, "empty batch");
+  const size_t need = crv_efb_project_batch_workspace(items, n);
+  CRV_CHECK(ws && ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
+  StreamPool* pool = stream_pool();
+  cudaStream_t caller = (cudaStream_t)stream;
+  std::vector<double> cost(n);
+  for (int i = 0; i < n; ++i) cost[i] = 2.0 * items[i].M * items[i].K * ((double)items[i].M + items[i].K) + 2e7;
+  const std::vector<int> lane = lanes_by_cost(cost);
+  if (pool) {
+    CRV_CUDA(cudaEventRecord(pool->fork, caller));
+    for (int l = 0; l < POOL; ++l) CRV_CUDA(cudaStreamWaitEvent(pool->s[l], pool->fork, 0));
+  }
+  const size_t per = need / POOL;
+  for (int i = 0; i < n; ++i) {
+    const crv_efb_item& it = items[i];
+    CRV_CHECK(it.QG && it.QA && it.G && it.lambdas, "null pointer in item %d", i);
+    cudaStream_t s = pool ? pool->s[lane[i]] : caller;
+    float* T = (float*)((char*)ws + (pool ? (size_t)lane[i] * per : 0));
+    if (it.round_g) {     // gradient copy rounded to the nearest TF32 in place (the tensor core would truncate it)
+      if (int rc = round_tf32_launch(it.G, const_cast<float*>(it.G), (size_t)it.M * it.K, s)) return rc;
+    }
+    if (int rc = efb_project_one(it.QG, it.QA, it.G, it.M, it.K, it.lambdas, T, precision, s)) return rc;
+  }
+  if (pool)
+    for (int l = 0; l < POOL; ++l) {
+      CRV_CUDA(cudaEventRecord(pool->done[l], pool->s[l]));
+      CRV_CUDA(cudaStreamWaitEvent(caller, pool->done[l], 0));
+    }
+  return 0;
+}
+
+size_t crv_sample_matrix_normal_batch_workspace(const crv_sample_item* items, int n) {
+  size_t mx = 0;
+  for (int i = 0; items && i < n; ++i) {
+    const size_t mk = (size_t)items[i].M * (size_t)(items[i].K0 + (items[i].has_bias ? 1 : 0));
+    mx = std::max(mx, mk * (items[i].row_scale ? 2 : 1));
+  }
+  return (size_t)POOL * ((mx * sizeof(float) + 255) & ~(size_t)255);
+}
+
+int crv_sample_matrix_normal_batch(const crv_sample_item* items, int n, void* ws, size_t ws_bytes, int precision,
+                                   crv_stream_t stream) {
+  CRV_CHECK(items != nullptr && n > 0, "empty batch");
+  const size_t need = crv_sample_matrix_normal_batch_workspace(items, n);
+  CRV_CHECK(ws && ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
+  StreamPool* pool = stream_pool();
+  cudaStream_t caller = (cudaStream_t)stream;
+  std::vector<double> cost(n);
+  for (int i = 0; i < n; ++i) {
+    const double M = items[i].M, K = items[i].K0 + (items[i].has_bias ? 1 : 0);
+    cost[i] = 2.0 * M * K * (M + K) + 2e7;
+  }
+  const std::vector<int> lane = lanes_by_cost(cost);
+  if (pool) {
+    CRV_CUDA(cudaEventRecord(pool->fork, caller));
+    for (int l = 0; l < POOL; ++l) CRV_CUDA(cudaStreamWaitEvent(pool->s[l], pool->fork, 0));
+  }
+  const size_t per = need / POOL;
+  for (int i = 0; i < n; ++i) {
+    const crv_sample_item& it = items[i];
+    cudaStream_t s = pool ? pool->s[lane[i]] : caller;
+    float* T = (float*)((char*)ws + (pool ? (size_t)lane[i] * per : 0));
+    if (int rc = sample_mn_one(it.LG, it.LA, it.z, it.row_scale, it.M, it.K0, it.has_bias, it.mu_w, it.mu_b, it.w_out,
+                               it.b_out, it.s_out, T, precision, s))
+      return rc;
+  }
+  if (pool)
+    for (int l = 0; l < POOL; ++l) {
+      CRV_CUDA(cudaEventRecord(pool->done[l], pool->s[l]));
+      CRV_CUDA(cudaStreamWaitEvent(caller, pool->done[l], 0));
+    }
+  return 0;
+}
+
 int crv_efb_project_accum(const float* QG, const float* QA, const float* G, int M, int K, float* lambdas,
                           void* ws, size_t ws_bytes, int precision, crv_stream_t stream) {
   CRV_CHECK(QG && QA && G && lambdas, "null pointer");
   CRV_CHECK(ws && ws_bytes >= (size_t)M * K * sizeof(float), "workspace too small");
-  float* T = (float*)ws;
+  return efb_project_one(QG, QA, G, M, K, lambdas, (float*)ws, precision, (cudaStream_t)stream);
+}
+
+static int efb_project_one(const float* QG, const float* QA, const float* G, int M, int K, float* lambdas, float* T,
+                           int precision, cudaStream_t stream) {
   // T = QG^T * G        (M x M)^T (M x K)
   if (int rc = gemm_dispatch(precision, QG, 1, M, G, K, 1, T, K, M, K, M, 1.f, 0.f, EPI_STORE, nullptr,
                              precision != CRV_PREC_FP32, (cudaStream_t)stream))
@@ -282,6 +417,16 @@ int crv_sample_matrix_normal(const float* LG, const float* LA, const float* z, c
                              int K0, int has_bias, const float* mu_w, const float* mu_b, float* w_out,
                              float* b_out, float* s_out, void* ws, size_t ws_bytes, int precision,
                              crv_stream_t stream) {
+  const size_t mk0 = (size_t)M * (K0 + (has_bias ? 1 : 0));
+  CRV_CHECK(ws && ws_bytes >= mk0 * sizeof(float) * (row_scale ? 2 : 1), "workspace too small");
+  return sample_mn_one(LG, LA, z, row_scale, M, K0, has_bias, mu_w, mu_b, w_out, b_out, s_out, (float*)ws, precision,
+                       (cudaStream_t)stream);
+}
+
+static int sample_mn_one(const float* LG, const float* LA, const float* z, const float* row_scale, int M, int K0,
+                         int has_bias, const float* mu_w, const float* mu_b, float* w_out, float* b_out, float* s_out,
+                         float* ws, int precision, cudaStream_t stream) {
+  const size_t ws_bytes = (size_t)M * (K0 + (has_bias ? 1 : 0)) * sizeof(float) * (row_scale ? 2 : 1);
   CRV_CHECK(LG && LA && z, "null pointer");
   CRV_CHECK(M > 0 && K0 > 0, "bad shape");
   CRV_CHECK(!w_out || mu_w, "w_out needs mu_w");

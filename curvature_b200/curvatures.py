@@ -95,6 +95,19 @@ def _rounded(cache: dict, key, tensors):
     return [h[1] for h in hit]
 
 
+def _flat_noise(shapes: dict, like: Tensor, tier: int) -> dict:
+    """{key: (K, M) standard-normal matrix}, all views of ONE flat draw (rounded to TF32 once on tensor-core tiers);
+    every view starts on a 16-byte boundary."""
+    offs, total = {}, 0
+    for key, (k, m) in shapes.items():
+        offs[key] = total
+        total += (k * m + 3) // 4 * 4
+    flat = torch.randn(total, device=like.device, dtype=like.dtype)
+    if tier != nat.PREC_FP32:
+        nat.round_tf32(flat, out=flat)
+    return {key: flat[offs[key]:offs[key] + k * m].view(k, m) for key, (k, m) in shapes.items()}
+
+
 class _DenseTarget:
     """Stands in for a parameter whose storage is not row-major: `.data` is a dense buffer of the same shape."""
 
@@ -198,6 +211,42 @@ class Curvature(ABC):
         names = self._param_names()
         current = self.model.state_dict(keep_vars=True)
         written = set()
+        # estimators whose draw is the two-GEMM kernel (KFAC, EFB) queue their layers here; the whole model is then
+        # one C-ABI call (crv_sample_matrix_normal_batch), the layers' GEMM chains overlapping on internal streams
+        self._deferred = []
+        self._noise_pool = self._draw_noise_pool() if noise is None else None
+        copies = []
+        try:
+            self._sample_and_replace_layers(names, noise, written, copies)
+            if self._deferred:
+                nat.sample_matrix_normal_batch(self._deferred, _gemm_tier(self.precision))
+        finally:
+            self._deferred = None
+            self._noise_pool = None
+        for weight, dense_w in copies:
+            weight.data.copy_(dense_w)
+        with torch.no_grad():   # everything else: restore the mean, as load_state_dict would (multi-tensor copies)
+            rest = [(v.data, self.model_state[k]) for k, v in current.items() if k not in written]
+            by_type = {}
+            for dst, src in rest:
+                by_type.setdefault((dst.dtype, src.dtype), ([], []))
+                by_type[(dst.dtype, src.dtype)][0].append(dst)
+                by_type[(dst.dtype, src.dtype)][1].append(src)
+            for dsts, srcs in by_type.values():
+                torch._foreach_copy_(dsts, srcs)
+
+    def _draw_noise_pool(self):
+        """Estimators that draw (K, M) Gaussian matrices per layer may return {key: tensor} drawn in one go."""
+        return None
+
+    def _pooled_noise(self, key, first, second, noise):
+        """(z, z_is_callers): the pre-drawn (and, on tensor-core tiers, already rounded) matrix of `key` if there is one."""
+        pool = getattr(self, '_noise_pool', None)
+        if noise is None and pool is not None and key in pool:
+            return pool[key], None
+        return self._noise(first, second, noise), noise is not None
+
+    def _sample_and_replace_layers(self, names, noise, written, copies):
         for name, layer in self._selected():
             if name in ['Linear', 'Conv2d']:
                 targets = [(layer, layer.weight, layer.bias)]
@@ -215,14 +264,10 @@ class Curvature(ABC):
                     # matrix, so sample into a dense buffer and let copy_ apply the parameter's strides
                     dense_w = torch.empty(weight.shape, dtype=weight.dtype, device=weight.device)
                     self._sample_into(key, _DenseTarget(dense_w), bias, mean_w.contiguous(), mean_b, z)
-                    weight.data.copy_(dense_w)
+                    copies.append((weight, dense_w))
                 written.add(names[id(weight)])
                 if bias is not None:
                     written.add(names[id(bias)])
-        with torch.no_grad():   # everything else: restore the mean, as load_state_dict would
-            for k, v in current.items():
-                if k not in written:
-                    v.data.copy_(self.model_state[k])
 
 
 class Diagonal(Curvature):
@@ -440,6 +485,11 @@ class KFAC(Curvature):
         for i, layer in enumerate(self.state.keys()):
             self.inv_state[layer] = (inv_arena.views[2 * i], inv_arena.views[2 * i + 1])
 
+    def _draw_noise_pool(self):
+        """One randn (and one TF32 rounding) for all layers of a sample_and_replace instead of one per layer."""
+        return _flat_noise({k: (f.size(0), s.size(0)) for k, (f, s) in self.inv_state.items()},
+                           next(iter(self.inv_state.values()))[0], _gemm_tier(self.precision)) if self.inv_state else None
+
     def _noise(self, first: Tensor, second: Tensor, noise: Optional[Tensor]) -> Tensor:
         if noise is None:   # same draw as the reference (curvatures.py:391)
             return torch.randn(first.size(0), second.size(0), device=first.device, dtype=first.dtype)
@@ -462,14 +512,22 @@ class KFAC(Curvature):
         tier = _gemm_tier(self.precision)
         if tier != nat.PREC_FP32:
             first, second = _rounded(self.__dict__.setdefault('_inv_tf32', {}), key, (first, second))
-            z = nat.round_tf32(z, out=None if z_is_callers else z)
+            if z is not None:
+                z = nat.round_tf32(z, out=None if z_is_callers else z)
         return tier, first, second, z
 
     def _sample_into(self, key, weight, bias, mean_w, mean_b, noise):
         assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
         first, second = self.inv_state[key]
-        z = self._noise(first, second, noise)
-        tier, first, second, z = self._gemm_operands(key, first, second, z, noise is not None)
+        z, callers = self._pooled_noise(key, first, second, noise)
+        if callers is None:        # pre-drawn and already rounded
+            tier, first, second, _ = self._gemm_operands(key, first, second, None, True)
+        else:
+            tier, first, second, z = self._gemm_operands(key, first, second, z, callers)
+        if getattr(self, '_deferred', None) is not None:
+            self._deferred.append(dict(LG=second, LA=first, z=z, has_bias=bias is not None, mu_w=mean_w, mu_b=mean_b,
+                                       w_out=weight.data, b_out=None if bias is None else bias.data))
+            return
         nat.sample_matrix_normal(second, first, z, bias is not None, mu_w=mean_w, mu_b=mean_b,
                                  w_out=weight.data, b_out=None if bias is None else bias.data,
                                  precision=tier)
@@ -519,12 +577,14 @@ class EFB(Curvature):
         # diags += batch_size * g^2 and the concatenated gradient copies, one launch for the whole model
         nat.diag_accum_batch(entries, batch_size)
         tier = _gemm_tier(self.precision)
+        batch = []
         for layer, grads in work:
             qa, qg = self.eigvecs[layer]
-            if tier != nat.PREC_FP32:      # eigenbases rounded to TF32 once, the gradient copy in place
+            if tier != nat.PREC_FP32:      # eigenbases rounded to TF32 once (the gradient copies: in place, by the call)
                 qa, qg = _rounded(self.__dict__.setdefault('_eig_tf32', {}), layer, (qa, qg))
-                nat.round_tf32(grads, out=grads)
-            nat.efb_project_accum(qg, qa, grads, self.state[layer], tier)
+            batch.append((qg, qa, grads, self.state[layer]))
+        # lambdas += (QG^T g QA)^2 for every layer: one C-ABI call (crv_efb_project_batch)
+        nat.efb_project_batch(batch, tier, round_g=tier != nat.PREC_FP32)
 
     def invert(self,
                add: Union[float, list, tuple] = 0.,
@@ -537,6 +597,11 @@ class EFB(Curvature):
             out = torch.empty_like(value)
             nat.elementwise_inv_sqrt(value, n, s, out)
             self.inv_state[layer] = out
+
+    def _draw_noise_pool(self):
+        # (EFB's draw scales the noise by the inverse state before the GEMMs: no rounding here)
+        return _flat_noise({k: (qa.size(0), qg.size(0)) for k, (qa, qg) in self.eigvecs.items()},
+                           next(iter(self.eigvecs.values()))[0], nat.PREC_FP32) if self.eigvecs else None
 
     def _noise(self, first, second, noise):
         if noise is None:
@@ -559,10 +624,15 @@ class EFB(Curvature):
     def _sample_into(self, key, weight, bias, mean_w, mean_b, noise):
         assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
         first, second = self.eigvecs[key]
-        z = self._noise(first, second, noise)
+        z, _ = self._pooled_noise(key, first, second, noise)
         tier = _gemm_tier(self.precision)
         if tier != nat.PREC_FP32:
             first, second = _rounded(self.__dict__.setdefault('_eig_tf32', {}), key, (first, second))
+        if getattr(self, '_deferred', None) is not None:
+            self._deferred.append(dict(LG=second, LA=first, z=z, has_bias=bias is not None, row_scale=self.inv_state[key],
+                                       mu_w=mean_w, mu_b=mean_b, w_out=weight.data,
+                                       b_out=None if bias is None else bias.data))
+            return
         nat.sample_matrix_normal(second, first, z, bias is not None, row_scale=self.inv_state[key],
                                  mu_w=mean_w, mu_b=mean_b, w_out=weight.data,
                                  b_out=None if bias is None else bias.data, precision=tier)

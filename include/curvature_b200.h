@@ -198,6 +198,32 @@ int crv_sample_matrix_normal(const float* LG, const float* LA, const float* z, c
                              float* s_out, void* ws, size_t ws_bytes, int precision,
                              crv_stream_t stream);
 
+/* K3b / K5b -- the per-layer loops of EFB.update (curvatures.py:424-433) and sample_and_replace (:117-129 with
+ * :387-392 / :453-460) as ONE call each.  The layers' GEMM chains are independent and mostly small, so the library
+ * spreads them over a pool of internal streams (balanced by flops) and joins them back into `stream`; every item
+ * computes exactly what K3 / K5 compute.  `round_g` rounds the item's gradient copy to the nearest TF32 in place
+ * first (tensor-core tiers).  The *_workspace functions return the bytes `ws` must have. */
+typedef struct {
+  const float* QG;      /* (M, M) */
+  const float* QA;      /* (K, K) */
+  const float* G;       /* (M, K) gradient copy [wgrad | bgrad] */
+  int M, K;
+  float* lambdas;       /* (M, K), accumulated into */
+  int round_g;
+} crv_efb_item;
+size_t crv_efb_project_batch_workspace(const crv_efb_item* items, int n);
+int crv_efb_project_batch(const crv_efb_item* items, int n, void* ws, size_t ws_bytes, int precision,
+                          crv_stream_t stream);
+typedef struct {
+  const float* LG; const float* LA; const float* z; const float* row_scale;
+  int M, K0, has_bias;
+  const float* mu_w; const float* mu_b;
+  float* w_out; float* b_out; float* s_out;
+} crv_sample_item;
+size_t crv_sample_matrix_normal_batch_workspace(const crv_sample_item* items, int n);
+int crv_sample_matrix_normal_batch(const crv_sample_item* items, int n, void* ws, size_t ws_bytes, int precision,
+                                   crv_stream_t stream);
+
 /* out[i] = in[i] rounded to the nearest TF32 value (in place if out == in).  The tensor-core GEMMs of K3 / K5 read fp32
  * words as TF32 (truncation); operands that stay constant over many calls (EFB eigenbases, inverse factors) are rounded
  * once with this call so that the products carry round-to-nearest instead of truncation error. */

@@ -703,3 +703,48 @@ def test_diag_accum_batch_matches_per_layer_calls():
     g2 = torch.empty(40, 9, device=DEV)
     nat.diag_accum_batch([(wg, None, s1, None), (wg, None, None, g2)], 2.0)
     assert torch.equal(s1, 2.0 * wg * wg) and torch.equal(g2, wg)
+
+
+@pytest.mark.parametrize("cls", ["KFAC", "EFB"])
+def test_sample_and_replace_batched_draw_equals_layer_by_layer(cls, golden):
+    """sample_and_replace goes through ONE batched C-ABI call (crv_sample_matrix_normal_batch, stream pool) and, without
+    caller noise, one flat randn for the whole model: with the same noise it must equal the layer-by-layer path
+    (`sample(layer, noise)` + mean), and without noise it must produce finite, fresh parameters each call."""
+    import curvature_b200 as cb
+    g = golden("convzoo")
+    model = model_from_golden("convzoo", g, DEV)
+    layers = selected_layers(model)
+    kfac = cb.KFAC(model)
+    for b in range(n_batches(g)):
+        x = torch.from_numpy(g[f"x/{b}"]).to(DEV)
+        logits = model(x)
+        labels = torch.from_numpy(g[f"labels/{b}"]).to(DEV)
+        loss = torch.nn.functional.cross_entropy(logits, labels)
+        model.zero_grad()
+        loss.backward()
+        kfac.update(x.shape[0])
+    est = kfac
+    if cls == "EFB":
+        est = cb.EFB(model, kfac.state)
+        est.update(4)
+    est.invert(1e-2, 1.0)
+    torch.manual_seed(4)
+    noise = {}
+    for l in layers:
+        K = l.weight[0].numel() + (l.bias is not None)
+        noise[l] = torch.randn(K, l.weight.shape[0], device=DEV)
+    mean = {k: v.clone() for k, v in model.state_dict().items()}
+    est.sample_and_replace(noise={k: v.clone() for k, v in noise.items()})
+    names = {id(v): k for k, v in model.state_dict(keep_vars=True).items()}
+    for l in layers:
+        s = est.sample(l, noise[l].clone())
+        K0 = l.weight[0].numel()
+        want_w = mean[names[id(l.weight)]] + s[:, :K0].reshape(l.weight.shape)
+        assert torch.allclose(l.weight.data, want_w, rtol=1e-5, atol=1e-6)
+        if l.bias is not None:
+            assert torch.allclose(l.bias.data, mean[names[id(l.bias)]] + s[:, K0], rtol=1e-5, atol=1e-6)
+    est.sample_and_replace()
+    w1 = [l.weight.data.clone() for l in layers]
+    est.sample_and_replace()
+    for l, a in zip(layers, w1):
+        assert torch.isfinite(l.weight.data).all() and not torch.equal(l.weight.data, a)
