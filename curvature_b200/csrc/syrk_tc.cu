@@ -1623,7 +1623,13 @@ void build_sk(const std::vector<const NhPlan*>& pls, int sms, GroupParams& gp, S
       const double mma = mh == 2 ? 150.0 * std::max(ncols / 256.0, 0.5) : 56.0 + 0.17 * ncols;
       const double bytes = (double)nslots * KPOS * 128;
       double c = std::max(mma, bytes / beta / 1.85);
-      if (pls.size() > 1 || p.T == 1) c = std::max(c, bytes / hbm);   // nobody else walks this operand at the same time
+      if (pls.size() > 1 || p.T == 1) {
+        // read-once operand: HBM time.  An off-diagonal pair of a two-block factor finds about half of its second block
+        // in L2 (the diagonal pairs of the same factor stream it at the same time on neighbouring CTAs): measured 248 ns
+        // per 16 KB k-group against 196 ns per 8 KB one (per-CTA timeline of the ResNet-50 group launch).
+        static const double offdiag_share = getenv("CURVATURE_B200_SK_OFFDIAG") ? atof(getenv("CURVATURE_B200_SK_OFFDIAG")) : 0.57;
+        c = std::max(c, bytes * (diag ? 1.0 : offdiag_share) / hbm);
+      }
       cbox.push_back(c * (p.PB / KPOS));
       nbq.push_back(diag ? p.NBdiag : p.NBoff);
       nboxq.push_back(p.nbox);
@@ -1902,6 +1908,10 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
   gp.nf = cnt;
   gp.ws = (float*)wsb;
   gp.tl = debug_timeline_buffer();
+  {
+    static const int tl_min_nf = getenv("CURVATURE_B200_TL_MIN_NF") ? atoi(getenv("CURVATURE_B200_TL_MIN_NF")) : 0;
+    if (cnt < tl_min_nf) gp.tl = nullptr;      // profiling aid: record only the launches with at least that many factors
+  }
   {
     const char* d = getenv("CURVATURE_B200_DBG");
     gp.dbg = d ? atoi(d) : 0;
