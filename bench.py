@@ -182,7 +182,7 @@ def main():
                 "resnet50": "ResNet-50 KFAC.update, synthetic 224x224 batch 256 per GPU (BASELINE metric config)",
                 "resnet152": "ResNet-152 KFAC.update, synthetic 224x224 batch 256 (BASELINE configs[4])"}[args.model]
     metric = METRIC if args.model == "resnet50" else METRIC.replace("ResNet-50", args.model)
-    config = {"workload": workload, "model": args.model, "batch_per_gpu": batch, "global_batch": batch * world,
+    config = {"workload": workload, "network": args.model, "batch_per_gpu": batch, "global_batch": batch * world,
               "image": "3x224x224" if args.model != "lenet5" else "1x28x28", "parallelism": f"dp{world}",
               "memory_format": args.layout if args.model != "lenet5" else "nchw",
               "l2": "inputs larger than L2 (recorded activations + gradients >> 126 MB); no flush needed"

@@ -5,6 +5,7 @@ from . import _native
 from .curvatures import Curvature, Diagonal, KFAC, EFB, INF, FactorArena
 from .utils import get_eigenvectors, get_eigenvalues, kron
 from .parallel import allreduce_arena, shard_indices
+from .io import save_factors, load_factors
 
 __all__ = ["Curvature", "Diagonal", "KFAC", "EFB", "INF", "FactorArena", "get_eigenvectors", "get_eigenvalues",
-           "kron", "allreduce_arena", "shard_indices"]
+           "kron", "allreduce_arena", "shard_indices", "save_factors", "load_factors"]

@@ -133,3 +133,38 @@ def test_shard_indices():
     assert sorted(parts[0] + parts[1]) == list(range(6))
     loads = [sum(costs[i] for i in p) for p in parts]
     assert max(loads) <= 103
+
+
+def test_factor_file_round_trip_is_name_keyed_and_pickle_free(tmp_path):
+    """save_factors / load_factors: plain tensors + layer names, loadable with weights_only=True into
+    a fresh estimator of another model instance; mismatching layers are refused; accumulate=True merges shards."""
+    import torch
+    import curvature_b200 as cb
+
+    def make():
+        torch.manual_seed(0)
+        return torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, bias=True), torch.nn.ReLU(), torch.nn.Flatten(),
+                                   torch.nn.Linear(4 * 6 * 6, 5, bias=False))
+    for cls in (cb.KFAC, cb.Diagonal):
+        a, b = cls(make()), cls(make())
+        a._ensure_arena()
+        a.arena.flat.copy_(torch.arange(a.arena.flat.numel(), dtype=torch.float32))
+        for key, views in a._views.items():
+            a.state[key] = views
+        path = str(tmp_path / f"{cls.__name__}.pt")
+        cb.save_factors(a, path)
+        blob = torch.load(path, weights_only=True)           # no pickled modules inside
+        assert blob["format"] == "curvature_b200.factors.v1" and [e["layer"] for e in blob["entries"]] == ["0", "3"]
+        cb.load_factors(b, path)
+        assert torch.equal(a.arena.flat, b.arena.flat) and len(b.state) == 2
+        for (ka, va), (kb, vb) in zip(a.state.items(), b.state.items()):
+            va = va if isinstance(va, (list, tuple)) else [va]
+            vb = vb if isinstance(vb, (list, tuple)) else [vb]
+            assert all(torch.equal(x, y) for x, y in zip(va, vb))
+        cb.load_factors(b, path, accumulate=True)
+        assert torch.equal(b.arena.flat, 2 * a.arena.flat)
+        other = cls(torch.nn.Sequential(torch.nn.Linear(7, 5)))
+        with pytest.raises(ValueError):
+            cb.load_factors(other, path)
+    with pytest.raises(ValueError):
+        cb.load_factors(cb.Diagonal(make()), str(tmp_path / "KFAC.pt"))
