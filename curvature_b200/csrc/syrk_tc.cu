@@ -1664,7 +1664,8 @@ void build_sk(const std::vector<const NhPlan*>& pls, int sms, GroupParams& gp, S
   sk.G = (int)bd.size();
   for (int c = 0; c < sk.G; ++c) { sk.q[c] = (uint16_t)bd[c].first; sk.b[c] = (uint32_t)bd[c].second; }
   sk.q[sk.G] = (uint16_t)P; sk.b[sk.G] = 0;
-  sk.have_slots = P <= SK_MAXP ? 1 : 0;
+  static const bool no_slots = getenv("CURVATURE_B200_SK_NOSLOTS") && atoi(getenv("CURVATURE_B200_SK_NOSLOTS")) != 0;   // (test hook)
+  sk.have_slots = (P <= SK_MAXP && !no_slots) ? 1 : 0;
   if (sk.have_slots) {
     int lo = 0, hi = 0;
     for (int qq = 0; qq < P; ++qq) {
