@@ -748,3 +748,50 @@ def test_sample_and_replace_batched_draw_equals_layer_by_layer(cls, golden):
     est.sample_and_replace()
     for l, a in zip(layers, w1):
         assert torch.isfinite(l.weight.data).all() and not torch.equal(l.weight.data, a)
+
+
+# ---- BASELINE full sizes (ResNet-50, batch 256): size-independent identities --------------------------------------
+# every unique convolution geometry of torchvision's ResNet-50: C_in, H(=W), k, stride, padding, C_out
+RESNET50_FULL = [(3, 224, 7, 2, 3, 64), (64, 56, 1, 1, 0, 64), (64, 56, 3, 1, 1, 64), (64, 56, 1, 1, 0, 256), (256, 56, 1, 1, 0, 64),
+                 (256, 56, 1, 1, 0, 128), (128, 56, 3, 2, 1, 128), (128, 28, 1, 1, 0, 512), (256, 56, 1, 2, 0, 512),
+                 (512, 28, 1, 1, 0, 128), (128, 28, 3, 1, 1, 128), (512, 28, 1, 1, 0, 256), (256, 28, 3, 2, 1, 256),
+                 (256, 14, 1, 1, 0, 1024), (512, 28, 1, 2, 0, 1024), (1024, 14, 1, 1, 0, 256), (256, 14, 3, 1, 1, 256),
+                 (1024, 14, 1, 1, 0, 512), (512, 14, 3, 2, 1, 512), (512, 7, 1, 1, 0, 2048), (1024, 14, 1, 2, 0, 2048),
+                 (2048, 7, 1, 1, 0, 512), (512, 7, 3, 1, 1, 512)]
+
+
+@pytest.mark.parametrize("geom", RESNET50_FULL, ids=[f"{g[0]}-{g[5]}ch_{g[1]}px_k{g[2]}s{g[3]}" for g in RESNET50_FULL])
+def test_full_size_resnet50_factors_row_sum_and_trace_identities(geom):
+    """At the benchmark's own sizes (N = 256) the oracle's unfold + matmul is out of reach, but two linear identities
+    of A = X X^T / R pin EVERY row of the factor against an independent computation in fp64:
+      row sums   A 1 = X s / R with s = X^T 1, i.e. s = conv2d(x, ones) and X s = conv2d_weight(x, s)   (tap by tap,
+                 padding and stride included: an indexing or partition error in any tile changes some row sum),
+      trace      tr A = sum_k ||X_k||^2 / R = conv2d_weight(x^2, ones),
+    and the same for G = g g^T N^2 / R.  Both factors go through ONE crv_syrk_batch_nhwc call (bench tier, bf16)."""
+    C, H, k, s, p, M = geom
+    N = 256
+    torch.manual_seed(C * 1000 + H + k)
+    x = torch.relu(torch.randn(N, C, H, H, device=DEV)).contiguous(memory_format=torch.channels_last)
+    OH = (H + 2 * p - k) // s + 1
+    g = (torch.randn(N, M, OH, OH, device=DEV) * 1e-2).contiguous(memory_format=torch.channels_last)
+    K, R = C * k * k, N * OH * OH
+    A = torch.zeros(K, K, device=DEV)
+    G = torch.zeros(M, M, device=DEV)
+    items = [nat.nhwc_item(x, (k, k), (s, s), (p, p), False, 1.0 / R, A, nat.PREC_BF16),
+             nat.nhwc_item(g, None, None, None, False, float(N) * N / R, G, nat.PREC_BF16)]
+    assert all(it is not None for it in items)
+    nat.syrk_batch_nhwc(items, nat.PREC_BF16, x.device)
+    assert torch.equal(A, A.t()) and torch.equal(G, G.t())
+    xd = x.double()
+    ones = torch.ones(1, C, k, k, device=DEV, dtype=torch.float64)
+    svec = F.conv2d(xd, ones, stride=s, padding=p)                                   # (N, 1, OH, OW): column sums of X
+    rows = torch.nn.grad.conv2d_weight(xd, (1, C, k, k), svec, stride=s, padding=p).reshape(-1) / R
+    assert rel_fro(A.double().sum(1), rows) <= 1e-3, rel_fro(A.double().sum(1), rows)
+    tr = torch.nn.grad.conv2d_weight(xd * xd, (1, C, k, k), torch.ones_like(svec), stride=s, padding=p).sum() / R
+    assert abs(A.double().trace().item() - tr.item()) <= 1e-3 * abs(tr.item())
+    gd = g.double()
+    sg = gd.sum(1, keepdim=True)
+    rows_g = (gd * sg).sum((0, 2, 3)) * (float(N) * N / R)
+    assert rel_fro(G.double().sum(1), rows_g) <= 1e-3, rel_fro(G.double().sum(1), rows_g)
+    tr_g = (gd * gd).sum() * (float(N) * N / R)
+    assert abs(G.double().trace().item() - tr_g.item()) <= 1e-3 * abs(tr_g.item())
