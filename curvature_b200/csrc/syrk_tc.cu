@@ -877,6 +877,7 @@ struct NhParams {
   int K0;                    // rows that are tap-major permuted (the reduction undoes it)
   int ldF;                   // order of the factor F (= D except on the packed path, where D counts padding rows)
   int pk_kh, pk_kw, pk_c;    // packed small-C path: the original filter and channel count (pk_c = 0: not packed)
+  int pack2;                 // D <= 64 single-tile TF32 factor: two position sets stacked along M (see seg_geom)
   float alpha;
   float* F;                  // the factor this item accumulates into
 };
@@ -950,6 +951,7 @@ struct SkTable {
 
 struct SegGeom {
   int I, J, rowsA, mh, ncols, nchA, nchB, nslots, NB, nstage;
+  int pk, poff, nbh;           // pack2: on; row / column offset of the second position set's block; boxes per set
   bool diag;
   uint32_t chunk_bytes, stage_bytes;
 };
@@ -969,6 +971,24 @@ __device__ __forceinline__ SegGeom seg_geom(const NhParams& p, int q) {
   const int slotsA = t.mh * (128 / CH);
   t.nslots = t.nchA + t.nchB;
   t.NB = t.diag ? p.NBdiag : p.NBoff;
+  t.pk = 0; t.poff = 0; t.nbh = t.NB;
+  if (p.pack2) {
+    // A factor of order <= 64 would use half (or a quarter) of the M = 128 rows of every MMA and is issue-bound at one
+    // 2 KB k-group per ~70 ns.  Instead the boxes of a stage are split into two position sets whose chunks are stacked
+    // along M: A = B = [set 1 channels | set 2 channels], so that ONE instruction contracts 2 x KPOS positions; the two
+    // diagonal blocks of the accumulator are the two sets' partial sums (the reduction adds them), the cross blocks
+    // are never read.
+    t.pk = 1;
+    t.poff = t.nchA * CH;
+    t.nbh = t.NB / 2;
+    t.nslots = 2 * t.nchA;
+    t.ncols = 2 * t.poff;
+    t.chunk_bytes = (uint32_t)(t.nbh * p.PB) * 128u;
+    t.stage_bytes = (uint32_t)t.nslots * t.chunk_bytes;
+    const uint32_t tail_pad = (uint32_t)(slotsA - t.nslots) * t.chunk_bytes;
+    t.nstage = min(NH_MAXSTAGE, (int)((NH_DATA_BYTES - tail_pad) / t.stage_bytes));
+    return t;
+  }
   t.chunk_bytes = (uint32_t)(t.NB * p.PB) * 128u;
   t.stage_bytes = (uint32_t)t.nslots * t.chunk_bytes;
   const uint32_t tail_pad = t.diag ? (uint32_t)(slotsA - t.nchA) * t.chunk_bytes : 0u;
@@ -1057,7 +1077,7 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       // the stage geometry of this segment is
       if (nseg > 0) mbar_wait(bar_tmem_full, (uint32_t)(nseg - 1) & 1u);
       asm volatile("bar.sync 1, %0;" ::"r"(NH_NPROD * 32) : "memory");  // nobody still reads the old chunk table
-      const int loaded = t.nslots;
+      const int loaded = t.pk ? t.nchA : t.nslots;           // chunks fetched per box
       if (me == 0 && lane < loaded) {
         const bool isB = lane >= t.nchA;
         const int kp = isB ? t.J * TB + (lane - t.nchA) * CH : t.I * TB + lane * CH;
@@ -1078,6 +1098,7 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       asm volatile("bar.sync 1, %0;" ::"r"(NH_NPROD * 32) : "memory");
       const int NB = (int)uni((uint32_t)t.NB), nstage = (int)uni((uint32_t)t.nstage), nld = (int)uni((uint32_t)loaded);
       const uint32_t stage_bytes = uni(t.stage_bytes), chunk_bytes = uni(t.chunk_bytes);
+      const int pk = (int)uni((uint32_t)t.pk), nbh = (int)uni((uint32_t)t.nbh), pk_nch = (int)uni((uint32_t)t.nchA);
       const int ub = (int)uni((uint32_t)b_begin), ue = (int)uni((uint32_t)b_end);
       const int nit = (ue - ub + NB - 1) / NB;
       int s = 0;
@@ -1089,6 +1110,21 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
         mbar_wait(bars + 8 * (NH_MAXSTAGE + s), ((pph >> s) & 1u) ^ 1u);
         pph ^= 1u << s;
         const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+        if (pk && nv < NB) {
+          // ragged last stage of a pack2 factor: the MMA still contracts both sets over all their box slots, so the slots
+          // no box is loaded into must hold zeros (stale rows of an earlier stage would be summed)
+          const int words = p.PB * 8;                            // 16-byte words per box slot
+          const int tot = (NB - nv) * nld * words;
+          for (int e = ptid; e < tot; e += NH_NPROD * 32) {
+            const int bx = e / words, wd = e - bx * words;
+            const int j = nv + bx / nld, qq = bx - (bx / nld) * nld;
+            const int set = j >= nbh ? 1 : 0, jj = j - set * nbh;
+            const uint32_t a = st + (uint32_t)(set * pk_nch + qq) * chunk_bytes + (uint32_t)(jj * p.PB) * 128u + (uint32_t)wd * 16u;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0) : "memory");
+          }
+          fence_proxy_async();
+          asm volatile("bar.sync 1, %0;" ::"r"(NH_NPROD * 32) : "memory");
+        }
         if (leader) {
           if (mine && !(gp.dbg & 1)) mbar_arrive_expect_tx(bars + 8 * s, (uint32_t)mine * box_bytes);
           else mbar_arrive(bars + 8 * s);
@@ -1108,8 +1144,10 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
               X0 = (int)pc * p.bw * p.sw; Y0 = (int)pr * p.bh * p.sh; Nn = (int)n * p.bn;
             }
             const int4 t4 = tab[qq];
+            const int set = (pk && j >= nbh) ? 1 : 0;            // pack2: second half of the stage's boxes = second set
+            const int jj = j - set * nbh, slot = t4.w + set * pk_nch;
             if (leader)
-              tma_load_4d(st + (uint32_t)(j * p.PB) * 128u + (uint32_t)t4.w * chunk_bytes, tmap, t4.x, X0 + t4.y, Y0 + t4.z,
+              tma_load_4d(st + (uint32_t)(jj * p.PB) * 128u + (uint32_t)slot * chunk_bytes, tmap, t4.x, X0 + t4.y, Y0 + t4.z,
                           Nn, bars + 8 * s);
           }
         }
@@ -1147,6 +1185,7 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       const uint32_t hstep = (uint32_t)(128 / CH) * u_chunk;              // second 128-row half of the A block
       const uint32_t boff = uni(t.diag ? 0u : (uint32_t)t.nchA * t.chunk_bytes);
       const bool two = uni((uint32_t)t.mh) == 2u;
+      const int u_pk = (int)uni((uint32_t)t.pk), u_nbh = (int)uni((uint32_t)t.nbh);
       if (nseg > 0) {                                                     // accumulator drained by the epilogue warps
         mbar_wait(bar_tmem_empty, (uint32_t)(nseg - 1) & 1u);
         tc_fence_after();
@@ -1161,7 +1200,7 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
         if (tl && lane == 0) tl[6] += nv_kg(u_NB, ue - (ub + it * u_NB), kpb);
         const uint32_t st = sbase + (uint32_t)s * u_stage;
         const int nv = min(u_NB, ue - (ub + it * u_NB));
-        const int nkg = run ? nv * kpb : 0;
+        const int nkg = run ? (u_pk ? u_nbh : nv) * kpb : 0;             // pack2: both sets in one instruction (ragged slots are zero)
         const uint32_t a0 = dlo | ((st >> 4) & 0x3FFFu);
         const uint32_t a1 = dlo | (((st + hstep) >> 4) & 0x3FFFu);
         const uint32_t b0 = dlo | (((st + boff) >> 4) & 0x3FFFu);
@@ -1192,7 +1231,7 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       if (b_begin >= b_end) continue;
       const SegGeom g = seg_geom<CH>(p, q - gp.qbeg[fi]);
       ItemShape t;
-      t.mh = g.mh; t.ncols = g.ncols; t.rowsA = g.rowsA;
+      t.mh = g.mh; t.ncols = g.ncols; t.rowsA = g.pk ? g.poff + g.rowsA : g.rowsA;
       epilogue_store_coalesced(t, bar_tmem_full, (uint32_t)nseg & 1u, tmem, gp.ws + (size_t)(blockIdx.x + q) * TILE_ELEMS,
                                warp & 3, lane, epi + (uint32_t)(warp & 3) * 4096u);
       tc_fence_before();
@@ -1213,7 +1252,7 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
 // Fixed-order reduction for the stream-K partition: the partial tiles of global pair q are slots (c + q) for the
 // CTAs c_lo..c_hi whose ranges intersect the pair, found from the boundary table; summed in CTA order, scaled,
 // un-permuted and added (tile + mirror image) into the pair's factor.  One launch reduces every factor of a group.
-__global__ void __launch_bounds__(256) syrk_sk_reduce_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ SkTable sk) {
+__global__ void __launch_bounds__(256, 4) syrk_sk_reduce_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ SkTable sk) {
   // 256 threads / 4 KB of shared memory per CTA: small enough to be co-resident with a SYRK CTA of the next launch
   // (416 threads, ~211 KB), so that on the side stream the reduction really overlaps it.
   __shared__ float tile[32][33];
@@ -1265,25 +1304,64 @@ __global__ void __launch_bounds__(256) syrk_sk_reduce_kernel(const __grid_consta
   const float* __restrict__ base = gp.ws + (size_t)(c_lo + q) * TILE_ELEMS;
   const int col = bc * 32 + lane;
   const int pcol = col < colsB ? perm(J * TB + col) : -1;
+  // pack2 factors: the partial tile holds two diagonal blocks (one per position set), `poff` rows / columns apart
+  const size_t second = p.pack2 ? (size_t)((p.D + 31) / 32 * 32) * (TB + 1) : 0;
+  // the thread's four rows are summed together: 4 x 8 (pack2: 4 x 4 x 2) independent loads in flight per round, each
+  // row's partial tiles still added in slot order (the reduction is a latency chain of nsl / 8 round trips)
+  float sum[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* bp[4];
+  bool valid[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int row = br * 32 + w0 + 8 * k;
+    valid[k] = row < rowsA && col < colsB;
+    bp[k] = base + (valid[k] ? row * TB + col : 0);
+  }
+  if (second) {
+    int s = 0;
+    for (; s + 4 <= nsl; s += 4) {
+      float t[4][4], t2[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          t[k][u] = valid[k] ? __ldcg(bp[k] + (size_t)(s + u) * TILE_ELEMS) : 0.f;
+          t2[k][u] = valid[k] ? __ldcg(bp[k] + (size_t)(s + u) * TILE_ELEMS + second) : 0.f;
+        }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sum[k] += t[k][u] + t2[k][u];
+    }
+    for (; s < nsl; ++s)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (valid[k]) sum[k] += __ldcg(bp[k] + (size_t)s * TILE_ELEMS) + __ldcg(bp[k] + (size_t)s * TILE_ELEMS + second);
+  } else {
+    int s = 0;
+    for (; s + 8 <= nsl; s += 8) {
+      float t[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[k][u] = valid[k] ? __ldcg(bp[k] + (size_t)(s + u) * TILE_ELEMS) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sum[k] += t[k][u];
+    }
+    for (; s < nsl; ++s)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (valid[k]) sum[k] += __ldcg(bp[k] + (size_t)s * TILE_ELEMS);
+  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int w = w0 + 8 * k;
     const int row = br * 32 + w;
-    const bool valid = row < rowsA && col < colsB;
     float v = 0.f;
-    if (valid) {
-      const float* __restrict__ b = base + row * TB + col;
-      float sum = 0.f;
-      int s = 0;
-      for (; s + 8 <= nsl; s += 8) {
-        float t[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) t[u] = __ldcg(b + (size_t)(s + u) * TILE_ELEMS);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) sum += t[u];
-      }
-      for (; s < nsl; ++s) sum += __ldcg(b + (size_t)s * TILE_ELEMS);
-      v = alpha * sum;
+    if (valid[k]) {
+      v = alpha * sum[k];
       const int pr = perm(I * TB + row);
       if (!(diag && col > row) && pr >= 0 && pcol >= 0) F[(size_t)pr * D + pcol] += v;
     }
@@ -1498,7 +1576,7 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl, bool src_i
   if (g.R >= (1LL << 31) - 512) return false;
   NhParams& p = pl.p;
   p.D = g.D; p.C = g.C; p.KK = KK; p.kw = g.kw; p.K0 = g.K0; p.alpha = 0.f; p.F = nullptr;
-  p.ldF = g.D; p.pk_kh = p.pk_kw = p.pk_c = 0;
+  p.ldF = g.D; p.pk_kh = p.pk_kw = p.pk_c = 0; p.pack2 = 0;
   p.divC = make_fastdiv((uint32_t)g.C);
   p.divKW = make_fastdiv((uint32_t)g.kw);
   p.T = (g.D + TB - 1) / TB;
@@ -1525,6 +1603,11 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl, bool src_i
   if (p.flat) {
     long long pb = (pcap < 256 ? pcap : 256) / gran * gran;     // whole MMA k-groups
     if (pb < gran) return false;
+    static const bool pack2_on = !(getenv("CURVATURE_B200_PACK2") && atoi(getenv("CURVATURE_B200_PACK2")) == 0);
+    if (pack2_on && !pl.bf16 && !src_is_bf16 && p.T == 1 && g.D <= 64 && pb >= 2 * gran && g.R >= 4 * pb) {
+      p.pack2 = 1;                                               // two boxes per stage, one per position set
+      pb = (pb / 2) / gran * gran;
+    }
     const long long rr = (g.R + gran - 1) / gran * gran;
     if (pb > rr) pb = rr;
     p.PB = p.PBv = (int)pb;
@@ -1573,6 +1656,10 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl, bool src_i
   };
   p.NBoff = boxes_per_stage(slots_off);
   p.NBdiag = boxes_per_stage(slots_diag);
+  if (p.pack2) {
+    p.NBdiag = p.NBdiag / 2 * 2;
+    if (p.NBdiag < 2) p.pack2 = 0;
+  }
   if (p.T > 1) p.NBdiag = p.NBoff * (p.NBdiag / p.NBoff > 0 ? p.NBdiag / p.NBoff : 1);
   if (slots_max * p.NBoff * p.PB * 128 * 2 > NH_DATA_BYTES && p.T > 1) return false;   // needs >= 2 stages
   if ((slots_diag * 2 + 3) * p.NBdiag * p.PB * 128 > NH_DATA_BYTES) return false;      // (+ tail pad)
@@ -1620,8 +1707,12 @@ void build_sk(const std::vector<const NhPlan*>& pls, int sms, GroupParams& gp, S
       const int nslots = (rowsA + CH - 1) / CH + (diag ? 0 : TB / CH);
       // measured with the per-CTA timeline (crv_debug_timeline), ns per k-group at ~1.85 GHz: two MMAs of N = 256:
       // 150; one MMA: 100 / 80 / 67 at N = 256 / 128 / 64 (one instruction per k-group is issue-bound, not pipe-bound)
-      const double mma = mh == 2 ? 150.0 * std::max(ncols / 256.0, 0.5) : 56.0 + 0.17 * ncols;
-      const double bytes = (double)nslots * KPOS * 128;
+      double mma = mh == 2 ? 150.0 * std::max(ncols / 256.0, 0.5) : 56.0 + 0.17 * ncols;
+      double bytes = (double)nslots * KPOS * 128;
+      if (p.pack2) {      // one instruction per 2 x KPOS positions (N = twice the padded order): cost per KPOS positions
+        const int n2 = 2 * ((rowsA + CH - 1) / CH) * CH;
+        mma = (56.0 + 0.17 * n2) / 2.0;
+      }
       double c = std::max(mma, bytes / beta / 1.85);
       if (pls.size() > 1 || p.T == 1) {
         // read-once operand: HBM time.  An off-diagonal pair of a two-block factor finds about half of its second block
