@@ -1,8 +1,15 @@
-// K1 (tensor-core tier): fused implicit-im2col + SYRK on the 5th-generation tensor cores.
+// K1 (tensor-core tiers): fused implicit-im2col + SYRK on the 5th-generation tensor cores.
 //
 //   F[k1,k2] += alpha * sum_r X[k1,r] * X[k2,r]       X = im2col(x) (+ ones row), never in HBM
 //
-// Structure (one work item per CTA, 17 warps, 1 CTA / SM):
+// Two kernel families live in this file.
+//
+// (1) Channels-last operands -- the fast path (second half of the file: syrk_nhwc_kernel, its stream-K partition,
+//     reductions, pre-passes, launch logic).  See the comment block "channels-last (NHWC) operands" below and DESIGN.md
+//     section 4 / K1.
+//
+// (2) NCHW-dense operands and bias rows (first half: syrk_tc_kernel / syrk_tc_tma_kernel) -- one work item per CTA, 17
+//     warps, 1 CTA / SM:
 //   * the factor is cut into 256-row blocks; only block pairs (I >= J) are computed, and the
 //     contraction axis R is split S ways so that pairs*S items fill the 148 SMs;
 //   * 16 PRODUCER warps gather activations straight from the NCHW tensor (lane <-> contraction
@@ -14,6 +21,8 @@
 //   * ONE thread of the MMA warp issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N<=256, K=8):
 //     per stage 2 row halves x 4 k-steps, accumulating a 256x256 fp32 tile in TMEM (2 x 256 columns
 //     = all 512 columns); tcgen05.commit releases the smem stage / signals the epilogue;
+//     (this family is only used for the few operands family (1) cannot take -- on ResNet-50 the fc layer's A factor --
+//     and still issues from one divergent thread; the channels-last kernel issues in uniform control flow)
 //   * mbarrier full/empty ring of 3 x 64 KB stages between producers and the MMA thread;
 //   * EPILOGUE (producer warps 0-3): tcgen05.ld the accumulator (32 lanes x 16 columns per
 //     instruction) and store the partial tile to the workspace; a second, small kernel sums the S
@@ -873,7 +882,6 @@ struct NhParams {
   FastDiv divPPI, divPCW;
   int ppi, pcw, bw, bh, bn;  // boxes per image group, boxes per box-row, box extent in output positions / images
   int sh, sw, ph, pw, flat;
-  int pfd;                   // L2 prefetch distance in ring revolutions (0 = off)
   int K0;                    // rows that are tap-major permuted (the reduction undoes it)
   int ldF;                   // order of the factor F (= D except on the packed path, where D counts padding rows)
   int pk_kh, pk_kw, pk_c;    // packed small-C path: the original filter and channel count (pk_c = 0: not packed)
@@ -1606,10 +1614,6 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl, bool src_i
   const int CH = pl.bf16 ? 64 : 32, gran = pl.bf16 ? 16 : 8;
   p.sh = g.sh; p.sw = g.sw; p.ph = g.ph; p.pw = g.pw;
   p.flat = (KK == 1 && g.sh == 1 && g.sw == 1 && g.ph == 0 && g.pw == 0) ? 1 : 0;
-  {
-    const char* e = getenv("CURVATURE_B200_PFD");
-    p.pfd = e ? atoi(e) : 0;   // measured on ResNet-50: 14.5k img/s without, 14.2k / 14.0k / 13.7k at 1 / 2 / 4 revolutions
-  }
   // chunk slots per stage of the two item kinds
   const int slots_diag = ((p.T > 1 ? TB : g.D) + CH - 1) / CH, slots_off = 2 * (TB / CH);   // chunks loaded per box
   const int slots_max = p.T > 1 ? slots_off : slots_diag;
