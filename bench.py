@@ -109,6 +109,29 @@ class ClockSampler:
     def __init__(self, index):
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
+        self.nvml = None
+        try:        # NVML in a sampling thread (every 10 ms): a K-step region is ~0.1 s, nvidia-smi -lms gives 1-2 samples
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = {"sm": [], "mx": pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM), "mask": 0, "stop": False}
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self.nvml["stop"]:
+                    try:
+                        self.nvml["sm"].append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        self.nvml["mask"] |= int(get_reasons(h))
+                    except Exception:
+                        pass
+                    time.sleep(0.01)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -117,6 +140,14 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.nvml is not None:
+            self.nvml["stop"] = True
+            self.thread.join(timeout=2)
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            sm = [x for x in self.nvml["sm"] if x > 0]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.nvml["mx"]),
+                    "samples": len(self.nvml["sm"]), "reasons": sorted(n for n, b in bits.items() if self.nvml["mask"] & b),
+                    "source": "nvml, 10 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
