@@ -1989,14 +1989,18 @@ int make_tensor_map(const ConvGeom& g, const NhPlan& pl, const void* src, CUtens
 
 // One launch of the stream-K kernel (+ its reduction) over the factors idx[0..cnt) -- all of the same operand type.
 int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, const std::vector<NhPlan>& plans,
-                 const int* idx, int cnt, void* ws, size_t ws_bytes, cudaStream_t caller) {
+                 const int* idx, int cnt, void* ws, size_t ws_bytes, size_t copy_off, cudaStream_t caller) {
   const int sms = device_sm_count();
   const bool bf16 = plans[idx[0]].bf16 != 0;
   size_t pairs = 0, copy_bytes = 0;
   for (int k = 0; k < cnt; ++k) { pairs += plans[idx[k]].pairs; copy_bytes += plans[idx[k]].copy_bytes; }
   CRV_CHECK(cnt == 1 || copy_bytes == 0, "internal: operands with a pre-pass copy are launched one by one");
   const size_t partial_bytes = (size_t)(SK_MAXG + pairs) * TILE_ELEMS * sizeof(float);
-  const size_t need = 2 * launch_need(pairs, copy_bytes);
+  // layout of a workspace half: [partial tiles of the launch | ... | pre-pass copy at copy_off].  The copy region sits
+  // at the SAME offset for every launch of a batch, beyond the largest partial-tile region: the pre-pass of launch i+2
+  // (which only waits for contraction i) must never write where reduction i may still be reading partial tiles.
+  const size_t need = 2 * (copy_off + copy_bytes + 4096);
+  CRV_CHECK(partial_bytes <= copy_off, "internal: partial tiles overlap the copy region");
   CRV_CHECK(ws != nullptr && ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
   CRV_CHECK(((uintptr_t)ws & 15) == 0, "workspace must be 16-byte aligned");
   // workspace half for this call; the main stream first waits for the reduction that last read it (two calls ago)
@@ -2039,13 +2043,14 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
     gp.f[k].F = Fs[idx[k]];
     const float* src = g.x;
     if (pl.copy_bytes) {   // pre-pass: bf16 copy (tier bf16) / TF32 round-to-nearest copy (tier tf32), same layout; or pack
-      float* copy = (float*)((((uintptr_t)wsb + partial_bytes) + 1023) & ~(uintptr_t)1023);
+      float* copy = (float*)((((uintptr_t)wsb + copy_off) + 1023) & ~(uintptr_t)1023);
       const size_t n4 = (size_t)g.N * g.C * g.H * g.W / 4;
       cudaStream_t cs = s;
       const bool side_cast = use_side && st->forked;
       if (side_cast) {      // wait only for the main kernel that last read this half's copy region (two calls ago)
         cs = st->cast;
         if (st->main_pending[buf]) CRV_CUDA(cudaStreamWaitEvent(cs, st->ev_main[buf], 0));
+        if (st->red_pending[buf]) CRV_CUDA(cudaStreamWaitEvent(cs, st->ev_red[buf], 0));   // (and the reduction that read this half)
       }
       if (pl.pack) {
         const ConvGeom& q = pl.gq;
@@ -2145,17 +2150,28 @@ int plan_batch(const ConvGeom* gs, int n, int precision, std::vector<NhPlan>& pl
 }
 }  // namespace
 
+namespace {
+// largest partial-tile region and largest pre-pass copy over the launches of a batch
+void batch_layout(const std::vector<NhPlan>& plans, const std::vector<std::vector<int>>& launches, size_t& copy_off, size_t& max_copy) {
+  size_t max_partial = 0;
+  max_copy = 0;
+  for (const auto& l : launches) {
+    size_t pairs = 0, copy = 0;
+    for (int i : l) { pairs += plans[i].pairs; copy += plans[i].copy_bytes; }
+    max_partial = std::max(max_partial, (size_t)(SK_MAXG + pairs) * TILE_ELEMS * sizeof(float));
+    max_copy = std::max(max_copy, copy);
+  }
+  copy_off = (max_partial + 2047) & ~(size_t)1023;
+}
+}  // namespace
+
 size_t syrk_nhwc_batch_workspace(const ConvGeom* gs, int n, int precision) {
   std::vector<NhPlan> plans;
   std::vector<std::vector<int>> launches;
   if (n <= 0 || plan_batch(gs, n, precision, plans, launches)) return 0;
-  size_t need = 0;
-  for (const auto& l : launches) {
-    size_t pairs = 0, copy = 0;
-    for (int i : l) { pairs += plans[i].pairs; copy += plans[i].copy_bytes; }
-    need = std::max(need, launch_need(pairs, copy));
-  }
-  return 2 * need;    // two halves: main kernel i+1 writes one while reduction i reads the other
+  size_t copy_off, max_copy;
+  batch_layout(plans, launches, copy_off, max_copy);
+  return 2 * (copy_off + max_copy + 4096);    // two halves: main kernel i+1 writes one while reduction i reads the other
 }
 
 // F_i += alpha_i * X_i X_i^T for a batch of channels-last operands.
@@ -2167,8 +2183,10 @@ int syrk_nhwc_batch_launch(const ConvGeom* gs, const float* alphas, float* const
   std::vector<NhPlan> plans;
   std::vector<std::vector<int>> launches;
   if (int rc = plan_batch(gs, n, precision, plans, launches)) return rc;
+  size_t copy_off, max_copy;
+  batch_layout(plans, launches, copy_off, max_copy);
   for (const auto& l : launches)
-    if (int rc = launch_group(gs, alphas, Fs, plans, l.data(), (int)l.size(), ws, ws_bytes, s)) return rc;
+    if (int rc = launch_group(gs, alphas, Fs, plans, l.data(), (int)l.size(), ws, ws_bytes, copy_off, s)) return rc;
   return 0;
 }
 

@@ -795,3 +795,42 @@ def test_full_size_resnet50_factors_row_sum_and_trace_identities(geom):
     assert rel_fro(G.double().sum(1), rows_g) <= 1e-3, rel_fro(G.double().sum(1), rows_g)
     tr_g = (gd * gd).sum() * (float(N) * N / R)
     assert abs(G.double().trace().item() - tr_g.item()) <= 1e-3 * abs(tr_g.item())
+
+
+def test_update_with_stream_overlap_equals_serialised_update():
+    """The whole KFAC.update pipeline (pre-passes, contractions and reductions of ~100 launches on four prioritised
+    streams over a double-buffered workspace) against the same update with everything serialised on one stream
+    (crv_profile_enable switches the side streams off): the reductions are fixed-order, so the factors must be
+    BIT-identical -- any workspace hazard between overlapping launches shows up as a difference.  ResNet-50 at batch
+    64: long tap-aware reductions (2304^2, 4608^2 factors) followed by short launches, the pattern that once let a
+    pre-pass overwrite partial tiles that were still being reduced.  Also: every factor symmetric and, damped, PD."""
+    import torchvision
+    import curvature_b200 as cb
+    torch.manual_seed(0)
+    model = torchvision.models.resnet50(weights=None).to(DEV).train().to(memory_format=torch.channels_last)
+    x = torch.randn(64, 3, 224, 224, device=DEV).contiguous(memory_format=torch.channels_last)
+    a = cb.KFAC(model, precision="bf16")
+    orc.fisher_step(model, x)
+    for _ in range(3):                      # several back-to-back updates: the pipeline is in steady state
+        a.update(64)
+    torch.cuda.synchronize()
+    b = cb.KFAC(model, precision="bf16")
+    b.record = a.record
+    nat.profile_enable(True)
+    try:
+        for _ in range(3):
+            b.update(64)
+        torch.cuda.synchronize()
+    finally:
+        nat.profile_collect()
+        nat.profile_enable(False)
+    worst = 0
+    for (la, fa), (lb, fb) in zip(a.state.items(), b.state.items()):
+        for u, v in zip(fa, fb):
+            assert torch.equal(u, u.t())
+            if not torch.equal(u, v):
+                worst = max(worst, float((u - v).abs().max()))
+    assert worst == 0, f"overlapped and serialised updates differ by up to {worst}"
+    a.invert(add=1.0, multiply=1.0)         # sqrt(s) F + sqrt(n) I is PD for every PSD factor
+    for h in a.hooks + b.hooks:
+        h.remove()
