@@ -102,6 +102,9 @@ class DiagItem(ctypes.Structure):
 
 
 _diag_batch = _sig("crv_diag_accum_batch", c_int, POINTER(DiagItem), c_int, c_float, c_void_p)
+_debug_partition = _sig("crv_debug_partition", c_int, POINTER(SyrkItem), c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int),
+                       POINTER(c_int), POINTER(c_int), POINTER(ctypes.c_uint), c_int, POINTER(c_int), POINTER(c_int),
+                       POINTER(c_int), c_int)
 _syrk_batch_ws = _sig("crv_syrk_batch_nhwc_workspace", c_size_t, POINTER(SyrkItem), c_int, c_int)
 _syrk_batch = _sig("crv_syrk_batch_nhwc", c_int, POINTER(SyrkItem), c_int, c_void_p, c_size_t, c_int, c_void_p)
 
@@ -109,7 +112,7 @@ ABI_VERSION = _abi_version()
 EXPORTED_SYMBOLS = (
     "crv_abi_version", "crv_last_error", "crv_device_sm_count", "crv_workspace_bytes", "crv_profile_enable",
     "crv_profile_collect", "crv_debug_timeline",
-    "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc", "crv_syrk_batch_nhwc", "crv_syrk_batch_nhwc_workspace", "crv_stream_join", "crv_stream_fork",
+    "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc", "crv_syrk_batch_nhwc", "crv_syrk_batch_nhwc_workspace", "crv_debug_partition", "crv_stream_join", "crv_stream_fork",
     "crv_diag_accum", "crv_diag_accum_batch", "crv_efb_project_accum", "crv_efb_project_batch",
     "crv_efb_project_batch_workspace", "crv_sample_matrix_normal_batch", "crv_sample_matrix_normal_batch_workspace",
     "crv_chol_inv_batched", "crv_sample_matrix_normal", "crv_round_tf32", "crv_elementwise_inv_sqrt", "crv_diag_sample",
@@ -350,6 +353,22 @@ def nhwc_item(t, kernel_size, stride, padding, has_bias, alpha, out, precision):
     if not _syrk_batch_ws(ctypes.byref(item), 1, precision):
         return None
     return item
+
+
+def debug_partition(geoms, precision, sms=148, which=0):
+    """Host-only: how the scheduler cuts a batch of (N, C, H, W, kh, kw, sh, sw, ph, pw) items into launches and CTA ranges.
+    Returns dict(launch_of_item, n_launches, boundaries=[(pair, box)...] of launch `which`, nbox, nb)."""
+    items = [SyrkItem(4096, *[int(v) for v in g], 1.0, 4096, 0) for g in geoms]
+    arr = (SyrkItem * len(items))(*items)
+    loi = (c_int * len(items))()
+    nl, G, pairs = c_int(0), c_int(0), c_int(0)
+    cap, pcap = 256, 1 << 16
+    q, b = (c_int * cap)(), (ctypes.c_uint * cap)()
+    nbox, nb = (c_int * pcap)(), (c_int * pcap)()
+    _check(_debug_partition(arr, len(items), precision, sms, which, loi, ctypes.byref(nl), ctypes.byref(G), q, b, cap,
+                            ctypes.byref(pairs), nbox, nb, pcap), "crv_debug_partition")
+    return {"launch_of_item": list(loi), "n_launches": nl.value, "boundaries": [(q[c], b[c]) for c in range(G.value + 1)],
+            "nbox": list(nbox[:pairs.value]), "nb": list(nb[:pairs.value])}
 
 
 def syrk_batch_nhwc(items, precision, device, join=True):

@@ -221,6 +221,20 @@ size_t crv_syrk_batch_nhwc_workspace(const crv_syrk_item* items, int n, int prec
   return syrk_nhwc_batch_workspace(gs.data(), n, precision);
 }
 
+int crv_debug_partition(const crv_syrk_item* items, int n, int precision, int sms, int which, int* launch_of_item,
+                        int* n_launches, int* G, int* q, unsigned* b, int cap, int* pairs, int* nbox_of_pair,
+                        int* nb_of_pair, int pair_cap) {
+  std::vector<ConvGeom> gs;
+  std::vector<float> alphas;
+  std::vector<float*> Fs;
+  if (int rc = batch_geoms(items, n, gs, alphas, Fs)) return rc;
+  const int rc = syrk_nhwc_debug_partition(gs.data(), n, precision, sms, which, launch_of_item, G, q, b, cap, pairs,
+                                           nbox_of_pair, nb_of_pair, pair_cap);
+  if (rc & 0xFFFF) return rc;
+  *n_launches = rc >> 16;
+  return 0;
+}
+
 int crv_syrk_batch_nhwc(const crv_syrk_item* items, int n, void* ws, size_t ws_bytes, int precision,
                         crv_stream_t stream) {
   std::vector<ConvGeom> gs;

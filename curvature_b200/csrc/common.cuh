@@ -96,6 +96,8 @@ int syrk_stream_fork(cudaStream_t s);
 bool syrk_nhwc_supported(const ConvGeom& g, int precision);
 size_t syrk_nhwc_workspace(const ConvGeom& g, int precision);
 size_t syrk_nhwc_batch_workspace(const ConvGeom* gs, int n, int precision);
+int syrk_nhwc_debug_partition(const ConvGeom* gs, int n, int precision, int sms, int which, int* launch_of_item, int* G,
+                              int* q, unsigned* b, int cap, int* pairs, int* nbox_of_pair, int* nb_of_pair, int pair_cap);
 int syrk_nhwc_batch_launch(const ConvGeom* gs, const float* alphas, float* const* Fs, int n, int precision, void* ws,
                            size_t ws_bytes, cudaStream_t s);
 int syrk_nhwc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,

@@ -2127,10 +2127,11 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
 }
 
 // plan every factor of a batch and cut the batch into launches (lists of indices into the batch)
-int plan_batch(const ConvGeom* gs, int n, int precision, std::vector<NhPlan>& plans, std::vector<std::vector<int>>& launches) {
+int plan_batch(const ConvGeom* gs, int n, int precision, std::vector<NhPlan>& plans, std::vector<std::vector<int>>& launches,
+               int sms_override = 0) {
   CRV_CHECK(precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32_TMA || precision == CRV_PREC_BF16,
             "channels-last SYRK: tier %d is not built (available: tf32, tf32_tma, bf16)", precision);
-  const int sms = device_sm_count();
+  const int sms = sms_override > 0 ? sms_override : device_sm_count();
   CRV_CHECK(sms > 0, "no CUDA device");
   plans.resize(n);
   std::vector<int> grp;
@@ -2188,6 +2189,38 @@ int syrk_nhwc_batch_launch(const ConvGeom* gs, const float* alphas, float* const
   for (const auto& l : launches)
     if (int rc = launch_group(gs, alphas, Fs, plans, l.data(), (int)l.size(), ws, ws_bytes, copy_off, s)) return rc;
   return 0;
+}
+
+// Host-only view of the scheduler (no device needed): how a batch is cut into launches and, for launch `which`, the
+// stream-K boundary table and the per-pair cost / stage granularity it was built from.  Used by the CPU tests.
+int syrk_nhwc_debug_partition(const ConvGeom* gs, int n, int precision, int sms, int which, int* launch_of_item, int* G,
+                              int* q, unsigned* b, int cap, int* pairs, int* nbox_of_pair, int* nb_of_pair, int pair_cap) {
+  std::vector<NhPlan> plans;
+  std::vector<std::vector<int>> launches;
+  if (int rc = plan_batch(gs, n, precision, plans, launches, sms)) return rc;
+  for (size_t l = 0; l < launches.size(); ++l)
+    for (int i : launches[l]) launch_of_item[i] = (int)l;
+  CRV_CHECK(which >= 0 && which < (int)launches.size(), "launch %d of %d", which, (int)launches.size());
+  std::vector<const NhPlan*> pls;
+  for (int i : launches[which]) pls.push_back(&plans[i]);
+  static GroupParams gp;
+  static SkTable sk;
+  gp.nf = (int)pls.size();
+  build_sk(pls, sms, gp, sk);
+  CRV_CHECK(sk.G + 1 <= cap, "boundary table needs %d entries", sk.G + 1);
+  *G = sk.G;
+  for (int c = 0; c <= sk.G; ++c) { q[c] = sk.q[c]; b[c] = sk.b[c]; }
+  int P = 0;
+  for (const NhPlan* pl : pls)
+    for (int k = 0; k < pl->pairs; ++k, ++P) {
+      CRV_CHECK(P < pair_cap, "pair table too small");
+      int I, J;
+      host_decode_pair(k, pl->p.T, I, J);
+      nbox_of_pair[P] = pl->p.nbox;
+      nb_of_pair[P] = I == J ? pl->p.NBdiag : pl->p.NBoff;
+    }
+  *pairs = P;
+  return (int)launches.size() << 16;      // (number of launches in the high half; 0 in the low half = ok)
 }
 
 size_t syrk_nhwc_workspace(const ConvGeom& g, int precision) { return syrk_nhwc_batch_workspace(&g, 1, precision); }

@@ -132,6 +132,13 @@ typedef struct {
 size_t crv_syrk_batch_nhwc_workspace(const crv_syrk_item* items, int n, int precision);
 int crv_syrk_batch_nhwc(const crv_syrk_item* items, int n, void* ws, size_t ws_bytes, int precision,
                         crv_stream_t stream);
+/* Host-only view of the K1e scheduler for `sms` SMs (no device needed; x / F of the items are not dereferenced but x must
+ * be non-null and 16-byte aligned): launch_of_item[i] = the launch item i rides in, *n_launches, and for launch `which`
+ * the stream-K boundary table -- CTA c starts at (pair q[c], box b[c]), c <= *G, (q[*G], b[*G]) = (*pairs, 0) -- plus
+ * per pair of that launch the number of boxes and the stage granularity.  Used by the CPU tests of the partition. */
+int crv_debug_partition(const crv_syrk_item* items, int n, int precision, int sms, int which, int* launch_of_item,
+                        int* n_launches, int* G, int* q, unsigned* b, int cap, int* pairs, int* nbox_of_pair,
+                        int* nb_of_pair, int pair_cap);
 
 /* The channels-last SYRK calls enqueue their split reduction (the kernel that adds the result into the factor) on an
  * internal side stream, so that it overlaps the next call's main kernel.  crv_stream_join() makes `stream` wait (on the

@@ -168,3 +168,50 @@ def test_factor_file_round_trip_is_name_keyed_and_pickle_free(tmp_path):
             cb.load_factors(other, path)
     with pytest.raises(ValueError):
         cb.load_factors(cb.Diagonal(make()), str(tmp_path / "KFAC.pt"))
+
+
+def _resnet50_items(batch=256):
+    """(N, C, H, W, kh, kw, sh, sw, ph, pw) of every channels-last factor operand of a ResNet-50 KFAC.update (fc excluded:
+    its A factor has a bias row), from a 1-image CPU forward (shapes only)."""
+    import torch
+    import torchvision
+    model = torchvision.models.resnet50(weights=None).eval()
+    shapes = {}
+    hooks = [m.register_forward_hook(lambda mod, inp, out: shapes.__setitem__(mod, (inp[0].shape, out.shape)))
+             for m in model.modules() if isinstance(m, torch.nn.Conv2d)]
+    with torch.no_grad():
+        model(torch.zeros(1, 3, 224, 224))
+    for h in hooks:
+        h.remove()
+    items = []
+    for m in model.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            (_, C, H, W), (_, M, OH, OW) = shapes[m]
+            items.append((batch, C, H, W, *m.kernel_size, *m.stride, *m.padding))      # A factor
+            items.append((batch, M, 1, OH * OW, 1, 1, 1, 1, 0, 0))                      # G factor (rows operand)
+    return items
+
+
+def test_stream_k_partition_of_a_resnet50_update_is_a_partition():
+    """Host logic of K1e (no GPU): crv_debug_partition exposes how the 106 channels-last factors of a ResNet-50 update are
+    cut into launches and each launch's work list into CTA ranges.  Invariants: re-read operands get a launch each and
+    read-once ones ride in groups of <= 48; boundaries start at (0, 0), end at (pairs, 0), are strictly increasing, lie
+    inside their pair on whole pipeline stages, and there are at most `sms` CTAs."""
+    items = _resnet50_items()
+    assert len(items) == 106
+    first = nat.debug_partition(items, nat.PREC_BF16, sms=148, which=0)
+    nl = first["n_launches"]
+    sizes = [first["launch_of_item"].count(l) for l in range(nl)]
+    assert sum(sizes) == len(items) and max(sizes) <= 48
+    assert sum(1 for s in sizes if s > 1) >= 2 and sizes.count(1) == 37          # two groups of read-once factors, 37 re-read operands with a launch each
+    for which in range(nl):
+        part = nat.debug_partition(items, nat.PREC_BF16, sms=148, which=which)
+        bd, nbox, nb = part["boundaries"], part["nbox"], part["nb"]
+        pairs = len(nbox)
+        assert bd[0] == (0, 0) and bd[-1] == (pairs, 0) and len(bd) - 1 <= 148
+        assert all(x < y for x, y in zip(bd, bd[1:])), which
+        for q, b in bd[:-1]:
+            assert 0 <= q < pairs and 0 <= b < nbox[q] and b % nb[q] == 0, (which, q, b)
+    # fewer SMs: still a partition with at most that many CTAs
+    part = nat.debug_partition(items, nat.PREC_BF16, sms=20, which=nl - 1)
+    assert len(part["boundaries"]) - 1 <= 20 and part["boundaries"][-1] == (len(part["nbox"]), 0)
