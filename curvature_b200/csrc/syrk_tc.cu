@@ -2043,14 +2043,16 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
     gp.f[k].F = Fs[idx[k]];
     const float* src = g.x;
     if (pl.copy_bytes) {   // pre-pass: bf16 copy (tier bf16) / TF32 round-to-nearest copy (tier tf32), same layout; or pack
-      float* copy = (float*)((((uintptr_t)wsb + copy_off) + 1023) & ~(uintptr_t)1023);
+      // (fault injection for the overlap test: CURVATURE_B200_FAULT_COPY_LAYOUT=1 restores the old, unsafe placement)
+      static const bool fault = getenv("CURVATURE_B200_FAULT_COPY_LAYOUT") && atoi(getenv("CURVATURE_B200_FAULT_COPY_LAYOUT")) != 0;
+      float* copy = (float*)((((uintptr_t)wsb + (fault ? partial_bytes : copy_off)) + 1023) & ~(uintptr_t)1023);
       const size_t n4 = (size_t)g.N * g.C * g.H * g.W / 4;
       cudaStream_t cs = s;
       const bool side_cast = use_side && st->forked;
       if (side_cast) {      // wait only for the main kernel that last read this half's copy region (two calls ago)
         cs = st->cast;
         if (st->main_pending[buf]) CRV_CUDA(cudaStreamWaitEvent(cs, st->ev_main[buf], 0));
-        if (st->red_pending[buf]) CRV_CUDA(cudaStreamWaitEvent(cs, st->ev_red[buf], 0));   // (and the reduction that read this half)
+        if (st->red_pending[buf] && !fault) CRV_CUDA(cudaStreamWaitEvent(cs, st->ev_red[buf], 0));   // (and the reduction that read this half)
       }
       if (pl.pack) {
         const ConvGeom& q = pl.gq;

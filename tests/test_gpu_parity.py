@@ -803,7 +803,8 @@ def test_update_with_stream_overlap_equals_serialised_update():
     (crv_profile_enable switches the side streams off): the reductions are fixed-order, so the factors must be
     BIT-identical -- any workspace hazard between overlapping launches shows up as a difference.  ResNet-50 at batch
     64: long tap-aware reductions (2304^2, 4608^2 factors) followed by short launches, the pattern that once let a
-    pre-pass overwrite partial tiles that were still being reduced.  Also: every factor symmetric and, damped, PD."""
+    pre-pass overwrite partial tiles that were still being reduced (CURVATURE_B200_FAULT_COPY_LAYOUT=1 re-injects that
+    layout: this test then fails on the symmetry check).  Also: every factor symmetric and, damped, PD."""
     import torchvision
     import curvature_b200 as cb
     torch.manual_seed(0)
