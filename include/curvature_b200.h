@@ -11,7 +11,11 @@
  *   - every data pointer is a DEVICE pointer to fp32 memory owned by the caller (torch);
  *   - `stream` is a cudaStream_t (pass torch.cuda.current_stream().cuda_stream); calls only
  *     enqueue work, never synchronise the device, never allocate persistent memory;
- *   - scratch memory is passed in as (ws, ws_bytes); size it with crv_workspace_bytes();
+ *   - the channels-last SYRK calls and the batched K3 / K5 calls run part of their work on a few internal streams
+ *     (created lazily, per device); everything is ordered against `stream` with events, see crv_stream_fork / _join;
+ *   - scratch memory is passed in as (ws, ws_bytes); size it with crv_workspace_bytes() or the call's own
+ *     *_workspace() function; the SAME buffer must be passed to consecutive calls of a fork .. join section (its two
+ *     halves are used alternately by overlapping launches);
  *   - return value 0 = ok, non-zero = error; crv_last_error() gives the message (thread-local);
  *   - there is no CPU fallback: without a CUDA device every compute call returns an error.
  *   - matrices are dense row-major.
