@@ -5,8 +5,34 @@
 #include <vector>
 #include <algorithm>
 #include <utility>
+#include <mutex>
 
 namespace crv {
+
+static std::recursive_mutex g_api_mutex;
+
+ApiGuard::ApiGuard(const void* ptr, cudaStream_t s) {
+  g_api_mutex.lock();
+  int want = -1;
+  if (ptr) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeDevice) want = at.device;
+    else cudaGetLastError();
+  }
+  if (want < 0 && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
+    int d = -1;
+    if (cudaStreamGetDevice(s, &d) == cudaSuccess) want = d;
+    else cudaGetLastError();
+  }
+  if (want >= 0) {
+    if (cudaGetDevice(&prev_) != cudaSuccess) { cudaGetLastError(); prev_ = -1; }
+    if (prev_ != want && cudaSetDevice(want) == cudaSuccess) switched_ = true;
+  }
+}
+ApiGuard::~ApiGuard() {
+  if (switched_ && prev_ >= 0) cudaSetDevice(prev_);
+  g_api_mutex.unlock();
+}
 
 static thread_local char g_err[512] = "";
 
@@ -100,6 +126,7 @@ int crv_profile_enable(int on) {
 }
 
 int crv_profile_collect(double* ms, double* flops, double* bytes, long long* launches, int nclasses) {
+  ApiGuard guard_(nullptr);
   CRV_CHECK(ms && flops && bytes && launches && nclasses >= KC_COUNT, "crv_profile_collect: need %d classes", (int)KC_COUNT);
   for (int i = 0; i < nclasses; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
   for (auto& r : g_prof) {
@@ -172,6 +199,7 @@ size_t crv_workspace_bytes(int op, const int64_t* dims, int ndims) {
 int crv_syrk_conv_accum(const float* x, int N, int C, int H, int W, int kh, int kw, int sh, int sw, int ph,
                         int pw, int has_bias, float alpha, float* A, void* ws, size_t ws_bytes,
                         int precision, crv_stream_t stream) {
+  ApiGuard guard_(x, (cudaStream_t)stream);
   ConvGeom g;
   if (int rc = make_geom(g, x, N, C, H, W, kh, kw, sh, sw, ph, pw, has_bias)) return rc;
   return syrk_dispatch(g, alpha, A, ws, ws_bytes, precision, (cudaStream_t)stream);
@@ -179,6 +207,7 @@ int crv_syrk_conv_accum(const float* x, int N, int C, int H, int W, int kh, int 
 
 int crv_syrk_rows_accum(const float* gptr, int N, int M, int L, int has_bias, float alpha, float* F,
                         void* ws, size_t ws_bytes, int precision, crv_stream_t stream) {
+  ApiGuard guard_(gptr, (cudaStream_t)stream);
   ConvGeom g;
   if (int rc = make_geom(g, gptr, N, M, 1, L, 1, 1, 1, 1, 0, 0, has_bias)) return rc;
   return syrk_dispatch(g, alpha, F, ws, ws_bytes, precision, (cudaStream_t)stream);
@@ -187,6 +216,7 @@ int crv_syrk_rows_accum(const float* gptr, int N, int M, int L, int has_bias, fl
 int crv_syrk_conv_accum_nhwc(const float* x, int N, int C, int H, int W, int kh, int kw, int sh, int sw, int ph,
                              int pw, int has_bias, float alpha, float* A, void* ws, size_t ws_bytes,
                              int precision, crv_stream_t stream) {
+  ApiGuard guard_(x, (cudaStream_t)stream);
   ConvGeom g;
   if (int rc = make_geom(g, x, N, C, H, W, kh, kw, sh, sw, ph, pw, has_bias)) return rc;
   return syrk_nhwc_launch(g, alpha, A, precision, ws, ws_bytes, (cudaStream_t)stream);
@@ -194,6 +224,7 @@ int crv_syrk_conv_accum_nhwc(const float* x, int N, int C, int H, int W, int kh,
 
 int crv_syrk_rows_accum_nhwc(const float* gptr, int N, int M, int L, int has_bias, float alpha, float* F,
                              void* ws, size_t ws_bytes, int precision, crv_stream_t stream) {
+  ApiGuard guard_(gptr, (cudaStream_t)stream);
   ConvGeom g;
   if (int rc = make_geom(g, gptr, N, M, 1, L, 1, 1, 1, 1, 0, 0, has_bias)) return rc;
   return syrk_nhwc_launch(g, alpha, F, precision, ws, ws_bytes, (cudaStream_t)stream);
@@ -237,6 +268,7 @@ int crv_debug_partition(const crv_syrk_item* items, int n, int precision, int sm
 
 int crv_syrk_batch_nhwc(const crv_syrk_item* items, int n, void* ws, size_t ws_bytes, int precision,
                         crv_stream_t stream) {
+  ApiGuard guard_(items && n > 0 ? items[0].x : nullptr, (cudaStream_t)stream);
   std::vector<ConvGeom> gs;
   std::vector<float> alphas;
   std::vector<float*> Fs;
@@ -244,15 +276,19 @@ int crv_syrk_batch_nhwc(const crv_syrk_item* items, int n, void* ws, size_t ws_b
   return syrk_nhwc_batch_launch(gs.data(), alphas.data(), Fs.data(), n, precision, ws, ws_bytes, (cudaStream_t)stream);
 }
 
-int crv_stream_join(crv_stream_t stream) { return syrk_stream_join((cudaStream_t)stream); }
-int crv_stream_fork(crv_stream_t stream) { return syrk_stream_fork((cudaStream_t)stream); }
+int crv_stream_join(crv_stream_t stream) {
+  ApiGuard guard_(nullptr, (cudaStream_t)stream); return syrk_stream_join((cudaStream_t)stream); }
+int crv_stream_fork(crv_stream_t stream) {
+  ApiGuard guard_(nullptr, (cudaStream_t)stream); return syrk_stream_fork((cudaStream_t)stream); }
 
 int crv_diag_accum(const float* wgrad, const float* bgrad, int M, int K0, float scale, float* state,
                    float* grads_out, crv_stream_t stream) {
+  ApiGuard guard_(wgrad, (cudaStream_t)stream);
   return diag_accum_launch(wgrad, bgrad, M, K0, scale, state, grads_out, (cudaStream_t)stream);
 }
 
 int crv_diag_accum_batch(const crv_diag_item* items, int n, float scale, crv_stream_t stream) {
+  ApiGuard guard_(items && n > 0 ? items[0].wgrad : nullptr, (cudaStream_t)stream);
   CRV_CHECK(items != nullptr && n > 0, "empty batch");
   std::vector<const float*> w(n), b(n);
   std::vector<float*> st(n), go(n);
@@ -266,6 +302,7 @@ int crv_diag_accum_batch(const crv_diag_item* items, int n, float scale, crv_str
 
 int crv_gemm(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc,
              int m, int n, int k, float alpha, float beta, int precision, crv_stream_t stream) {
+  ApiGuard guard_(A, (cudaStream_t)stream);
   // op(A)(i,kk): A[i*lda + kk] or, transposed, A[kk*lda + i]
   const long long sa_m = transA ? 1 : lda, sa_k = transA ? lda : 1;
   const long long sb_k = transB ? 1 : ldb, sb_n = transB ? ldb : 1;
@@ -329,6 +366,7 @@ size_t crv_efb_project_batch_workspace(const crv_efb_item* items, int n) {
 
 int crv_efb_project_batch(const crv_efb_item* items, int n, void* ws, size_t ws_bytes, int precision,
                           crv_stream_t stream) {
+  ApiGuard guard_(items && n > 0 ? items[0].G : nullptr, (cudaStream_t)stream);
   CRV_CHECK(items != nullptr && n > 0, "empty batch");
   const size_t need = crv_efb_project_batch_workspace(items, n);
   CRV_CHECK(ws && ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
@@ -371,6 +409,7 @@ size_t crv_sample_matrix_normal_batch_workspace(const crv_sample_item* items, in
 
 int crv_sample_matrix_normal_batch(const crv_sample_item* items, int n, void* ws, size_t ws_bytes, int precision,
                                    crv_stream_t stream) {
+  ApiGuard guard_(items && n > 0 ? items[0].LG : nullptr, (cudaStream_t)stream);
   CRV_CHECK(items != nullptr && n > 0, "empty batch");
   const size_t need = crv_sample_matrix_normal_batch_workspace(items, n);
   CRV_CHECK(ws && ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
@@ -405,6 +444,7 @@ int crv_sample_matrix_normal_batch(const crv_sample_item* items, int n, void* ws
 
 int crv_efb_project_accum(const float* QG, const float* QA, const float* G, int M, int K, float* lambdas,
                           void* ws, size_t ws_bytes, int precision, crv_stream_t stream) {
+  ApiGuard guard_(G, (cudaStream_t)stream);
   CRV_CHECK(QG && QA && G && lambdas, "null pointer");
   CRV_CHECK(ws && ws_bytes >= (size_t)M * K * sizeof(float), "workspace too small");
   return efb_project_one(QG, QA, G, M, K, lambdas, (float*)ws, precision, (cudaStream_t)stream);
@@ -424,6 +464,7 @@ static int efb_project_one(const float* QG, const float* QA, const float* G, int
 int crv_chol_inv_batched(const float* const* F, const int* dims, int count, const float* add,
                          const float* mul, float* const* L_out, int* info, void* ws, size_t ws_bytes,
                          crv_stream_t stream) {
+  ApiGuard guard_(info, (cudaStream_t)stream);
   return chol_inv_batched_launch(F, dims, count, add, mul, L_out, info, ws, ws_bytes, (cudaStream_t)stream);
 }
 
@@ -431,6 +472,7 @@ int crv_sample_matrix_normal(const float* LG, const float* LA, const float* z, c
                              int K0, int has_bias, const float* mu_w, const float* mu_b, float* w_out,
                              float* b_out, float* s_out, void* ws, size_t ws_bytes, int precision,
                              crv_stream_t stream) {
+  ApiGuard guard_(LG, (cudaStream_t)stream);
   const size_t mk0 = (size_t)M * (K0 + (has_bias ? 1 : 0));
   CRV_CHECK(ws && ws_bytes >= mk0 * sizeof(float) * (row_scale ? 2 : 1), "workspace too small");
   return sample_mn_one(LG, LA, z, row_scale, M, K0, has_bias, mu_w, mu_b, w_out, b_out, s_out, (float*)ws, precision,
@@ -468,15 +510,18 @@ static int sample_mn_one(const float* LG, const float* LA, const float* z, const
 }
 
 int crv_round_tf32(const float* in, float* out, size_t n, crv_stream_t stream) {
+  ApiGuard guard_(in, (cudaStream_t)stream);
   return round_tf32_launch(in, out, n, (cudaStream_t)stream);
 }
 
 int crv_elementwise_inv_sqrt(const float* v, float add, float mul, float* out, size_t n, crv_stream_t stream) {
+  ApiGuard guard_(v, (cudaStream_t)stream);
   return inv_sqrt_launch(v, add, mul, out, n, (cudaStream_t)stream);
 }
 
 int crv_diag_sample(const float* z, const float* inv, int M, int K0, int has_bias, const float* mu_w,
                     const float* mu_b, float* w_out, float* b_out, float* s_out, crv_stream_t stream) {
+  ApiGuard guard_(z, (cudaStream_t)stream);
   return diag_sample_launch(z, inv, M, K0, has_bias, mu_w, mu_b, w_out, b_out, s_out, (cudaStream_t)stream);
 }
 

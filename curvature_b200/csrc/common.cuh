@@ -69,6 +69,21 @@ inline int make_geom(ConvGeom& g, const float* x, int N, int C, int H, int W, in
 
 int device_sm_count();
 
+// Every launching entry point of the C ABI holds one of these for the duration of the call: it serialises the host-side
+// launch paths (kernel parameter blocks, stream-K tables, side-stream bookkeeping and the profiler records are
+// process-wide state) and makes the device that owns `ptr` (else the device of `s`, else the current one) current, so
+// that the per-device stream pools / SM counts the library looks up belong to the tensors it is handed.
+class ApiGuard {
+ public:
+  explicit ApiGuard(const void* ptr, cudaStream_t s = nullptr);
+  ~ApiGuard();
+  ApiGuard(const ApiGuard&) = delete;
+  ApiGuard& operator=(const ApiGuard&) = delete;
+ private:
+  int prev_ = -1;
+  bool switched_ = false;
+};
+
 // ---- optional per-kernel CUDA-event timing (crv_profile_*): a scope records one event pair on the launching stream
 // around one kernel launch when profiling is enabled, and costs one predictable branch when it is not.
 enum KernelClass {

@@ -210,7 +210,7 @@ gemm_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap ta, const _
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128) : "memory");
 }
 
-__global__ void __launch_bounds__(256) round_tf32_inplace_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n) {
+__global__ void __launch_bounds__(256) round_tf32_inplace_kernel(const float* in, float* out, size_t n) /* in == out allowed: no __restrict__ */ {
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = rna_tf32(in[i]);
 }
 

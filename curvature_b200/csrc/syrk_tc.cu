@@ -1929,6 +1929,25 @@ int syrk_stream_join(cudaStream_t s) {
   return 0;
 }
 
+// A launch of a fork .. join section failed: order the caller's stream behind everything the section enqueued so far and
+// clear the section's bookkeeping, so that later (non-forked) calls do not run on the internal streams or skip a wait.
+static void side_abort(cudaStream_t s) {
+  SideState* st = side_state();
+  if (!st || !st->enabled) return;
+  for (int b = 0; b < 2; ++b) {
+    if (st->red_pending[b]) cudaStreamWaitEvent(s, st->ev_red[b], 0);
+    if (st->main_pending[b]) cudaStreamWaitEvent(s, st->ev_main[b], 0);
+    st->red_pending[b] = st->main_pending[b] = false;
+  }
+  if (st->forked) {
+    if (cudaEventRecord(st->ev_hp, st->hp) == cudaSuccess) cudaStreamWaitEvent(s, st->ev_hp, 0);
+    if (cudaEventRecord(st->ev_fork, st->cast) == cudaSuccess) cudaStreamWaitEvent(s, st->ev_fork, 0);
+  }
+  st->forked = false;
+  st->toggle = 0;
+  cudaGetLastError();
+}
+
 // Declare that every operand tensor of the SYRK calls that follow (until the next join) is complete on `s` NOW: the
 // cast / rounding pre-pass of call i may then run on a side stream, concurrently with the main kernel of call i-1
 // (an HBM-bound copy beside an L2/TMA-bound contraction), instead of in order behind it.
@@ -2189,7 +2208,10 @@ int syrk_nhwc_batch_launch(const ConvGeom* gs, const float* alphas, float* const
   size_t copy_off, max_copy;
   batch_layout(plans, launches, copy_off, max_copy);
   for (const auto& l : launches)
-    if (int rc = launch_group(gs, alphas, Fs, plans, l.data(), (int)l.size(), ws, ws_bytes, copy_off, s)) return rc;
+    if (int rc = launch_group(gs, alphas, Fs, plans, l.data(), (int)l.size(), ws, ws_bytes, copy_off, s)) {
+      side_abort(s);
+      return rc;
+    }
   return 0;
 }
 

@@ -452,14 +452,17 @@ class KFAC(Curvature):
                         nat.syrk_rows_accum(g, False, alpha_g, second, self.precision, join=False)
                 elif module_class == 'MultiheadAttention':
                     raise NotImplementedError
-        if batch:
-            # every recorded tensor is complete on the current stream: between this fork and the join below the library
-            # runs pre-passes, contractions and reductions on its own prioritised streams
-            nat.stream_fork(device)
-            nat.syrk_batch_nhwc(batch, self.precision, device, join=False)
-        # the split reductions run on the library's side stream: order the caller's stream after them
-        if device is not None:
-            nat.stream_join(device)
+        try:
+            if batch:
+                # every recorded tensor is complete on the current stream: between this fork and the join below the
+                # library runs pre-passes, contractions and reductions on its own prioritised streams
+                nat.stream_fork(device)
+                nat.syrk_batch_nhwc(batch, self.precision, device, join=False)
+        finally:
+            # the split reductions run on the library's side stream: order the caller's stream after them (also when
+            # a launch failed: the fork must not stay open)
+            if device is not None:
+                nat.stream_join(device)
 
     def invert(self,
                add: Union[float, list, tuple] = 0.,

@@ -283,7 +283,11 @@ def main():
         return orc.lenet5()
 
     bad = False
-    bad |= run_case("lenet5", lenet, (32, 1, 28, 28), 2, 100, (0.5, 1.0), (0.1, 1e3), (0.1, 1e3),
+    # BASELINE configs 1 / 2: batches of 100, 3 batches, rank 100, KFAC invert(0.5, 1) (README),
+    # INF invert(1e15, 1e20) (tutorial cell 17), Diagonal / EFB invert(0.1, 1e3).  Weights: seeded random init (the
+    # bundled lenet5_mnist.pth is reference data and is not copied; tests/test_oracle_golden.py pins the oracle on it
+    # through SURVEY 8(c)'s known-answer table wherever the reference tree is present).
+    bad |= run_case("lenet5", lenet, (100, 1, 28, 28), 3, 100, (0.5, 1.0), (0.1, 1e3), (1e15, 1e20),
                     ref_curv, ref_utils, orc, full=False)
     # rank 40: keeps every low-rank index list >= 32 long -- the reference's
     # `lambda_vec[[...list of 0-d tensors...]]` (curvatures.py:643) raises IndexError for

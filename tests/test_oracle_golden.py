@@ -84,3 +84,48 @@ def test_flip_cholesky_identity(golden):
             Cinv = torch.linalg.inv(C)
             L = Cinv.t().flip(0).flip(1)
             assert rel_fro(L, g[f"{Lkey}/{li}"]) <= 1e-5
+
+
+REF_WEIGHTS = "/root/reference/curvature/lenet5_mnist.pth"
+
+# known answers of the REAL reference on its bundled LeNet-5 weights (BASELINE configs 1 / 2: three
+# batches of 100, sampled-label Fisher, KFAC.invert(0.5, 1)).  Columns: tr A, |A|_F, tr G, |G|_F, sum Diagonal.state,
+# tr L_A, tr L_G.
+KNOWN_ANSWERS = [
+    (25.935345, 19.379271, 1.258251e-3, 6.356086e-4, 11.94352, 25.098049, 7.134185),
+    (558.588440, 521.087219, 5.661512e-3, 2.574870e-3, 188.7346, 157.176849, 19.022558),
+    (28.024693, 9.075549, 2.322013, 0.6647527, 20.07698, 462.779999, 140.977631),
+    (5.670164, 4.185143, 2.926824, 0.9636346, 4.899538, 141.880829, 97.875572),
+    (5.301585, 4.446790, 2.671096, 0.9185417, 4.128474, 99.562302, 10.173796)]
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(REF_WEIGHTS),
+                    reason="the reference tree (its bundled lenet5_mnist.pth is reference data, not copied here) is absent")
+def test_oracle_reproduces_reference_known_answers_on_bundled_weights():
+    """BASELINE config 1 proper: the reference's own weights (read in place from the reference tree, build container
+    only), the recipe of SURVEY 8(c), every number of its table to 1e-5 relative."""
+    from torch.distributions import Categorical
+    torch.manual_seed(0)
+    model = orc.lenet5()
+    model.load_state_dict(torch.load(REF_WEIGHTS, weights_only=True, map_location="cpu"))
+    kfac, diag = orc.KFAC(model), orc.Diagonal(model)
+    gen = torch.Generator().manual_seed(123)
+    crit = torch.nn.CrossEntropyLoss()
+    for _ in range(3):
+        x = torch.rand(100, 1, 28, 28, generator=gen)
+        logits = model(x)
+        labels = Categorical(logits=logits).sample()
+        loss = crit(logits, labels)
+        model.zero_grad()
+        loss.backward()
+        kfac.update(100)
+        diag.update(100)
+    assert labels[:5].tolist() == [9, 7, 8, 4, 0] and abs(loss.item() - 2.260454) < 1e-5
+    kfac.invert(add=0.5, multiply=1)
+    for layer, want in zip(kfac.state, KNOWN_ANSWERS):
+        A, G = kfac.state[layer]
+        LA, LG = kfac.inv_state[layer]
+        got = (A.trace(), A.norm(), G.trace(), G.norm(), diag.state[layer].sum(), LA.trace(), LG.trace())
+        assert A[-1, -1].item() == 3.0          # ones row x 3 summed updates: plain running sum
+        for v, w in zip(got, want):
+            assert abs(v.item() - w) <= 1e-5 * abs(w), (str(layer), v.item(), w)
