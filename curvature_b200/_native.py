@@ -40,6 +40,8 @@ _last_error = _sig("crv_last_error", c_char_p)
 _sm_count = _sig("crv_device_sm_count", c_int)
 _profile_enable = _sig("crv_profile_enable", c_int, c_int)
 _debug_timeline = _sig("crv_debug_timeline", c_int, ctypes.c_void_p)
+_debug_trace = _sig("crv_debug_trace", c_int, ctypes.c_void_p, c_int)
+_debug_trace_count = _sig("crv_debug_trace_count", c_int)
 _profile_collect = _sig("crv_profile_collect", c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double),
                        POINTER(ctypes.c_double), POINTER(ctypes.c_longlong), c_int)
 _workspace_bytes = _sig("crv_workspace_bytes", c_size_t, c_int, POINTER(c_int64), c_int)
@@ -111,7 +113,7 @@ _syrk_batch = _sig("crv_syrk_batch_nhwc", c_int, POINTER(SyrkItem), c_int, c_voi
 ABI_VERSION = _abi_version()
 EXPORTED_SYMBOLS = (
     "crv_abi_version", "crv_last_error", "crv_device_sm_count", "crv_workspace_bytes", "crv_profile_enable",
-    "crv_profile_collect", "crv_debug_timeline",
+    "crv_profile_collect", "crv_debug_timeline", "crv_debug_trace", "crv_debug_trace_count",
     "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc", "crv_syrk_batch_nhwc", "crv_syrk_batch_nhwc_workspace", "crv_debug_partition", "crv_stream_join", "crv_stream_fork",
     "crv_diag_accum", "crv_diag_accum_batch", "crv_efb_project_accum", "crv_efb_project_batch",
     "crv_efb_project_batch_workspace", "crv_sample_matrix_normal_batch", "crv_sample_matrix_normal_batch_workspace",
@@ -212,6 +214,23 @@ def profile_enable(on=True):
 def debug_timeline(buf=None):
     """Profiling aid: per-CTA time stamps of the channels-last SYRK kernel into `buf` (int64 CUDA tensor, >= 1280)."""
     _check(_debug_timeline(None if buf is None else buf.data_ptr()), "crv_debug_timeline")
+
+
+def debug_trace(slots=0, device=None):
+    """Profiling aid: start (slots > 0; returns the int64 buffer, shape (slots, 8)) or stop (slots = 0) the launch-level
+    trace of the channels-last SYRK path -- device-clock first-start / last-end of every contraction, reduction and pre-pass
+    kernel with the stream overlap left on.  debug_trace_count() = launches recorded so far."""
+    if not slots:
+        _check(_debug_trace(None, 0), "crv_debug_trace")
+        return None
+    buf = torch.zeros(slots, 8, dtype=torch.int64, device=device)
+    buf[:, 0:6:2] = -1
+    _check(_debug_trace(buf.data_ptr(), slots), "crv_debug_trace")
+    return buf
+
+
+def debug_trace_count():
+    return _debug_trace_count()
 
 
 def profile_collect():

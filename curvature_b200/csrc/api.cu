@@ -71,6 +71,13 @@ std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
 bool profile_on() { return g_prof_on; }
 static long long* g_timeline = nullptr;
 long long* debug_timeline_buffer() { return g_timeline; }
+// launch-level trace (crv_debug_trace): slot i = 8 words of launch i of the channels-last SYRK path
+static unsigned long long* g_trace = nullptr;
+static int g_trace_cap = 0, g_trace_next = 0;
+unsigned long long* debug_trace_slot() {
+  if (!g_trace || g_trace_next >= g_trace_cap) return nullptr;
+  return g_trace + 8 * (size_t)(g_trace_next++);
+}
 
 void profile_begin(int kclass, double flops, double bytes, cudaStream_t s) {
   if (!g_prof_on) return;
@@ -119,6 +126,11 @@ const char* crv_last_error(void) { return last_error(); }
 int crv_device_sm_count(void) { return device_sm_count(); }
 
 int crv_debug_timeline(long long* buf) { g_timeline = buf; return 0; }
+int crv_debug_trace(unsigned long long* buf, int slots) {
+  g_trace = buf; g_trace_cap = buf ? slots : 0; g_trace_next = 0;
+  return 0;
+}
+int crv_debug_trace_count(void) { return g_trace_next; }
 
 int crv_profile_enable(int on) {
   g_prof_on = on != 0;

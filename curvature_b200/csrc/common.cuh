@@ -96,6 +96,7 @@ enum KernelClass {
   KC_COUNT          = 6
 };
 long long* debug_timeline_buffer();
+unsigned long long* debug_trace_slot();
 bool profile_on();
 void profile_begin(int kclass, double flops, double bytes, cudaStream_t s);
 void profile_end(cudaStream_t s);

@@ -148,6 +148,18 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// launch-level trace: first-start / last-end of a kernel's CTAs into two words of the launch's slot
+__device__ __forceinline__ void trace_begin(unsigned long long* tr, int w) {
+  if (tr && threadIdx.x == 0) atomicMin(tr + w, gtimer());
+}
+__device__ __forceinline__ void trace_end(unsigned long long* tr, int w) {
+  if (tr && threadIdx.x == 0) atomicMax(tr + w + 1, gtimer());
+}
+struct TraceScope {
+  unsigned long long* tr; int w;
+  __device__ __forceinline__ TraceScope(unsigned long long* t, int word) : tr(t), w(word) { trace_begin(tr, w); }
+  __device__ __forceinline__ ~TraceScope() { trace_end(tr, w); }
+};
 __device__ __forceinline__ long long nv_kg(int NB, int left, int kpb) { return (long long)min(NB, left) * kpb; }
 // 1 in exactly one (elected) lane of a fully converged warp
 __device__ __forceinline__ uint32_t elect_one() {
@@ -900,6 +912,7 @@ struct GroupParams {
   int nf;
   int dbg;                   // ablation switches for profiling (bit 0: no TMA loads, bit 1: no MMAs); 0 in production
   long long* tl;             // per-CTA timeline (profiling aid, see crv_debug_timeline); null in production
+  unsigned long long* trace; // launch-level trace slot (crv_debug_trace); null in production
   float* ws;                 // partial tiles, slot = CTA + q
   int qbeg[GRP_MAXF + 1];
   NhParams f[GRP_MAXF];
@@ -1031,6 +1044,11 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     tl[0] = (long long)gtimer(); tl[7] = smid;
+  }
+  trace_begin(gp.trace, 0);
+  if (gp.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    gp.trace[6] = (unsigned long long)gp.f[0].D | ((unsigned long long)gp.nf << 20) | ((unsigned long long)(BF16 ? 1 : 0) << 30);
+    gp.trace[7] = (unsigned long long)gp.qbeg[gp.nf];
   }
   // this CTA's range of the work list
   const int q0 = (int)sk.q[blockIdx.x], q1 = (int)sk.q[blockIdx.x + 1];
@@ -1252,6 +1270,7 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  trace_end(gp.trace, 0);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
@@ -1265,6 +1284,7 @@ __global__ void __launch_bounds__(256, 4) syrk_sk_reduce_kernel(const __grid_con
   // (416 threads, ~211 KB), so that on the side stream the reduction really overlaps it.
   __shared__ float tile[32][33];
   __shared__ int s_lo, s_hi;
+  TraceScope trace_scope(gp.trace, 2);
   const int q = blockIdx.x >> 6, sub = blockIdx.x & 63;
   int fi = 0;
   while (fi + 1 < gp.nf && q >= gp.qbeg[fi + 1]) ++fi;
@@ -1397,6 +1417,7 @@ __global__ void __launch_bounds__(256, 4) syrk_sk_reduce_kernel(const __grid_con
 __global__ void __launch_bounds__(256, 4) syrk_sk_reduce_taps_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ SkTable sk) {
   extern __shared__ float outbuf[];                  // [8][KK*32 + 1]
   __shared__ int s_lo[9], s_hi[9];
+  TraceScope trace_scope(gp.trace, 2);
   const NhParams& p = gp.f[0];
   const int C = p.C, KK = p.KK, T = p.T, D = p.ldF;
   const int ncb = C >> 5;
@@ -1484,7 +1505,8 @@ __global__ void __launch_bounds__(256, 4) syrk_sk_reduce_taps_kernel(const __gri
 // element strides, so NCHW-dense and channels-last inputs both work.
 __global__ void __launch_bounds__(256) pack_smallc_kernel(const float* __restrict__ x, uint4* __restrict__ Q, int N, int C, int H, int W,
                                                           long long sN, long long sC, long long sH, long long sW, int Hq, int OW,
-                                                          int kw, int sw, int ph, int pw) {
+                                                          int kw, int sw, int ph, int pw, unsigned long long* tr) {
+  TraceScope trace_scope(tr, 4);
   const long long total = (long long)N * Hq * OW * 2;
   for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
     const int i2 = (int)(t & 1);
@@ -1520,7 +1542,8 @@ __global__ void __launch_bounds__(256) pack_smallc_kernel(const float* __restric
 }
 
 // out[i] = round-to-nearest TF32 of in[i] (layout preserved): the rounding pre-pass of the `tf32` tier.
-__global__ void __launch_bounds__(256) round_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, size_t n4) {
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, size_t n4, unsigned long long* tr) {
+  TraceScope trace_scope(tr, 4);
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
     const float4 v = __ldg(in + i);
     float4 o;
@@ -1534,7 +1557,8 @@ __global__ void __launch_bounds__(256) round_tf32_kernel(const float4* __restric
 // The fp32 source is read exactly once (L2 evict-first), the bf16 copy is about to be read several times by the
 // contraction kernel (L2 evict-last): without the hints the streaming reads push most of the freshly written copy out
 // to DRAM before the contraction starts (ncu: 76 of 103 MB written back during the cast, then read again from DRAM).
-__global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, size_t n4, int hints) {
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, size_t n4, int hints, unsigned long long* tr) {
+  TraceScope trace_scope(tr, 4);
   uint64_t pol_first = 0, pol_last = 0;
   if (hints) {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
@@ -2043,6 +2067,7 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
   gp.nf = cnt;
   gp.ws = (float*)wsb;
   gp.tl = debug_timeline_buffer();
+  gp.trace = debug_trace_slot();
   {
     static const int tl_min_nf = getenv("CURVATURE_B200_TL_MIN_NF") ? atoi(getenv("CURVATURE_B200_TL_MIN_NF")) : 0;
     if (cnt < tl_min_nf) gp.tl = nullptr;      // profiling aid: record only the launches with at least that many factors
@@ -2082,13 +2107,13 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
         else { sC = 1; sW = g.C; sH = (long long)g.W * g.C; sN = sH * g.H; }
         profile_begin(KC_PREPASS, 0.0, 4.0 * g.N * g.C * g.H * g.W + (double)nt * 64.0, cs);
         pack_smallc_kernel<<<blocks, 256, 0, cs>>>(g.x, (uint4*)copy, g.N, g.C, g.H, g.W, sN, sC, sH, sW, q.H, q.W, g.kw,
-                                                   g.sw, g.ph, g.pw);
+                                                   g.sw, g.ph, g.pw, gp.trace);
       } else {
         const unsigned blocks = (unsigned)((n4 + 255) / 256 < (size_t)sms * 16 ? (n4 + 255) / 256 : (size_t)sms * 16);
         profile_begin(KC_PREPASS, 0.0, (pl.bf16 ? 6.0 : 8.0) * (double)n4 * 4.0, cs);
         static const int cast_hints = getenv("CURVATURE_B200_CAST_HINT") ? atoi(getenv("CURVATURE_B200_CAST_HINT")) : 1;
-        if (pl.bf16) cast_bf16_kernel<<<blocks, 256, 0, cs>>>((const float4*)g.x, (uint2*)copy, n4, cast_hints);
-        else round_tf32_kernel<<<blocks, 256, 0, cs>>>((const float4*)g.x, (float4*)copy, n4);
+        if (pl.bf16) cast_bf16_kernel<<<blocks, 256, 0, cs>>>((const float4*)g.x, (uint2*)copy, n4, cast_hints, gp.trace);
+        else round_tf32_kernel<<<blocks, 256, 0, cs>>>((const float4*)g.x, (float4*)copy, n4, gp.trace);
       }
       profile_end(cs);
       CRV_CUDA(cudaGetLastError());
@@ -2230,6 +2255,7 @@ int syrk_nhwc_debug_partition(const ConvGeom* gs, int n, int precision, int sms,
   static GroupParams gp;
   static SkTable sk;
   gp.nf = (int)pls.size();
+  gp.trace = nullptr;
   build_sk(pls, sms, gp, sk);
   CRV_CHECK(sk.G + 1 <= cap, "boundary table needs %d entries", sk.G + 1);
   *G = sk.G;

@@ -77,6 +77,13 @@ int         crv_profile_collect(double* ms, double* flops, double* bytes, long l
  * operand arrival / when the last MMA was issued / when the accumulator was drained, the number of (CTA, pair)
  * segments, MMA k-groups issued, SM id.  Pass null to switch it off (the default). */
 int         crv_debug_timeline(long long* buf);
+/* Profiling aid: launch-level trace of the channels-last SYRK path WITH its stream overlap left on.  `buf` is device
+ * memory of `slots` x 8 uint64, words {0, 2, 4} of every slot preset to ~0 and the others to 0; launch i (in enqueue
+ * order since this call) records globaltimer ns into slot i: [0] / [1] first CTA start / last CTA end of the contraction
+ * kernel, [2] / [3] of its reduction, [4] / [5] of its pre-pass (cast / rounding / pack), [6] = order of the first factor
+ * | factors << 20 | bf16 << 30, [7] = block pairs.  crv_debug_trace_count() = launches recorded.  Null switches it off. */
+int         crv_debug_trace(unsigned long long* buf, int slots);
+int         crv_debug_trace_count(void);
 
 /* K1a -- first Kronecker factor of a Conv2d layer, fused implicit im2col + SYRK + running sum:
  *   A[k1,k2] += alpha * sum_r X[k1,r] X[k2,r],   X = unfold(x) in the reference's row order
