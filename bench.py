@@ -567,7 +567,7 @@ def main():
                                      for k, v in busy.items()}}
     line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3", "bf16": "bf16", "tf32_tma": "tf32"}[tier],
+            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16x3": "bf16x3", "bf16": "bf16", "tf32_tma": "tf32"}[tier],
             "tolerance": "factors within 1e-3 relative Frobenius of the fp32 reference (north-star tensor-core tier)" if tier != "fp32" else "1e-5",
             "data": "synthetic", "config": config, "roofline": roofline, "step_breakdown": whole_step, "e2e": e2e,
             "gpu_launches": sum(v["launches"] for v in busy.values()) or launches,

@@ -13,9 +13,12 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcurvature_b200.so")
 
-PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_BF16, PREC_TF32_TMA = 0, 1, 2, 3, 4
-PRECISION_NAMES = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16,
+PREC_FP32, PREC_TF32, PREC_BF16X3, PREC_BF16, PREC_TF32_TMA = 0, 1, 2, 3, 4
+PRECISION_NAMES = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16,
                    "tf32_tma": PREC_TF32_TMA}
+# parity tier of each arithmetic tier (relative Frobenius error of a factor against the fp32 reference)
+PRECISION_TOLERANCE = {PREC_FP32: 1e-5, PREC_BF16X3: 1e-5, PREC_TF32: 1e-3, PREC_BF16: 1e-3, PREC_TF32_TMA: 1e-3}
+DEFAULT_PRECISION = "bf16x3"
 OP_SYRK_CONV, OP_SYRK_ROWS, OP_EFB_PROJECT, OP_CHOL_INV, OP_SAMPLE_MN, OP_SYRK_CONV_NHWC, OP_SYRK_ROWS_NHWC = range(7)
 
 if not os.path.exists(LIB_PATH):
@@ -149,7 +152,7 @@ def _stream(t):
 
 
 def default_precision():
-    name = os.environ.get("CURVATURE_B200_PRECISION", "fp32").lower()
+    name = os.environ.get("CURVATURE_B200_PRECISION", DEFAULT_PRECISION).lower()
     if name not in PRECISION_NAMES:
         raise ValueError(f"CURVATURE_B200_PRECISION={name!r}; expected one of {sorted(PRECISION_NAMES)}")
     return PRECISION_NAMES[name]
@@ -159,7 +162,11 @@ def resolve_precision(p):
     if p is None:
         return default_precision()
     if isinstance(p, str):
+        if p.lower() not in PRECISION_NAMES:
+            raise ValueError(f"precision={p!r}; expected one of {sorted(PRECISION_NAMES)}")
         return PRECISION_NAMES[p.lower()]
+    if int(p) not in PRECISION_NAMES.values():
+        raise ValueError(f"precision={p!r}; expected one of {sorted(PRECISION_NAMES.values())}")
     return int(p)
 
 
@@ -260,7 +267,13 @@ def _is_channels_last(t):
 
 
 def _tensor_core(precision):
-    return precision in (PREC_TF32, PREC_TF32_TMA, PREC_BF16)
+    return precision in (PREC_TF32, PREC_TF32_TMA, PREC_BF16, PREC_BF16X3)
+
+
+def _copy_tier(precision):
+    """Tiers whose pre-pass writes a bf16 copy of the operand anyway and can therefore also take NCHW-dense sources
+    (the pre-pass then transposes to channels-last)."""
+    return precision in (PREC_BF16, PREC_BF16X3)
 
 
 def syrk_conv_accum(x, kernel_size, stride, padding, has_bias, alpha, out, precision=PREC_FP32, join=True):
@@ -278,25 +291,17 @@ def syrk_conv_accum(x, kernel_size, stride, padding, has_bias, alpha, out, preci
     if tuple(out.shape) != (K, K):
         raise ValueError(f"factor has shape {tuple(out.shape)}, expected {(K, K)}")
     dims = [N, C, H, W, kh, kw, sh, sw, ph, pw, int(bool(has_bias)), precision]
-    if _tensor_core(precision) and not has_bias and _is_channels_last(x):
-        nb = workspace_bytes(OP_SYRK_CONV_NHWC, dims)
-        if nb and x.data_ptr() % 16 == 0:
-            ws = workspace(nb, x.device)
-            launch_calls += 2 + int(precision in (PREC_TF32, PREC_BF16))
-            _check(_syrk_conv_nhwc(_dense(x, "activation"), N, C, H, W, kh, kw, sh, sw, ph, pw, 0, float(alpha),
-                                   _dev(out, "factor"), ws.data_ptr(), ws.numel(), precision, _stream(x)),
-                   "crv_syrk_conv_accum_nhwc")
-            if join:
-                _check(_stream_join(_stream(x)), "crv_stream_join")
-            return
+    item = nhwc_item(x, kernel_size, stride, padding, has_bias, alpha, out, precision)
+    if item is not None:
+        syrk_batch_nhwc([item], precision, x.device, join=join)
+        return
     if not x.is_contiguous():
         x = x.contiguous()
-    if precision == PREC_BF16:        # operands the channels-last kernel cannot take: thread-staged TF32 kernel
-        precision = PREC_TF32
-        dims[-1] = precision
+    # operands the channels-last kernel cannot take: thread-staged TF32 kernel for the 1e-3 tiers, fp32 CUDA cores for the
+    # 1e-5 tiers (the library maps bf16 -> tf32 and bf16x3 -> fp32 itself)
     nb = workspace_bytes(OP_SYRK_CONV, dims)
     ws = workspace(nb, x.device)
-    launch_calls += 1 if precision == PREC_FP32 else 2
+    launch_calls += 1 if precision in (PREC_FP32, PREC_BF16X3) else 2
     _check(_syrk_conv(_dev(x, "activation"), N, C, H, W, kh, kw, sh, sw, ph, pw, int(bool(has_bias)),
                       float(alpha), _dev(out, "factor"), ws.data_ptr(), ws.numel(), precision, _stream(x)),
            "crv_syrk_conv_accum")
@@ -315,25 +320,15 @@ def syrk_rows_accum(g, has_bias, alpha, out, precision=PREC_FP32, join=True):
     D = M + int(bool(has_bias))
     if tuple(out.shape) != (D, D):
         raise ValueError(f"factor has shape {tuple(out.shape)}, expected {(D, D)}")
-    rows_major = _is_channels_last(g) or (g.dim() == 2 and g.is_contiguous()) or \
-        (g.dim() == 4 and L == 1 and g.is_contiguous())
-    if _tensor_core(precision) and not has_bias and rows_major:
-        nb = workspace_bytes(OP_SYRK_ROWS_NHWC, [N, M, L, 0, precision])
-        if nb and g.data_ptr() % 16 == 0:
-            ws = workspace(nb, g.device)
-            launch_calls += 2 + int(precision in (PREC_TF32, PREC_BF16))
-            _check(_syrk_rows_nhwc(_dense(g, "operand"), N, M, L, 0, float(alpha), _dev(out, "factor"),
-                                   ws.data_ptr(), ws.numel(), precision, _stream(g)), "crv_syrk_rows_accum_nhwc")
-            if join:
-                _check(_stream_join(_stream(g)), "crv_stream_join")
-            return
+    item = nhwc_item(g, None, None, None, has_bias, alpha, out, precision)
+    if item is not None:
+        syrk_batch_nhwc([item], precision, g.device, join=join)
+        return
     if not g.is_contiguous():
         g = g.contiguous()
-    if precision == PREC_BF16:
-        precision = PREC_TF32
     nb = workspace_bytes(OP_SYRK_ROWS, [N, M, L, int(bool(has_bias)), precision])
     ws = workspace(nb, g.device)
-    launch_calls += 1 if precision == PREC_FP32 else 2
+    launch_calls += 1 if precision in (PREC_FP32, PREC_BF16X3) else 2
     _check(_syrk_rows(_dev(g, "operand"), N, M, L, int(bool(has_bias)), float(alpha), _dev(out, "factor"),
                       ws.data_ptr(), ws.numel(), precision, _stream(g)), "crv_syrk_rows_accum")
 
@@ -349,12 +344,19 @@ def nhwc_item(t, kernel_size, stride, padding, has_bias, alpha, out, precision):
         for s in t.shape[2:]:
             L *= s
         rows_major = _is_channels_last(t) or (t.dim() == 2 and t.is_contiguous()) or \
-            (t.dim() == 4 and L == 1 and t.is_contiguous())
-        if not rows_major or tuple(out.shape) != (M, M):
+            (t.dim() >= 3 and L == 1 and t.is_contiguous())
+        if tuple(out.shape) != (M, M):
             return None
-        if not workspace_bytes(OP_SYRK_ROWS_NHWC, [N, M, L, 0, precision]):
+        if rows_major:
+            nchw = 0
+        elif t.is_contiguous() and _copy_tier(precision):     # (N, M, L) dense: the pre-pass transposes it
+            nchw = 1
+        else:
             return None
-        return SyrkItem(_dense(t, "operand"), N, M, 1, L, 1, 1, 1, 1, 0, 0, float(alpha), _dev(out, "factor"), 0)
+        item = SyrkItem(_dense(t, "operand"), N, M, 1, L, 1, 1, 1, 1, 0, 0, float(alpha), _dev(out, "factor"), nchw)
+        if not _syrk_batch_ws(ctypes.byref(item), 1, precision):
+            return None
+        return item
     N, C, H, W = t.shape
     kh, kw = kernel_size
     sh, sw = stride
@@ -364,8 +366,8 @@ def nhwc_item(t, kernel_size, stride, padding, has_bias, alpha, out, precision):
         return None
     if _is_channels_last(t):
         nchw = 0
-    elif t.is_contiguous() and C <= 4:       # the packed small-C path also takes NCHW-dense inputs
-        nchw = 1
+    elif t.is_contiguous() and (C <= 4 or _copy_tier(precision)):
+        nchw = 1          # NCHW-dense: the packed small-C path and the transposing pre-pass of the copy tiers take it
     else:
         return None
     item = SyrkItem(_dense(t, "activation"), N, C, H, W, kh, kw, sh, sw, ph, pw, float(alpha), _dev(out, "factor"), nchw)

@@ -108,8 +108,9 @@ static int gemm_dispatch(int precision, const float* A, long long sa_m, long lon
 static int syrk_dispatch(const ConvGeom& g, float alpha, float* F, void* ws, size_t ws_bytes, int precision,
                          cudaStream_t s) {
   if (precision == CRV_PREC_FP32) return syrk_simt_launch(g, alpha, F, s);
-  if (precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32X3 || precision == CRV_PREC_BF16 ||
-      precision == CRV_PREC_TF32_TMA)
+  if (precision == CRV_PREC_BF16X3) return syrk_simt_launch(g, alpha, F, s);   // 1e-5 tier, operand not TMA-addressable
+  if (precision == CRV_PREC_BF16) precision = CRV_PREC_TF32;                   // 1e-3 tier, likewise: thread-staged TF32
+  if (precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32_TMA)
     return syrk_tc_launch(g, alpha, F, precision, ws, ws_bytes, s);
   set_error("unknown precision tier %d", precision);
   return 1;

@@ -898,6 +898,7 @@ struct NhParams {
   int ldF;                   // order of the factor F (= D except on the packed path, where D counts padding rows)
   int pk_kh, pk_kw, pk_c;    // packed small-C path: the original filter and channel count (pk_c = 0: not packed)
   int pack2;                 // D <= 64 single-tile TF32 factor: two position sets stacked along M (see seg_geom)
+  int x3;                    // bf16x3 tier: the operand copy has two bf16 planes, x = hi + lo; three MMAs per k-group
   float alpha;
   float* F;                  // the factor this item accumulates into
 };
@@ -974,7 +975,7 @@ struct SegGeom {
   int I, J, rowsA, mh, ncols, nchA, nchB, nslots, NB, nstage;
   int pk, poff, nbh;           // pack2: on; row / column offset of the second position set's block; boxes per set
   bool diag;
-  uint32_t chunk_bytes, stage_bytes;
+  uint32_t chunk_bytes, stage_bytes, plane_bytes;
 };
 template <int CH>
 __device__ __forceinline__ SegGeom seg_geom(const NhParams& p, int q) {
@@ -1006,12 +1007,15 @@ __device__ __forceinline__ SegGeom seg_geom(const NhParams& p, int q) {
     t.ncols = 2 * t.poff;
     t.chunk_bytes = (uint32_t)(t.nbh * p.PB) * 128u;
     t.stage_bytes = (uint32_t)t.nslots * t.chunk_bytes;
+    t.plane_bytes = t.stage_bytes;
     const uint32_t tail_pad = (uint32_t)(slotsA - t.nslots) * t.chunk_bytes;
     t.nstage = min(NH_MAXSTAGE, (int)((NH_DATA_BYTES - tail_pad) / t.stage_bytes));
     return t;
   }
   t.chunk_bytes = (uint32_t)(t.NB * p.PB) * 128u;
-  t.stage_bytes = (uint32_t)t.nslots * t.chunk_bytes;
+  // bf16x3: a stage holds the chunks of the hi plane, then the same chunks of the lo plane
+  t.plane_bytes = (uint32_t)t.nslots * t.chunk_bytes;
+  t.stage_bytes = (p.x3 ? 2u : 1u) * t.plane_bytes;
   const uint32_t tail_pad = t.diag ? (uint32_t)(slotsA - t.nchA) * t.chunk_bytes : 0u;
   t.nstage = min(NH_MAXSTAGE, (int)((NH_DATA_BYTES - tail_pad) / t.stage_bytes));
   return t;
@@ -1094,11 +1098,14 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       const int fi = factor_of(q);
       const NhParams& p = gp.f[fi];
       const CUtensorMap* tmap = &maps.m[fi];
+      const CUtensorMap* tmap_lo = &maps.m[fi + 1];          // bf16x3 (always a group of one): the lo plane's map
       const int b_begin = q == q0 ? bq0 : 0, b_end = q == q1 ? bq1 : p.nbox;
       if (b_begin >= b_end) continue;
       const SegGeom t = seg_geom<CH>(p, q - gp.qbeg[fi]);
       const uint32_t box_bytes = (uint32_t)p.PBv * 128u;
+      const int planes = (int)uni(p.x3 ? 2u : 1u);
       if (leader) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+      if (leader && planes == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap_lo)) : "memory");
       // the previous segment's MMAs have all retired (its accumulator is complete): every stage is free, whatever
       // the stage geometry of this segment is
       if (nseg > 0) mbar_wait(bar_tmem_full, (uint32_t)(nseg - 1) & 1u);
@@ -1113,7 +1120,7 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       }
       if (p.PB > p.PBv) {   // zero the rows of every box slot that no box ever writes (TMA never touches them)
         const int pad16 = (p.PB - p.PBv) * 8;                       // 16-byte words per box slot
-        const int total = t.nstage * t.nslots * t.NB * pad16;
+        const int total = t.nstage * t.nslots * t.NB * pad16 * planes;
         for (int e = ptid; e < total; e += NH_NPROD * 32) {
           const int slot = e / pad16, w = e - slot * pad16;
           const uint32_t a = sbase + (uint32_t)slot * (uint32_t)p.PB * 128u + (uint32_t)p.PBv * 128u + (uint32_t)w * 16u;
@@ -1123,7 +1130,7 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       }
       asm volatile("bar.sync 1, %0;" ::"r"(NH_NPROD * 32) : "memory");
       const int NB = (int)uni((uint32_t)t.NB), nstage = (int)uni((uint32_t)t.nstage), nld = (int)uni((uint32_t)loaded);
-      const uint32_t stage_bytes = uni(t.stage_bytes), chunk_bytes = uni(t.chunk_bytes);
+      const uint32_t stage_bytes = uni(t.stage_bytes), chunk_bytes = uni(t.chunk_bytes), plane_bytes = uni(t.plane_bytes);
       const int pk = (int)uni((uint32_t)t.pk), nbh = (int)uni((uint32_t)t.nbh), pk_nch = (int)uni((uint32_t)t.nchA);
       const int ub = (int)uni((uint32_t)b_begin), ue = (int)uni((uint32_t)b_end);
       const int nit = (ue - ub + NB - 1) / NB;
@@ -1131,7 +1138,8 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       for (int it = 0; it < nit; ++it) {
         const int b0 = ub + it * NB;
         const int nv = min(NB, ue - b0);
-        const int total = nv * nld;                             // TMA instructions of this stage
+        const int per_plane = nv * nld;
+        const int total = per_plane * planes;                   // TMA instructions of this stage
         const int mine = total > me ? (total - me + NH_NPROD - 1) / NH_NPROD : 0;
         mbar_wait(bars + 8 * (NH_MAXSTAGE + s), ((pph >> s) & 1u) ^ 1u);
         pph ^= 1u << s;
@@ -1156,7 +1164,9 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
           else mbar_arrive(bars + 8 * s);
         }
         if (!(gp.dbg & 1)) {
-          for (int e = me; e < total; e += NH_NPROD) {
+          for (int e2 = me; e2 < total; e2 += NH_NPROD) {
+            const int plane = e2 >= per_plane ? 1 : 0;
+            const int e = e2 - plane * per_plane;
             const int j = e / nld, qq = e - j * nld;
             const uint32_t b = (uint32_t)(b0 + j);
             int X0, Y0, Nn;
@@ -1173,8 +1183,8 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
             const int set = (pk && j >= nbh) ? 1 : 0;            // pack2: second half of the stage's boxes = second set
             const int jj = j - set * nbh, slot = t4.w + set * pk_nch;
             if (leader)
-              tma_load_4d(st + (uint32_t)(jj * p.PB) * 128u + (uint32_t)slot * chunk_bytes, tmap, t4.x, X0 + t4.y, Y0 + t4.z,
-                          Nn, bars + 8 * s);
+              tma_load_4d(st + (uint32_t)plane * plane_bytes + (uint32_t)(jj * p.PB) * 128u + (uint32_t)slot * chunk_bytes,
+                          plane ? tmap_lo : tmap, t4.x, X0 + t4.y, Y0 + t4.z, Nn, bars + 8 * s);
           }
         }
         if (++s == nstage) s = 0;
@@ -1211,6 +1221,8 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       const uint32_t hstep = (uint32_t)(128 / CH) * u_chunk;              // second 128-row half of the A block
       const uint32_t boff = uni(t.diag ? 0u : (uint32_t)t.nchA * t.chunk_bytes);
       const bool two = uni((uint32_t)t.mh) == 2u;
+      const bool x3 = uni((uint32_t)p.x3) != 0u;
+      const uint32_t lo16 = uni(t.plane_bytes) >> 4;                       // hi plane -> lo plane of a stage, in 16-byte units
       const int u_pk = (int)uni((uint32_t)t.pk), u_nbh = (int)uni((uint32_t)t.nbh);
       if (nseg > 0) {                                                     // accumulator drained by the epilogue warps
         mbar_wait(bar_tmem_empty, (uint32_t)(nseg - 1) & 1u);
@@ -1231,11 +1243,27 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
         const uint32_t a1 = dlo | (((st + hstep) >> 4) & 0x3FFFu);
         const uint32_t b0 = dlo | (((st + boff) >> 4) & 0x3FFFu);
         if (leader) {
-          for (int kg = 0; kg < nkg; ++kg) {
-            const uint32_t ko = (uint32_t)kg * KSTEP;
-            tc_mma_lohi(BF16, u_tmem, a0 + ko, b0 + ko, dhi32, idesc, acc);
-            if (two) tc_mma_lohi(BF16, u_tmem + 256u, a1 + ko, b0 + ko, dhi32, idesc, acc);
-            acc = 1;
+          if (BF16 && x3) {
+            // x = hi + lo (two bf16 planes): X X^T ~= hi hi^T + hi lo^T + lo hi^T, three instructions per row half
+            for (int kg = 0; kg < nkg; ++kg) {
+              const uint32_t ko = (uint32_t)kg * KSTEP;
+              tc_mma_lohi(true, u_tmem, a0 + ko, b0 + ko, dhi32, idesc, acc);
+              tc_mma_lohi(true, u_tmem, a0 + ko, b0 + lo16 + ko, dhi32, idesc, 1u);
+              tc_mma_lohi(true, u_tmem, a0 + lo16 + ko, b0 + ko, dhi32, idesc, 1u);
+              if (two) {
+                tc_mma_lohi(true, u_tmem + 256u, a1 + ko, b0 + ko, dhi32, idesc, acc);
+                tc_mma_lohi(true, u_tmem + 256u, a1 + ko, b0 + lo16 + ko, dhi32, idesc, 1u);
+                tc_mma_lohi(true, u_tmem + 256u, a1 + lo16 + ko, b0 + ko, dhi32, idesc, 1u);
+              }
+              acc = 1;
+            }
+          } else {
+            for (int kg = 0; kg < nkg; ++kg) {
+              const uint32_t ko = (uint32_t)kg * KSTEP;
+              tc_mma_lohi(BF16, u_tmem, a0 + ko, b0 + ko, dhi32, idesc, acc);
+              if (two) tc_mma_lohi(BF16, u_tmem + 256u, a1 + ko, b0 + ko, dhi32, idesc, acc);
+              acc = 1;
+            }
           }
         }
         if (nkg > 0) acc = 1;
@@ -1581,11 +1609,77 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict
   }
 }
 
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi), both round-to-nearest-even: 16 significand bits of the fp32 value
+// survive (|x - hi - lo| <= 2^-16 |x|), which is what the bf16x3 tier contracts with three bf16 MMAs per k-group.
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));          // low half = first element
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+
+// Split pre-pass of the bf16x3 tier for a channels-last (or 2-D) operand: same layout, two bf16 planes.
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ hi, uint2* __restrict__ lo,
+                                                         size_t n4, unsigned long long* tr) {
+  TraceScope trace_scope(tr, 4);
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(in + i));
+    uint2 h, l;
+    split_bf16x2(v.x, v.y, h.x, l.x);
+    split_bf16x2(v.z, v.w, h.y, l.y);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// Layout-normalising pre-pass: an NCHW-dense fp32 operand [N][C][HW] becomes the channels-last bf16 copy [N][HW][C] the
+// TMA-fed kernel reads (plus the lo plane on the bf16x3 tier).  One 64-channel x 64-position tile per CTA through shared
+// memory: reads are 256-byte runs along HW, writes 128-byte runs along C.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, uint32_t* __restrict__ hi,
+                                                                uint32_t* __restrict__ lo, int C, int HW, int ctiles, int ptiles,
+                                                                unsigned long long* tr) {
+  __shared__ float t[64][65];
+  TraceScope trace_scope(tr, 4);
+  const int pt = blockIdx.x % ptiles;
+  const int ct = (blockIdx.x / ptiles) % ctiles;
+  const int n = blockIdx.x / (ptiles * ctiles);
+  const int c0 = ct * 64, p0 = pt * 64;
+  const float* __restrict__ src = x + ((size_t)n * C + c0) * (size_t)HW + p0;
+  {
+    const int pp = threadIdx.x & 63, cc0 = threadIdx.x >> 6;
+    const bool pv = p0 + pp < HW;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int cc = cc0 + 4 * i;
+      float v = 0.f;
+      if (pv && c0 + cc < C) v = __ldg(src + (size_t)cc * HW + pp);
+      t[cc][pp] = v;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int ch = 2 * lane;                                  // this thread's channel pair (C % 8 == 0: pairs never straddle C)
+  if (c0 + ch < C) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int pp = w + 8 * i;
+      if (p0 + pp < HW) {
+        const size_t o = (((size_t)n * HW + p0 + pp) * (size_t)C + c0 + ch) >> 1;
+        uint32_t h, l;
+        split_bf16x2(t[ch][pp], t[ch + 1][pp], h, l);
+        hi[o] = h;
+        if (lo) lo[o] = l;
+      }
+    }
+  }
+}
+
 struct NhPlan {
   NhParams p;
   int pairs;
   int bf16;                      // operands go through the bf16 copy
   int pack;                      // packed small-C path: the operand the kernel sees is Q (geometry gq), made by the pack pre-pass
+  int transpose;                 // the source is NCHW-dense: the pre-pass also transposes it to channels-last
   ConvGeom gq;
   size_t partial_bytes, copy_bytes;
 };
@@ -1615,8 +1709,14 @@ bool pack_plan(const ConvGeom& g, int sms, NhPlan& pl) {
 bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl, bool src_is_bf16) {
   const int KK = g.kh * g.kw;
   pl.pack = 0;
+  pl.transpose = 0;
   if (!src_is_bf16 && packable(g, precision)) return pack_plan(g, sms, pl);
-  if (g.x_nchw) return false;
+  // operands the bf16 kernel instance can take: whole 16-byte channel groups, whole 64-channel chunks per filter tap
+  const bool bf16_geom = g.C >= 64 && (g.C & 7) == 0 && (KK == 1 || (g.C & 63) == 0);
+  const bool x3 = !src_is_bf16 && precision == CRV_PREC_BF16X3;
+  if (x3 && !bf16_geom) return false;
+  // an NCHW-dense source is taken when a bf16 copy is made anyway: the pre-pass then transposes it to channels-last
+  if (g.x_nchw && !(bf16_geom && (precision == CRV_PREC_BF16 || x3))) return false;
   if (g.has_bias || g.C < 32 || (g.C & 3) != 0) return false;
   if (KK > 1 && (g.C & 31) != 0) return false;
   if (((uintptr_t)g.x & 15) != 0) return false;
@@ -1624,7 +1724,7 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl, bool src_i
   if (g.R >= (1LL << 31) - 512) return false;
   NhParams& p = pl.p;
   p.D = g.D; p.C = g.C; p.KK = KK; p.kw = g.kw; p.K0 = g.K0; p.alpha = 0.f; p.F = nullptr;
-  p.ldF = g.D; p.pk_kh = p.pk_kw = p.pk_c = 0; p.pack2 = 0;
+  p.ldF = g.D; p.pk_kh = p.pk_kw = p.pk_c = 0; p.pack2 = 0; p.x3 = x3 ? 1 : 0;
   p.divC = make_fastdiv((uint32_t)g.C);
   p.divKW = make_fastdiv((uint32_t)g.kw);
   p.T = (g.D + TB - 1) / TB;
@@ -1633,9 +1733,10 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl, bool src_i
   // element then travels L2 -> SM several times -- k x k convolutions (each element feeds kh*kw operand rows) and
   // factors of three or more row blocks.  Single-tile, read-once operands are HBM-bound and stay on the direct path.
   static const int bf16_min_t = getenv("CURVATURE_B200_BF16_MIN_T") ? atoi(getenv("CURVATURE_B200_BF16_MIN_T")) : 3;
-  pl.bf16 = (src_is_bf16 || (precision == CRV_PREC_BF16 && (KK > 1 || p.T >= bf16_min_t) && g.C >= 64 && (g.C & 7) == 0 &&
-                             (KK == 1 || (g.C & 63) == 0))) ? 1 : 0;
+  pl.bf16 = (src_is_bf16 || x3 || (precision == CRV_PREC_BF16 && (KK > 1 || p.T >= bf16_min_t || g.x_nchw) && bf16_geom)) ? 1 : 0;
+  pl.transpose = (g.x_nchw && !src_is_bf16) ? 1 : 0;
   const int CH = pl.bf16 ? 64 : 32, gran = pl.bf16 ? 16 : 8;
+  const int planes = x3 ? 2 : 1;
   p.sh = g.sh; p.sw = g.sw; p.ph = g.ph; p.pw = g.pw;
   p.flat = (KK == 1 && g.sh == 1 && g.sw == 1 && g.ph == 0 && g.pw == 0) ? 1 : 0;
   // chunk slots per stage of the two item kinds
@@ -1643,7 +1744,7 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl, bool src_i
   const int slots_max = p.T > 1 ? slots_off : slots_diag;
   // positions per stage at the target stage size (single-tile factors stream from HBM: smaller stages, more of them)
   const int stage_target = p.T > 1 ? NH_STAGE_TARGET : NH_STAGE_TARGET / 2;   // single-tile factors stream from HBM
-  const int pcap = stage_target / (slots_max * 128);
+  const int pcap = stage_target / (slots_max * planes * 128);
   if (p.flat) {
     long long pb = (pcap < 256 ? pcap : 256) / gran * gran;     // whole MMA k-groups
     if (pb < gran) return false;
@@ -1695,7 +1796,7 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl, bool src_i
   p.divPPI = make_fastdiv((uint32_t)p.ppi);
   p.divPCW = make_fastdiv((uint32_t)p.pcw);
   auto boxes_per_stage = [&](int slots) {
-    int nb = stage_target / (slots * p.PB * 128);
+    int nb = stage_target / (slots * planes * p.PB * 128);
     return nb < 1 ? 1 : nb;
   };
   p.NBoff = boxes_per_stage(slots_off);
@@ -1705,12 +1806,12 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl, bool src_i
     if (p.NBdiag < 2) p.pack2 = 0;
   }
   if (p.T > 1) p.NBdiag = p.NBoff * (p.NBdiag / p.NBoff > 0 ? p.NBdiag / p.NBoff : 1);
-  if (slots_max * p.NBoff * p.PB * 128 * 2 > NH_DATA_BYTES && p.T > 1) return false;   // needs >= 2 stages
-  if ((slots_diag * 2 + 3) * p.NBdiag * p.PB * 128 > NH_DATA_BYTES) return false;      // (+ tail pad)
+  if (slots_max * planes * p.NBoff * p.PB * 128 * 2 > NH_DATA_BYTES && p.T > 1) return false;   // needs >= 2 stages
+  if ((slots_diag * planes * 2 + 3) * p.NBdiag * p.PB * 128 > NH_DATA_BYTES) return false;      // (+ tail pad)
   p.bps = 0; p.splits = 0;                                   // (stream-K: the partition lives in the SkTable)
   pl.partial_bytes = (size_t)(SK_MAXG + pl.pairs) * TILE_ELEMS * sizeof(float);
   const size_t numel = (size_t)g.N * g.C * g.H * g.W;
-  pl.copy_bytes = pl.bf16 ? ((numel * 2 + 1023) & ~(size_t)1023)
+  pl.copy_bytes = pl.bf16 ? (size_t)planes * ((numel * 2 + 1023) & ~(size_t)1023)
                           : (precision == CRV_PREC_TF32 ? ((numel * 4 + 1023) & ~(size_t)1023) : 0);
   return true;
 }
@@ -1757,6 +1858,7 @@ void build_sk(const std::vector<const NhPlan*>& pls, int sms, GroupParams& gp, S
         const int n2 = 2 * ((rowsA + CH - 1) / CH) * CH;
         mma = (56.0 + 0.17 * n2) / 2.0;
       }
+      if (p.x3) { mma *= 3.0; bytes *= 2.0; }
       double c = std::max(mma, bytes / beta / 1.85);
       if (pls.size() > 1 || p.T == 1) {
         // read-once operand: HBM time.  An off-diagonal pair of a two-block factor finds about half of its second block
@@ -1832,7 +1934,7 @@ size_t syrk_tc_workspace(const ConvGeom& g, int precision) {
 int syrk_tc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,
                    cudaStream_t s) {
   CRV_CHECK(precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32_TMA,
-            "tensor-core tier %d is not built (available: tf32, tf32_tma)", precision);
+            "NCHW staged SYRK: tier %d is not built (available: tf32, tf32_tma)", precision);
   CRV_CHECK(F != nullptr, "null factor pointer");
   const int sms = device_sm_count();
   CRV_CHECK(sms > 0, "no CUDA device");
@@ -1987,7 +2089,9 @@ int syrk_stream_fork(cudaStream_t s) {
 
 // ---- channels-last entry points ----------------------------------------------------------------------
 bool syrk_nhwc_supported(const ConvGeom& g, int precision) {
-  if (precision != CRV_PREC_TF32 && precision != CRV_PREC_TF32_TMA && precision != CRV_PREC_BF16) return false;
+  if (precision != CRV_PREC_TF32 && precision != CRV_PREC_TF32_TMA && precision != CRV_PREC_BF16 &&
+      precision != CRV_PREC_BF16X3)
+    return false;
   NhPlan pl;
   return nhwc_plan(g, precision, 148, pl);
 }
@@ -2108,6 +2212,19 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
         profile_begin(KC_PREPASS, 0.0, 4.0 * g.N * g.C * g.H * g.W + (double)nt * 64.0, cs);
         pack_smallc_kernel<<<blocks, 256, 0, cs>>>(g.x, (uint4*)copy, g.N, g.C, g.H, g.W, sN, sC, sH, sW, q.H, q.W, g.kw,
                                                    g.sw, g.ph, g.pw, gp.trace);
+      } else if (pl.transpose) {
+        // NCHW-dense source: transposing cast into the channels-last bf16 copy (+ lo plane on the bf16x3 tier)
+        const int HW = g.H * g.W;
+        const int ctiles = (g.C + 63) / 64, ptiles = (HW + 63) / 64;
+        const size_t plane = (((size_t)g.N * g.C * HW * 2) + 1023) & ~(size_t)1023;
+        profile_begin(KC_PREPASS, 0.0, (pl.p.x3 ? 8.0 : 6.0) * (double)n4 * 4.0, cs);
+        nchw_to_nhwc_bf16_kernel<<<(unsigned)((size_t)g.N * ctiles * ptiles), 256, 0, cs>>>(
+            g.x, (uint32_t*)copy, pl.p.x3 ? (uint32_t*)((char*)copy + plane) : nullptr, g.C, HW, ctiles, ptiles, gp.trace);
+      } else if (pl.p.x3) {
+        const unsigned blocks = (unsigned)((n4 + 255) / 256 < (size_t)sms * 16 ? (n4 + 255) / 256 : (size_t)sms * 16);
+        const size_t plane = ((n4 * 8) + 1023) & ~(size_t)1023;
+        profile_begin(KC_PREPASS, 0.0, 8.0 * (double)n4 * 4.0, cs);
+        split_bf16_kernel<<<blocks, 256, 0, cs>>>((const float4*)g.x, (uint2*)copy, (uint2*)((char*)copy + plane), n4, gp.trace);
       } else {
         const unsigned blocks = (unsigned)((n4 + 255) / 256 < (size_t)sms * 16 ? (n4 + 255) / 256 : (size_t)sms * 16);
         profile_begin(KC_PREPASS, 0.0, (pl.bf16 ? 6.0 : 8.0) * (double)n4 * 4.0, cs);
@@ -2124,6 +2241,10 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
       src = copy;
     }
     if (int rc = make_tensor_map(pl.pack ? pl.gq : g, pl, src, &maps.m[k])) return rc;
+    if (pl.p.x3) {         // (a group of one: the lo plane's map sits in the next slot)
+      const size_t plane = (((size_t)g.N * g.C * g.H * g.W * 2) + 1023) & ~(size_t)1023;
+      if (int rc = make_tensor_map(g, pl, (const char*)src + plane, &maps.m[k + 1])) return rc;
+    }
     flops += (double)g.R * g.D * (g.D + 1);
     bytes += pl.pack ? 2.0 * pl.gq.N * pl.gq.C * pl.gq.H * pl.gq.W : (pl.bf16 ? 2.0 : 4.0) * g.N * g.C * g.H * g.W;
     fbytes += 8.0 * g.D * g.D;
@@ -2175,8 +2296,9 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
 // plan every factor of a batch and cut the batch into launches (lists of indices into the batch)
 int plan_batch(const ConvGeom* gs, int n, int precision, std::vector<NhPlan>& plans, std::vector<std::vector<int>>& launches,
                int sms_override = 0) {
-  CRV_CHECK(precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32_TMA || precision == CRV_PREC_BF16,
-            "channels-last SYRK: tier %d is not built (available: tf32, tf32_tma, bf16)", precision);
+  CRV_CHECK(precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32_TMA || precision == CRV_PREC_BF16 ||
+                precision == CRV_PREC_BF16X3,
+            "channels-last SYRK: tier %d is not built (available: tf32, tf32_tma, bf16, bf16x3)", precision);
   const int sms = sms_override > 0 ? sms_override : device_sm_count();
   CRV_CHECK(sms > 0, "no CUDA device");
   plans.resize(n);
@@ -2184,7 +2306,8 @@ int plan_batch(const ConvGeom* gs, int n, int precision, std::vector<NhPlan>& pl
   static const int grp_max = getenv("CURVATURE_B200_GROUP") ? std::max(1, std::min(GRP_MAXF, atoi(getenv("CURVATURE_B200_GROUP")))) : GRP_MAXF;
   for (int i = 0; i < n; ++i) {
     CRV_CHECK(nhwc_plan(gs[i], precision, sms, plans[i]),
-              "channels-last SYRK: unsupported geometry (needs no bias row, C %% 4 == 0, C >= 32, C %% 32 == 0 for k x k)");
+              "channels-last SYRK: unsupported geometry (needs no bias row, C %% 4 == 0, C >= 32, C %% 32 == 0 for k x k; "
+              "bf16x3 tier and NCHW-dense sources: C >= 64, C %% 8 == 0, C %% 64 == 0 for k x k)");
     if (rides_in_group(plans[i])) {
       grp.push_back(i);
       if ((int)grp.size() == grp_max) { launches.push_back(grp); grp.clear(); }

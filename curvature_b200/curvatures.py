@@ -82,8 +82,9 @@ def _grad_of(p: Tensor, what: str) -> Tensor:
 
 
 def _gemm_tier(precision: int) -> int:
-    """Tier of the chained GEMMs (K3 / K5): fp32 stays on the CUDA cores, every tensor-core tier uses the TF32 GEMM."""
-    return nat.PREC_FP32 if precision == nat.PREC_FP32 else nat.PREC_TF32
+    """Tier of the chained GEMMs (K3 / K5): the 1e-5 tiers (fp32, bf16x3) use the fp32 CUDA-core GEMM, the 1e-3 tiers the
+    TF32 tensor-core GEMM."""
+    return nat.PREC_FP32 if precision in (nat.PREC_FP32, nat.PREC_BF16X3) else nat.PREC_TF32
 
 
 def _rounded(cache: dict, key, tensors):
@@ -127,8 +128,10 @@ class Curvature(ABC):
         Args:
             model: Any (pre-trained) PyTorch model, on a CUDA device.
             layer_types: `Linear`, `Conv2d`, `MultiheadAttention`; all three if `None` or `[]`.
-            precision: arithmetic tier of the dense contractions (`'fp32'`, `'tf32'`, `'tf32x3'`, `'bf16'`);
-                       default from `CURVATURE_B200_PRECISION`, else fp32.
+            precision: arithmetic tier of the dense contractions: `'bf16x3'` (default: two-term bf16 split on the tensor
+                       cores, 1e-5 parity tier), `'fp32'` (CUDA cores, 1e-5), `'bf16'` / `'tf32'` / `'tf32_tma'` (tensor
+                       cores, stated 1e-3 tier; `'bf16'` is the benchmark tier).  Default from
+                       `CURVATURE_B200_PRECISION`, else `'bf16x3'`.
         """
         self.model = model
         self.model_state = copy.deepcopy(model.state_dict())

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CRV_ABI_VERSION 3
+#define CRV_ABI_VERSION 4
 
 typedef void* crv_stream_t; /* cudaStream_t */
 
@@ -38,7 +38,10 @@ typedef void* crv_stream_t; /* cudaStream_t */
 enum crv_precision {
   CRV_PREC_FP32   = 0, /* CUDA-core fp32 FMA (exact fp32 products); parity tier 1e-5            */
   CRV_PREC_TF32   = 1, /* tcgen05 kind::tf32, operands rounded to nearest (cvt.rna), fp32 accum  */
-  CRV_PREC_TF32X3 = 2, /* tcgen05 3xTF32 error-compensated split (hi*hi + hi*lo + lo*hi)          */
+  CRV_PREC_BF16X3 = 2, /* tcgen05 kind::f16 on a TWO-TERM bf16 split of the fp32 operand, x = hi + lo (both round-to-nearest,
+                          16 significand bits survive), made by a pre-pass: X X^T = hi hi^T + hi lo^T + lo hi^T, three MMAs
+                          per k-group, fp32 accumulation; parity tier 1e-5 on the tensor cores.  Channels-last entry points
+                          (K1c / K1d / K1e); operands need C >= 64, C % 8 == 0 (C % 64 == 0 for k x k filters)            */
   CRV_PREC_BF16   = 3, /* tcgen05 kind::f16 on a bf16 copy of the operand (cast pre-pass), fp32 accum; parity tier
                           1e-3.  Channels-last entry points only; read-once operands stay on the TF32 path    */
   CRV_PREC_TF32_TMA = 4 /* tcgen05 kind::tf32 fed by TMA where the geometry allows (hardware TF32

@@ -1,0 +1,161 @@
+"""GPU (-m gpu): the 1e-5 tier on the tensor cores (`bf16x3`: two-term bf16 split, three tcgen05 MMAs per k-group) and the
+layout-normalising pre-pass (NCHW-dense sources transposed to the channels-last bf16 copy the TMA-fed kernel reads).
+
+  * indexing: bit-exact on integer-valued inputs (hi plane exact, lo plane zero), channels-last and NCHW sources;
+  * arithmetic: random fp32 data against fp64 at 2e-6 -- the lo plane carries bits 9-16 of every operand: a wrong, missing
+    or mis-addressed lo plane shows up as ~4e-3 (bf16 precision);
+  * the default tier of `cb.KFAC(model)` is bf16x3.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import orc, rel_fro
+
+pytestmark = pytest.mark.gpu
+
+import curvature_b200 as cb                      # noqa: E402
+from curvature_b200 import _native as nat        # noqa: E402
+
+DEV = "cuda:0"
+X3, BF16 = nat.PREC_BF16X3, nat.PREC_BF16
+
+GEOMS = [
+    # N, C, H, W, kernel, stride, padding
+    (3, 64, 14, 14, (3, 3), (1, 1), (1, 1)),
+    (2, 64, 7, 7, (3, 3), (1, 1), (1, 1)),
+    (2, 128, 14, 14, (3, 3), (1, 1), (1, 1)),     # K = 1152: five row blocks
+    (3, 64, 28, 28, (3, 3), (1, 1), (1, 1)),
+    (2, 64, 12, 10, (3, 5), (1, 2), (1, 2)),      # non-square kernel, mixed stride / padding
+    (2, 128, 9, 9, (1, 1), (2, 2), (0, 0)),       # 1x1 stride 2
+    (3, 288, 5, 5, (1, 1), (1, 1), (0, 0)),       # flat, two row blocks, ragged last box, C % 64 != 0
+    (4, 72, 6, 6, (1, 1), (1, 1), (0, 0)),        # flat, C = 72: channel tail of the second 64-chunk by OOB fill
+    (1, 64, 4, 4, (3, 3), (1, 1), (0, 0)),
+    (70, 64, 6, 6, (3, 3), (1, 1), (1, 1)),       # many boxes: several contraction splits
+    (2, 64, 30, 30, (3, 3), (2, 2), (1, 1)),      # stride 2 through elementStrides; HW = 900: ragged transpose tiles
+]
+
+
+def oracle_A(x, k, s, p):
+    cols = orc.unfold_patches(x.double(), k, p, s)
+    X = cols.permute(1, 0, 2).reshape(cols.shape[1], -1)
+    return X @ X.t(), X.shape[1]
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+@pytest.mark.parametrize("layout", ["channels_last", "nchw"])
+@pytest.mark.parametrize("prec", [X3, BF16])
+def test_conv_syrk_bit_exact_on_integers(geom, layout, prec):
+    N, C, H, W, k, s, p = geom
+    gen = torch.Generator().manual_seed(hash(geom) % (2 ** 31))
+    x = torch.randint(-2, 3, (N, C, H, W), generator=gen).float()
+    want, R = oracle_A(x, k, s, p)
+    xd = x.to(DEV)
+    if layout == "channels_last":
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    K = want.shape[0]
+    out = torch.zeros(K, K, device=DEV)
+    item = nat.nhwc_item(xd, k, s, p, False, 1.0, out, prec)
+    assert item is not None, "the TMA-fed path must take this operand"
+    assert item.nchw == (0 if layout == "channels_last" else 1)
+    nat.syrk_conv_accum(xd, k, s, p, False, 1.0, out, prec)
+    assert torch.equal(out.cpu().double(), want), f"max diff {(out.cpu().double() - want).abs().max()}"
+    nat.syrk_conv_accum(xd, k, s, p, False, 2.0, out, prec)
+    assert torch.equal(out.cpu().double(), 3 * want)
+
+
+@pytest.mark.parametrize("shape", [(256, 1000), (5, 64), (3, 72, 5, 5), (2, 256, 14, 14), (7, 2048, 1, 1), (40, 776, 3, 3),
+                                   (3, 128, 31)])
+@pytest.mark.parametrize("layout", ["channels_last", "nchw"])
+@pytest.mark.parametrize("prec", [X3, BF16])
+def test_rows_syrk_bit_exact_on_integers(shape, layout, prec):
+    gen = torch.Generator().manual_seed(len(shape) * 1000 + shape[1])
+    g = torch.randint(-3, 4, shape, generator=gen).float()
+    M = shape[1]
+    X = g.reshape(shape[0], M, -1).permute(1, 0, 2).reshape(M, -1).double()
+    want = X @ X.t()
+    gd = g.to(DEV)
+    if gd.dim() == 4 and layout == "channels_last":
+        gd = gd.contiguous(memory_format=torch.channels_last)
+    out = torch.zeros(M, M, device=DEV)
+    assert nat.nhwc_item(gd, None, None, None, False, 1.0, out, prec) is not None
+    nat.syrk_rows_accum(gd, False, 1.0, out, prec)
+    assert torch.equal(out.cpu().double(), want)
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+@pytest.mark.parametrize("layout", ["channels_last", "nchw"])
+def test_bf16x3_random_data_against_fp64(geom, layout):
+    """16 significand bits per operand: measured ~1e-7; 2e-6 leaves no room for a broken lo plane (4e-3)."""
+    N, C, H, W, k, s, p = geom
+    torch.manual_seed(C + H)
+    x = torch.randn(N, C, H, W, device=DEV)
+    cols = F.unfold(x.double(), k, padding=p, stride=s)
+    X = cols.permute(1, 0, 2).reshape(cols.shape[1], -1)
+    want = (X @ X.t()) / X.shape[1]
+    xd = x if layout == "nchw" else x.contiguous(memory_format=torch.channels_last)
+    out = torch.zeros_like(want, dtype=torch.float32)
+    nat.syrk_conv_accum(xd, k, s, p, False, 1.0 / X.shape[1], out, X3)
+    err = rel_fro(out, want)
+    assert err <= 2e-6, (geom, layout, err)
+    assert torch.equal(out, out.t())
+    bf = torch.zeros_like(out)
+    nat.syrk_conv_accum(xd, k, s, p, False, 1.0 / X.shape[1], bf, BF16)
+    assert 10 * err < rel_fro(bf, want) <= 5e-3        # the single-plane tier on the same zero-mean data, for scale
+
+
+RESNET_LAYERS = [
+    ("3x3 64ch 56^2", 2, 64, 56, 56, 3, 1, 1),
+    ("3x3 s2 128ch", 2, 128, 56, 56, 3, 2, 1),
+    ("1x1 256ch 56^2", 2, 256, 56, 56, 1, 1, 0),
+    ("1x1 s2 256ch", 2, 256, 56, 56, 1, 2, 0),
+    ("3x3 256ch 14^2", 4, 256, 14, 14, 3, 1, 1),
+    ("3x3 512ch 7^2", 4, 512, 7, 7, 3, 1, 1),
+    ("1x1 2048ch 7^2", 4, 2048, 7, 7, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("layer", RESNET_LAYERS, ids=[l[0] for l in RESNET_LAYERS])
+@pytest.mark.parametrize("layout", ["channels_last", "nchw"])
+def test_bf16x3_resnet_shaped_factors_against_fp64(layer, layout):
+    name, N, C, H, W, k, s, p = layer
+    torch.manual_seed(1)
+    x = torch.relu(torch.randn(N, C, H, W, device=DEV))
+    cols = F.unfold(x.double(), k, padding=p, stride=s)
+    X = cols.permute(1, 0, 2).reshape(cols.shape[1], -1)
+    want = (X @ X.t()) / X.shape[1]
+    xd = x if layout == "nchw" else x.contiguous(memory_format=torch.channels_last)
+    out = torch.zeros_like(want, dtype=torch.float32)
+    nat.syrk_conv_accum(xd, (k, k), (s, s), (p, p), False, 1.0 / X.shape[1], out, X3)
+    err = rel_fro(out, want)
+    assert err <= 1e-5, (name, err)
+    print(f"[bf16x3 {name} {layout}] rel. Frobenius error {err:.3e}")
+    OH = (H + 2 * p - k) // s + 1
+    g = torch.randn(N, min(C, 1024), OH, OH, device=DEV) * 1e-3
+    Xg = g.double().permute(1, 0, 2, 3).reshape(g.shape[1], -1)
+    wantg = (Xg @ Xg.t()) * (N * N / Xg.shape[1])
+    gd = g if layout == "nchw" else g.contiguous(memory_format=torch.channels_last)
+    outg = torch.zeros_like(wantg, dtype=torch.float32)
+    nat.syrk_rows_accum(gd, False, N * N / Xg.shape[1], outg, X3)
+    assert rel_fro(outg, wantg) <= 1e-5, (name, rel_fro(outg, wantg))
+
+
+def test_default_tier_is_bf16x3_and_batch_call_matches_single_calls():
+    model = torch.nn.Sequential(torch.nn.Conv2d(64, 128, 3, padding=1, bias=False), torch.nn.ReLU(),
+                                torch.nn.Conv2d(128, 64, 1, bias=False), torch.nn.Flatten(),
+                                torch.nn.Linear(64 * 8 * 8, 10)).to(DEV)
+    kfac = cb.KFAC(model)
+    assert kfac.precision == nat.PREC_BF16X3
+    torch.manual_seed(0)
+    x = torch.randn(6, 64, 8, 8, device=DEV)
+    orc.fisher_step(model, x)
+    kfac.update(6)
+    torch.cuda.synchronize()
+    for layer, (A, G) in kfac.state.items():
+        xr, gr = kfac.record[layer]
+        twin = (torch.nn.Conv2d(1, 1, layer.kernel_size, stride=layer.stride, padding=layer.padding, bias=layer.bias is not None)
+                if layer.__class__.__name__ == "Conv2d" else torch.nn.Linear(1, 1, bias=layer.bias is not None))
+        A_ref, G_ref = orc.kfac_factors(xr.detach().double().cpu(), (gr.detach() * gr.size(0)).double().cpu(), twin)
+        assert rel_fro(A, A_ref) <= 1e-5 and rel_fro(G, G_ref) <= 1e-5, (str(layer), rel_fro(A, A_ref), rel_fro(G, G_ref))
+    for h in kfac.hooks:
+        h.remove()

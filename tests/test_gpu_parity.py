@@ -15,7 +15,7 @@ import curvature_b200 as cb                      # noqa: E402
 from curvature_b200 import _native as nat        # noqa: E402
 
 DEV = "cuda:0"
-FACTOR_TOL = {nat.PREC_FP32: 1e-5, nat.PREC_TF32: 1e-3, nat.PREC_TF32X3: 1e-5, nat.PREC_BF16: 1e-3,
+FACTOR_TOL = {nat.PREC_FP32: 1e-5, nat.PREC_TF32: 1e-3, nat.PREC_BF16X3: 1e-5, nat.PREC_BF16: 1e-3,
               nat.PREC_TF32_TMA: 1e-3}
 
 
