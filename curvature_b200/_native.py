@@ -78,7 +78,7 @@ class SyrkItem(ctypes.Structure):
     """crv_syrk_item (include/curvature_b200.h)"""
     _fields_ = [("x", c_void_p), ("N", c_int), ("C", c_int), ("H", c_int), ("W", c_int), ("kh", c_int), ("kw", c_int),
                 ("sh", c_int), ("sw", c_int), ("ph", c_int), ("pw", c_int), ("alpha", c_float), ("F", c_void_p),
-                ("nchw", c_int)]
+                ("nchw", c_int), ("zero_mean", c_int)]
 
 
 class EfbItem(ctypes.Structure):
@@ -333,9 +333,10 @@ def syrk_rows_accum(g, has_bias, alpha, out, precision=PREC_FP32, join=True):
                       ws.data_ptr(), ws.numel(), precision, _stream(g)), "crv_syrk_rows_accum")
 
 
-def nhwc_item(t, kernel_size, stride, padding, has_bias, alpha, out, precision):
+def nhwc_item(t, kernel_size, stride, padding, has_bias, alpha, out, precision, zero_mean=None):
     """The crv_syrk_item of `out += alpha * X X^T` if the channels-last kernel can take the operand, else None.
-    `t` is a conv input (N,C,H,W) with the layer's geometry, or -- kernel_size None -- a rows operand (N,M,...)."""
+    `t` is a conv input (N,C,H,W) with the layer's geometry, or -- kernel_size None -- a rows operand (N,M,...).
+    `zero_mean` (default: True for rows operands, False for convolution inputs): see crv_syrk_item::zero_mean."""
     if not _tensor_core(precision) or has_bias or t.data_ptr() % 16:
         return None
     if kernel_size is None:
@@ -353,7 +354,8 @@ def nhwc_item(t, kernel_size, stride, padding, has_bias, alpha, out, precision):
             nchw = 1
         else:
             return None
-        item = SyrkItem(_dense(t, "operand"), N, M, 1, L, 1, 1, 1, 1, 0, 0, float(alpha), _dev(out, "factor"), nchw)
+        item = SyrkItem(_dense(t, "operand"), N, M, 1, L, 1, 1, 1, 1, 0, 0, float(alpha), _dev(out, "factor"), nchw,
+                        1 if zero_mean is None else int(bool(zero_mean)))
         if not _syrk_batch_ws(ctypes.byref(item), 1, precision):
             return None
         return item
@@ -370,7 +372,8 @@ def nhwc_item(t, kernel_size, stride, padding, has_bias, alpha, out, precision):
         nchw = 1          # NCHW-dense: the packed small-C path and the transposing pre-pass of the copy tiers take it
     else:
         return None
-    item = SyrkItem(_dense(t, "activation"), N, C, H, W, kh, kw, sh, sw, ph, pw, float(alpha), _dev(out, "factor"), nchw)
+    item = SyrkItem(_dense(t, "activation"), N, C, H, W, kh, kw, sh, sw, ph, pw, float(alpha), _dev(out, "factor"), nchw,
+                    int(bool(zero_mean)))
     if not _syrk_batch_ws(ctypes.byref(item), 1, precision):
         return None
     return item
@@ -379,7 +382,7 @@ def nhwc_item(t, kernel_size, stride, padding, has_bias, alpha, out, precision):
 def debug_partition(geoms, precision, sms=148, which=0):
     """Host-only: how the scheduler cuts a batch of (N, C, H, W, kh, kw, sh, sw, ph, pw) items into launches and CTA ranges.
     Returns dict(launch_of_item, n_launches, boundaries=[(pair, box)...] of launch `which`, nbox, nb)."""
-    items = [SyrkItem(4096, *[int(v) for v in g], 1.0, 4096, 0) for g in geoms]
+    items = [SyrkItem(4096, *[int(v) for v in g], 1.0, 4096, 0, 0) for g in geoms]
     arr = (SyrkItem * len(items))(*items)
     loi = (c_int * len(items))()
     nl, G, pairs = c_int(0), c_int(0), c_int(0)

@@ -251,6 +251,7 @@ static int batch_geoms(const crv_syrk_item* items, int n, std::vector<ConvGeom>&
     const crv_syrk_item& it = items[i];
     if (int rc = make_geom(gs[i], it.x, it.N, it.C, it.H, it.W, it.kh, it.kw, it.sh, it.sw, it.ph, it.pw, 0)) return rc;
     gs[i].x_nchw = it.nchw ? 1 : 0;
+    gs[i].zero_mean = it.zero_mean ? 1 : 0;
     alphas[i] = it.alpha;
     Fs[i] = it.F;
   }

@@ -43,7 +43,8 @@ struct ConvGeom {
   int D;         // K0 + has_bias
   int has_bias;
   long long R;   // N*L
-  int x_nchw;    // channels-last entry points only: 1 = x is NCHW-dense (accepted for the packed small-C path)
+  int x_nchw;    // channels-last entry points only: 1 = x is NCHW-dense (packed small-C path, copy tiers)
+  int zero_mean; // channels-last entry points only: crv_syrk_item::zero_mean
 };
 
 inline int make_geom(ConvGeom& g, const float* x, int N, int C, int H, int W, int kh, int kw, int sh,
@@ -63,6 +64,7 @@ inline int make_geom(ConvGeom& g, const float* x, int N, int C, int H, int W, in
   g.D = g.K0 + g.has_bias;
   g.R = (long long)N * g.L;
   g.x_nchw = 0;
+  g.zero_mean = 0;
   CRV_CHECK((long long)N * C * H * W < (1LL << 31), "input tensor too large for 32-bit indexing");
   return 0;
 }

@@ -1528,10 +1528,19 @@ __global__ void __launch_bounds__(256, 4) syrk_sk_reduce_taps_kernel(const __gri
   for (int k = lane; k < KK * 32; k += 32) Frow[k] += alpha * outbuf[w * pitch + k];
 }
 
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi), both round-to-nearest-even: 16 significand bits of the fp32 value
+// survive (|x - hi - lo| <= 2^-16 |x|), which is what the bf16x3 tier contracts with three bf16 MMAs per k-group.
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));          // low half = first element
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+
 // Pack pre-pass of the small-C path: Q[n][r][ow][i2*32 + j*4 + c] = bf16(x[n][c][2r + i2 - ph][ow*sw + j - pw]) (0 outside
 // the image, for j >= kw and for c >= C).  One thread writes the 64 bytes of one (n, r, ow, i2); x is addressed through
 // element strides, so NCHW-dense and channels-last inputs both work.
-__global__ void __launch_bounds__(256) pack_smallc_kernel(const float* __restrict__ x, uint4* __restrict__ Q, int N, int C, int H, int W,
+__global__ void __launch_bounds__(256) pack_smallc_kernel(const float* __restrict__ x, uint4* __restrict__ Q, uint4* __restrict__ Qlo,
+                                                          int N, int C, int H, int W,
                                                           long long sN, long long sC, long long sH, long long sW, int Hq, int OW,
                                                           int kw, int sw, int ph, int pw, unsigned long long* tr) {
   TraceScope trace_scope(tr, 4);
@@ -1543,9 +1552,9 @@ __global__ void __launch_bounds__(256) pack_smallc_kernel(const float* __restric
     const int r = (int)(u % Hq);
     const int n = (int)(u / Hq);
     const int h = 2 * r + i2 - ph;
-    uint32_t o[16];
+    uint32_t o[16], ol[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) o[k] = 0u;
+    for (int k = 0; k < 16; ++k) { o[k] = 0u; ol[k] = 0u; }
     if (h >= 0 && h < H) {
       const float* __restrict__ row = x + n * sN + h * sH;
 #pragma unroll
@@ -1556,8 +1565,8 @@ __global__ void __launch_bounds__(256) pack_smallc_kernel(const float* __restric
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             if (c < C) v[c] = __ldg(row + c * sC + w * sW);
-          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o[2 * j]) : "f"(v[1]), "f"(v[0]));
-          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o[2 * j + 1]) : "f"(v[3]), "f"(v[2]));
+          split_bf16x2(v[0], v[1], o[2 * j], ol[2 * j]);
+          split_bf16x2(v[2], v[3], o[2 * j + 1], ol[2 * j + 1]);
         }
       }
     }
@@ -1566,6 +1575,13 @@ __global__ void __launch_bounds__(256) pack_smallc_kernel(const float* __restric
     dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
     dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
     dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+    if (Qlo) {                                  // bf16x3 tier: the second plane
+      uint4* dl = Qlo + t * 4;
+      dl[0] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+      dl[1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+      dl[2] = make_uint4(ol[8], ol[9], ol[10], ol[11]);
+      dl[3] = make_uint4(ol[12], ol[13], ol[14], ol[15]);
+    }
   }
 }
 
@@ -1607,14 +1623,6 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict
     else
       out[i] = o;
   }
-}
-
-// x = hi + lo with hi = bf16(x), lo = bf16(x - hi), both round-to-nearest-even: 16 significand bits of the fp32 value
-// survive (|x - hi - lo| <= 2^-16 |x|), which is what the bf16x3 tier contracts with three bf16 MMAs per k-group.
-__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));          // low half = first element
-  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 
 // Split pre-pass of the bf16x3 tier for a channels-last (or 2-D) operand: same layout, two bf16 planes.
@@ -1682,39 +1690,49 @@ struct NhPlan {
   int transpose;                 // the source is NCHW-dense: the pre-pass also transposes it to channels-last
   ConvGeom gq;
   size_t partial_bytes, copy_bytes;
+  size_t plane_bytes;            // bytes of one bf16 plane of the copy (copy_bytes = planes * plane_bytes)
 };
 
 bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl, bool src_is_bf16 = false);
 
 // Small-C convolutions (the ResNet stem): see the header, "packed small-C path".
 bool packable(const ConvGeom& g, int precision) {
-  return precision == CRV_PREC_BF16 && !g.has_bias && g.C <= 4 && g.kw <= 8 && g.sh == 2 && g.kh >= 2 && g.kh <= 16 &&
+  return (precision == CRV_PREC_BF16 || precision == CRV_PREC_BF16X3) && !g.has_bias && g.C <= 4 && g.kw <= 8 && g.sh == 2 &&
+         g.kh >= 2 && g.kh <= 16 &&
          g.sw <= 8 && g.R < (1LL << 31) - 512;
 }
-bool pack_plan(const ConvGeom& g, int sms, NhPlan& pl) {
+bool pack_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl) {
   const int nip = (g.kh + 1) / 2;
   ConvGeom gq;
   static const float dummy = 0.f;
   if (make_geom(gq, &dummy, g.N, 64, g.OH + nip - 1, g.OW, nip, 1, 1, 1, 0, 0, 0)) return false;
   gq.x = nullptr;
-  if (!nhwc_plan(gq, CRV_PREC_BF16, sms, pl, true) || !pl.bf16) return false;
+  if (!nhwc_plan(gq, precision, sms, pl, true) || !pl.bf16) return false;
   pl.pack = 1;
   pl.gq = gq;
   pl.p.ldF = g.D;
   pl.p.pk_kh = g.kh; pl.p.pk_kw = g.kw; pl.p.pk_c = g.C;
-  pl.copy_bytes = ((size_t)gq.N * gq.H * gq.W * 64 * 2 + 1023) & ~(size_t)1023;
+  pl.plane_bytes = ((size_t)gq.N * gq.H * gq.W * 64 * 2 + 1023) & ~(size_t)1023;
+  pl.copy_bytes = (pl.p.x3 ? 2 : 1) * pl.plane_bytes;
   return true;
+}
+
+// operands the bf16 kernel instance can take: whole 16-byte channel groups, whole 64-channel chunks per filter tap
+static bool bf16_geom_ok(const ConvGeom& g) {
+  return g.C >= 64 && (g.C & 7) == 0 && (g.kh * g.kw == 1 || (g.C & 63) == 0) && !g.has_bias;
 }
 
 bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl, bool src_is_bf16) {
   const int KK = g.kh * g.kw;
   pl.pack = 0;
   pl.transpose = 0;
-  if (!src_is_bf16 && packable(g, precision)) return pack_plan(g, sms, pl);
-  // operands the bf16 kernel instance can take: whole 16-byte channel groups, whole 64-channel chunks per filter tap
-  const bool bf16_geom = g.C >= 64 && (g.C & 7) == 0 && (KK == 1 || (g.C & 63) == 0);
-  const bool x3 = !src_is_bf16 && precision == CRV_PREC_BF16X3;
-  if (x3 && !bf16_geom) return false;
+  if (!src_is_bf16 && packable(g, precision)) return pack_plan(g, precision, sms, pl);
+  const bool bf16_geom = bf16_geom_ok(g);
+  // two bf16 planes: the bf16x3 tier, and -- inside the bf16 tier -- zero-mean operands with few contraction rows per
+  // factor row (crv_syrk_item::zero_mean), whose single-plane error 2^-9 sqrt(2 D / R) would exceed the stated 1e-3
+  const bool x3 = bf16_geom_ok(g) &&
+                  (precision == CRV_PREC_BF16X3 || (!src_is_bf16 && precision == CRV_PREC_BF16 && g.zero_mean && g.R < 5LL * g.D));
+  if (precision == CRV_PREC_BF16X3 && !x3) return false;
   // an NCHW-dense source is taken when a bf16 copy is made anyway: the pre-pass then transposes it to channels-last
   if (g.x_nchw && !(bf16_geom && (precision == CRV_PREC_BF16 || x3))) return false;
   if (g.has_bias || g.C < 32 || (g.C & 3) != 0) return false;
@@ -1811,7 +1829,8 @@ bool nhwc_plan(const ConvGeom& g, int precision, int sms, NhPlan& pl, bool src_i
   p.bps = 0; p.splits = 0;                                   // (stream-K: the partition lives in the SkTable)
   pl.partial_bytes = (size_t)(SK_MAXG + pl.pairs) * TILE_ELEMS * sizeof(float);
   const size_t numel = (size_t)g.N * g.C * g.H * g.W;
-  pl.copy_bytes = pl.bf16 ? (size_t)planes * ((numel * 2 + 1023) & ~(size_t)1023)
+  pl.plane_bytes = pl.bf16 ? ((numel * 2 + 1023) & ~(size_t)1023) : 0;
+  pl.copy_bytes = pl.bf16 ? (size_t)planes * pl.plane_bytes
                           : (precision == CRV_PREC_TF32 ? ((numel * 4 + 1023) & ~(size_t)1023) : 0);
   return true;
 }
@@ -2002,11 +2021,19 @@ struct SideState {
                                      // scheduler places a SYRK CTA on every SM first and fills the rest of the SM with
                                      // reduction / pre-pass CTAs (queued earlier, they would otherwise crowd it out)
   cudaEvent_t ev_hp = nullptr;
-  cudaEvent_t ev_main[2] = {nullptr, nullptr}, ev_red[2] = {nullptr, nullptr}, ev_cast[2] = {nullptr, nullptr};
+  // Workspace rings.  Partial tiles: 2 buffers -- contraction j writes buffer j % 2 and first waits for reduction j - 2.
+  // Pre-pass copies: NCOPY slots of their own -- pre-pass c (the c-th launch that has one) writes slot c % ncopy and waits
+  // only for the CONTRACTION that last read that slot (c - ncopy): pre-passes run up to ncopy - 1 launches ahead of the
+  // contractions, whatever the reductions are doing.
+  static constexpr int NCOPY_MAX = 6;
+  cudaEvent_t ev_main[2] = {nullptr, nullptr}, ev_red[2] = {nullptr, nullptr};
+  cudaEvent_t ev_cast[NCOPY_MAX] = {}, ev_used[NCOPY_MAX] = {};
   cudaEvent_t ev_fork = nullptr;
   bool red_pending[2] = {false, false}, main_pending[2] = {false, false};
+  bool used_pending[NCOPY_MAX] = {};
   bool forked = false;
-  int toggle = 0;
+  int toggle = 0, ctoggle = 0, ncopy = 3;
+  size_t sig[4] = {0, 0, 0, 0};      // workspace layout of the last batch (base, bytes, partial size, copy size)
   bool enabled = true, init = false;
 };
 SideState g_side_state[16];
@@ -2029,8 +2056,12 @@ SideState* side_state() {
                 cudaEventCreateWithFlags(&st.ev_fork, cudaEventDisableTiming) == cudaSuccess;
       for (int i = 0; i < 2 && ok; ++i)
         ok = cudaEventCreateWithFlags(&st.ev_main[i], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&st.ev_red[i], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&st.ev_cast[i], cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&st.ev_red[i], cudaEventDisableTiming) == cudaSuccess;
+      for (int i = 0; i < SideState::NCOPY_MAX && ok; ++i)
+        ok = cudaEventCreateWithFlags(&st.ev_cast[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&st.ev_used[i], cudaEventDisableTiming) == cudaSuccess;
+      const char* nc = getenv("CURVATURE_B200_NCOPY");
+      if (nc) st.ncopy = std::max(1, std::min((int)SideState::NCOPY_MAX, atoi(nc)));
       if (!ok) { cudaGetLastError(); st.enabled = false; }
     }
   }
@@ -2065,6 +2096,11 @@ static void side_abort(cudaStream_t s) {
     if (st->main_pending[b]) cudaStreamWaitEvent(s, st->ev_main[b], 0);
     st->red_pending[b] = st->main_pending[b] = false;
   }
+  for (int c = 0; c < SideState::NCOPY_MAX; ++c) {
+    if (st->used_pending[c]) cudaStreamWaitEvent(s, st->ev_used[c], 0);
+    st->used_pending[c] = false;
+  }
+  st->ctoggle = 0;
   if (st->forked) {
     if (cudaEventRecord(st->ev_hp, st->hp) == cudaSuccess) cudaStreamWaitEvent(s, st->ev_hp, 0);
     if (cudaEventRecord(st->ev_fork, st->cast) == cudaSuccess) cudaStreamWaitEvent(s, st->ev_fork, 0);
@@ -2136,22 +2172,23 @@ int make_tensor_map(const ConvGeom& g, const NhPlan& pl, const void* src, CUtens
 
 // One launch of the stream-K kernel (+ its reduction) over the factors idx[0..cnt) -- all of the same operand type.
 int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, const std::vector<NhPlan>& plans,
-                 const int* idx, int cnt, void* ws, size_t ws_bytes, size_t copy_off, cudaStream_t caller) {
+                 const int* idx, int cnt, void* ws, size_t ws_bytes, size_t copy_off, size_t max_copy, cudaStream_t caller) {
   const int sms = device_sm_count();
   const bool bf16 = plans[idx[0]].bf16 != 0;
   size_t pairs = 0, copy_bytes = 0;
   for (int k = 0; k < cnt; ++k) { pairs += plans[idx[k]].pairs; copy_bytes += plans[idx[k]].copy_bytes; }
   CRV_CHECK(cnt == 1 || copy_bytes == 0, "internal: operands with a pre-pass copy are launched one by one");
   const size_t partial_bytes = (size_t)(SK_MAXG + pairs) * TILE_ELEMS * sizeof(float);
-  // layout of a workspace half: [partial tiles of the launch | ... | pre-pass copy at copy_off].  The copy region sits
-  // at the SAME offset for every launch of a batch, beyond the largest partial-tile region: the pre-pass of launch i+2
-  // (which only waits for contraction i) must never write where reduction i may still be reading partial tiles.
-  const size_t need = 2 * (copy_off + copy_bytes + 4096);
-  CRV_CHECK(partial_bytes <= copy_off, "internal: partial tiles overlap the copy region");
+  // Workspace layout of a batch: [partial tiles 0 | partial tiles 1 | copy slot 0 | ... | copy slot ncopy-1]; partial
+  // buffers are `copy_off` bytes (the largest partial-tile region of any launch of the batch), copy slots `max_copy`.
+  // The two rings are independent: see SideState.
+  SideState* st = side_state();
+  const int ncopy = st ? st->ncopy : 1;
+  const size_t slot_bytes = (max_copy + 4095) & ~(size_t)1023;
+  const size_t need = 2 * copy_off + (size_t)ncopy * slot_bytes + 2048;
+  CRV_CHECK(partial_bytes <= copy_off && copy_bytes <= max_copy, "internal: launch exceeds the batch layout");
   CRV_CHECK(ws != nullptr && ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
   CRV_CHECK(((uintptr_t)ws & 15) == 0, "workspace must be 16-byte aligned");
-  // workspace half for this call; the main stream first waits for the reduction that last read it (two calls ago)
-  SideState* st = side_state();
   // (while per-kernel event timing is on, everything runs in order on the caller's stream: an event bracket then
   // times the kernel alone, not the kernel plus whatever shares the SMs with it)
   const bool use_side = st && st->enabled && !profile_on();
@@ -2161,10 +2198,10 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
   if (use_side) {
     buf = st->toggle;
     st->toggle ^= 1;
-    if (st->red_pending[buf]) CRV_CUDA(cudaStreamWaitEvent(s, st->ev_red[buf], 0));
+    if (st->red_pending[buf]) CRV_CUDA(cudaStreamWaitEvent(s, st->ev_red[buf], 0));   // reduction j - 2 read this buffer
   }
-  const size_t half = (ws_bytes / 2) & ~(size_t)1023;
-  char* wsb = (char*)((((uintptr_t)ws + 1023) & ~(uintptr_t)1023) + (size_t)buf * (half - 1024));
+  char* base = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  char* wsb = base + (size_t)buf * copy_off;
   static GroupParams gp;       // (8 KB: kept off the stack; the library is not re-entrant, see the header)
   static GroupMaps maps;
   static SkTable sk;
@@ -2181,6 +2218,7 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
     gp.dbg = d ? atoi(d) : 0;
   }
   double flops = 0.0, bytes = 0.0, fbytes = 0.0;
+  int used_slot = -1;                  // copy slot this launch's contraction reads (launches with a copy are groups of one)
   std::vector<const NhPlan*> pls(cnt);
   for (int k = 0; k < cnt; ++k) {
     const ConvGeom& g = gs[idx[k]];
@@ -2190,17 +2228,19 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
     gp.f[k].alpha = alphas[idx[k]];
     gp.f[k].F = Fs[idx[k]];
     const float* src = g.x;
-    if (pl.copy_bytes) {   // pre-pass: bf16 copy (tier bf16) / TF32 round-to-nearest copy (tier tf32), same layout; or pack
-      // (fault injection for the overlap test: CURVATURE_B200_FAULT_COPY_LAYOUT=1 restores the old, unsafe placement)
-      static const bool fault = getenv("CURVATURE_B200_FAULT_COPY_LAYOUT") && atoi(getenv("CURVATURE_B200_FAULT_COPY_LAYOUT")) != 0;
-      float* copy = (float*)((((uintptr_t)wsb + (fault ? partial_bytes : copy_off)) + 1023) & ~(uintptr_t)1023);
+    int cslot = -1;
+    if (pl.copy_bytes) {   // pre-pass: bf16 copy (tiers bf16 / bf16x3) / TF32 round-to-nearest copy (tier tf32), or pack
+      cslot = use_side ? st->ctoggle : 0;
+      if (use_side) st->ctoggle = (st->ctoggle + 1) % ncopy;
+      float* copy = (float*)(base + 2 * copy_off + (size_t)cslot * slot_bytes);
       const size_t n4 = (size_t)g.N * g.C * g.H * g.W / 4;
       cudaStream_t cs = s;
       const bool side_cast = use_side && st->forked;
-      if (side_cast) {      // wait only for the main kernel that last read this half's copy region (two calls ago)
-        cs = st->cast;
-        if (st->main_pending[buf]) CRV_CUDA(cudaStreamWaitEvent(cs, st->ev_main[buf], 0));
-        if (st->red_pending[buf] && !fault) CRV_CUDA(cudaStreamWaitEvent(cs, st->ev_red[buf], 0));   // (and the reduction that read this half)
+      if (side_cast) cs = st->cast;
+      // the contraction that last read this slot (ncopy pre-passes ago) must have finished
+      if (use_side && st->used_pending[cslot]) {
+        CRV_CUDA(cudaStreamWaitEvent(cs, st->ev_used[cslot], 0));
+        st->used_pending[cslot] = false;
       }
       if (pl.pack) {
         const ConvGeom& q = pl.gq;
@@ -2210,19 +2250,19 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
         if (g.x_nchw) { sW = 1; sH = g.W; sC = (long long)g.H * g.W; sN = sC * g.C; }
         else { sC = 1; sW = g.C; sH = (long long)g.W * g.C; sN = sH * g.H; }
         profile_begin(KC_PREPASS, 0.0, 4.0 * g.N * g.C * g.H * g.W + (double)nt * 64.0, cs);
-        pack_smallc_kernel<<<blocks, 256, 0, cs>>>(g.x, (uint4*)copy, g.N, g.C, g.H, g.W, sN, sC, sH, sW, q.H, q.W, g.kw,
-                                                   g.sw, g.ph, g.pw, gp.trace);
+        pack_smallc_kernel<<<blocks, 256, 0, cs>>>(g.x, (uint4*)copy, pl.p.x3 ? (uint4*)((char*)copy + pl.plane_bytes) : nullptr,
+                                                   g.N, g.C, g.H, g.W, sN, sC, sH, sW, q.H, q.W, g.kw, g.sw, g.ph, g.pw, gp.trace);
       } else if (pl.transpose) {
         // NCHW-dense source: transposing cast into the channels-last bf16 copy (+ lo plane on the bf16x3 tier)
         const int HW = g.H * g.W;
         const int ctiles = (g.C + 63) / 64, ptiles = (HW + 63) / 64;
-        const size_t plane = (((size_t)g.N * g.C * HW * 2) + 1023) & ~(size_t)1023;
+        const size_t plane = pl.plane_bytes;
         profile_begin(KC_PREPASS, 0.0, (pl.p.x3 ? 8.0 : 6.0) * (double)n4 * 4.0, cs);
         nchw_to_nhwc_bf16_kernel<<<(unsigned)((size_t)g.N * ctiles * ptiles), 256, 0, cs>>>(
             g.x, (uint32_t*)copy, pl.p.x3 ? (uint32_t*)((char*)copy + plane) : nullptr, g.C, HW, ctiles, ptiles, gp.trace);
       } else if (pl.p.x3) {
         const unsigned blocks = (unsigned)((n4 + 255) / 256 < (size_t)sms * 16 ? (n4 + 255) / 256 : (size_t)sms * 16);
-        const size_t plane = ((n4 * 8) + 1023) & ~(size_t)1023;
+        const size_t plane = pl.plane_bytes;
         profile_begin(KC_PREPASS, 0.0, 8.0 * (double)n4 * 4.0, cs);
         split_bf16_kernel<<<blocks, 256, 0, cs>>>((const float4*)g.x, (uint2*)copy, (uint2*)((char*)copy + plane), n4, gp.trace);
       } else {
@@ -2235,15 +2275,15 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
       profile_end(cs);
       CRV_CUDA(cudaGetLastError());
       if (side_cast) {
-        CRV_CUDA(cudaEventRecord(st->ev_cast[buf], cs));
-        CRV_CUDA(cudaStreamWaitEvent(s, st->ev_cast[buf], 0));
+        CRV_CUDA(cudaEventRecord(st->ev_cast[cslot], cs));
+        CRV_CUDA(cudaStreamWaitEvent(s, st->ev_cast[cslot], 0));
       }
       src = copy;
+      used_slot = cslot;
     }
     if (int rc = make_tensor_map(pl.pack ? pl.gq : g, pl, src, &maps.m[k])) return rc;
     if (pl.p.x3) {         // (a group of one: the lo plane's map sits in the next slot)
-      const size_t plane = (((size_t)g.N * g.C * g.H * g.W * 2) + 1023) & ~(size_t)1023;
-      if (int rc = make_tensor_map(g, pl, (const char*)src + plane, &maps.m[k + 1])) return rc;
+      if (int rc = make_tensor_map(pl.pack ? pl.gq : g, pl, (const char*)src + pl.plane_bytes, &maps.m[k + 1])) return rc;
     }
     flops += (double)g.R * g.D * (g.D + 1);
     bytes += pl.pack ? 2.0 * pl.gq.N * pl.gq.C * pl.gq.H * pl.gq.W : (pl.bf16 ? 2.0 : 4.0) * g.N * g.C * g.H * g.W;
@@ -2272,6 +2312,10 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
     st->main_pending[buf] = true;
     CRV_CUDA(cudaStreamWaitEvent(st->side, st->ev_main[buf], 0));
     rs = st->side;
+    if (used_slot >= 0) {
+      CRV_CUDA(cudaEventRecord(st->ev_used[used_slot], s));
+      st->used_pending[used_slot] = true;
+    }
   }
   profile_begin(KC_SYRK_REDUCE, 0.0, (double)(sk.G + pairs) * TILE_ELEMS * 4.0 + fbytes, rs);
   static const bool taps_reduce = !(getenv("CURVATURE_B200_TAPS_REDUCE") && atoi(getenv("CURVATURE_B200_TAPS_REDUCE")) == 0);
@@ -2316,6 +2360,30 @@ int plan_batch(const ConvGeom* gs, int n, int precision, std::vector<NhPlan>& pl
     }
   }
   if (!grp.empty()) launches.push_back(grp);
+  // Order of the launches (the factors are independent: any order gives the same sums).  Group launches have no pre-pass
+  // and are HBM-bound; launches of one re-read factor are tensor-bound and need their pre-pass copy first.  The lightest
+  // group goes first (it covers the first pre-passes, which have nothing else to hide behind), the other groups go last
+  // (they stream from HBM at full rate while only the last reductions are still running beside them).
+  static const bool reorder = !(getenv("CURVATURE_B200_REORDER") && atoi(getenv("CURVATURE_B200_REORDER")) == 0);
+  if (reorder && launches.size() > 2) {
+    auto weight = [&](const std::vector<int>& l) {
+      double w = 0.0;
+      for (int i : l) w += (double)gs[i].N * gs[i].C * gs[i].H * gs[i].W;
+      return w;
+    };
+    std::vector<std::vector<int>> groups, singles;
+    for (auto& l : launches) {
+      if (plans[l[0]].copy_bytes == 0 && rides_in_group(plans[l[0]])) groups.push_back(l);
+      else singles.push_back(l);
+    }
+    if (!groups.empty() && !singles.empty()) {
+      std::stable_sort(groups.begin(), groups.end(), [&](const std::vector<int>& a, const std::vector<int>& b) { return weight(a) < weight(b); });
+      launches.clear();
+      launches.push_back(groups[0]);
+      for (auto& l : singles) launches.push_back(l);
+      for (size_t k = 1; k < groups.size(); ++k) launches.push_back(groups[k]);
+    }
+  }
   return 0;
 }
 }  // namespace
@@ -2341,7 +2409,9 @@ size_t syrk_nhwc_batch_workspace(const ConvGeom* gs, int n, int precision) {
   if (n <= 0 || plan_batch(gs, n, precision, plans, launches)) return 0;
   size_t copy_off, max_copy;
   batch_layout(plans, launches, copy_off, max_copy);
-  return 2 * (copy_off + max_copy + 4096);    // two halves: main kernel i+1 writes one while reduction i reads the other
+  SideState* st = side_state();
+  const size_t slot_bytes = (max_copy + 4095) & ~(size_t)1023;
+  return 2 * copy_off + (size_t)(st ? st->ncopy : 1) * slot_bytes + 2048;   // see launch_group: two partial buffers + copy ring
 }
 
 // F_i += alpha_i * X_i X_i^T for a batch of channels-last operands.
@@ -2355,8 +2425,27 @@ int syrk_nhwc_batch_launch(const ConvGeom* gs, const float* alphas, float* const
   if (int rc = plan_batch(gs, n, precision, plans, launches)) return rc;
   size_t copy_off, max_copy;
   batch_layout(plans, launches, copy_off, max_copy);
+  if (SideState* st = side_state()) {
+    // a batch whose workspace layout differs from the previous one's: nothing of the earlier calls may still be reading
+    // or writing the buffer where this batch is about to put other things
+    const size_t sig[4] = {(size_t)(uintptr_t)ws, ws_bytes, copy_off, max_copy};
+    if (st->enabled && memcmp(sig, st->sig, sizeof(sig)) != 0) {
+      cudaStream_t w = st->forked ? st->hp : s;
+      for (int b = 0; b < 2; ++b) {
+        if (st->red_pending[b]) CRV_CUDA(cudaStreamWaitEvent(w, st->ev_red[b], 0));
+        if (st->main_pending[b]) CRV_CUDA(cudaStreamWaitEvent(w, st->ev_main[b], 0));
+      }
+      if (st->forked) {        // pre-passes of this batch run on the cast stream: order it behind the same events
+        for (int b = 0; b < 2; ++b) {
+          if (st->red_pending[b]) CRV_CUDA(cudaStreamWaitEvent(st->cast, st->ev_red[b], 0));
+          if (st->main_pending[b]) CRV_CUDA(cudaStreamWaitEvent(st->cast, st->ev_main[b], 0));
+        }
+      }
+      memcpy(st->sig, sig, sizeof(sig));
+    }
+  }
   for (const auto& l : launches)
-    if (int rc = launch_group(gs, alphas, Fs, plans, l.data(), (int)l.size(), ws, ws_bytes, copy_off, s)) {
+    if (int rc = launch_group(gs, alphas, Fs, plans, l.data(), (int)l.size(), ws, ws_bytes, copy_off, max_copy, s)) {
       side_abort(s);
       return rc;
     }

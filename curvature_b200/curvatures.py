@@ -440,7 +440,8 @@ class KFAC(Curvature):
                     else:
                         if x.dim() != 2:
                             raise NotImplementedError("KFAC supports 2-D Linear inputs only (as the reference)")
-                        item = nat.nhwc_item(x, None, None, None, has_bias, 1.0 / x.size(0), first, self.precision)
+                        item = nat.nhwc_item(x, None, None, None, has_bias, 1.0 / x.size(0), first, self.precision,
+                                             zero_mean=False)
                         if item is not None:
                             batch.append(item)
                         else:

@@ -141,7 +141,14 @@ typedef struct {
   int kh, kw, sh, sw, ph, pw;
   float alpha;
   float* F;
-  int nchw;          /* 1: x is NCHW-dense instead of channels-last; accepted only for the packed small-C path below */
+  int nchw;          /* 1: x is NCHW-dense instead of channels-last: accepted for the packed small-C path below and on the
+                        tiers whose pre-pass writes a bf16 copy anyway (CRV_PREC_BF16, CRV_PREC_BF16X3; the pre-pass then
+                        also transposes to channels-last; needs C >= 64, C % 8 == 0, C % 64 == 0 for k x k filters)       */
+  int zero_mean;     /* 1: the operand may be zero-mean (an output GRADIENT rather than a post-activation input).  Tier
+                        CRV_PREC_BF16 only: a Gram matrix of zero-mean rows has no dominant mean component to hide operand
+                        rounding behind, its relative error is ~ 2^-9 sqrt(2 D / R): such operands get the two-term split
+                        of CRV_PREC_BF16X3 when R < 5 D (few contraction rows per factor row, e.g. Linear layers), so that
+                        the tier's stated 1e-3 holds for them too                                                          */
 } crv_syrk_item;
 size_t crv_syrk_batch_nhwc_workspace(const crv_syrk_item* items, int n, int precision);
 int crv_syrk_batch_nhwc(const crv_syrk_item* items, int n, void* ws, size_t ws_bytes, int precision,

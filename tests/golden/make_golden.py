@@ -292,8 +292,11 @@ def main():
     # rank 40: keeps every low-rank index list >= 32 long -- the reference's
     # `lambda_vec[[...list of 0-d tensors...]]` (curvatures.py:643) raises IndexError for
     # shorter lists (torch treats a short list of tensors as a tuple of indices).
-    bad |= run_case("convzoo", conv_zoo, (6, 3, 11, 9), 2, 40, (0.5, 1.0), (0.1, 1e3), (0.1, 1e3),
-                    ref_curv, ref_utils, orc)
+    # (regenerating re-runs torch's CPU kernels: results move at the 1e-8 level between machines / torch builds, which
+    # the ill-conditioned INF chain of the last convzoo layer amplifies -- regenerate a fixture only when its recipe changes)
+    if not only or "convzoo" in only:
+      bad |= run_case("convzoo", conv_zoo, (6, 3, 11, 9), 2, 40, (0.5, 1.0), (0.1, 1e3), (0.1, 1e3),
+                      ref_curv, ref_utils, orc)
     if bad:
         raise SystemExit("restatement deviates from the reference: fixtures NOT trustworthy")
 

@@ -2,7 +2,7 @@
 layout-normalising pre-pass (NCHW-dense sources transposed to the channels-last bf16 copy the TMA-fed kernel reads).
 
   * indexing: bit-exact on integer-valued inputs (hi plane exact, lo plane zero), channels-last and NCHW sources;
-  * arithmetic: random fp32 data against fp64 at 2e-6 -- the lo plane carries bits 9-16 of every operand: a wrong, missing
+  * arithmetic: random fp32 data against fp64 at 8e-6 -- the lo plane carries bits 9-16 of every operand: a wrong, missing
     or mis-addressed lo plane shows up as ~4e-3 (bf16 precision);
   * the default tier of `cb.KFAC(model)` is bf16x3.
 """
@@ -86,7 +86,9 @@ def test_rows_syrk_bit_exact_on_integers(shape, layout, prec):
 @pytest.mark.parametrize("geom", GEOMS)
 @pytest.mark.parametrize("layout", ["channels_last", "nchw"])
 def test_bf16x3_random_data_against_fp64(geom, layout):
-    """16 significand bits per operand: measured ~1e-7; 2e-6 leaves no room for a broken lo plane (4e-3)."""
+    """Two bf16 terms keep x to 2^-17 (rms 2^-18 / sqrt 3); on zero-mean data with few contraction rows nothing averages
+    out and the factor error is ~ sqrt(2) times that plus the dropped lo lo^T term: measured 3.5e-6 .. 4.6e-6, the tier's
+    worst case.  8e-6 leaves no room for a broken lo plane (4e-3, bf16 precision)."""
     N, C, H, W, k, s, p = geom
     torch.manual_seed(C + H)
     x = torch.randn(N, C, H, W, device=DEV)
@@ -97,7 +99,7 @@ def test_bf16x3_random_data_against_fp64(geom, layout):
     out = torch.zeros_like(want, dtype=torch.float32)
     nat.syrk_conv_accum(xd, k, s, p, False, 1.0 / X.shape[1], out, X3)
     err = rel_fro(out, want)
-    assert err <= 2e-6, (geom, layout, err)
+    assert err <= 8e-6, (geom, layout, err)
     assert torch.equal(out, out.t())
     bf = torch.zeros_like(out)
     nat.syrk_conv_accum(xd, k, s, p, False, 1.0 / X.shape[1], bf, BF16)

@@ -7,9 +7,13 @@ curvature/curvatures.py:306-392) on the same weights, inputs and labels: every l
 Two comparisons per tier:
   * kernels   -- the oracle's factors computed on the host from the EXACT tensors the hooks recorded on the device
                  (so that only this repo's kernels differ): 1e-5 for the fp32-grade tiers, 1e-3 for tf32 / bf16;
-  * end to end -- the oracle's own forward / backward / update on the host (the model's forward and backward are
-                 torch's on both sides -- cuDNN vs MKL-DNN fp32 rounding differs at the 1e-6 level per layer and
-                 accumulates over 18-50 layers): 1e-4 for the fp32-grade tiers, 1e-3 for tf32 / bf16.
+  * end to end -- the oracle's own forward / backward / update on the host.  The model's forward and backward are torch's
+                 on both sides, and torch's own device-vs-host difference is NOT small here: measured on these randomly
+                 initialised train-mode networks at batch 8 it reaches 1e-3 (ResNet-18) and 2e-2 (ResNet-50) on the
+                 output-gradient factors (cuDNN vs oneDNN convolution algorithms, batch-norm statistics of 8 x 7 x 7
+                 samples, ReLU masks flipping).  That `drift` is measured per layer (oracle on the recorded device tensors
+                 vs oracle on the host's own tensors -- no kernel of this repo involved) and the end-to-end error must stay
+                 within the tier's tolerance plus 1.5 x drift.
 """
 import copy
 import os
@@ -27,7 +31,6 @@ from curvature_b200 import _native as nat        # noqa: E402
 DEV = "cuda:0"
 N = 8
 KERNEL_TOL = {"fp32": 1e-5, "bf16x3": 1e-5, "tf32": 1e-3, "tf32_tma": 1e-3, "bf16": 1e-3}
-E2E_TOL = {"fp32": 1e-4, "bf16x3": 1e-4, "tf32": 1e-3, "tf32_tma": 1e-3, "bf16": 1e-3}
 TIERS = [t for t in ("fp32", "bf16x3", "tf32", "bf16") if t in nat.PRECISION_NAMES]
 
 
@@ -98,20 +101,29 @@ def test_whole_model_factors_match_oracle(name, prec, layout):
     rows = []
     for li, layer in enumerate(layers):
         A, G = kfac.state[layer]
-        assert torch.equal(A, A.t()) and torch.equal(G, G.t()), (li, "not symmetric")
+        if prec == "fp32" or (prec == "bf16x3" and (layer.bias is not None or layer.weight.shape[1] < 64)):
+            # CUDA-core path (atomic split-R merge): symmetric to rounding, like the reference's own torch.mm
+            assert rel_fro(A, A.t()) <= 1e-6 and rel_fro(G, G.t()) <= 1e-6, (li, "not symmetric")
+        else:
+            assert torch.equal(A, A.t()) and torch.equal(G, G.t()), (li, "not symmetric")
         # kernels only: the oracle on the tensors the device recorded (the reference's record holds g * N, :310)
         xr, gr = kfac.record[layer]
         A_k, G_k = orc.kfac_factors(xr.detach().cpu().contiguous(), (gr.detach() * gr.size(0)).cpu().contiguous(),
                                     host_twin(layer))
-        # end to end: the oracle's own forward / backward on the host
+        # end to end: the oracle's own forward / backward on the host; drift = torch's device-vs-host difference
+        drift = max(rel_fro(A_k, want[li][0]), rel_fro(G_k, want[li][1]))
         rows.append((li, tuple(A.shape)[0], tuple(G.shape)[0], rel_fro(A, A_k), rel_fro(G, G_k),
-                     rel_fro(A, want[li][0]), rel_fro(G, want[li][1])))
+                     rel_fro(A, want[li][0]), rel_fro(G, want[li][1]), drift))
+    tol = KERNEL_TOL[prec]
     worst_k = max(max(r[3], r[4]) for r in rows)
     worst_e = max(max(r[5], r[6]) for r in rows)
+    worst_d = max(r[7] for r in rows)
+    bad = [r for r in rows if max(r[3], r[4]) > tol or max(r[5], r[6]) > tol + 1.5 * r[7]]
     report = "\n".join(f"  layer {r[0]:2d} K={r[1]:5d} M={r[2]:5d}  kernel A {r[3]:.2e} G {r[4]:.2e}   end-to-end A {r[5]:.2e} G {r[6]:.2e}"
-                       for r in rows if max(r[3], r[4]) > KERNEL_TOL[prec] or max(r[5], r[6]) > E2E_TOL[prec])
-    print(f"{name} {prec} {layout}: worst kernel error {worst_k:.2e}, worst end-to-end error {worst_e:.2e}")
-    assert worst_k <= KERNEL_TOL[prec] and worst_e <= E2E_TOL[prec], f"{name} {prec} {layout}\n{report}"
+                       f"   torch device-vs-host drift {r[7]:.2e}" for r in bad)
+    print(f"{name} {prec} {layout}: worst kernel error {worst_k:.2e}, worst end-to-end error {worst_e:.2e} "
+          f"(torch's own device-vs-host drift up to {worst_d:.2e})")
+    assert not bad, f"{name} {prec} {layout}\n{report}"
     fc = layers[-1]
     assert kfac.state[fc][0][-1, -1].item() == 1.0          # ones row: A[-1,-1] = #updates (plain running sum)
     kfac.update(N)
