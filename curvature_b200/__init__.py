@@ -4,8 +4,8 @@ library; it raises if the library has not been built (there is no fallback imple
 from . import _native
 from .curvatures import Curvature, Diagonal, KFAC, EFB, INF, FactorArena
 from .utils import get_eigenvectors, get_eigenvalues, kron
-from .parallel import allreduce_arena, shard_indices
+from .parallel import allreduce_arena, shard_indices, invert_plan, allgather_segments
 from .io import save_factors, load_factors
 
 __all__ = ["Curvature", "Diagonal", "KFAC", "EFB", "INF", "FactorArena", "get_eigenvectors", "get_eigenvalues",
-           "kron", "allreduce_arena", "shard_indices", "save_factors", "load_factors"]
+           "kron", "allreduce_arena", "shard_indices", "invert_plan", "allgather_segments", "save_factors", "load_factors"]

@@ -231,6 +231,7 @@ __device__ __forceinline__ void decode_pair(int pair, int T, int& I, int& J) {
 // ---- pieces shared by the thread-staged and the TMA-fed kernels ------------------------------------
 struct ItemShape {
   int I, J, rowsA, mh, ncols, RP, SC, cb, ce, nstage_it;
+  int ncols0;      // columns of the first 128-row half that hold results (channels-last kernel: 128 for a two-half diagonal tile)
   bool diag;
 };
 __device__ __forceinline__ ItemShape item_shape(const TcParams& p, int item) {
@@ -318,7 +319,8 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ItemShape& t, uin
   const int sub = lane >> 3, ch = lane & 7;             // read-back role: row within a group of 4, 16-byte chunk
   for (int h = 0; h < t.mh; ++h) {
     const int row0 = h * 128 + quad * 32;
-    for (int cc = 0; cc < t.ncols; cc += 32) {
+    const int nc = h == 0 ? t.ncols0 : t.ncols;
+    for (int cc = 0; cc < nc; cc += 32) {
       uint32_t a[32];
       const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * 256 + cc);
       asm volatile(
@@ -1216,6 +1218,10 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       const int ub = (int)uni((uint32_t)b_begin), ue = (int)uni((uint32_t)b_end);
       const int u_nit = (ue - ub + u_NB - 1) / u_NB;
       const uint32_t idesc = uni(BF16 ? umma_idesc_mn16(128, (uint32_t)t.ncols) : umma_idesc_mn(128, (uint32_t)t.ncols));
+      // diagonal tile of two row halves: only the lower triangle is ever read, so rows 0-127 need columns 0-127 only --
+      // the first half's instruction runs with N = 128 (half the tensor-pipe time; a quarter of the tile's work saved)
+      const uint32_t nc0 = uni((t.diag && t.mh == 2 && !(gp.dbg & 4)) ? 128u : (uint32_t)t.ncols);
+      const uint32_t idesc0 = uni(BF16 ? umma_idesc_mn16(128, nc0) : umma_idesc_mn(128, nc0));
       const uint64_t dfull = (BF16 ? umma_desc_mn16(0u, u_chunk) : umma_desc_mn(0u, u_chunk));
       const uint32_t dlo = (uint32_t)dfull, dhi32 = (uint32_t)(dfull >> 32);
       const uint32_t hstep = (uint32_t)(128 / CH) * u_chunk;              // second 128-row half of the A block
@@ -1247,9 +1253,9 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
             // x = hi + lo (two bf16 planes): X X^T ~= hi hi^T + hi lo^T + lo hi^T, three instructions per row half
             for (int kg = 0; kg < nkg; ++kg) {
               const uint32_t ko = (uint32_t)kg * KSTEP;
-              tc_mma_lohi(true, u_tmem, a0 + ko, b0 + ko, dhi32, idesc, acc);
-              tc_mma_lohi(true, u_tmem, a0 + ko, b0 + lo16 + ko, dhi32, idesc, 1u);
-              tc_mma_lohi(true, u_tmem, a0 + lo16 + ko, b0 + ko, dhi32, idesc, 1u);
+              tc_mma_lohi(true, u_tmem, a0 + ko, b0 + ko, dhi32, idesc0, acc);
+              tc_mma_lohi(true, u_tmem, a0 + ko, b0 + lo16 + ko, dhi32, idesc0, 1u);
+              tc_mma_lohi(true, u_tmem, a0 + lo16 + ko, b0 + ko, dhi32, idesc0, 1u);
               if (two) {
                 tc_mma_lohi(true, u_tmem + 256u, a1 + ko, b0 + ko, dhi32, idesc, acc);
                 tc_mma_lohi(true, u_tmem + 256u, a1 + ko, b0 + lo16 + ko, dhi32, idesc, 1u);
@@ -1260,7 +1266,7 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
           } else {
             for (int kg = 0; kg < nkg; ++kg) {
               const uint32_t ko = (uint32_t)kg * KSTEP;
-              tc_mma_lohi(BF16, u_tmem, a0 + ko, b0 + ko, dhi32, idesc, acc);
+              tc_mma_lohi(BF16, u_tmem, a0 + ko, b0 + ko, dhi32, idesc0, acc);
               if (two) tc_mma_lohi(BF16, u_tmem + 256u, a1 + ko, b0 + ko, dhi32, idesc, acc);
               acc = 1;
             }
@@ -1286,6 +1292,7 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       const SegGeom g = seg_geom<CH>(p, q - gp.qbeg[fi]);
       ItemShape t;
       t.mh = g.mh; t.ncols = g.ncols; t.rowsA = g.pk ? g.poff + g.rowsA : g.rowsA;
+      t.ncols0 = (g.diag && g.mh == 2 && !(gp.dbg & 4)) ? 128 : g.ncols;
       epilogue_store_coalesced(t, bar_tmem_full, (uint32_t)nseg & 1u, tmem, gp.ws + (size_t)(blockIdx.x + q) * TILE_ELEMS,
                                warp & 3, lane, epi + (uint32_t)(warp & 3) * 4096u);
       tc_fence_before();
@@ -1871,7 +1878,7 @@ void build_sk(const std::vector<const NhPlan*>& pls, int sms, GroupParams& gp, S
       const int nslots = (rowsA + CH - 1) / CH + (diag ? 0 : TB / CH);
       // measured with the per-CTA timeline (crv_debug_timeline), ns per k-group at ~1.85 GHz: two MMAs of N = 256:
       // 150; one MMA: 100 / 80 / 67 at N = 256 / 128 / 64 (one instruction per k-group is issue-bound, not pipe-bound)
-      double mma = mh == 2 ? 150.0 * std::max(ncols / 256.0, 0.5) : 56.0 + 0.17 * ncols;
+      double mma = mh == 2 ? 150.0 * std::max(ncols / 256.0, 0.5) * (diag ? 0.75 : 1.0) : 56.0 + 0.17 * ncols;
       double bytes = (double)nslots * KPOS * 128;
       if (p.pack2) {      // one instruction per 2 x KPOS positions (N = twice the padded order): cost per KPOS positions
         const int n2 = 2 * ((rowsA + CH - 1) / CH) * CH;
@@ -2021,18 +2028,20 @@ struct SideState {
                                      // scheduler places a SYRK CTA on every SM first and fills the rest of the SM with
                                      // reduction / pre-pass CTAs (queued earlier, they would otherwise crowd it out)
   cudaEvent_t ev_hp = nullptr;
-  // Workspace rings.  Partial tiles: 2 buffers -- contraction j writes buffer j % 2 and first waits for reduction j - 2.
+  // Workspace rings.  Partial tiles: npart buffers -- contraction j writes buffer j % npart and first waits for reduction
+  // j - npart (3 by default: the reduction of a 4608^2 factor outlasts the next, short contraction).
   // Pre-pass copies: NCOPY slots of their own -- pre-pass c (the c-th launch that has one) writes slot c % ncopy and waits
   // only for the CONTRACTION that last read that slot (c - ncopy): pre-passes run up to ncopy - 1 launches ahead of the
   // contractions, whatever the reductions are doing.
   static constexpr int NCOPY_MAX = 6;
-  cudaEvent_t ev_main[2] = {nullptr, nullptr}, ev_red[2] = {nullptr, nullptr};
+  static constexpr int NPART_MAX = 4;
+  cudaEvent_t ev_main[NPART_MAX] = {}, ev_red[NPART_MAX] = {};
   cudaEvent_t ev_cast[NCOPY_MAX] = {}, ev_used[NCOPY_MAX] = {};
   cudaEvent_t ev_fork = nullptr;
-  bool red_pending[2] = {false, false}, main_pending[2] = {false, false};
+  bool red_pending[NPART_MAX] = {}, main_pending[NPART_MAX] = {};
   bool used_pending[NCOPY_MAX] = {};
   bool forked = false;
-  int toggle = 0, ctoggle = 0, ncopy = 3;
+  int toggle = 0, ctoggle = 0, ncopy = 3, npart = 3;
   size_t sig[4] = {0, 0, 0, 0};      // workspace layout of the last batch (base, bytes, partial size, copy size)
   bool enabled = true, init = false;
 };
@@ -2054,9 +2063,11 @@ SideState* side_state() {
                 cudaStreamCreateWithPriority(&st.hp, cudaStreamNonBlocking, greatest) == cudaSuccess &&
                 cudaEventCreateWithFlags(&st.ev_hp, cudaEventDisableTiming) == cudaSuccess &&
                 cudaEventCreateWithFlags(&st.ev_fork, cudaEventDisableTiming) == cudaSuccess;
-      for (int i = 0; i < 2 && ok; ++i)
+      for (int i = 0; i < SideState::NPART_MAX && ok; ++i)
         ok = cudaEventCreateWithFlags(&st.ev_main[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&st.ev_red[i], cudaEventDisableTiming) == cudaSuccess;
+      const char* np = getenv("CURVATURE_B200_NPART");
+      if (np) st.npart = std::max(2, std::min((int)SideState::NPART_MAX, atoi(np)));
       for (int i = 0; i < SideState::NCOPY_MAX && ok; ++i)
         ok = cudaEventCreateWithFlags(&st.ev_cast[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&st.ev_used[i], cudaEventDisableTiming) == cudaSuccess;
@@ -2073,7 +2084,7 @@ SideState* side_state() {
 int syrk_stream_join(cudaStream_t s) {
   SideState* st = side_state();
   if (!st || !st->enabled) return 0;
-  for (int b = 0; b < 2; ++b)
+  for (int b = 0; b < SideState::NPART_MAX; ++b)
     if (st->red_pending[b]) {
       CRV_CUDA(cudaStreamWaitEvent(s, st->ev_red[b], 0));
       st->red_pending[b] = false;
@@ -2091,7 +2102,7 @@ int syrk_stream_join(cudaStream_t s) {
 static void side_abort(cudaStream_t s) {
   SideState* st = side_state();
   if (!st || !st->enabled) return;
-  for (int b = 0; b < 2; ++b) {
+  for (int b = 0; b < SideState::NPART_MAX; ++b) {
     if (st->red_pending[b]) cudaStreamWaitEvent(s, st->ev_red[b], 0);
     if (st->main_pending[b]) cudaStreamWaitEvent(s, st->ev_main[b], 0);
     st->red_pending[b] = st->main_pending[b] = false;
@@ -2183,9 +2194,9 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
   // buffers are `copy_off` bytes (the largest partial-tile region of any launch of the batch), copy slots `max_copy`.
   // The two rings are independent: see SideState.
   SideState* st = side_state();
-  const int ncopy = st ? st->ncopy : 1;
+  const int ncopy = st ? st->ncopy : 1, npart = st ? st->npart : 1;
   const size_t slot_bytes = (max_copy + 4095) & ~(size_t)1023;
-  const size_t need = 2 * copy_off + (size_t)ncopy * slot_bytes + 2048;
+  const size_t need = (size_t)npart * copy_off + (size_t)ncopy * slot_bytes + 2048;
   CRV_CHECK(partial_bytes <= copy_off && copy_bytes <= max_copy, "internal: launch exceeds the batch layout");
   CRV_CHECK(ws != nullptr && ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
   CRV_CHECK(((uintptr_t)ws & 15) == 0, "workspace must be 16-byte aligned");
@@ -2197,8 +2208,8 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
   int buf = 0;
   if (use_side) {
     buf = st->toggle;
-    st->toggle ^= 1;
-    if (st->red_pending[buf]) CRV_CUDA(cudaStreamWaitEvent(s, st->ev_red[buf], 0));   // reduction j - 2 read this buffer
+    st->toggle = (st->toggle + 1) % npart;
+    if (st->red_pending[buf]) CRV_CUDA(cudaStreamWaitEvent(s, st->ev_red[buf], 0));   // reduction j - npart read this buffer
   }
   char* base = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
   char* wsb = base + (size_t)buf * copy_off;
@@ -2232,7 +2243,7 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
     if (pl.copy_bytes) {   // pre-pass: bf16 copy (tiers bf16 / bf16x3) / TF32 round-to-nearest copy (tier tf32), or pack
       cslot = use_side ? st->ctoggle : 0;
       if (use_side) st->ctoggle = (st->ctoggle + 1) % ncopy;
-      float* copy = (float*)(base + 2 * copy_off + (size_t)cslot * slot_bytes);
+      float* copy = (float*)(base + (size_t)npart * copy_off + (size_t)cslot * slot_bytes);
       const size_t n4 = (size_t)g.N * g.C * g.H * g.W / 4;
       cudaStream_t cs = s;
       const bool side_cast = use_side && st->forked;
@@ -2411,7 +2422,7 @@ size_t syrk_nhwc_batch_workspace(const ConvGeom* gs, int n, int precision) {
   batch_layout(plans, launches, copy_off, max_copy);
   SideState* st = side_state();
   const size_t slot_bytes = (max_copy + 4095) & ~(size_t)1023;
-  return 2 * copy_off + (size_t)(st ? st->ncopy : 1) * slot_bytes + 2048;   // see launch_group: two partial buffers + copy ring
+  return (size_t)(st ? st->npart : 1) * copy_off + (size_t)(st ? st->ncopy : 1) * slot_bytes + 2048;   // see launch_group
 }
 
 // F_i += alpha_i * X_i X_i^T for a batch of channels-last operands.
@@ -2431,12 +2442,12 @@ int syrk_nhwc_batch_launch(const ConvGeom* gs, const float* alphas, float* const
     const size_t sig[4] = {(size_t)(uintptr_t)ws, ws_bytes, copy_off, max_copy};
     if (st->enabled && memcmp(sig, st->sig, sizeof(sig)) != 0) {
       cudaStream_t w = st->forked ? st->hp : s;
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < SideState::NPART_MAX; ++b) {
         if (st->red_pending[b]) CRV_CUDA(cudaStreamWaitEvent(w, st->ev_red[b], 0));
         if (st->main_pending[b]) CRV_CUDA(cudaStreamWaitEvent(w, st->ev_main[b], 0));
       }
       if (st->forked) {        // pre-passes of this batch run on the cast stream: order it behind the same events
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < SideState::NPART_MAX; ++b) {
           if (st->red_pending[b]) CRV_CUDA(cudaStreamWaitEvent(st->cast, st->ev_red[b], 0));
           if (st->main_pending[b]) CRV_CUDA(cudaStreamWaitEvent(st->cast, st->ev_main[b], 0));
         }

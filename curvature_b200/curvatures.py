@@ -470,7 +470,15 @@ class KFAC(Curvature):
 
     def invert(self,
                add: Union[float, list, tuple] = 0.,
-               multiply: Union[float, list, tuple] = 1.):
+               multiply: Union[float, list, tuple] = 1.,
+               group=None,
+               shard: Optional[bool] = None):
+        """Damped Cholesky factors of the inverse factors (reference: curvatures.py:354-385), one batched kernel call (K4).
+
+        With `torch.distributed` initialised on more than one rank (and `shard` not False) the factors are sharded over
+        the ranks of `group` by their D^3 cost, every rank inverts its own and ONE all-gather of the rank-major inverse
+        arena gives every rank all of `inv_state` (the state must already be merged, see
+        `allreduce_arena`).  The result is the same as every rank inverting everything."""
         assert self.state, "State dict is empty. Did you call 'update' prior to this?"
         if self.inv_state:
             Warning("State has already been inverted. Is this expected?")
@@ -481,14 +489,35 @@ class KFAC(Curvature):
             factors += [first, second]
             adds += [n, n]
             muls += [s, s]
-        inv_arena = FactorArena([f.shape for f in factors], factors[0].device)
-        info = nat.chol_inv_batched(factors, adds, muls, inv_arena.views)
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        if shard is None:
+            shard = world > 1
+        if shard and world > 1:
+            from .parallel import invert_plan, allgather_segments
+            rank = dist.get_rank(group)
+            plan = invert_plan([f.shape[0] for f in factors], world)
+            flat = torch.zeros(plan["total"], dtype=factors[0].dtype, device=factors[0].device)
+            views = [flat[o:o + f.numel()].view(f.shape) for o, f in zip(plan["offset"], factors)]
+            mine = [i for i, r in enumerate(plan["owner"]) if r == rank]
+            info = torch.zeros(len(factors), dtype=torch.int32, device=factors[0].device)
+            if mine:
+                info[mine] = nat.chol_inv_batched([factors[i] for i in mine], [adds[i] for i in mine],
+                                                  [muls[i] for i in mine], [views[i] for i in mine])
+            allgather_segments(flat, plan["segment"], group)          # the one exchange step
+            dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)  # (count ints: every rank raises on any failure)
+            inv_arena = FactorArena.__new__(FactorArena)
+            inv_arena.flat, inv_arena.views = flat, views
+        else:
+            inv_arena = FactorArena([f.shape for f in factors], factors[0].device)
+            info = nat.chol_inv_batched(factors, adds, muls, inv_arena.views)
         bad = torch.nonzero(info).flatten().tolist()   # one sync per invert; invert is not the hot loop
         if bad:
             raise RuntimeError("KFAC.invert: damped factor is not positive definite for matrices "
                                f"{bad[:8]} (factor index = 2*layer + {{0: A, 1: G}}); increase `add`. "
                                "(The reference falls back to numpy here; this implementation has no CPU path.)")
         self._inv_arena = inv_arena
+        self.__dict__.pop('_inv_tf32', None)           # rounded copies of the previous inverse factors are stale
         for i, layer in enumerate(self.state.keys()):
             self.inv_state[layer] = (inv_arena.views[2 * i], inv_arena.views[2 * i + 1])
 

@@ -36,3 +36,44 @@ def shard_indices(count: int, rank: int, world_size: int, costs: Optional[Iterab
         owner[i] = r
         load[r] += costs[i]
     return [i for i in range(count) if owner[i] == rank]
+
+
+def invert_plan(dims, world_size: int, align: int = 64):
+    """Layer-sharded `KFAC.invert`: which rank inverts which factor, and where every inverse lives.
+
+    `dims[i]` is the order of factor i (2 per layer, in state order).  Factors are assigned greedily, largest first, by
+    their D^3 cost (LPT).  The inverse arena is laid out RANK-MAJOR: rank r's matrices are contiguous in segment r, every
+    segment padded to the same `segment` floats, so that one in-place all-gather (`all_gather_into_tensor` of the arena
+    with each rank's own segment as its input) gives every rank every inverse factor -- the one exchange step.
+    Returns dict(owner=[rank per factor], offset=[float offset per factor], segment=floats per rank, total=floats)."""
+    count = len(dims)
+    order = sorted(range(count), key=lambda i: (-int(dims[i]) ** 3, i))
+    load = [0] * world_size
+    owner = [0] * count
+    for i in order:
+        r = min(range(world_size), key=lambda q: (load[q], q))
+        owner[i] = r
+        load[r] += int(dims[i]) ** 3
+    fill = [0] * world_size
+    local = [0] * count
+    for i in range(count):                      # state order within a segment
+        local[i] = fill[owner[i]]
+        n = int(dims[i]) ** 2
+        fill[owner[i]] += (n + align - 1) // align * align
+    segment = max(max(fill), align)
+    return {"owner": owner, "offset": [owner[i] * segment + local[i] for i in range(count)], "segment": segment,
+            "total": segment * world_size}
+
+
+def allgather_segments(flat: torch.Tensor, segment: int, group: Optional["dist.ProcessGroup"] = None):
+    """In-place all-gather of a rank-major arena: rank r contributes flat[r * segment : (r + 1) * segment].  One collective."""
+    if not dist.is_available() or not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    assert flat.numel() == segment * world
+    mine = flat[rank * segment:(rank + 1) * segment]
+    if flat.is_cuda:
+        return dist.all_gather_into_tensor(flat, mine, group=group)
+    # (gloo has no all_gather_into_tensor on every build: gather into views of the same buffer)
+    return dist.all_gather([flat[r * segment:(r + 1) * segment] for r in range(world)], mine.clone(), group=group)

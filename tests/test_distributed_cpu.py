@@ -75,3 +75,57 @@ def test_shard_sum_equals_consecutive_batches():
         for f in range(2):
             assert torch.allclose(seq.state[layer][f], parts[0].state[layer][f] + parts[1].state[layer][f],
                                   rtol=1e-6, atol=1e-8)
+
+
+def _invert_worker(rank, world, port, out_dir):
+    """Layer-sharded invert on two ranks (gloo): every rank fills ONLY the inverse factors the plan assigns to it (here
+    with the oracle's curvatures.py:368-379 restatement standing in for the CUDA kernel), one all-gather of the
+    rank-major arena, and every rank ends up with every inverse factor."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import curvature_b200 as cb
+    torch.manual_seed(0)                                   # same (already merged) factors on every rank
+    dims = [26, 6, 151, 16, 401, 120, 121, 84, 85, 10]     # LeNet-5's factor orders
+    factors = []
+    for D in dims:
+        X = torch.randn(D, 2 * D + 3)
+        factors.append(X @ X.t() / X.shape[1])
+    plan = cb.invert_plan(dims, world)
+    flat = torch.zeros(plan["total"])
+    views = [flat[o:o + D * D].view(D, D) for o, D in zip(plan["offset"], dims)]
+    for i, owner in enumerate(plan["owner"]):
+        if owner == rank:
+            views[i].copy_(orc.damped_inverse_cholesky(factors[i], 0.5, 1.0))
+    cb.allgather_segments(flat, plan["segment"])
+    for i, D in enumerate(dims):
+        want = orc.damped_inverse_cholesky(factors[i], 0.5, 1.0)
+        assert torch.equal(views[i], want), (rank, i)
+    torch.save(flat, os.path.join(out_dir, f"inv{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_gloo_sharded_invert_allgather(tmp_path):
+    port = _free_port()
+    mp.spawn(_invert_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert torch.equal(torch.load(tmp_path / "inv0.pt"), torch.load(tmp_path / "inv1.pt"))
+
+
+def test_invert_plan_is_a_balanced_partition():
+    import curvature_b200 as cb
+    # ResNet-152's factor orders (SURVEY 8(a) multiplicities): 312 matrices
+    shapes = [(147, 64)] + [(64, 64)] + [(576, 64)] * 3 + [(64, 256)] * 4 + [(256, 64)] * 2 + [(256, 128)] + [(1152, 128)] * 8 + \
+             [(128, 512)] * 8 + [(256, 512)] + [(512, 128)] * 7 + [(512, 256)] + [(2304, 256)] * 36 + [(256, 1024)] * 36 + \
+             [(512, 1024)] + [(1024, 256)] * 35 + [(1024, 512)] + [(4608, 512)] * 3 + [(512, 2048)] * 3 + [(1024, 2048)] + \
+             [(2048, 512)] * 2 + [(2049, 1000)]
+    dims = [d for kd in shapes for d in kd]
+    for world in (1, 2, 4, 8):
+        plan = cb.invert_plan(dims, world)
+        assert len(plan["owner"]) == len(dims) and set(plan["owner"]) == set(range(world))
+        spans = sorted((o, o + d * d) for o, d in zip(plan["offset"], dims))
+        assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))                       # no two inverses overlap
+        for i, (o, d) in enumerate(zip(plan["offset"], dims)):                           # each inside its owner's segment
+            r = plan["owner"][i]
+            assert r * plan["segment"] <= o and o + d * d <= (r + 1) * plan["segment"]
+        load = [sum(d ** 3 for d, r in zip(dims, plan["owner"]) if r == q) for q in range(world)]
+        assert max(load) <= 1.1 * sum(load) / world, (world, load)                       # LPT by D^3: within 10 % of even

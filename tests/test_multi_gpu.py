@@ -43,11 +43,22 @@ def _worker(rank, world, port, out_dir):
     if rank == 0:
         torch.save({"kfac": [[f.cpu() for f in v] for v in kfac.state.values()],
                     "diag": [v.cpu() for v in diag.state.values()]}, os.path.join(out_dir, "reduced.pt"))
-    # layer-sharded invert needs no communication to be set up: every rank owns a disjoint subset
-    mine = cb.shard_indices(len(kfac.state), rank, world, costs=[v[0].shape[0] ** 3 for v in kfac.state.values()])
-    got = [None] * world
-    dist.all_gather_object(got, mine)
-    assert sorted(sum(got, [])) == list(range(len(kfac.state)))
+    # layer-sharded invert + one all-gather == every rank inverting everything
+    kfac.invert(0.5, 1.0)                                   # sharded: torch.distributed is initialised, world 2
+    sharded = [[t.clone() for t in v] for v in kfac.inv_state.values()]
+    kfac.invert(0.5, 1.0, shard=False)
+    for a, b in zip(sharded, kfac.inv_state.values()):
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    kfac.sample_and_replace()                               # posterior samples: per-rank RNG, no communication
+    # a model on a device that is not the current one (the C ABI switches to the operand's device itself)
+    other = (rank + 1) % world
+    torch.cuda.set_device(other)
+    k2 = cb.KFAC(model)                                     # model lives on `dev`, current device is the other GPU
+    k2.record = kfac.record
+    k2.update(16)
+    k2.invert(0.5, 1.0, shard=False)
+    torch.cuda.synchronize(dev)
+    torch.cuda.set_device(rank)
     dist.destroy_process_group()
 
 
