@@ -61,6 +61,10 @@ def parse():
     ap.add_argument("--allreduce-every", type=int, default=0,
                     help="all-reduce the factor arena every this many updates inside the timed region (0 = once per pass, "
                          "the design point; 1 = the per-update stress variant of SURVEY 8(d) config 3)")
+    ap.add_argument("--mode", default="update", choices=["update", "invert"],
+                    help="update: the headline metric (KFAC.update images/s).  invert: BASELINE configs[4] -- KFAC.invert of "
+                         "every factor of the model with the README damping, layer-sharded over the GPUs + one all-gather; "
+                         "value = ms per invert (lower is better)")
     ap.add_argument("--no-context", action="store_true",
                     help="skip the context lines (eigensolver timing, the reference algorithm on torch-CUDA)")
     return ap.parse_args()
@@ -278,6 +282,84 @@ def eigh_timing(kfac):
             "what": "cuSOLVER syevd via torch.linalg.eigh (the library call the north star allows for the one-shot eigenbases)"}
 
 
+README_DAMPING = {"resnet18": (1.0, 18916.0), "resnet50": (69.0, 25771.0), "resnet152": (2765.0, 10162.0),
+                  "lenet5": (0.5, 1.0)}            # README.rst:262-264 "KFAC Norm" / "KFAC Scale"; README.rst:148 for LeNet-5
+
+
+def invert_mode(args, rank, world, local):
+    """BASELINE configs[4]: `KFAC.invert(add, multiply)` of all factors (ResNet-152: 312 matrices, orders 64 .. 4608) --
+    sharded over the ranks by D^3 (LPT), every rank runs the batched Cholesky-of-inverse kernel on its own matrices, ONE
+    all-gather of the rank-major inverse arena (curvature_b200/parallel.py).  Time = device time of K inverts, max over
+    ranks.  The factors come from one update on a small synthetic batch (their values do not change the work)."""
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import curvature_b200 as cb
+    model, shape = make_model(args.model)
+    model = model.to(dev).train()
+    if args.model != "lenet5":
+        model = model.to(memory_format=torch.channels_last)
+    kfac = cb.KFAC(model, precision=args.precision)
+    torch.manual_seed(1000)                                  # same batch on every rank: the state is the merged one
+    nb = args.batch or 32
+    x = torch.randn(nb, *shape, device=dev)
+    fisher_step(model, x)
+    kfac.update(nb)
+    kfac.record = {k: [None, None] for k in kfac.record}     # release the recorded activations
+    del x
+    torch.cuda.empty_cache()
+    add, mul = README_DAMPING[args.model]
+    dims = [f.shape[0] for v in kfac.state.values() for f in v]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        kfac.invert(add, mul)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        kfac.invert(add, mul)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / args.steps
+    # the same without sharding (every rank inverts everything): what the exchange step buys
+    unsharded = None
+    if world > 1:
+        kfac.invert(add, mul, shard=False)
+        barrier()
+        e0.record()
+        for _ in range(max(1, args.steps // 2)):
+            kfac.invert(add, mul, shard=False)
+        e1.record()
+        barrier()
+        unsharded = e0.elapsed_time(e1) / max(1, args.steps // 2)
+    if rank == 0:
+        plan = cb.invert_plan(dims, world)
+        line = {"metric": f"{args.model} KFAC invert ms (all factors, README damping)", "value": ms, "unit": "ms",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{args.model} KFAC.invert{(add, mul)}: {len(dims)} matrices, orders {min(dims)}..{max(dims)} "
+                                       "(BASELINE configs[4])", "network": args.model, "parallelism": f"layer-sharded x{world}",
+                           "arena_bytes": 4 * plan["total"]},
+                "unsharded_ms_per_invert_on_every_rank": unsharded, "clocks": clocks,
+                "gpu_launches": None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     # the model's own forward / backward (torch + cuDNN, not this repo's code) is part of `e2e` only; let cuDNN pick
@@ -307,6 +389,31 @@ def main():
             return
         # torchrun exports OMP_NUM_THREADS=1 to every rank: the reference arm uses all host cores at every N
         torch.set_num_threads(os.cpu_count() or 1)
+        if args.mode == "invert":
+            # the reference's own invert (oracle port of curvatures.py:354-385: inverse + cholesky per matrix, serial loop)
+            import oracle.curvature_oracle as orc
+            model, shape = make_model(args.model)
+            model.train()
+            kfac = orc.KFAC(model)
+            torch.manual_seed(1000)
+            nb = min(args.batch or 8, 8)
+            fisher_step(model, torch.randn(nb, *shape))
+            kfac.update(nb)
+            add, mul = README_DAMPING[args.model]
+            t0 = time.perf_counter()
+            kfac.invert(add, mul)
+            ms = 1e3 * (time.perf_counter() - t0)
+            dims = [f.shape[0] for v in kfac.state.values() for f in v]
+            print(json.dumps({"impl": "reference", "metric": f"{args.model} KFAC invert ms (all factors, README damping)",
+                              "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": ms,
+                              "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                              "data": "synthetic", "config": {"workload": f"{args.model} KFAC.invert{(add, mul)}: {len(dims)} "
+                                                              "matrices (BASELINE configs[4])", "network": args.model},
+                              "cpu_baseline": {"value": ms, "unit": "ms", "cores": torch.get_num_threads(), "kind": "port",
+                                               "sample": "one full invert (inverse + cholesky per matrix, fp32, torch CPU)"},
+                              "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                              "gpu_launches": 0}))
+            return
         cb_ = batch if args.model == "lenet5" else min(args.cpu_batch, batch)
         res = cpu_reference_run(args, args.steps, args.warmup, args.model, cb_)
         line = {"impl": "reference", "metric": metric, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -318,6 +425,9 @@ def main():
                 "gpu_launches": 0}
         print(json.dumps(line))
         return
+
+    if args.mode == "invert":
+        return invert_mode(args, rank, world, local)
 
     import torch.distributed as dist
     torch.cuda.set_device(local)

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcurvature_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
-SOURCES = ["api.cu", "syrk_simt.cu", "syrk_tc.cu", "gemm_simt.cu", "gemm_tc.cu", "elementwise.cu", "chol.cu"]
+SOURCES = ["api.cu", "syrk_simt.cu", "syrk_tc.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_chain.cu", "elementwise.cu", "chol.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC", "-Xptxas=-v"]

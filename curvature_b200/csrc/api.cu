@@ -2,6 +2,7 @@
 #include "../../include/curvature_b200.h"
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <vector>
 #include <algorithm>
 #include <utility>
@@ -372,10 +373,57 @@ static int sample_mn_one(const float* LG, const float* LA, const float* z, const
                          int has_bias, const float* mu_w, const float* mu_b, float* w_out, float* b_out, float* s_out,
                          float* T, int precision, cudaStream_t s);
 
-size_t crv_efb_project_batch_workspace(const crv_efb_item* items, int n) {
+// ---- K3 / K5 batches: every layer whose operands TMA can address rides in ONE persistent launch of the chain kernel
+// (gemm_chain.cu: both GEMMs of every layer, the second waiting on the first through device-side counters, the intermediate
+// consumed out of L2); the others (leading dimension not a multiple of 4 floats: the 147-wide stem, the 2049-wide fc
+// factor) keep the per-layer path on the stream pool.  Workspace: [chain tables | one (M, K) intermediate per chained
+// layer (+ one scaled noise matrix where row_scale is given) | POOL intermediates for the per-layer path].
+static inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+static bool chain_enabled() {
+  static const bool on = !(getenv("CURVATURE_B200_CHAIN") && atoi(getenv("CURVATURE_B200_CHAIN")) == 0);
+  return on;
+}
+
+static void efb_chain(const crv_efb_item& it, float* T, int first, ChainGemm* g) {
+  memset(g, 0, 2 * sizeof(ChainGemm));
+  // T = QG^T * G: A(i, kk) = QG[kk * M + i]; B(kk, n) = G[kk * K + n]
+  g[0].A = it.QG; g[0].sa_m = 1; g[0].sa_k = it.M; g[0].B = it.G; g[0].sb_k = it.K; g[0].sb_n = 1;
+  g[0].C = T; g[0].ldc = it.K; g[0].m = it.M; g[0].n = it.K; g[0].k = it.M; g[0].alpha = 1.f; g[0].epi = EPI_STORE;
+  g[0].round_out = 1; g[0].dep = -1;
+  // lambdas += (T * QA)^2: A = T; B(kk, n) = QA[kk * K + n]
+  g[1].A = T; g[1].sa_m = it.K; g[1].sa_k = 1; g[1].B = it.QA; g[1].sb_k = it.K; g[1].sb_n = 1;
+  g[1].C = it.lambdas; g[1].ldc = it.K; g[1].m = it.M; g[1].n = it.K; g[1].k = it.K; g[1].alpha = 1.f;
+  g[1].epi = EPI_SQUARE_ACCUM; g[1].dep = first;
+}
+
+struct EfbSplit { std::vector<int> chained, single; std::vector<ChainGemm> gemms; size_t t_bytes = 0, chain_bytes = 0, pool_bytes = 0; };
+static void efb_split(const crv_efb_item* items, int n, int precision, char* tbase, EfbSplit& sp) {
   size_t mx = 0;
-  for (int i = 0; items && i < n; ++i) mx = std::max(mx, (size_t)items[i].M * (size_t)items[i].K);
-  return (size_t)POOL * ((mx * sizeof(float) + 255) & ~(size_t)255);
+  for (int i = 0; items && i < n; ++i) {
+    const crv_efb_item& it = items[i];
+    ChainGemm g[2];
+    efb_chain(it, (float*)(tbase ? tbase + sp.t_bytes : nullptr) , (int)sp.gemms.size(), g);
+    if (tbase == nullptr) { g[0].C = (float*)16; g[1].A = (const float*)16; }       // (sizing pass: alignment only)
+    const bool ok = precision != CRV_PREC_FP32 && chain_enabled() && it.QG && it.QA && it.G && it.lambdas &&
+                    gemm_chain_supported(g[0]) && gemm_chain_supported(g[1]);
+    if (ok) {
+      sp.chained.push_back(i);
+      sp.gemms.push_back(g[0]); sp.gemms.push_back(g[1]);
+      sp.t_bytes += al256((size_t)it.M * it.K * sizeof(float));
+    } else {
+      sp.single.push_back(i);
+      mx = std::max(mx, (size_t)it.M * (size_t)it.K);
+    }
+  }
+  sp.chain_bytes = sp.gemms.empty() ? 0 : al256(gemm_chain_workspace(sp.gemms.data(), (int)sp.gemms.size()));
+  sp.pool_bytes = (size_t)POOL * al256(mx * sizeof(float));
+}
+
+size_t crv_efb_project_batch_workspace(const crv_efb_item* items, int n) {
+  EfbSplit sp, fp;                                                   // (the tier is not known here: enough for either)
+  efb_split(items, n, CRV_PREC_TF32, nullptr, sp);
+  efb_split(items, n, CRV_PREC_FP32, nullptr, fp);
+  return std::max(sp.chain_bytes + sp.t_bytes + sp.pool_bytes, fp.pool_bytes) + 512;
 }
 
 int crv_efb_project_batch(const crv_efb_item* items, int n, void* ws, size_t ws_bytes, int precision,
@@ -384,22 +432,44 @@ int crv_efb_project_batch(const crv_efb_item* items, int n, void* ws, size_t ws_
   CRV_CHECK(items != nullptr && n > 0, "empty batch");
   const size_t need = crv_efb_project_batch_workspace(items, n);
   CRV_CHECK(ws && ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
-  StreamPool* pool = stream_pool();
   cudaStream_t caller = (cudaStream_t)stream;
-  std::vector<double> cost(n);
-  for (int i = 0; i < n; ++i) cost[i] = 2.0 * items[i].M * items[i].K * ((double)items[i].M + items[i].K) + 2e7;
+  char* base = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  EfbSplit sz;
+  efb_split(items, n, precision, nullptr, sz);                       // sizes first, then the real pointers
+  EfbSplit sp;
+  efb_split(items, n, precision, base + sz.chain_bytes, sp);
+  for (int i = 0; i < n; ++i) {
+    const crv_efb_item& it = items[i];
+    CRV_CHECK(it.QG && it.QA && it.G && it.lambdas, "null pointer in item %d", i);
+  }
+  if (!sp.chained.empty()) {
+    for (int i : sp.chained)
+      if (items[i].round_g)     // gradient copy rounded to the nearest TF32 in place (the tensor core would truncate it)
+        if (int rc = round_tf32_launch(items[i].G, const_cast<float*>(items[i].G), (size_t)items[i].M * items[i].K, caller)) return rc;
+    const int rc = gemm_chain_launch(sp.gemms.data(), (int)sp.gemms.size(), base, sp.chain_bytes, caller);
+    CRV_CHECK(rc >= 0, "internal: chain kernel rejected operands it had accepted");
+    if (rc) return rc;
+  }
+  if (sp.single.empty()) return 0;
+  StreamPool* pool = stream_pool();
+  const int ns = (int)sp.single.size();
+  std::vector<double> cost(ns);
+  for (int j = 0; j < ns; ++j) {
+    const crv_efb_item& it = items[sp.single[j]];
+    cost[j] = 2.0 * it.M * it.K * ((double)it.M + it.K) + 2e7;
+  }
   const std::vector<int> lane = lanes_by_cost(cost);
   if (pool) {
     CRV_CUDA(cudaEventRecord(pool->fork, caller));
     for (int l = 0; l < POOL; ++l) CRV_CUDA(cudaStreamWaitEvent(pool->s[l], pool->fork, 0));
   }
-  const size_t per = need / POOL;
-  for (int i = 0; i < n; ++i) {
-    const crv_efb_item& it = items[i];
-    CRV_CHECK(it.QG && it.QA && it.G && it.lambdas, "null pointer in item %d", i);
-    cudaStream_t s = pool ? pool->s[lane[i]] : caller;
-    float* T = (float*)((char*)ws + (pool ? (size_t)lane[i] * per : 0));
-    if (it.round_g) {     // gradient copy rounded to the nearest TF32 in place (the tensor core would truncate it)
+  const size_t per = sp.pool_bytes / POOL;
+  char* pbase = base + sp.chain_bytes + sp.t_bytes;
+  for (int j = 0; j < ns; ++j) {
+    const crv_efb_item& it = items[sp.single[j]];
+    cudaStream_t s = pool ? pool->s[lane[j]] : caller;
+    float* T = (float*)(pbase + (pool ? (size_t)lane[j] * per : 0));
+    if (it.round_g) {
       if (int rc = round_tf32_launch(it.G, const_cast<float*>(it.G), (size_t)it.M * it.K, s)) return rc;
     }
     if (int rc = efb_project_one(it.QG, it.QA, it.G, it.M, it.K, it.lambdas, T, precision, s)) return rc;
@@ -412,13 +482,49 @@ int crv_efb_project_batch(const crv_efb_item* items, int n, void* ws, size_t ws_
   return 0;
 }
 
-size_t crv_sample_matrix_normal_batch_workspace(const crv_sample_item* items, int n) {
+struct SampleSplit { std::vector<int> chained, single; std::vector<ChainGemm> gemms; std::vector<size_t> t_off, z_off;
+                     size_t t_bytes = 0, chain_bytes = 0, pool_bytes = 0; };
+static void sample_split(const crv_sample_item* items, int n, int precision, char* tbase, SampleSplit& sp) {
   size_t mx = 0;
   for (int i = 0; items && i < n; ++i) {
-    const size_t mk = (size_t)items[i].M * (size_t)(items[i].K0 + (items[i].has_bias ? 1 : 0));
-    mx = std::max(mx, mk * (items[i].row_scale ? 2 : 1));
+    const crv_sample_item& it = items[i];
+    const int K = it.K0 + (it.has_bias ? 1 : 0), M = it.M;
+    const size_t mk = al256((size_t)M * K * sizeof(float));
+    float* T = (float*)(tbase ? tbase + sp.t_bytes : (char*)16);
+    const float* zz = it.row_scale ? (const float*)(tbase ? tbase + sp.t_bytes + mk : (char*)16) : it.z;
+    ChainGemm g[2];
+    memset(g, 0, sizeof(g));
+    // T = LG * z^T: A = LG (M x M); B(kk, n) = z[n * M + kk]
+    g[0].A = it.LG; g[0].sa_m = M; g[0].sa_k = 1; g[0].B = zz; g[0].sb_k = 1; g[0].sb_n = M;
+    g[0].C = T; g[0].ldc = K; g[0].m = M; g[0].n = K; g[0].k = M; g[0].alpha = 1.f; g[0].epi = EPI_STORE; g[0].round_out = 1;
+    g[0].dep = -1;
+    // S = T * LA^T: B(kk, n) = LA[n * K + kk]; epilogue adds the mean and splits weight / bias columns
+    g[1].A = T; g[1].sa_m = K; g[1].sa_k = 1; g[1].B = it.LA; g[1].sb_k = 1; g[1].sb_n = K;
+    g[1].C = nullptr; g[1].ldc = K; g[1].m = M; g[1].n = K; g[1].k = K; g[1].alpha = 1.f; g[1].epi = 2;
+    g[1].se.mu_w = it.mu_w; g[1].se.mu_b = it.mu_b; g[1].se.w_out = it.w_out; g[1].se.b_out = it.b_out; g[1].se.s_out = it.s_out;
+    g[1].se.K0 = it.K0; g[1].se.has_bias = it.has_bias ? 1 : 0;
+    g[1].dep = (int)sp.gemms.size();
+    const bool ok = precision != CRV_PREC_FP32 && chain_enabled() && it.LG && it.LA && it.z && M > 0 && it.K0 > 0 &&
+                    gemm_chain_supported(g[0]) && gemm_chain_supported(g[1]);
+    if (ok) {
+      sp.chained.push_back(i);
+      sp.gemms.push_back(g[0]); sp.gemms.push_back(g[1]);
+      sp.t_off.push_back(sp.t_bytes);
+      sp.t_bytes += mk * (it.row_scale ? 2 : 1);
+    } else {
+      sp.single.push_back(i);
+      mx = std::max(mx, (size_t)M * K * (it.row_scale ? 2 : 1));
+    }
   }
-  return (size_t)POOL * ((mx * sizeof(float) + 255) & ~(size_t)255);
+  sp.chain_bytes = sp.gemms.empty() ? 0 : al256(gemm_chain_workspace(sp.gemms.data(), (int)sp.gemms.size()));
+  sp.pool_bytes = (size_t)POOL * al256(mx * sizeof(float));
+}
+
+size_t crv_sample_matrix_normal_batch_workspace(const crv_sample_item* items, int n) {
+  SampleSplit sp, fp;
+  sample_split(items, n, CRV_PREC_TF32, nullptr, sp);
+  sample_split(items, n, CRV_PREC_FP32, nullptr, fp);
+  return std::max(sp.chain_bytes + sp.t_bytes + sp.pool_bytes, fp.pool_bytes) + 512;
 }
 
 int crv_sample_matrix_normal_batch(const crv_sample_item* items, int n, void* ws, size_t ws_bytes, int precision,
@@ -427,23 +533,46 @@ int crv_sample_matrix_normal_batch(const crv_sample_item* items, int n, void* ws
   CRV_CHECK(items != nullptr && n > 0, "empty batch");
   const size_t need = crv_sample_matrix_normal_batch_workspace(items, n);
   CRV_CHECK(ws && ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
-  StreamPool* pool = stream_pool();
   cudaStream_t caller = (cudaStream_t)stream;
-  std::vector<double> cost(n);
-  for (int i = 0; i < n; ++i) {
-    const double M = items[i].M, K = items[i].K0 + (items[i].has_bias ? 1 : 0);
-    cost[i] = 2.0 * M * K * (M + K) + 2e7;
+  char* base = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  SampleSplit sz;
+  sample_split(items, n, precision, nullptr, sz);
+  SampleSplit sp;
+  sample_split(items, n, precision, base + sz.chain_bytes, sp);
+  if (!sp.chained.empty()) {
+    for (size_t j = 0; j < sp.chained.size(); ++j) {
+      const crv_sample_item& it = items[sp.chained[j]];
+      CRV_CHECK(!it.w_out || it.mu_w, "w_out needs mu_w");
+      CRV_CHECK(!it.b_out || it.mu_b, "b_out needs mu_b");
+      if (it.row_scale) {         // EFB's draw: the noise is scaled elementwise first (curvatures.py:458)
+        const int K = it.K0 + (it.has_bias ? 1 : 0);
+        if (int rc = scale_transpose_launch(it.z, it.row_scale, K, it.M, const_cast<float*>(sp.gemms[2 * j].B), caller)) return rc;
+      }
+    }
+    const int rc = gemm_chain_launch(sp.gemms.data(), (int)sp.gemms.size(), base, sp.chain_bytes, caller);
+    CRV_CHECK(rc >= 0, "internal: chain kernel rejected operands it had accepted");
+    if (rc) return rc;
+  }
+  if (sp.single.empty()) return 0;
+  StreamPool* pool = stream_pool();
+  const int ns = (int)sp.single.size();
+  std::vector<double> cost(ns);
+  for (int j = 0; j < ns; ++j) {
+    const crv_sample_item& it = items[sp.single[j]];
+    const double M = it.M, K = it.K0 + (it.has_bias ? 1 : 0);
+    cost[j] = 2.0 * M * K * (M + K) + 2e7;
   }
   const std::vector<int> lane = lanes_by_cost(cost);
   if (pool) {
     CRV_CUDA(cudaEventRecord(pool->fork, caller));
     for (int l = 0; l < POOL; ++l) CRV_CUDA(cudaStreamWaitEvent(pool->s[l], pool->fork, 0));
   }
-  const size_t per = need / POOL;
-  for (int i = 0; i < n; ++i) {
-    const crv_sample_item& it = items[i];
-    cudaStream_t s = pool ? pool->s[lane[i]] : caller;
-    float* T = (float*)((char*)ws + (pool ? (size_t)lane[i] * per : 0));
+  const size_t per = sp.pool_bytes / POOL;
+  char* pbase = base + sp.chain_bytes + sp.t_bytes;
+  for (int j = 0; j < ns; ++j) {
+    const crv_sample_item& it = items[sp.single[j]];
+    cudaStream_t s = pool ? pool->s[lane[j]] : caller;
+    float* T = (float*)(pbase + (pool ? (size_t)lane[j] * per : 0));
     if (int rc = sample_mn_one(it.LG, it.LA, it.z, it.row_scale, it.M, it.K0, it.has_bias, it.mu_w, it.mu_b, it.w_out,
                                it.b_out, it.s_out, T, precision, s))
       return rc;

@@ -132,6 +132,24 @@ int gemm_simt_launch(const float* A, long long sa_m, long long sa_k, const float
                      long long sb_n, float* C, int ldc, int m, int n, int k, float alpha, float beta,
                      int epilogue, const SampleEpilogue* sample, cudaStream_t s);
 
+// K3 / K5 chains: many GEMMs (with dependencies between them) in ONE persistent launch, 256 x 256 tcgen05 TF32 tiles
+// (gemm_chain.cu).  C (m x n) = alpha * A (m x k) * B (k x n) through element strides, epilogues as below.
+constexpr int SK_MAX_CTAS = 160;
+struct ChainGemm {
+  const float* A; long long sa_m, sa_k;
+  const float* B; long long sb_k, sb_n;
+  float* C; int ldc;
+  int m, n, k;
+  float alpha;
+  int epi;          // EPI_STORE / EPI_SQUARE_ACCUM / 2 = sample epilogue (se)
+  int round_out;    // EPI_STORE: round the result to the nearest TF32 (it is the next GEMM's A operand)
+  SampleEpilogue se;
+  int dep;          // index of an EARLIER GEMM of the same call whose output C is this GEMM's A operand, or -1
+};
+bool gemm_chain_supported(const ChainGemm& g);
+size_t gemm_chain_workspace(const ChainGemm* gemms, int count);
+int gemm_chain_launch(const ChainGemm* gemms, int count, void* ws, size_t ws_bytes, cudaStream_t s);
+
 // tensor-core (TF32) GEMM with the same epilogues; returns -1 when the operands cannot be fed by TMA
 int gemm_tc_launch(const float* A, long long sa_m, long long sa_k, const float* B, long long sb_k,
                    long long sb_n, float* C, int ldc, int m, int n, int k, float alpha, float beta,

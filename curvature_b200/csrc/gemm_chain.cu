@@ -1,0 +1,490 @@
+// K3 / K5 as ONE kernel launch per call: every two-GEMM chain of a model -- the EFB projection (QG^T g QA)^2
+// (curvature/curvatures.py:424-433) or the matrix-normal draw mu + L_G z^T L_A^T (:387-392, :78-82, :119) of every layer,
+// and with S stacked samples the posterior-sampling loop of scripts/evaluate.py:121-152 -- runs in a single persistent
+// grid.  The work list holds 256 x 256 output tiles of ALL GEMMs of the call in a dependency-respecting order; a tile of a
+// second GEMM waits (device-side counter, acquire) until the tiles of the first GEMM that produce its rows of the
+// intermediate are complete.  The (M, K) intermediate lives in the caller's workspace but is produced and consumed
+// inside one launch while it is still in L2 (<= 9.4 MB per layer against 126 MB of L2): no launch boundary, no host
+// round trip, no HBM round trip between the two products.
+//
+//   tile      256 x 256 fp32 accumulator = all 512 TMEM columns (two M = 128 halves x N <= 256), like the SYRK kernel;
+//   operands  fp32 words fed as TF32 by TMA, each of A and B either contraction-contiguous ("K-major", SWIZZLE_128B,
+//             boxes of [32 k][128 rows]) or row-contiguous ("MN-major", SWIZZLE_128B_ATOM_32B, boxes of [32 rows][32 k]);
+//             64 KB per 32-deep stage, 3 stages; per stage 4 k-steps x 2 halves of tcgen05.mma.kind::tf32 (M 128, N 256, K 8):
+//             64 B per tensor-pipe clock per SM of L2 -> SM traffic, half of what the 128 x 128 tiles of gemm_tc.cu need
+//             (those are ingest-bound at 30 % tensor pipe);
+//   issue     the MMA warp runs its loop in uniform control flow, tcgen05 instructions predicated on one elected lane
+//             (see syrk_tc.cu); TMA issue is spread over 4 warps;
+//   epilogue  4 warps drain TMEM through a swizzled shared-memory tile and touch global memory in whole 128-byte row
+//             segments; epilogues: store (optionally rounded to TF32 for the next GEMM), accumulate the square, add the
+//             posterior mean and split weight / bias columns;
+//   schedule  static: the host assigns tiles to CTAs (longest first within a phase) and every CTA walks its list in global
+//             order, so a waiting tile only ever waits for tiles that are earlier in the global order -- no deadlock.
+#include "common.cuh"
+#include "../../include/curvature_b200.h"
+#include <cuda.h>
+#include <vector>
+#include <algorithm>
+
+namespace crv {
+namespace {
+
+constexpr int CT = 256;                       // tile edge
+constexpr int CK = 32;                        // contraction depth per stage (one 128-byte row of fp32)
+constexpr int C_STAGE = 64 * 1024, C_NSTAGE = 3;
+constexpr int C_EPI = 16 * 1024;
+constexpr int C_NPROD = 4;                    // TMA-issuing warps: 0, 6, 7, 8
+constexpr int C_THREADS = 9 * 32;             // warp 1: MMA + TMEM owner; warps 2-5: epilogue
+constexpr int C_SMEM = C_NSTAGE * C_STAGE + C_EPI + 1024 + 1024;
+constexpr uint32_t C_SPIN = 1u << 26;
+
+struct ChainItemDev {
+  int m, n, k, ldc;
+  int a_mn, b_mn, mapA, mapB;
+  int epi, round_out, dep_counters, dep_need;   // dep_counters: first per-row-tile counter of the producer GEMM (-1: none)
+  int counters, pad;                            // this GEMM's own per-row-tile counters (-1: nobody waits for it)
+  float alpha;
+  float* C;
+  SampleEpilogue se;
+};
+struct ChainTile { int item, tm, tn, pad; };
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > C_SPIN) asm volatile("trap;");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t desc_k(uint32_t a) {          // K-major SWIZZLE_128B, 8-row atoms 1024 B apart
+  return (uint64_t)((a >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t desc_mn(uint32_t a, uint32_t lbo) {   // MN-major SW128_32B (see syrk_tc.cu)
+  return (uint64_t)((a >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(512 >> 4) << 32) |
+         (1ull << 46) | (1ull << 61);
+}
+__device__ __forceinline__ float rna_tf32(float f) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(f));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct TileShape { int m0, n0, rows, mh, ncols, nk; };
+__device__ __forceinline__ TileShape tile_shape(const ChainItemDev& it, const ChainTile& t) {
+  TileShape s;
+  s.m0 = t.tm * CT; s.n0 = t.tn * CT;
+  s.rows = min(CT, it.m - s.m0);
+  s.mh = (s.rows + 127) >> 7;
+  s.ncols = min(CT, (it.n - s.n0 + 15) & ~15);
+  s.nk = (it.k + CK - 1) / CK;
+  return s;
+}
+
+__global__ void __launch_bounds__(C_THREADS, 1)
+gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __restrict__ tiles, const int* __restrict__ cta_begin,
+                  const CUtensorMap* __restrict__ maps, int* __restrict__ counters) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t sbase = (s32(raw) + 1023u) & ~1023u;
+  const uint32_t epi = sbase + C_NSTAGE * C_STAGE;
+  const uint32_t bars = epi + C_EPI;                         // full[3] | empty[3] | tmem_full | tmem_empty
+  const uint32_t bar_tfull = bars + 8 * (2 * C_NSTAGE), bar_tempty = bar_tfull + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw + (sbase - s32(raw)) + C_NSTAGE * C_STAGE + C_EPI + 8 * (2 * C_NSTAGE + 2));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t_begin = cta_begin[blockIdx.x], t_end = cta_begin[blockIdx.x + 1];
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C_NSTAGE; ++s) {
+      bar_init(bars + 8 * s, C_NPROD);
+      bar_init(bars + 8 * (C_NSTAGE + s), 1);
+    }
+    bar_init(bar_tfull, 1);
+    bar_init(bar_tempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0 || warp >= 6) {
+    // ---- TMA producers ----
+    const uint32_t leader = elect_one();
+    const int me = (int)uni((uint32_t)(warp == 0 ? 0 : warp - 5));       // 0 .. 3
+    uint32_t git = 0;                                                     // stage iterations since kernel start
+    for (int ti = t_begin; ti < t_end; ++ti) {
+      const ChainTile t = tiles[ti];
+      const ChainItemDev& it = items[t.item];
+      const TileShape sh = tile_shape(it, t);
+      const CUtensorMap* ma = maps + it.mapA;
+      const CUtensorMap* mb = maps + it.mapB;
+      if (leader) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(ma)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(mb)) : "memory");
+      }
+      if (it.dep_counters >= 0) {
+        // rows [m0, m0 + 256) of the A operand are written by the tiles (tm, *) of the producer GEMM of this chain
+        const int* c = counters + it.dep_counters + t.tm;
+        uint32_t spins = 0;
+        while (ld_acquire(c) < it.dep_need) {
+          __nanosleep(64);
+          if (++spins > (1u << 24)) asm volatile("trap;");
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy writes of the other CTAs -> this CTA's TMA reads
+      }
+      // boxes of one stage: A then B; K-major 16 KB boxes of 128 rows, MN-major 4 KB boxes of 32 rows
+      const int na = it.a_mn ? (sh.rows + 31) / 32 : sh.mh;
+      const int nb = it.b_mn ? (sh.ncols + 31) / 32 : (sh.ncols + 127) / 128;
+      const uint32_t ba = it.a_mn ? 4096u : 16384u, bb = it.b_mn ? 4096u : 16384u;
+      const int total = na + nb;
+      uint32_t mine = 0;
+      for (int e = me; e < total; e += C_NPROD) mine += e < na ? ba : bb;
+      const int u_na = (int)uni((uint32_t)na), u_total = (int)uni((uint32_t)total), u_nk = (int)uni((uint32_t)sh.nk);
+      const int a_mn = (int)uni((uint32_t)it.a_mn), b_mn = (int)uni((uint32_t)it.b_mn);
+      for (int kb = 0; kb < u_nk; ++kb, ++git) {
+        const uint32_t s = git % C_NSTAGE, ph = (git / C_NSTAGE) & 1u;
+        bar_wait(bars + 8 * (C_NSTAGE + s), ph ^ 1u);
+        if (leader) {
+          if (mine) bar_expect(bars + 8 * s, mine); else bar_arrive(bars + 8 * s);
+        }
+        const uint32_t sa = sbase + s * C_STAGE, sb = sa + 32768u;
+        const int k0 = kb * CK;
+        for (int e = me; e < u_total; e += C_NPROD) {
+          if (e < u_na) {
+            if (leader) {
+              if (a_mn) tma_2d(sa + (uint32_t)e * 4096u, ma, sh.m0 + 32 * e, k0, bars + 8 * s);
+              else tma_2d(sa + (uint32_t)e * 16384u, ma, k0, sh.m0 + 128 * e, bars + 8 * s);
+            }
+          } else {
+            const int q = e - u_na;
+            if (leader) {
+              if (b_mn) tma_2d(sb + (uint32_t)q * 4096u, mb, sh.n0 + 32 * q, k0, bars + 8 * s);
+              else tma_2d(sb + (uint32_t)q * 16384u, mb, k0, sh.n0 + 128 * q, bars + 8 * s);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer (uniform control flow, one elected lane issues) ----
+    const uint32_t leader = elect_one();
+    const uint32_t u_tmem = uni(tmem);
+    uint32_t git = 0;
+    int ntile = 0;
+    for (int ti = t_begin; ti < t_end; ++ti, ++ntile) {
+      const ChainTile t = tiles[ti];
+      const ChainItemDev& it = items[t.item];
+      const TileShape sh = tile_shape(it, t);
+      const uint32_t a_mn = uni((uint32_t)it.a_mn), b_mn = uni((uint32_t)it.b_mn);
+      const uint32_t idesc = uni((1u << 4) | (2u << 7) | (2u << 10) | (a_mn << 15) | (b_mn << 16) |
+                                 ((uint32_t)(sh.ncols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24));
+      const uint64_t da = a_mn ? desc_mn(0u, 4096u) : desc_k(0u), db = b_mn ? desc_mn(0u, 4096u) : desc_k(0u);
+      const uint32_t a_lo = (uint32_t)da, a_hi = (uint32_t)(da >> 32), b_lo = (uint32_t)db, b_hi = (uint32_t)(db >> 32);
+      const uint32_t a_step = a_mn ? (1024u >> 4) : (32u >> 4), b_step = b_mn ? (1024u >> 4) : (32u >> 4);
+      const bool two = uni((uint32_t)sh.mh) == 2u;
+      const int u_nk = (int)uni((uint32_t)sh.nk);
+      if (ntile > 0) {                                       // the previous tile's accumulator has been drained
+        bar_wait(bar_tempty, (uint32_t)(ntile - 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      uint32_t acc = 0;
+      for (int kb = 0; kb < u_nk; ++kb, ++git) {
+        const uint32_t s = git % C_NSTAGE, ph = (git / C_NSTAGE) & 1u;
+        bar_wait(bars + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = sbase + s * C_STAGE, sb = sa + 32768u;
+        const uint32_t a0 = a_lo | ((sa >> 4) & 0x3FFFu), a1 = a_lo | (((sa + 16384u) >> 4) & 0x3FFFu);
+        const uint32_t b0 = b_lo | ((sb >> 4) & 0x3FFFu);
+        if (leader) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            asm volatile("{\n\t.reg .pred q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+                         "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, q;\n\t}"
+                         ::"r"(u_tmem), "r"(a0 + (uint32_t)ks * a_step), "r"(a_hi), "r"(b0 + (uint32_t)ks * b_step), "r"(b_hi),
+                           "r"(idesc), "r"(ks == 0 ? acc : 1u) : "memory");
+            if (two)
+              asm volatile("{\n\t.reg .pred q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+                           "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                           "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, q;\n\t}"
+                           ::"r"(u_tmem + 256u), "r"(a1 + (uint32_t)ks * a_step), "r"(a_hi), "r"(b0 + (uint32_t)ks * b_step),
+                             "r"(b_hi), "r"(idesc), "r"(ks == 0 ? acc : 1u) : "memory");
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                       ::"r"(bars + 8 * (C_NSTAGE + s)) : "memory");
+        }
+        acc = 1;
+      }
+      if (leader)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_tfull) : "memory");
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue warps 2..5: TMEM lane quadrant = warp & 3 ----
+    const int quad = warp & 3;
+    const uint32_t stg = epi + (uint32_t)quad * 4096u;
+    const int sub = lane >> 3, ch = lane & 7;               // read-back role: row within a group of 4, 16-byte chunk
+    int ntile = 0;
+    for (int ti = t_begin; ti < t_end; ++ti, ++ntile) {
+      const ChainTile t = tiles[ti];
+      const ChainItemDev& it = items[t.item];
+      const TileShape sh = tile_shape(it, t);
+      bar_wait(bar_tfull, (uint32_t)ntile & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int h = 0; h < sh.mh; ++h) {
+        const int row0 = sh.m0 + h * 128 + quad * 32;
+        for (int cc = 0; cc < sh.ncols; cc += 32) {
+          uint32_t a[32];
+          const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * 256 + cc);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+                "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]),
+                "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]),
+                "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          __syncwarp();                                     // the previous block has been read back
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((k ^ (lane & 7)) * 16);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a[4 * k]), "r"(a[4 * k + 1]),
+                         "r"(a[4 * k + 2]), "r"(a[4 * k + 3]) : "memory");
+          }
+          __syncwarp();
+#pragma unroll
+          for (int r4 = 0; r4 < 8; ++r4) {
+            const int r = r4 * 4 + sub;
+            float v[4];
+            const uint32_t addr = stg + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) * 16);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
+            const int gm = row0 + r;
+            if (gm >= it.m) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int gn = sh.n0 + cc + ch * 4 + j;
+              if (gn >= it.n) break;
+              if (it.epi == EPI_STORE) {
+                const float o = it.alpha * v[j];
+                it.C[(size_t)gm * it.ldc + gn] = it.round_out ? rna_tf32(o) : o;
+              } else if (it.epi == EPI_SQUARE_ACCUM) {
+                it.C[(size_t)gm * it.ldc + gn] += v[j] * v[j];
+              } else {
+                const float sv = it.alpha * v[j];
+                if (it.se.s_out) it.se.s_out[(size_t)gm * it.n + gn] = sv;
+                if (gn < it.se.K0) {
+                  if (it.se.w_out) it.se.w_out[(size_t)gm * it.se.K0 + gn] = it.se.mu_w[(size_t)gm * it.se.K0 + gn] + sv;
+                } else {
+                  if (it.se.b_out) it.se.b_out[gm] = it.se.mu_b[gm] + sv;
+                }
+              }
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) bar_arrive(bar_tempty);
+      if (it.counters >= 0) {
+        // publish: every epilogue thread's stores -> gpu scope, then ONE increment of the row tile's counter
+        __threadfence();
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (warp == 2 && lane == 0) atomicAdd(counters + it.counters + t.tm, 1);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+typedef CUresult (*EncFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                          const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncFn encoder() {
+  static EncFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncFn)ptr;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// rows x depth operand with element strides (s_row, s_k): which form it has and (map != null) its tensor map
+bool operand_form(const float* base, int rows, int depth, long long s_row, long long s_k, int& mn, CUtensorMap* map) {
+  if (((uintptr_t)base & 15) != 0) return false;
+  cuuint64_t gd[2], gs[1];
+  cuuint32_t box[2], es[2] = {1, 1};
+  CUtensorMapSwizzle sw;
+  if (s_k == 1 && (s_row % 4) == 0 && s_row >= depth) {          // contraction-contiguous
+    mn = 0;
+    gd[0] = (cuuint64_t)depth; gd[1] = (cuuint64_t)rows; gs[0] = (cuuint64_t)s_row * 4;
+    box[0] = CK; box[1] = 128;
+    sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  } else if (s_row == 1 && (s_k % 4) == 0 && s_k >= rows) {      // row-contiguous
+    mn = 1;
+    gd[0] = (cuuint64_t)rows; gd[1] = (cuuint64_t)depth; gs[0] = (cuuint64_t)s_k * 4;
+    box[0] = 32; box[1] = CK;
+    sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  } else {
+    return false;
+  }
+  if (!map) return true;
+  return encoder()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+bool gemm_chain_supported(const ChainGemm& g) {
+  int mn;
+  return encoder() != nullptr && g.m > 0 && g.n > 0 && g.k > 0 &&
+         operand_form(g.A, g.m, g.k, g.sa_m, g.sa_k, mn, nullptr) && operand_form(g.B, g.n, g.k, g.sb_n, g.sb_k, mn, nullptr);
+}
+
+size_t gemm_chain_workspace(const ChainGemm* gemms, int count) {
+  size_t tiles = 0, rows = 0;
+  for (int i = 0; i < count; ++i) {
+    const size_t tm = (gemms[i].m + CT - 1) / CT, tn = (gemms[i].n + CT - 1) / CT;
+    tiles += tm * tn;
+    rows += tm;
+  }
+  return al(sizeof(ChainItemDev) * (size_t)count) + al(sizeof(ChainTile) * tiles) + al(sizeof(int) * (SK_MAX_CTAS + 1)) +
+         al(sizeof(CUtensorMap) * 2 * (size_t)count) + al(sizeof(int) * rows) + 1024;
+}
+
+// One launch for `count` GEMMs; gemms[i].dep (if >= 0) names an EARLIER GEMM of the call whose output C is this one's A
+// operand (same m, same row tiling).  Returns -1 if an operand cannot be fed by TMA.
+int gemm_chain_launch(const ChainGemm* gemms, int count, void* ws, size_t ws_bytes, cudaStream_t s) {
+  CRV_CHECK(gemms && count > 0, "empty GEMM chain");
+  CRV_CHECK(ws && ws_bytes >= gemm_chain_workspace(gemms, count), "workspace too small: %zu < %zu", ws_bytes,
+            gemm_chain_workspace(gemms, count));
+  CRV_CHECK(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  if (!encoder()) return -1;
+  const int sms = device_sm_count();
+  CRV_CHECK(sms > 0, "no CUDA device");
+  const int G = std::min(sms, (int)SK_MAX_CTAS);
+  std::vector<ChainItemDev> items(count);
+  std::vector<CUtensorMap> maps(2 * (size_t)count);
+  std::vector<int> tm_of(count), tn_of(count);
+  int ncounters = 0;
+  std::vector<int> counter_base(count, -1);
+  for (int i = 0; i < count; ++i) {
+    const ChainGemm& g = gemms[i];
+    CRV_CHECK(g.A && g.B && g.m > 0 && g.n > 0 && g.k > 0, "bad GEMM %d: %d x %d x %d", i, g.m, g.n, g.k);
+    CRV_CHECK(g.dep < i, "GEMM %d depends on a later one", i);
+    ChainItemDev& d = items[i];
+    memset(&d, 0, sizeof(d));
+    if (!operand_form(g.A, g.m, g.k, g.sa_m, g.sa_k, d.a_mn, &maps[2 * i])) return -1;
+    if (!operand_form(g.B, g.n, g.k, g.sb_n, g.sb_k, d.b_mn, &maps[2 * i + 1])) return -1;
+    d.m = g.m; d.n = g.n; d.k = g.k; d.ldc = g.ldc; d.mapA = 2 * i; d.mapB = 2 * i + 1;
+    d.epi = g.epi; d.round_out = g.round_out; d.alpha = g.alpha; d.C = g.C; d.se = g.se;
+    if (g.epi == 2) CRV_CHECK(g.se.mu_w || g.se.s_out || !g.se.w_out, "sample epilogue needs its descriptor");
+    else CRV_CHECK(g.C != nullptr, "null GEMM output");
+    tm_of[i] = (g.m + CT - 1) / CT; tn_of[i] = (g.n + CT - 1) / CT;
+    d.dep_counters = -1; d.counters = -1;
+  }
+  for (int i = 0; i < count; ++i)
+    if (gemms[i].dep >= 0) {
+      const int p = gemms[i].dep;
+      CRV_CHECK(gemms[p].m == gemms[i].m && gemms[p].C == gemms[i].A, "GEMM %d: its producer %d does not write its A operand", i, p);
+      if (counter_base[p] < 0) { counter_base[p] = ncounters; ncounters += tm_of[p]; }
+      items[p].counters = counter_base[p];
+      items[i].dep_counters = counter_base[p];
+      items[i].dep_need = tn_of[p];
+    }
+  // global order: producers (GEMMs somebody waits for, and independent ones) first, then consumers; within each phase
+  // the most expensive tiles first.  Tiles are dealt to the CTAs in that order, always to the least loaded CTA; every CTA
+  // keeps its tiles in global order.
+  struct T { int item, tm, tn, phase; double cost; };
+  std::vector<T> all;
+  for (int i = 0; i < count; ++i)
+    for (int a = 0; a < tm_of[i]; ++a)
+      for (int b = 0; b < tn_of[i]; ++b) {
+        const int rows = std::min(CT, gemms[i].m - a * CT), cols = std::min(CT, gemms[i].n - b * CT);
+        const double c = (double)((rows + 127) / 128) * std::max(cols, 64) * gemms[i].k + 40000.0;
+        all.push_back({i, a, b, gemms[i].dep >= 0 ? 1 : 0, c});
+      }
+  std::stable_sort(all.begin(), all.end(), [](const T& x, const T& y) {
+    if (x.phase != y.phase) return x.phase < y.phase;
+    return x.cost > y.cost;
+  });
+  std::vector<std::vector<int>> lists(G);
+  std::vector<double> load(G, 0.0);
+  for (size_t e = 0; e < all.size(); ++e) {
+    int best = 0;
+    for (int c = 1; c < G; ++c) if (load[c] < load[best]) best = c;
+    lists[best].push_back((int)e);
+    load[best] += all[e].cost;
+  }
+  std::vector<ChainTile> tiles;
+  std::vector<int> begin(SK_MAX_CTAS + 1, 0);
+  for (int c = 0; c < G; ++c) {
+    begin[c] = (int)tiles.size();
+    for (int e : lists[c]) tiles.push_back({all[e].item, all[e].tm, all[e].tn, 0});
+  }
+  for (int c = G; c <= SK_MAX_CTAS; ++c) begin[c] = (int)tiles.size();
+  // upload (pageable sources: staged by the runtime before the call returns)
+  char* base = (char*)ws;
+  size_t off = 0;
+  ChainItemDev* d_items = (ChainItemDev*)(base + off); off += al(sizeof(ChainItemDev) * (size_t)count);
+  ChainTile* d_tiles = (ChainTile*)(base + off); off += al(sizeof(ChainTile) * tiles.size());
+  int* d_begin = (int*)(base + off); off += al(sizeof(int) * (SK_MAX_CTAS + 1));
+  CUtensorMap* d_maps = (CUtensorMap*)(base + off); off += al(sizeof(CUtensorMap) * maps.size());
+  int* d_counters = (int*)(base + off); off += al(sizeof(int) * (size_t)std::max(ncounters, 1));
+  CRV_CUDA(cudaMemcpyAsync(d_items, items.data(), sizeof(ChainItemDev) * (size_t)count, cudaMemcpyHostToDevice, s));
+  CRV_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(ChainTile) * tiles.size(), cudaMemcpyHostToDevice, s));
+  CRV_CUDA(cudaMemcpyAsync(d_begin, begin.data(), sizeof(int) * (SK_MAX_CTAS + 1), cudaMemcpyHostToDevice, s));
+  CRV_CUDA(cudaMemcpyAsync(d_maps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice, s));
+  CRV_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(int) * (size_t)std::max(ncounters, 1), s));
+  static bool attr = false;
+  if (!attr) {
+    attr = true;
+    CRV_CUDA(cudaFuncSetAttribute(gemm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));
+  }
+  gemm_chain_kernel<<<G, C_THREADS, C_SMEM, s>>>(d_items, d_tiles, d_begin, d_maps, d_counters);
+  CRV_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace crv

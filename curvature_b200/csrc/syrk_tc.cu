@@ -1552,7 +1552,9 @@ __global__ void __launch_bounds__(256) pack_smallc_kernel(const float* __restric
                                                           int kw, int sw, int ph, int pw, unsigned long long* tr) {
   TraceScope trace_scope(tr, 4);
   const long long total = (long long)N * Hq * OW * 2;
-  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+  {
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;      // one 64-byte group per thread: short-lived blocks
+    if (t >= total) return;
     const int i2 = (int)(t & 1);
     long long u = t >> 1;
     const int ow = (int)(u % OW); u /= OW;
@@ -1592,15 +1594,32 @@ __global__ void __launch_bounds__(256) pack_smallc_kernel(const float* __restric
   }
 }
 
+// Pre-pass kernels are SHORT-LIVED blocks (256 threads x 4 float4 each, no grid-stride loop): they run on a low-priority
+// stream beside the contraction kernels, and a contraction CTA (416 threads, ~211 KB of shared memory) can only be placed
+// on an SM once enough resident pre-pass CTAs have exited.  Long-lived grid-stride blocks (8 x 256 threads per SM until the
+// whole copy is done) kept every SM full and delayed the next contraction kernel by the rest of the copy (15-50 us gaps in
+// the launch trace); with 16 KB blocks an SM frees up within a microsecond or two.
+constexpr int PRE_V4 = 4;                     // float4 per thread
+
 // out[i] = round-to-nearest TF32 of in[i] (layout preserved): the rounding pre-pass of the `tf32` tier.
 __global__ void __launch_bounds__(256) round_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, size_t n4, unsigned long long* tr) {
   TraceScope trace_scope(tr, 4);
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
-    const float4 v = __ldg(in + i);
-    float4 o;
-    o.x = __uint_as_float(cvt_tf32(v.x)); o.y = __uint_as_float(cvt_tf32(v.y));
-    o.z = __uint_as_float(cvt_tf32(v.z)); o.w = __uint_as_float(cvt_tf32(v.w));
-    out[i] = o;
+  const size_t i0 = (size_t)blockIdx.x * (256 * PRE_V4) + threadIdx.x;
+  float4 v[PRE_V4];
+#pragma unroll
+  for (int u = 0; u < PRE_V4; ++u) {
+    const size_t i = i0 + (size_t)u * 256;
+    if (i < n4) v[u] = __ldg(in + i);
+  }
+#pragma unroll
+  for (int u = 0; u < PRE_V4; ++u) {
+    const size_t i = i0 + (size_t)u * 256;
+    if (i < n4) {
+      float4 o;
+      o.x = __uint_as_float(cvt_tf32(v[u].x)); o.y = __uint_as_float(cvt_tf32(v[u].y));
+      o.z = __uint_as_float(cvt_tf32(v[u].z)); o.w = __uint_as_float(cvt_tf32(v[u].w));
+      out[i] = o;
+    }
   }
 }
 
@@ -1615,20 +1634,31 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
   }
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
-    float4 v;
-    if (hints)
-      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(in + i), "l"(pol_first));
-    else
-      v = __ldg(in + i);
-    uint2 o;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(v.y), "f"(v.x));   // low half = first element
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(v.w), "f"(v.z));
-    if (hints)
-      asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(out + i), "r"(o.x), "r"(o.y), "l"(pol_last) : "memory");
-    else
-      out[i] = o;
+  const size_t i0 = (size_t)blockIdx.x * (256 * PRE_V4) + threadIdx.x;
+  float4 v[PRE_V4];
+#pragma unroll
+  for (int u = 0; u < PRE_V4; ++u) {
+    const size_t i = i0 + (size_t)u * 256;
+    if (i < n4) {
+      if (hints)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(in + i), "l"(pol_first));
+      else
+        v[u] = __ldg(in + i);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < PRE_V4; ++u) {
+    const size_t i = i0 + (size_t)u * 256;
+    if (i < n4) {
+      uint2 o;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(v[u].y), "f"(v[u].x));   // low half = first element
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(v[u].w), "f"(v[u].z));
+      if (hints)
+        asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(out + i), "r"(o.x), "r"(o.y), "l"(pol_last) : "memory");
+      else
+        out[i] = o;
+    }
   }
 }
 
@@ -1636,14 +1666,25 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ hi, uint2* __restrict__ lo,
                                                          size_t n4, unsigned long long* tr) {
   TraceScope trace_scope(tr, 4);
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(in + i));
-    uint2 h, l;
-    split_bf16x2(v.x, v.y, h.x, l.x);
-    split_bf16x2(v.z, v.w, h.y, l.y);
-    hi[i] = h;
-    lo[i] = l;
+  const size_t i0 = (size_t)blockIdx.x * (256 * PRE_V4) + threadIdx.x;
+  float4 v[PRE_V4];
+#pragma unroll
+  for (int u = 0; u < PRE_V4; ++u) {
+    const size_t i = i0 + (size_t)u * 256;
+    if (i < n4)
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(in + i));
+  }
+#pragma unroll
+  for (int u = 0; u < PRE_V4; ++u) {
+    const size_t i = i0 + (size_t)u * 256;
+    if (i < n4) {
+      uint2 h, l;
+      split_bf16x2(v[u].x, v[u].y, h.x, l.x);
+      split_bf16x2(v[u].z, v[u].w, h.y, l.y);
+      hi[i] = h;
+      lo[i] = l;
+    }
   }
 }
 
@@ -2256,7 +2297,7 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
       if (pl.pack) {
         const ConvGeom& q = pl.gq;
         const long long nt = (long long)q.N * q.H * q.W * 2;
-        const unsigned blocks = (unsigned)std::min<long long>((nt + 255) / 256, (long long)sms * 32);
+        const unsigned blocks = (unsigned)((nt + 255) / 256);
         long long sN, sC, sH, sW;
         if (g.x_nchw) { sW = 1; sH = g.W; sC = (long long)g.H * g.W; sN = sC * g.C; }
         else { sC = 1; sW = g.C; sH = (long long)g.W * g.C; sN = sH * g.H; }
@@ -2272,12 +2313,12 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
         nchw_to_nhwc_bf16_kernel<<<(unsigned)((size_t)g.N * ctiles * ptiles), 256, 0, cs>>>(
             g.x, (uint32_t*)copy, pl.p.x3 ? (uint32_t*)((char*)copy + plane) : nullptr, g.C, HW, ctiles, ptiles, gp.trace);
       } else if (pl.p.x3) {
-        const unsigned blocks = (unsigned)((n4 + 255) / 256 < (size_t)sms * 16 ? (n4 + 255) / 256 : (size_t)sms * 16);
+        const unsigned blocks = (unsigned)((n4 + 256 * PRE_V4 - 1) / (256 * PRE_V4));
         const size_t plane = pl.plane_bytes;
         profile_begin(KC_PREPASS, 0.0, 8.0 * (double)n4 * 4.0, cs);
         split_bf16_kernel<<<blocks, 256, 0, cs>>>((const float4*)g.x, (uint2*)copy, (uint2*)((char*)copy + plane), n4, gp.trace);
       } else {
-        const unsigned blocks = (unsigned)((n4 + 255) / 256 < (size_t)sms * 16 ? (n4 + 255) / 256 : (size_t)sms * 16);
+        const unsigned blocks = (unsigned)((n4 + 256 * PRE_V4 - 1) / (256 * PRE_V4));
         profile_begin(KC_PREPASS, 0.0, (pl.bf16 ? 6.0 : 8.0) * (double)n4 * 4.0, cs);
         static const int cast_hints = getenv("CURVATURE_B200_CAST_HINT") ? atoi(getenv("CURVATURE_B200_CAST_HINT")) : 1;
         if (pl.bf16) cast_bf16_kernel<<<blocks, 256, 0, cs>>>((const float4*)g.x, (uint2*)copy, n4, cast_hints, gp.trace);
@@ -2391,6 +2432,16 @@ int plan_batch(const ConvGeom* gs, int n, int precision, std::vector<NhPlan>& pl
       std::stable_sort(groups.begin(), groups.end(), [&](const std::vector<int>& a, const std::vector<int>& b) { return weight(a) < weight(b); });
       launches.clear();
       launches.push_back(groups[0]);
+      // (the packed stem's pre-pass is the longest of all -- it writes a 422 MB tensor: not first among the singles, so
+      // that it runs behind two contractions instead of in front of an idle GPU)
+      std::vector<std::vector<int>> packed, rest;
+      for (auto& l : singles) (plans[l[0]].pack ? packed : rest).push_back(l);
+      singles.clear();
+      for (size_t k = 0; k < rest.size(); ++k) {
+        if (k == 2) for (auto& l : packed) singles.push_back(l);
+        singles.push_back(rest[k]);
+      }
+      if (rest.size() <= 2) for (auto& l : packed) singles.push_back(l);
       for (auto& l : singles) launches.push_back(l);
       for (size_t k = 1; k < groups.size(); ++k) launches.push_back(groups[k]);
     }
