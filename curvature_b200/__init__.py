@@ -6,6 +6,7 @@ from .curvatures import Curvature, Diagonal, KFAC, EFB, INF, FactorArena
 from .utils import get_eigenvectors, get_eigenvalues, kron
 from .parallel import allreduce_arena, shard_indices, invert_plan, allgather_segments
 from .io import save_factors, load_factors
+from .evaluate import eval_nn, eval_bnn
 
 __all__ = ["Curvature", "Diagonal", "KFAC", "EFB", "INF", "FactorArena", "get_eigenvectors", "get_eigenvalues",
-           "kron", "allreduce_arena", "shard_indices", "invert_plan", "allgather_segments", "save_factors", "load_factors"]
+           "kron", "allreduce_arena", "shard_indices", "invert_plan", "allgather_segments", "save_factors", "load_factors", "eval_nn", "eval_bnn"]

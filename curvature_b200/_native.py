@@ -100,6 +100,16 @@ _sample_batch_ws = _sig("crv_sample_matrix_normal_batch_workspace", c_size_t, PO
 _sample_batch = _sig("crv_sample_matrix_normal_batch", c_int, POINTER(SampleItem), c_int, c_void_p, c_size_t, c_int, c_void_p)
 
 
+class SampleMultiItem(ctypes.Structure):
+    """crv_sample_multi_item (include/curvature_b200.h)"""
+    _fields_ = [("LG", c_void_p), ("LA", c_void_p), ("z", c_void_p), ("M", c_int), ("K", c_int), ("s_out", c_void_p)]
+
+
+_sample_multi_ws = _sig("crv_sample_matrix_normal_multi_workspace", c_size_t, POINTER(SampleMultiItem), c_int, c_int)
+_sample_multi = _sig("crv_sample_matrix_normal_multi", c_int, POINTER(SampleMultiItem), c_int, c_int, c_void_p, c_size_t, c_int,
+                     c_void_p)
+
+
 class DiagItem(ctypes.Structure):
     """crv_diag_item (include/curvature_b200.h)"""
     _fields_ = [("wgrad", c_void_p), ("bgrad", c_void_p), ("M", c_int), ("K0", c_int), ("state", c_void_p),
@@ -120,6 +130,7 @@ EXPORTED_SYMBOLS = (
     "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc", "crv_syrk_batch_nhwc", "crv_syrk_batch_nhwc_workspace", "crv_debug_partition", "crv_stream_join", "crv_stream_fork",
     "crv_diag_accum", "crv_diag_accum_batch", "crv_efb_project_accum", "crv_efb_project_batch",
     "crv_efb_project_batch_workspace", "crv_sample_matrix_normal_batch", "crv_sample_matrix_normal_batch_workspace",
+    "crv_sample_matrix_normal_multi", "crv_sample_matrix_normal_multi_workspace",
     "crv_chol_inv_batched", "crv_sample_matrix_normal", "crv_round_tf32", "crv_elementwise_inv_sqrt", "crv_diag_sample",
     "crv_gemm")
 
@@ -484,6 +495,25 @@ def sample_matrix_normal_batch(entries, precision):
     launch_calls += 2 * len(items)
     _check(_sample_batch(arr, len(items), ws.data_ptr(), ws.numel(), precision, _stream(entries[0]["LG"])),
            "crv_sample_matrix_normal_batch")
+
+
+def sample_matrix_normal_multi(entries, S, precision):
+    """S stacked draws per layer in one call (K5c): entries = [(LG (M,M), LA (K,K), z (S*K, M), out (M, S, K))]."""
+    global launch_calls
+    if not entries or S <= 0:
+        return
+    items = []
+    for LG, LA, z, out in entries:
+        M, K = LG.shape[0], LA.shape[0]
+        if tuple(z.shape) != (S * K, M) or tuple(out.shape) != (M, S, K):
+            raise ValueError(f"noise {tuple(z.shape)} / output {tuple(out.shape)}, expected {(S * K, M)} / {(M, S, K)}")
+        items.append(SampleMultiItem(_dev(LG, "LG"), _dev(LA, "LA"), _dev(z, "noise"), M, K, _dev(out, "samples")))
+    arr = (SampleMultiItem * len(items))(*items)
+    dev = entries[0][0].device
+    ws = workspace(_sample_multi_ws(arr, len(items), S), dev)
+    launch_calls += 1
+    _check(_sample_multi(arr, len(items), S, ws.data_ptr(), ws.numel(), precision, _stream(entries[0][0])),
+           "crv_sample_matrix_normal_multi")
 
 
 def chol_inv_batched(factors, adds, muls, outs):

@@ -585,6 +585,82 @@ int crv_sample_matrix_normal_batch(const crv_sample_item* items, int n, void* ws
   return 0;
 }
 
+// ---- K5c: S stacked samples per layer ----
+struct MultiSplit { std::vector<int> chained, single; std::vector<ChainGemm> gemms; size_t t_bytes = 0, chain_bytes = 0, pool_bytes = 0; };
+static void multi_split(const crv_sample_multi_item* items, int n, int S, int precision, char* tbase, MultiSplit& sp) {
+  size_t mx = 0;
+  for (int i = 0; items && i < n; ++i) {
+    const crv_sample_multi_item& it = items[i];
+    const int M = it.M, K = it.K;
+    float* T = (float*)(tbase ? tbase + sp.t_bytes : (char*)16);
+    ChainGemm g[2];
+    memset(g, 0, sizeof(g));
+    // T (M, S*K) = LG * [z_0^T ... z_{S-1}^T]: B(kk, n) = z[n * M + kk], n over the S*K stacked noise rows
+    g[0].A = it.LG; g[0].sa_m = M; g[0].sa_k = 1; g[0].B = it.z; g[0].sb_k = 1; g[0].sb_n = M;
+    g[0].C = T; g[0].ldc = S * K; g[0].m = M; g[0].n = S * K; g[0].k = M; g[0].alpha = 1.f; g[0].epi = EPI_STORE;
+    g[0].round_out = 1; g[0].dep = -1;
+    // s_out (M*S, K) = T viewed as (M*S, K) * LA^T
+    g[1].A = T; g[1].sa_m = K; g[1].sa_k = 1; g[1].B = it.LA; g[1].sb_k = 1; g[1].sb_n = K;
+    g[1].C = it.s_out; g[1].ldc = K; g[1].m = M * S; g[1].n = K; g[1].k = K; g[1].alpha = 1.f; g[1].epi = EPI_STORE;
+    g[1].dep = (int)sp.gemms.size(); g[1].dep_div = S;
+    const bool ok = precision != CRV_PREC_FP32 && chain_enabled() && it.LG && it.LA && it.z && it.s_out && M > 0 && K > 0 &&
+                    gemm_chain_supported(g[0]) && gemm_chain_supported(g[1]);
+    if (ok) {
+      sp.chained.push_back(i);
+      sp.gemms.push_back(g[0]); sp.gemms.push_back(g[1]);
+      sp.t_bytes += al256((size_t)M * K * S * sizeof(float));
+    } else {
+      sp.single.push_back(i);
+      mx = std::max(mx, (size_t)M * K);
+    }
+  }
+  sp.chain_bytes = sp.gemms.empty() ? 0 : al256(gemm_chain_workspace(sp.gemms.data(), (int)sp.gemms.size()));
+  sp.pool_bytes = 2 * al256(mx * sizeof(float));      // per-layer path: intermediate + one dense (M, K) sample
+}
+
+size_t crv_sample_matrix_normal_multi_workspace(const crv_sample_multi_item* items, int n, int S) {
+  if (S <= 0) return 0;
+  MultiSplit sp, fp;
+  multi_split(items, n, S, CRV_PREC_TF32, nullptr, sp);
+  multi_split(items, n, S, CRV_PREC_FP32, nullptr, fp);
+  return std::max(sp.chain_bytes + sp.t_bytes + sp.pool_bytes, fp.pool_bytes) + 512;
+}
+
+int crv_sample_matrix_normal_multi(const crv_sample_multi_item* items, int n, int S, void* ws, size_t ws_bytes,
+                                   int precision, crv_stream_t stream) {
+  ApiGuard guard_(items && n > 0 ? items[0].LG : nullptr, (cudaStream_t)stream);
+  CRV_CHECK(items != nullptr && n > 0 && S > 0, "empty batch");
+  const size_t need = crv_sample_matrix_normal_multi_workspace(items, n, S);
+  CRV_CHECK(ws && ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
+  cudaStream_t caller = (cudaStream_t)stream;
+  char* base = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  MultiSplit sz;
+  multi_split(items, n, S, precision, nullptr, sz);
+  MultiSplit sp;
+  multi_split(items, n, S, precision, base + sz.chain_bytes, sp);
+  if (!sp.chained.empty()) {
+    const int rc = gemm_chain_launch(sp.gemms.data(), (int)sp.gemms.size(), base, sp.chain_bytes, caller);
+    CRV_CHECK(rc >= 0, "internal: chain kernel rejected operands it had accepted");
+    if (rc) return rc;
+  }
+  // layers the chain kernel cannot take: sample by sample through K5 into a dense (M, K) buffer, scattered to (M, S, K)
+  char* pbase = base + sp.chain_bytes + sp.t_bytes;
+  for (int i : sp.single) {
+    const crv_sample_multi_item& it = items[i];
+    CRV_CHECK(it.LG && it.LA && it.z && it.s_out, "null pointer in item %d", i);
+    float* T = (float*)pbase;
+    float* dense = (float*)(pbase + sp.pool_bytes / 2);
+    for (int sidx = 0; sidx < S; ++sidx) {
+      if (int rc = sample_mn_one(it.LG, it.LA, it.z + (size_t)sidx * it.K * it.M, nullptr, it.M, it.K, 0, nullptr, nullptr, nullptr,
+                                 nullptr, dense, T, precision, caller))
+        return rc;
+      CRV_CUDA(cudaMemcpy2DAsync(it.s_out + (size_t)sidx * it.K, (size_t)S * it.K * sizeof(float), dense, (size_t)it.K * sizeof(float),
+                                 (size_t)it.K * sizeof(float), (size_t)it.M, cudaMemcpyDeviceToDevice, caller));
+    }
+  }
+  return 0;
+}
+
 int crv_efb_project_accum(const float* QG, const float* QA, const float* G, int M, int K, float* lambdas,
                           void* ws, size_t ws_bytes, int precision, crv_stream_t stream) {
   ApiGuard guard_(G, (cudaStream_t)stream);

@@ -145,6 +145,8 @@ struct ChainGemm {
   int round_out;    // EPI_STORE: round the result to the nearest TF32 (it is the next GEMM's A operand)
   SampleEpilogue se;
   int dep;          // index of an EARLIER GEMM of the same call whose output C is this GEMM's A operand, or -1
+  int dep_div;      // rows of this GEMM per row of the producer (S stacked samples: row r of A is row r / S of the
+                    // producer's output); 0 or 1 = same rows
 };
 bool gemm_chain_supported(const ChainGemm& g);
 size_t gemm_chain_workspace(const ChainGemm* gemms, int count);

@@ -42,7 +42,9 @@ struct ChainItemDev {
   int m, n, k, ldc;
   int a_mn, b_mn, mapA, mapB;
   int epi, round_out, dep_counters, dep_need;   // dep_counters: first per-row-tile counter of the producer GEMM (-1: none)
-  int counters, pad;                            // this GEMM's own per-row-tile counters (-1: nobody waits for it)
+  int counters, dep_div;                        // this GEMM's own per-row-tile counters (-1: nobody waits for it);
+                                                // dep_div: rows of this GEMM per producer row (stacked samples)
+  int dep_rows, pad;                            // rows of the producer GEMM
   float alpha;
   float* C;
   SampleEpilogue se;
@@ -152,12 +154,17 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(mb)) : "memory");
       }
       if (it.dep_counters >= 0) {
-        // rows [m0, m0 + 256) of the A operand are written by the tiles (tm, *) of the producer GEMM of this chain
-        const int* c = counters + it.dep_counters + t.tm;
-        uint32_t spins = 0;
-        while (ld_acquire(c) < it.dep_need) {
-          __nanosleep(64);
-          if (++spins > (1u << 24)) asm volatile("trap;");
+        // rows [m0, m0 + 256) of the A operand are rows [m0 / div, (m0 + 255) / div] of the producer GEMM's output:
+        // written by its row tiles lo .. hi (one tile when div = 1)
+        const int lo = (sh.m0 / it.dep_div) / CT;
+        const int hi = min(it.dep_rows - 1, (sh.m0 + sh.rows - 1) / it.dep_div) / CT;
+        for (int rt = lo; rt <= hi; ++rt) {
+          const int* c = counters + it.dep_counters + rt;
+          uint32_t spins = 0;
+          while (ld_acquire(c) < it.dep_need) {
+            __nanosleep(64);
+            if (++spins > (1u << 24)) asm volatile("trap;");
+          }
         }
         asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy writes of the other CTAs -> this CTA's TMA reads
       }
@@ -422,12 +429,15 @@ int gemm_chain_launch(const ChainGemm* gemms, int count, void* ws, size_t ws_byt
     if (g.epi == 2) CRV_CHECK(g.se.mu_w || g.se.s_out || !g.se.w_out, "sample epilogue needs its descriptor");
     else CRV_CHECK(g.C != nullptr, "null GEMM output");
     tm_of[i] = (g.m + CT - 1) / CT; tn_of[i] = (g.n + CT - 1) / CT;
-    d.dep_counters = -1; d.counters = -1;
+    d.dep_counters = -1; d.counters = -1; d.dep_div = 1; d.dep_rows = g.m;
   }
   for (int i = 0; i < count; ++i)
     if (gemms[i].dep >= 0) {
       const int p = gemms[i].dep;
-      CRV_CHECK(gemms[p].m == gemms[i].m && gemms[p].C == gemms[i].A, "GEMM %d: its producer %d does not write its A operand", i, p);
+      const int div = gemms[i].dep_div > 1 ? gemms[i].dep_div : 1;
+      CRV_CHECK(gemms[p].m * div == gemms[i].m && gemms[p].C == gemms[i].A, "GEMM %d: its producer %d does not write its A operand", i, p);
+      items[i].dep_div = div;
+      items[i].dep_rows = gemms[p].m;
       if (counter_base[p] < 0) { counter_base[p] = ncounters; ncounters += tm_of[p]; }
       items[p].counters = counter_base[p];
       items[i].dep_counters = counter_base[p];

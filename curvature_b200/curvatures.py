@@ -542,6 +542,60 @@ class KFAC(Curvature):
         nat.sample_matrix_normal(second, first, z, False, s_out=out, precision=tier)
         return out
 
+    def sample_many(self,
+                    samples: int,
+                    noise: Optional[Dict] = None) -> Dict[Module, Tensor]:
+        """`samples` posterior draws of EVERY layer at once: {layer: (samples, M, K) tensor}, draw s of a layer being what
+        `sample(layer)` returns (reference: curvatures.py:387-392) for the s-th noise matrix.  The S draws of a layer are
+        one pair of GEMMs and all layers share one kernel launch (crv_sample_matrix_normal_multi) -- the sampling half of
+        the BNN evaluation loop (scripts/evaluate.py:121-152).  `noise` optionally maps layer -> (samples, K, M)."""
+        assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
+        tier = _gemm_tier(self.precision)
+        entries, outs = [], {}
+        for layer, (first, second) in self.inv_state.items():
+            K, M = first.size(0), second.size(0)
+            if noise is None:
+                z = torch.randn(samples * K, M, device=first.device, dtype=first.dtype)
+                callers = False
+            else:
+                z = noise[layer].reshape(samples * K, M)
+                z = z if z.is_contiguous() else z.contiguous()
+                callers = True
+            _, la, lg, z = self._gemm_operands(layer, first, second, z, callers)
+            out = torch.empty(M, samples, K, device=first.device, dtype=first.dtype)
+            entries.append((lg, la, z, out))
+            outs[layer] = out.permute(1, 0, 2)          # (samples, M, K) view
+        nat.sample_matrix_normal_multi(entries, samples, tier)
+        return outs
+
+    def replace_with(self, draws: Dict[Module, Tensor], index: int):
+        """Install draw `index` of `sample_many`: selected layers get mean + sample, every other parameter and buffer
+        its mean -- the state `sample_and_replace` leaves behind (reference: curvatures.py:117-129)."""
+        names = self._param_names()
+        current = self.model.state_dict(keep_vars=True)
+        written = set()
+        with torch.no_grad():
+            for layer, d in draws.items():
+                s = d[index]
+                weight, bias = layer.weight, layer.bias
+                mean_w = self.model_state[names[id(weight)]]
+                if bias is not None:
+                    bias.data.copy_(self.model_state[names[id(bias)]])
+                    bias.data.add_(s[:, -1])
+                    s = s[:, :-1]
+                    written.add(names[id(bias)])
+                weight.data.copy_(mean_w)
+                weight.data.add_(s.reshape(weight.shape))
+                written.add(names[id(weight)])
+            rest = [(v.data, self.model_state[k]) for k, v in current.items() if k not in written]
+            by_type = {}
+            for dst, src in rest:
+                by_type.setdefault((dst.dtype, src.dtype), ([], []))
+                by_type[(dst.dtype, src.dtype)][0].append(dst)
+                by_type[(dst.dtype, src.dtype)][1].append(src)
+            for dsts, srcs in by_type.values():
+                torch._foreach_copy_(dsts, srcs)
+
     def _gemm_operands(self, key, first, second, z, z_is_callers):
         """Operands of the two-GEMM draw for this estimator's tier: tensor-core tiers get the inverse factors rounded
         to TF32 once per `invert` (cached) and the noise rounded (a copy if the caller owns it)."""

@@ -252,6 +252,22 @@ size_t crv_sample_matrix_normal_batch_workspace(const crv_sample_item* items, in
 int crv_sample_matrix_normal_batch(const crv_sample_item* items, int n, void* ws, size_t ws_bytes, int precision,
                                    crv_stream_t stream);
 
+/* K5c -- S posterior samples of every layer in one call (the sampling half of the BNN evaluation loop,
+ * scripts/evaluate.py:121-152, which calls sample_and_replace() once per sample): for every item
+ *   s_out[m][s][:] = (LG * z_s^T * LA^T)[m][:]   for s < S,   z = [z_0; ...; z_{S-1}] stacked, (S*K, M),
+ * i.e. s_out is (M, S, K) row-major.  On the tensor-core tiers the S draws of a layer are ONE pair of GEMMs
+ * ((M x M)(M x S K), then (M S x K)(K x K)) and all layers share one persistent launch of the chain kernel; layers TMA
+ * cannot address (K or M not a multiple of 4) and the fp32 tier run sample by sample through K5.  The mean is not added:
+ * the caller adds S_s to the posterior mean when it installs sample s.  *_workspace gives the bytes `ws` must have. */
+typedef struct {
+  const float* LG; const float* LA; const float* z;
+  int M, K;          /* K includes the bias column */
+  float* s_out;      /* (M, S, K) */
+} crv_sample_multi_item;
+size_t crv_sample_matrix_normal_multi_workspace(const crv_sample_multi_item* items, int n, int S);
+int crv_sample_matrix_normal_multi(const crv_sample_multi_item* items, int n, int S, void* ws, size_t ws_bytes,
+                                   int precision, crv_stream_t stream);
+
 /* out[i] = in[i] rounded to the nearest TF32 value (in place if out == in).  The tensor-core GEMMs of K3 / K5 read fp32
  * words as TF32 (truncation); operands that stay constant over many calls (EFB eigenbases, inverse factors) are rounded
  * once with this call so that the products carry round-to-nearest instead of truncation error. */
