@@ -208,6 +208,8 @@ def stream_fork(device=None):
 
 def stream_join(device=None):
     """Make torch's current stream wait for the split reductions still running on the library's side stream."""
+    if device is not None and torch.device(device).type != "cuda":
+        return          # (nothing can have been enqueued for a CPU model: every launch refuses CPU tensors)
     with torch.cuda.device(device):
         _check(_stream_join(torch.cuda.current_stream().cuda_stream), "crv_stream_join")
 
@@ -424,6 +426,29 @@ def syrk_batch_nhwc(items, precision, device, join=True):
             _check(_stream_join(stream), "crv_stream_join")
 
 
+def syrk_item_array(items, precision):
+    """(ctypes array of the items, workspace bytes of the batch call) -- built once per geometry by KFAC.update."""
+    if not items:
+        return None, 0
+    arr = (SyrkItem * len(items))(*items)
+    nb = _syrk_batch_ws(arr, len(items), precision)
+    if not nb:
+        raise RuntimeError("crv_syrk_batch_nhwc_workspace: " + (_last_error() or b"unsupported item").decode())
+    return arr, nb
+
+
+def syrk_batch_arr(arr, n, ws_bytes, precision, device, join=True):
+    """crv_syrk_batch_nhwc on a prebuilt item array (see syrk_item_array)."""
+    global launch_calls
+    ws = workspace(ws_bytes, device)
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream().cuda_stream
+        launch_calls += 2 * n
+        _check(_syrk_batch(arr, n, ws.data_ptr(), ws.numel(), precision, stream), "crv_syrk_batch_nhwc")
+        if join:
+            _check(_stream_join(stream), "crv_stream_join")
+
+
 def diag_accum(wgrad, bgrad, scale, state=None, grads_out=None):
     """state (M,K) += scale * [wgrad | bgrad]^2; optionally also emit the concatenated grads (K2)."""
     global launch_calls
@@ -434,19 +459,28 @@ def diag_accum(wgrad, bgrad, scale, state=None, grads_out=None):
                        _opt(state, "state"), _opt(grads_out, "grads_out"), _stream(wgrad)), "crv_diag_accum")
 
 
-def diag_accum_batch(entries, scale):
-    """One launch for a list of (wgrad, bgrad or None, state or None, grads_out or None) (K2b)."""
-    global launch_calls
-    if not entries:
-        return
+def prepare_diag_batch(entries):
+    """ctypes item array of crv_diag_accum_batch for (wgrad, bgrad or None, state or None, grads_out or None) entries;
+    callers that repeat the call every step keep the array and only refresh the gradient pointers."""
     items = []
     for wgrad, bgrad, state, grads_out in entries:
         M = wgrad.shape[0]
         items.append(DiagItem(_dev(wgrad, "weight.grad"), _opt(bgrad, "bias.grad"), M, wgrad.numel() // M,
                               _opt(state, "state"), _opt(grads_out, "grads_out")))
-    arr = (DiagItem * len(items))(*items)
+    return (DiagItem * len(items))(*items)
+
+
+def run_diag_batch(arr, n, scale, like):
+    global launch_calls
     launch_calls += 1
-    _check(_diag_batch(arr, len(items), float(scale), _stream(entries[0][0])), "crv_diag_accum_batch")
+    _check(_diag_batch(arr, n, float(scale), _stream(like)), "crv_diag_accum_batch")
+
+
+def diag_accum_batch(entries, scale):
+    """One launch for a list of (wgrad, bgrad or None, state or None, grads_out or None) (K2b)."""
+    if not entries:
+        return
+    run_diag_batch(prepare_diag_batch(entries), len(entries), scale, entries[0][0])
 
 
 def efb_project_accum(QG, QA, G, lambdas, precision=PREC_FP32):
@@ -459,26 +493,31 @@ def efb_project_accum(QG, QA, G, lambdas, precision=PREC_FP32):
                         ws.data_ptr(), ws.numel(), precision, _stream(G)), "crv_efb_project_accum")
 
 
-def efb_project_batch(entries, precision, round_g):
-    """One call for a list of (QG, QA, G, lambdas) (K3b): lambdas += (QG^T G QA)^2 per entry."""
-    global launch_calls
-    if not entries:
-        return
+def prepare_efb_batch(entries, round_g):
+    """(item array, workspace bytes) of crv_efb_project_batch for (QG, QA, G, lambdas) entries."""
     items = [EfbItem(_dev(QG, "QG"), _dev(QA, "QA"), _dev(G, "grads"), G.shape[0], G.shape[1], _dev(lam, "lambdas"),
                      int(bool(round_g))) for QG, QA, G, lam in entries]
     arr = (EfbItem * len(items))(*items)
-    dev = entries[0][2].device
-    ws = workspace(_efb_batch_ws(arr, len(items)), dev)
-    launch_calls += 2 * len(items)
-    _check(_efb_batch(arr, len(items), ws.data_ptr(), ws.numel(), precision, _stream(entries[0][2])),
-           "crv_efb_project_batch")
+    return arr, _efb_batch_ws(arr, len(items))
 
 
-def sample_matrix_normal_batch(entries, precision):
-    """One call for a list of dicts with the arguments of sample_matrix_normal (K5b)."""
+def run_efb_batch(arr, n, ws_bytes, precision, like):
     global launch_calls
+    ws = workspace(ws_bytes, like.device)
+    launch_calls += 1
+    _check(_efb_batch(arr, n, ws.data_ptr(), ws.numel(), precision, _stream(like)), "crv_efb_project_batch")
+
+
+def efb_project_batch(entries, precision, round_g):
+    """One call for a list of (QG, QA, G, lambdas) (K3b): lambdas += (QG^T G QA)^2 per entry."""
     if not entries:
         return
+    arr, nb = prepare_efb_batch(entries, round_g)
+    run_efb_batch(arr, len(entries), nb, precision, entries[0][2])
+
+
+def prepare_sample_batch(entries):
+    """(item array, workspace bytes) of crv_sample_matrix_normal_batch for dicts with the arguments of K5."""
     items = []
     for e in entries:
         LG, LA, z = e["LG"], e["LA"], e["z"]
@@ -490,11 +529,22 @@ def sample_matrix_normal_batch(entries, precision):
                                 K - has_bias, has_bias, _opt(e.get("mu_w"), "mu_w"), _opt(e.get("mu_b"), "mu_b"),
                                 _opt(e.get("w_out"), "weight"), _opt(e.get("b_out"), "bias"), _opt(e.get("s_out"), "sample")))
     arr = (SampleItem * len(items))(*items)
-    dev = entries[0]["LG"].device
-    ws = workspace(_sample_batch_ws(arr, len(items)), dev)
-    launch_calls += 2 * len(items)
-    _check(_sample_batch(arr, len(items), ws.data_ptr(), ws.numel(), precision, _stream(entries[0]["LG"])),
-           "crv_sample_matrix_normal_batch")
+    return arr, _sample_batch_ws(arr, len(items))
+
+
+def run_sample_batch(arr, n, ws_bytes, precision, like):
+    global launch_calls
+    ws = workspace(ws_bytes, like.device)
+    launch_calls += 1
+    _check(_sample_batch(arr, n, ws.data_ptr(), ws.numel(), precision, _stream(like)), "crv_sample_matrix_normal_batch")
+
+
+def sample_matrix_normal_batch(entries, precision):
+    """One call for a list of dicts with the arguments of sample_matrix_normal (K5b)."""
+    if not entries:
+        return
+    arr, nb = prepare_sample_batch(entries)
+    run_sample_batch(arr, len(entries), nb, precision, entries[0]["LG"])
 
 
 def sample_matrix_normal_multi(entries, S, precision):

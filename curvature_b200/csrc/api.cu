@@ -384,37 +384,64 @@ static bool chain_enabled() {
   return on;
 }
 
-static void efb_chain(const crv_efb_item& it, float* T, int first, ChainGemm* g) {
-  memset(g, 0, 2 * sizeof(ChainGemm));
-  // T = QG^T * G: A(i, kk) = QG[kk * M + i]; B(kk, n) = G[kk * K + n]
-  g[0].A = it.QG; g[0].sa_m = 1; g[0].sa_k = it.M; g[0].B = it.G; g[0].sb_k = it.K; g[0].sb_n = 1;
-  g[0].C = T; g[0].ldc = it.K; g[0].m = it.M; g[0].n = it.K; g[0].k = it.M; g[0].alpha = 1.f; g[0].epi = EPI_STORE;
-  g[0].round_out = 1; g[0].dep = -1;
-  // lambdas += (T * QA)^2: A = T; B(kk, n) = QA[kk * K + n]
-  g[1].A = T; g[1].sa_m = it.K; g[1].sa_k = 1; g[1].B = it.QA; g[1].sb_k = it.K; g[1].sb_n = 1;
-  g[1].C = it.lambdas; g[1].ldc = it.K; g[1].m = it.M; g[1].n = it.K; g[1].k = it.K; g[1].alpha = 1.f;
-  g[1].epi = EPI_SQUARE_ACCUM; g[1].dep = first;
+// Operands whose rows are not 16-byte aligned (K % 4 != 0: a bias column, e.g. the 2049-wide fc factor) are copied into
+// row-padded buffers of the workspace first (a 2-D device copy of a few MB); TMA never reads the padding (the tensor map
+// has the logical extents).  Without this such a layer falls to the CUDA-core GEMM and, alone, takes longer than all
+// other layers of the model together.
+struct PadCopy { float* dst; size_t ld_dst; const float* src; size_t ld_src; int rows, cols; };
+struct Bump {
+  char* base; size_t off;
+  float* take(size_t bytes) { float* p = (float*)(base ? base + off : (char*)16); off += al256(bytes); return p; }
+};
+static int run_pad_copies(const std::vector<PadCopy>& cps, cudaStream_t s) {
+  for (const PadCopy& c : cps)
+    CRV_CUDA(cudaMemcpy2DAsync(c.dst, c.ld_dst * sizeof(float), c.src, c.ld_src * sizeof(float), (size_t)c.cols * sizeof(float),
+                               (size_t)c.rows, cudaMemcpyDeviceToDevice, s));
+  return 0;
 }
 
-struct EfbSplit { std::vector<int> chained, single; std::vector<ChainGemm> gemms; size_t t_bytes = 0, chain_bytes = 0, pool_bytes = 0; };
+struct EfbSplit { std::vector<int> chained, single; std::vector<ChainGemm> gemms; std::vector<PadCopy> copies;
+                  size_t t_bytes = 0, chain_bytes = 0, pool_bytes = 0; };
 static void efb_split(const crv_efb_item* items, int n, int precision, char* tbase, EfbSplit& sp) {
   size_t mx = 0;
+  Bump bump{tbase, 0};
   for (int i = 0; items && i < n; ++i) {
     const crv_efb_item& it = items[i];
+    const int M = it.M, K = it.K, Kp = (K + 3) & ~3;
+    const bool pad = Kp != K;
+    const size_t mark = bump.off, ncopies = sp.copies.size();
+    float* T = bump.take((size_t)M * Kp * sizeof(float));
+    const float* Gop = it.G; const float* QAop = it.QA;
+    if (pad) {
+      float* Gp = bump.take((size_t)M * Kp * sizeof(float));
+      float* QAp = bump.take((size_t)K * Kp * sizeof(float));
+      sp.copies.push_back({Gp, (size_t)Kp, it.G, (size_t)K, M, K});
+      sp.copies.push_back({QAp, (size_t)Kp, it.QA, (size_t)K, K, K});
+      Gop = Gp; QAop = QAp;
+    }
     ChainGemm g[2];
-    efb_chain(it, (float*)(tbase ? tbase + sp.t_bytes : nullptr) , (int)sp.gemms.size(), g);
-    if (tbase == nullptr) { g[0].C = (float*)16; g[1].A = (const float*)16; }       // (sizing pass: alignment only)
+    memset(g, 0, sizeof(g));
+    // T = QG^T * G: A(i, kk) = QG[kk * M + i]; B(kk, n) = G[kk * ld + n]
+    g[0].A = it.QG; g[0].sa_m = 1; g[0].sa_k = M; g[0].B = Gop; g[0].sb_k = Kp; g[0].sb_n = 1;
+    g[0].C = T; g[0].ldc = Kp; g[0].m = M; g[0].n = K; g[0].k = M; g[0].alpha = 1.f; g[0].epi = EPI_STORE;
+    g[0].round_out = 1; g[0].dep = -1;
+    // lambdas += (T * QA)^2: A = T; B(kk, n) = QA[kk * ld + n]
+    g[1].A = T; g[1].sa_m = Kp; g[1].sa_k = 1; g[1].B = QAop; g[1].sb_k = Kp; g[1].sb_n = 1;
+    g[1].C = it.lambdas; g[1].ldc = K; g[1].m = M; g[1].n = K; g[1].k = K; g[1].alpha = 1.f;
+    g[1].epi = EPI_SQUARE_ACCUM; g[1].dep = (int)sp.gemms.size();
     const bool ok = precision != CRV_PREC_FP32 && chain_enabled() && it.QG && it.QA && it.G && it.lambdas &&
                     gemm_chain_supported(g[0]) && gemm_chain_supported(g[1]);
     if (ok) {
       sp.chained.push_back(i);
       sp.gemms.push_back(g[0]); sp.gemms.push_back(g[1]);
-      sp.t_bytes += al256((size_t)it.M * it.K * sizeof(float));
     } else {
+      bump.off = mark;
+      sp.copies.resize(ncopies);
       sp.single.push_back(i);
-      mx = std::max(mx, (size_t)it.M * (size_t)it.K);
+      mx = std::max(mx, (size_t)M * (size_t)K);
     }
   }
+  sp.t_bytes = bump.off;
   sp.chain_bytes = sp.gemms.empty() ? 0 : al256(gemm_chain_workspace(sp.gemms.data(), (int)sp.gemms.size()));
   sp.pool_bytes = (size_t)POOL * al256(mx * sizeof(float));
 }
@@ -446,6 +473,7 @@ int crv_efb_project_batch(const crv_efb_item* items, int n, void* ws, size_t ws_
     for (int i : sp.chained)
       if (items[i].round_g)     // gradient copy rounded to the nearest TF32 in place (the tensor core would truncate it)
         if (int rc = round_tf32_launch(items[i].G, const_cast<float*>(items[i].G), (size_t)items[i].M * items[i].K, caller)) return rc;
+    if (int rc = run_pad_copies(sp.copies, caller)) return rc;
     const int rc = gemm_chain_launch(sp.gemms.data(), (int)sp.gemms.size(), base, sp.chain_bytes, caller);
     CRV_CHECK(rc >= 0, "internal: chain kernel rejected operands it had accepted");
     if (rc) return rc;
@@ -482,24 +510,33 @@ int crv_efb_project_batch(const crv_efb_item* items, int n, void* ws, size_t ws_
   return 0;
 }
 
-struct SampleSplit { std::vector<int> chained, single; std::vector<ChainGemm> gemms; std::vector<size_t> t_off, z_off;
+struct SampleSplit { std::vector<int> chained, single; std::vector<ChainGemm> gemms; std::vector<PadCopy> copies;
                      size_t t_bytes = 0, chain_bytes = 0, pool_bytes = 0; };
 static void sample_split(const crv_sample_item* items, int n, int precision, char* tbase, SampleSplit& sp) {
   size_t mx = 0;
+  Bump bump{tbase, 0};
   for (int i = 0; items && i < n; ++i) {
     const crv_sample_item& it = items[i];
-    const int K = it.K0 + (it.has_bias ? 1 : 0), M = it.M;
-    const size_t mk = al256((size_t)M * K * sizeof(float));
-    float* T = (float*)(tbase ? tbase + sp.t_bytes : (char*)16);
-    const float* zz = it.row_scale ? (const float*)(tbase ? tbase + sp.t_bytes + mk : (char*)16) : it.z;
+    const int K = it.K0 + (it.has_bias ? 1 : 0), M = it.M, Kp = (K + 3) & ~3;
+    const bool pad = Kp != K;
+    const size_t mark = bump.off, ncopies = sp.copies.size();
+    float* T = bump.take((size_t)M * Kp * sizeof(float));
+    const float* zz = it.z;
+    if (it.row_scale) zz = bump.take((size_t)K * M * sizeof(float));      // scaled noise (EFB's draw)
+    const float* LAop = it.LA;
+    if (pad) {
+      float* LAp = bump.take((size_t)K * Kp * sizeof(float));
+      sp.copies.push_back({LAp, (size_t)Kp, it.LA, (size_t)K, K, K});
+      LAop = LAp;
+    }
     ChainGemm g[2];
     memset(g, 0, sizeof(g));
     // T = LG * z^T: A = LG (M x M); B(kk, n) = z[n * M + kk]
     g[0].A = it.LG; g[0].sa_m = M; g[0].sa_k = 1; g[0].B = zz; g[0].sb_k = 1; g[0].sb_n = M;
-    g[0].C = T; g[0].ldc = K; g[0].m = M; g[0].n = K; g[0].k = M; g[0].alpha = 1.f; g[0].epi = EPI_STORE; g[0].round_out = 1;
+    g[0].C = T; g[0].ldc = Kp; g[0].m = M; g[0].n = K; g[0].k = M; g[0].alpha = 1.f; g[0].epi = EPI_STORE; g[0].round_out = 1;
     g[0].dep = -1;
-    // S = T * LA^T: B(kk, n) = LA[n * K + kk]; epilogue adds the mean and splits weight / bias columns
-    g[1].A = T; g[1].sa_m = K; g[1].sa_k = 1; g[1].B = it.LA; g[1].sb_k = 1; g[1].sb_n = K;
+    // S = T * LA^T: B(kk, n) = LA[n * ld + kk]; epilogue adds the mean and splits weight / bias columns
+    g[1].A = T; g[1].sa_m = Kp; g[1].sa_k = 1; g[1].B = LAop; g[1].sb_k = 1; g[1].sb_n = Kp;
     g[1].C = nullptr; g[1].ldc = K; g[1].m = M; g[1].n = K; g[1].k = K; g[1].alpha = 1.f; g[1].epi = 2;
     g[1].se.mu_w = it.mu_w; g[1].se.mu_b = it.mu_b; g[1].se.w_out = it.w_out; g[1].se.b_out = it.b_out; g[1].se.s_out = it.s_out;
     g[1].se.K0 = it.K0; g[1].se.has_bias = it.has_bias ? 1 : 0;
@@ -509,13 +546,14 @@ static void sample_split(const crv_sample_item* items, int n, int precision, cha
     if (ok) {
       sp.chained.push_back(i);
       sp.gemms.push_back(g[0]); sp.gemms.push_back(g[1]);
-      sp.t_off.push_back(sp.t_bytes);
-      sp.t_bytes += mk * (it.row_scale ? 2 : 1);
     } else {
+      bump.off = mark;
+      sp.copies.resize(ncopies);
       sp.single.push_back(i);
       mx = std::max(mx, (size_t)M * K * (it.row_scale ? 2 : 1));
     }
   }
+  sp.t_bytes = bump.off;
   sp.chain_bytes = sp.gemms.empty() ? 0 : al256(gemm_chain_workspace(sp.gemms.data(), (int)sp.gemms.size()));
   sp.pool_bytes = (size_t)POOL * al256(mx * sizeof(float));
 }
@@ -549,6 +587,7 @@ int crv_sample_matrix_normal_batch(const crv_sample_item* items, int n, void* ws
         if (int rc = scale_transpose_launch(it.z, it.row_scale, K, it.M, const_cast<float*>(sp.gemms[2 * j].B), caller)) return rc;
       }
     }
+    if (int rc = run_pad_copies(sp.copies, caller)) return rc;
     const int rc = gemm_chain_launch(sp.gemms.data(), (int)sp.gemms.size(), base, sp.chain_bytes, caller);
     CRV_CHECK(rc >= 0, "internal: chain kernel rejected operands it had accepted");
     if (rc) return rc;
@@ -586,34 +625,55 @@ int crv_sample_matrix_normal_batch(const crv_sample_item* items, int n, void* ws
 }
 
 // ---- K5c: S stacked samples per layer ----
-struct MultiSplit { std::vector<int> chained, single; std::vector<ChainGemm> gemms; size_t t_bytes = 0, chain_bytes = 0, pool_bytes = 0; };
+struct MultiSplit { std::vector<int> chained, single; std::vector<ChainGemm> gemms; std::vector<PadCopy> copies;
+                    size_t t_bytes = 0, chain_bytes = 0, pool_bytes = 0; };
 static void multi_split(const crv_sample_multi_item* items, int n, int S, int precision, char* tbase, MultiSplit& sp) {
   size_t mx = 0;
+  Bump bump{tbase, 0};
   for (int i = 0; items && i < n; ++i) {
     const crv_sample_multi_item& it = items[i];
-    const int M = it.M, K = it.K;
-    float* T = (float*)(tbase ? tbase + sp.t_bytes : (char*)16);
-    ChainGemm g[2];
-    memset(g, 0, sizeof(g));
-    // T (M, S*K) = LG * [z_0^T ... z_{S-1}^T]: B(kk, n) = z[n * M + kk], n over the S*K stacked noise rows
-    g[0].A = it.LG; g[0].sa_m = M; g[0].sa_k = 1; g[0].B = it.z; g[0].sb_k = 1; g[0].sb_n = M;
-    g[0].C = T; g[0].ldc = S * K; g[0].m = M; g[0].n = S * K; g[0].k = M; g[0].alpha = 1.f; g[0].epi = EPI_STORE;
-    g[0].round_out = 1; g[0].dep = -1;
-    // s_out (M*S, K) = T viewed as (M*S, K) * LA^T
-    g[1].A = T; g[1].sa_m = K; g[1].sa_k = 1; g[1].B = it.LA; g[1].sb_k = 1; g[1].sb_n = K;
-    g[1].C = it.s_out; g[1].ldc = K; g[1].m = M * S; g[1].n = K; g[1].k = K; g[1].alpha = 1.f; g[1].epi = EPI_STORE;
-    g[1].dep = (int)sp.gemms.size(); g[1].dep_div = S;
-    const bool ok = precision != CRV_PREC_FP32 && chain_enabled() && it.LG && it.LA && it.z && it.s_out && M > 0 && K > 0 &&
-                    gemm_chain_supported(g[0]) && gemm_chain_supported(g[1]);
+    const int M = it.M, K = it.K, Kp = (K + 3) & ~3;
+    const bool pad = Kp != K;
+    const size_t mark = bump.off, ncopies = sp.copies.size(), ngemms = sp.gemms.size();
+    float* T = bump.take((size_t)M * S * Kp * sizeof(float));               // (M, S, Kp)
+    const float* LAop = it.LA;
+    if (pad) {
+      float* LAp = bump.take((size_t)K * Kp * sizeof(float));
+      sp.copies.push_back({LAp, (size_t)Kp, it.LA, (size_t)K, K, K});
+      LAop = LAp;
+    }
+    bool ok = precision != CRV_PREC_FP32 && chain_enabled() && it.LG && it.LA && it.z && it.s_out && M > 0 && K > 0;
+    ChainGemm g;
+    const int first = (int)sp.gemms.size();
+    // first products: T[:, s, :] = LG * z_s^T.  Unpadded rows: ONE GEMM over the stacked noise (n = S K columns);
+    // padded rows: one GEMM per sample, each writing its column slab of T
+    const int nfirst = pad ? S : 1;
+    for (int sidx = 0; sidx < nfirst && ok; ++sidx) {
+      memset(&g, 0, sizeof(g));
+      g.A = it.LG; g.sa_m = M; g.sa_k = 1; g.B = it.z + (size_t)sidx * K * M; g.sb_k = 1; g.sb_n = M;
+      g.C = T + (size_t)sidx * Kp; g.ldc = S * Kp; g.m = M; g.n = pad ? K : S * K; g.k = M; g.alpha = 1.f; g.epi = EPI_STORE;
+      g.round_out = 1; g.dep = -1;
+      if (sidx == 0) ok = ok && gemm_chain_supported(g);
+      sp.gemms.push_back(g);
+    }
+    // s_out (M*S, K) = T viewed as (M*S, Kp) * LA^T
+    memset(&g, 0, sizeof(g));
+    g.A = T; g.sa_m = Kp; g.sa_k = 1; g.B = LAop; g.sb_k = 1; g.sb_n = Kp;
+    g.C = it.s_out; g.ldc = K; g.m = M * S; g.n = K; g.k = K; g.alpha = 1.f; g.epi = EPI_STORE;
+    g.dep = first; g.dep_div = S; g.dep_count = nfirst;
+    ok = ok && gemm_chain_supported(g);
+    sp.gemms.push_back(g);
     if (ok) {
       sp.chained.push_back(i);
-      sp.gemms.push_back(g[0]); sp.gemms.push_back(g[1]);
-      sp.t_bytes += al256((size_t)M * K * S * sizeof(float));
     } else {
+      bump.off = mark;
+      sp.copies.resize(ncopies);
+      sp.gemms.resize(ngemms);
       sp.single.push_back(i);
       mx = std::max(mx, (size_t)M * K);
     }
   }
+  sp.t_bytes = bump.off;
   sp.chain_bytes = sp.gemms.empty() ? 0 : al256(gemm_chain_workspace(sp.gemms.data(), (int)sp.gemms.size()));
   sp.pool_bytes = 2 * al256(mx * sizeof(float));      // per-layer path: intermediate + one dense (M, K) sample
 }
@@ -639,6 +699,7 @@ int crv_sample_matrix_normal_multi(const crv_sample_multi_item* items, int n, in
   MultiSplit sp;
   multi_split(items, n, S, precision, base + sz.chain_bytes, sp);
   if (!sp.chained.empty()) {
+    if (int rc = run_pad_copies(sp.copies, caller)) return rc;
     const int rc = gemm_chain_launch(sp.gemms.data(), (int)sp.gemms.size(), base, sp.chain_bytes, caller);
     CRV_CHECK(rc >= 0, "internal: chain kernel rejected operands it had accepted");
     if (rc) return rc;

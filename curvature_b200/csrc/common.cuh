@@ -147,6 +147,8 @@ struct ChainGemm {
   int dep;          // index of an EARLIER GEMM of the same call whose output C is this GEMM's A operand, or -1
   int dep_div;      // rows of this GEMM per row of the producer (S stacked samples: row r of A is row r / S of the
                     // producer's output); 0 or 1 = same rows
+  int dep_count;    // number of consecutive producer GEMMs dep, dep + 1, ... that together write the A operand (each a
+                    // column slab of it, same rows); 0 or 1 = one
 };
 bool gemm_chain_supported(const ChainGemm& g);
 size_t gemm_chain_workspace(const ChainGemm* gemms, int count);

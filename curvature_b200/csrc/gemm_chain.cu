@@ -435,13 +435,22 @@ int gemm_chain_launch(const ChainGemm* gemms, int count, void* ws, size_t ws_byt
     if (gemms[i].dep >= 0) {
       const int p = gemms[i].dep;
       const int div = gemms[i].dep_div > 1 ? gemms[i].dep_div : 1;
-      CRV_CHECK(gemms[p].m * div == gemms[i].m && gemms[p].C == gemms[i].A, "GEMM %d: its producer %d does not write its A operand", i, p);
+      const int np = gemms[i].dep_count > 1 ? gemms[i].dep_count : 1;
+      CRV_CHECK(p + np <= i, "GEMM %d depends on a later one", i);
+      CRV_CHECK(gemms[p].C == gemms[i].A, "GEMM %d: its producer %d does not write its A operand", i, p);
+      int need = 0;
+      for (int j = p; j < p + np; ++j) {       // the producers of one consumer share one set of per-row-tile counters
+        CRV_CHECK(gemms[j].m * div == gemms[i].m, "GEMM %d: producer %d has %d rows, expected %d", i, j, gemms[j].m, gemms[i].m / div);
+        CRV_CHECK(counter_base[j] < 0 || (j > p && counter_base[j] == counter_base[p]), "GEMM %d feeds two consumers", j);
+        if (j == p) { if (counter_base[p] < 0) { counter_base[p] = ncounters; ncounters += tm_of[p]; } }
+        else counter_base[j] = counter_base[p];
+        items[j].counters = counter_base[p];
+        need += tn_of[j];
+      }
+      items[i].dep_counters = counter_base[p];
+      items[i].dep_need = need;
       items[i].dep_div = div;
       items[i].dep_rows = gemms[p].m;
-      if (counter_base[p] < 0) { counter_base[p] = ncounters; ncounters += tm_of[p]; }
-      items[p].counters = counter_base[p];
-      items[i].dep_counters = counter_base[p];
-      items[i].dep_need = tn_of[p];
     }
   // global order: producers (GEMMs somebody waits for, and independent ones) first, then consumers; within each phase
   // the most expensive tiles first.  Tiles are dealt to the CTAs in that order, always to the least loaded CTA; every CTA

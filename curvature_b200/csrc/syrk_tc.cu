@@ -2224,7 +2224,8 @@ int make_tensor_map(const ConvGeom& g, const NhPlan& pl, const void* src, CUtens
 
 // One launch of the stream-K kernel (+ its reduction) over the factors idx[0..cnt) -- all of the same operand type.
 int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, const std::vector<NhPlan>& plans,
-                 const int* idx, int cnt, void* ws, size_t ws_bytes, size_t copy_off, size_t max_copy, cudaStream_t caller) {
+                 const int* idx, int cnt, void* ws, size_t ws_bytes, size_t copy_off, size_t max_copy, cudaStream_t caller,
+                 SkTable* cached_sk = nullptr, std::vector<int>* cached_qbeg = nullptr, char* cached_valid = nullptr) {
   const int sms = device_sm_count();
   const bool bf16 = plans[idx[0]].bf16 != 0;
   size_t pairs = 0, copy_bytes = 0;
@@ -2341,7 +2342,17 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
     bytes += pl.pack ? 2.0 * pl.gq.N * pl.gq.C * pl.gq.H * pl.gq.W : (pl.bf16 ? 2.0 : 4.0) * g.N * g.C * g.H * g.W;
     fbytes += 8.0 * g.D * g.D;
   }
-  build_sk(pls, sms, gp, sk);
+  if (cached_valid && *cached_valid) {          // same batch geometry as last time: the partition is unchanged
+    sk = *cached_sk;
+    for (int k = 0; k <= cnt; ++k) gp.qbeg[k] = (*cached_qbeg)[k];
+  } else {
+    build_sk(pls, sms, gp, sk);
+    if (cached_valid) {
+      *cached_sk = sk;
+      cached_qbeg->assign(gp.qbeg, gp.qbeg + cnt + 1);
+      *cached_valid = 1;
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     attr_set = true;
@@ -2389,9 +2400,67 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
   return 0;
 }
 
-// plan every factor of a batch and cut the batch into launches (lists of indices into the batch)
+// Host-side plan cache.  Planning a ResNet-50 step (108 factors: box search, stream-K partition of 40 launches) costs about
+// as much host time as enqueueing it, and an estimation pass repeats the SAME geometry every step -- only the tensor
+// pointers change.  The plans, the launch order and the stream-K tables of the last batch are kept, keyed by everything
+// they depend on (geometry, layout flags, pointer alignment, tier, SM count).
+struct BatchCache {
+  std::vector<ConvGeom> key;
+  int precision = -1, sms = 0;
+  std::vector<NhPlan> plans;
+  std::vector<std::vector<int>> launches;
+  std::vector<SkTable> sk;              // per launch
+  std::vector<std::vector<int>> qbeg;   // per launch: GroupParams::qbeg
+  std::vector<char> sk_valid;
+};
+BatchCache g_batch_cache;
+static const bool g_plan_cache_on = !(getenv("CURVATURE_B200_PLAN_CACHE") && atoi(getenv("CURVATURE_B200_PLAN_CACHE")) == 0);
+
+bool cache_matches(const ConvGeom* gs, int n, int precision, int sms) {
+  const BatchCache& c = g_batch_cache;
+  if (!g_plan_cache_on || c.precision != precision || c.sms != sms || (int)c.key.size() != n) return false;
+  for (int i = 0; i < n; ++i) {
+    const ConvGeom& a = gs[i];
+    const ConvGeom& b = c.key[i];
+    if (((uintptr_t)a.x & 15) != (uintptr_t)b.x || a.N != b.N || a.C != b.C || a.H != b.H || a.W != b.W || a.kh != b.kh ||
+        a.kw != b.kw || a.sh != b.sh || a.sw != b.sw || a.ph != b.ph || a.pw != b.pw || a.has_bias != b.has_bias ||
+        a.x_nchw != b.x_nchw || a.zero_mean != b.zero_mean)
+      return false;
+  }
+  return true;
+}
+
+int plan_batch_uncached(const ConvGeom* gs, int n, int precision, std::vector<NhPlan>& plans, std::vector<std::vector<int>>& launches,
+                        int sms_override);
+
+// plans / launches of the batch, through the cache (sms_override > 0: the host-only debug view, never cached)
 int plan_batch(const ConvGeom* gs, int n, int precision, std::vector<NhPlan>& plans, std::vector<std::vector<int>>& launches,
                int sms_override = 0) {
+  const int sms = sms_override > 0 ? sms_override : device_sm_count();
+  if (sms_override <= 0 && cache_matches(gs, n, precision, sms)) {
+    plans = g_batch_cache.plans;
+    launches = g_batch_cache.launches;
+    return 0;
+  }
+  if (int rc = plan_batch_uncached(gs, n, precision, plans, launches, sms_override)) return rc;
+  if (sms_override <= 0 && g_plan_cache_on) {
+    BatchCache& c = g_batch_cache;
+    c.key.resize(n);
+    for (int i = 0; i < n; ++i) {
+      c.key[i] = gs[i];
+      c.key[i].x = (const float*)((uintptr_t)gs[i].x & 15);
+    }
+    c.precision = precision; c.sms = sms;
+    c.plans = plans; c.launches = launches;
+    c.sk.assign(launches.size(), SkTable());
+    c.qbeg.assign(launches.size(), std::vector<int>());
+    c.sk_valid.assign(launches.size(), 0);
+  }
+  return 0;
+}
+
+int plan_batch_uncached(const ConvGeom* gs, int n, int precision, std::vector<NhPlan>& plans, std::vector<std::vector<int>>& launches,
+                        int sms_override) {
   CRV_CHECK(precision == CRV_PREC_TF32 || precision == CRV_PREC_TF32_TMA || precision == CRV_PREC_BF16 ||
                 precision == CRV_PREC_BF16X3,
             "channels-last SYRK: tier %d is not built (available: tf32, tf32_tma, bf16, bf16x3)", precision);
@@ -2506,11 +2575,16 @@ int syrk_nhwc_batch_launch(const ConvGeom* gs, const float* alphas, float* const
       memcpy(st->sig, sig, sizeof(sig));
     }
   }
-  for (const auto& l : launches)
-    if (int rc = launch_group(gs, alphas, Fs, plans, l.data(), (int)l.size(), ws, ws_bytes, copy_off, max_copy, s)) {
+  const bool cached = cache_matches(gs, n, precision, device_sm_count()) && g_batch_cache.sk.size() == launches.size();
+  for (size_t li = 0; li < launches.size(); ++li) {
+    const auto& l = launches[li];
+    BatchCache& c = g_batch_cache;
+    if (int rc = launch_group(gs, alphas, Fs, plans, l.data(), (int)l.size(), ws, ws_bytes, copy_off, max_copy, s,
+                              cached ? &c.sk[li] : nullptr, cached ? &c.qbeg[li] : nullptr, cached ? &c.sk_valid[li] : nullptr)) {
       side_abort(s);
       return rc;
     }
+  }
   return 0;
 }
 

@@ -408,7 +408,10 @@ class KFAC(Curvature):
         device = None
         if self.record:
             device = next(iter(self.record)).weight.device
-        batch = []           # channels-last operands: one C-ABI call for the whole step (crv_syrk_batch_nhwc)
+        # The geometry of an estimation pass repeats every step: the C-ABI item array, which factors ride in the batch
+        # call and the workspace size are built once per (shapes, strides, alignment, tier) signature; afterwards a step
+        # only refreshes the operand pointers.
+        recorded = []
         for layer in self.model.modules():
             module_class = layer.__class__.__name__
             if module_class in self.layer_types:
@@ -417,56 +420,76 @@ class KFAC(Curvature):
                     if forward is None or backward is None:
                         raise RuntimeError("KFAC.update: no recorded input / output gradient for "
                                            f"{module_class}; run a forward and backward pass first")
-                    x = forward.detach()     # any dense layout: the binding picks the NCHW or the
-                    g = backward.detach()    # channels-last kernel (and copies only if neither applies)
-                    if layer not in self.state:
-                        self.state[layer] = self._views[layer]
-                    first, second = self.state[layer]
-                    has_bias = layer.bias is not None
-                    n_g = g.size(0)
-                    if module_class == 'Conv2d':
-                        N, _, H, W = x.shape
-                        kh, kw = _pair(layer.kernel_size)
-                        sh, sw = _pair(layer.stride)
-                        ph, pw = _pair(layer.padding)
-                        r_x = N * ((H + 2 * ph - kh) // sh + 1) * ((W + 2 * pw - kw) // sw + 1)
-                        item = nat.nhwc_item(x, (kh, kw), (sh, sw), (ph, pw), has_bias, 1.0 / r_x, first, self.precision)
-                        if item is not None:
-                            batch.append(item)
-                        else:
-                            nat.syrk_conv_accum(x, (kh, kw), (sh, sw), (ph, pw), has_bias, 1.0 / r_x, first,
-                                                self.precision, join=False)
-                        r_g = n_g * g.shape[2] * g.shape[3]
-                    else:
-                        if x.dim() != 2:
-                            raise NotImplementedError("KFAC supports 2-D Linear inputs only (as the reference)")
-                        item = nat.nhwc_item(x, None, None, None, has_bias, 1.0 / x.size(0), first, self.precision,
-                                             zero_mean=False)
-                        if item is not None:
-                            batch.append(item)
-                        else:
-                            nat.syrk_rows_accum(x, has_bias, 1.0 / x.size(0), first, self.precision, join=False)
-                        r_g = n_g
-                    # reference: (g * N)(g * N)^T / R  ==  g g^T * N^2 / R
-                    alpha_g = float(n_g) * float(n_g) / float(r_g)
-                    item = nat.nhwc_item(g, None, None, None, False, alpha_g, second, self.precision)
-                    if item is not None:
-                        batch.append(item)
-                    else:
-                        nat.syrk_rows_accum(g, False, alpha_g, second, self.precision, join=False)
-                elif module_class == 'MultiheadAttention':
+                    recorded.append((layer, forward.detach(), backward.detach()))   # any dense layout: the binding picks
+                elif module_class == 'MultiheadAttention':                          # the kernel (and copies only if none applies)
                     raise NotImplementedError
+        sig = (self.precision,) + tuple((x.shape, x.stride(), x.dtype, x.data_ptr() & 15, g.shape, g.stride(), g.dtype,
+                                         g.data_ptr() & 15) for _, x, g in recorded)
+        plan = self.__dict__.get('_update_plan')
+        if plan is None or plan['sig'] != sig:
+            plan = self._plan_update(recorded, sig)
+            self._update_plan = plan
+        arr = plan['arr']
+        for slot, li, which in plan['slots']:                  # refresh the operand pointers of the batch items
+            arr[slot].x = recorded[li][1 + which].data_ptr()
         try:
-            if batch:
+            for li, which, args in plan['fallback']:           # operands the channels-last kernel cannot take
+                t = recorded[li][1 + which]
+                if args[0] == 'conv':
+                    nat.syrk_conv_accum(t, *args[1:], join=False)
+                else:
+                    nat.syrk_rows_accum(t, *args[1:], join=False)
+            if plan['n']:
                 # every recorded tensor is complete on the current stream: between this fork and the join below the
                 # library runs pre-passes, contractions and reductions on its own prioritised streams
                 nat.stream_fork(device)
-                nat.syrk_batch_nhwc(batch, self.precision, device, join=False)
+                nat.syrk_batch_arr(arr, plan['n'], plan['ws_bytes'], self.precision, device, join=False)
         finally:
             # the split reductions run on the library's side stream: order the caller's stream after them (also when
             # a launch failed: the fork must not stay open)
             if device is not None:
                 nat.stream_join(device)
+
+    def _plan_update(self, recorded, sig):
+        """Which factor goes where (see `update`): the crv_syrk_item array of the batch call, the (slot, layer, operand)
+        triples whose pointer must be refreshed every step, and the per-factor calls for everything else."""
+        items, slots, fallback = [], [], []
+        for li, (layer, x, g) in enumerate(recorded):
+            if layer not in self.state:
+                self.state[layer] = self._views[layer]
+            first, second = self.state[layer]
+            has_bias = layer.bias is not None
+            n_g = g.size(0)
+            if layer.__class__.__name__ == 'Conv2d':
+                N, _, H, W = x.shape
+                kh, kw = _pair(layer.kernel_size)
+                sh, sw = _pair(layer.stride)
+                ph, pw = _pair(layer.padding)
+                r_x = N * ((H + 2 * ph - kh) // sh + 1) * ((W + 2 * pw - kw) // sw + 1)
+                item = nat.nhwc_item(x, (kh, kw), (sh, sw), (ph, pw), has_bias, 1.0 / r_x, first, self.precision)
+                if item is None:
+                    fallback.append((li, 0, ('conv', (kh, kw), (sh, sw), (ph, pw), has_bias, 1.0 / r_x, first, self.precision)))
+                r_g = n_g * g.shape[2] * g.shape[3]
+            else:
+                if x.dim() != 2:
+                    raise NotImplementedError("KFAC supports 2-D Linear inputs only (as the reference)")
+                item = nat.nhwc_item(x, None, None, None, has_bias, 1.0 / x.size(0), first, self.precision, zero_mean=False)
+                if item is None:
+                    fallback.append((li, 0, ('rows', has_bias, 1.0 / x.size(0), first, self.precision)))
+                r_g = n_g
+            if item is not None:
+                slots.append((len(items), li, 0))
+                items.append(item)
+            # reference: (g * N)(g * N)^T / R  ==  g g^T * N^2 / R
+            alpha_g = float(n_g) * float(n_g) / float(r_g)
+            item = nat.nhwc_item(g, None, None, None, False, alpha_g, second, self.precision)
+            if item is not None:
+                slots.append((len(items), li, 1))
+                items.append(item)
+            else:
+                fallback.append((li, 1, ('rows', False, alpha_g, second, self.precision)))
+        arr, ws_bytes = nat.syrk_item_array(items, self.precision)
+        return {'sig': sig, 'arr': arr, 'n': len(items), 'ws_bytes': ws_bytes, 'slots': slots, 'fallback': fallback}
 
     def invert(self,
                add: Union[float, list, tuple] = 0.,
@@ -541,6 +564,73 @@ class KFAC(Curvature):
         tier, first, second, z = self._gemm_operands(layer, first, second, z, noise is not None)
         nat.sample_matrix_normal(second, first, z, False, s_out=out, precision=tier)
         return out
+
+    def sample_and_replace(self, noise: Optional[Dict] = None):
+        """As `Curvature.sample_and_replace` (reference: curvatures.py:117-129).  Without supplied noise the whole call
+        is prebuilt once per `invert`: one persistent noise buffer (drawn and rounded in place), one C-ABI item array for
+        the batched two-GEMM draw of all layers, the multi-tensor copies that restore every other parameter and buffer
+        to its mean -- a posterior sample then costs four launches and no per-layer Python."""
+        if noise is not None:
+            return super().sample_and_replace(noise)
+        assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
+        tier = _gemm_tier(self.precision)
+        key = (id(self.__dict__.get('_inv_arena')), tier, tuple(p.data_ptr() for p in self.model.parameters()))
+        plan = self.__dict__.get('_sample_plan')
+        if plan is None or plan['key'] != key:
+            plan = self._plan_sample(tier, key)
+            self._sample_plan = plan
+        flat = plan['noise']
+        flat.normal_()                               # same distribution as the reference's per-layer randn (:391)
+        if tier != nat.PREC_FP32:
+            nat.round_tf32(flat, out=flat)
+        nat.run_sample_batch(plan['arr'], plan['n'], plan['ws_bytes'], tier, flat)
+        with torch.no_grad():
+            for weight, dense_w in plan['copies']:
+                weight.data.copy_(dense_w)
+            for dsts, srcs in plan['rest']:          # everything else: restore the mean, as load_state_dict would
+                torch._foreach_copy_(dsts, srcs)
+
+    def _plan_sample(self, tier, key):
+        names = self._param_names()
+        current = self.model.state_dict(keep_vars=True)
+        offs, total = {}, 0
+        for layer, (first, second) in self.inv_state.items():
+            offs[layer] = total
+            total += (first.size(0) * second.size(0) + 3) // 4 * 4
+        like = next(iter(self.inv_state.values()))[0]
+        flat = torch.empty(total, device=like.device, dtype=like.dtype)
+        entries, copies, written = [], [], set()
+        for name, layer in self._selected():
+            if name not in ['Linear', 'Conv2d']:
+                continue
+            weight, bias = layer.weight, layer.bias
+            first, second = self.inv_state[layer]
+            K, M = first.size(0), second.size(0)
+            z = flat[offs[layer]:offs[layer] + K * M].view(K, M)
+            _, la, lg, _ = self._gemm_operands(layer, first, second, None, True)
+            mean_w = self.model_state[names[id(weight)]]
+            mean_b = self.model_state[names[id(bias)]] if bias is not None else None
+            if weight.is_contiguous():
+                w_out = weight.data
+            else:                      # e.g. a channels-last convolution weight: sample into a dense buffer, copy_ applies
+                w_out = torch.empty(weight.shape, dtype=weight.dtype, device=weight.device)      # the parameter's strides
+                mean_w = mean_w.contiguous()
+                copies.append((weight, w_out))
+            entries.append(dict(LG=lg, LA=la, z=z, has_bias=bias is not None, mu_w=mean_w, mu_b=mean_b, w_out=w_out,
+                                b_out=None if bias is None else bias.data))
+            written.add(names[id(weight)])
+            if bias is not None:
+                written.add(names[id(bias)])
+        by_type = {}
+        for k, v in current.items():
+            if k not in written:
+                src = self.model_state[k]
+                by_type.setdefault((v.dtype, src.dtype), ([], []))
+                by_type[(v.dtype, src.dtype)][0].append(v.data)
+                by_type[(v.dtype, src.dtype)][1].append(src)
+        arr, ws_bytes = nat.prepare_sample_batch(entries)
+        return {'key': key, 'noise': flat, 'arr': arr, 'n': len(entries), 'ws_bytes': ws_bytes, 'copies': copies,
+                'rest': list(by_type.values()), 'keep': entries}
 
     def sample_many(self,
                     samples: int,
@@ -652,29 +742,63 @@ class EFB(Curvature):
     def update(self,
                batch_size: int):
         self._ensure_arena()
-        entries, work = [], []
+        tier = _gemm_tier(self.precision)
+        plan = self.__dict__.get('_update_plan')
+        if plan is None or plan['tier'] != tier:
+            plan = self._plan_update(tier)
+            self._update_plan = plan
+        # per step only the gradient pointers change: refresh them in the prebuilt C-ABI item arrays
+        keep = []
+        darr = plan['diag']
+        for i, (weight, bias) in enumerate(plan['params']):
+            wg = _grad_of(weight, 'weight')
+            if not (wg.is_cuda and wg.dtype == torch.float32):
+                nat._dev(wg, 'weight.grad')
+            darr[i].wgrad = wg.data_ptr()
+            keep.append(wg)
+            if bias is not None:
+                bg = _grad_of(bias, 'bias')
+                if not (bg.is_cuda and bg.dtype == torch.float32):
+                    nat._dev(bg, 'bias.grad')
+                darr[i].bgrad = bg.data_ptr()
+                keep.append(bg)
+        # diags += batch_size * g^2 and the concatenated gradient copies, one launch for the whole model
+        nat.run_diag_batch(darr, len(plan['params']), batch_size, plan['grads'])
+        if tier != nat.PREC_FP32:      # the gradient copies live in one flat buffer: one rounding launch for all layers
+            nat.round_tf32(plan['grads'], out=plan['grads'])
+        # lambdas += (QG^T g QA)^2 for every layer: one C-ABI call (crv_efb_project_batch)
+        nat.run_efb_batch(plan['efb'], len(plan['params']), plan['ws_bytes'], tier, plan['grads'])
+
+    def _plan_update(self, tier):
+        layers = []
         for name, layer in self._selected():
             if name in ['Linear', 'Conv2d']:
-                wg = _grad_of(layer.weight, 'weight')
-                bg = _grad_of(layer.bias, 'bias') if layer.bias is not None else None
-                if layer not in self.state:
-                    self.state[layer], self.diags[layer] = self._views[layer]
-                grads = torch.empty_like(self.state[layer])
-                entries.append((wg, bg, self.diags[layer], grads))
-                work.append((layer, grads))
+                layers.append(layer)
             elif name == 'MultiheadAttention':
                 raise NotImplementedError
-        # diags += batch_size * g^2 and the concatenated gradient copies, one launch for the whole model
-        nat.diag_accum_batch(entries, batch_size)
-        tier = _gemm_tier(self.precision)
-        batch = []
-        for layer, grads in work:
+        sizes = []
+        for layer in layers:
+            if layer not in self.state:
+                self.state[layer], self.diags[layer] = self._views[layer]
+            sizes.append((self.state[layer].numel() + 63) // 64 * 64)
+        dev = self.state[layers[0]].device
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)       # gradient copies [wgrad | bgrad] of all layers
+        diag_entries, efb_entries, params, off = [], [], [], 0
+        for layer, sz in zip(layers, sizes):
+            lam = self.state[layer]
+            grads = flat[off:off + lam.numel()].view_as(lam)
+            off += sz
             qa, qg = self.eigvecs[layer]
-            if tier != nat.PREC_FP32:      # eigenbases rounded to TF32 once (the gradient copies: in place, by the call)
+            if tier != nat.PREC_FP32:      # eigenbases rounded to TF32 once
                 qa, qg = _rounded(self.__dict__.setdefault('_eig_tf32', {}), layer, (qa, qg))
-            batch.append((qg, qa, grads, self.state[layer]))
-        # lambdas += (QG^T g QA)^2 for every layer: one C-ABI call (crv_efb_project_batch)
-        nat.efb_project_batch(batch, tier, round_g=tier != nat.PREC_FP32)
+            diag_entries.append((flat[:layer.weight.numel()].view(layer.weight.shape[0], -1), flat[:lam.shape[0]] if layer.bias is not None
+                                 else None, self.diags[layer], grads))
+            efb_entries.append((qg, qa, grads, lam))
+            params.append((layer.weight, layer.bias))
+        darr = nat.prepare_diag_batch(diag_entries)       # (gradient pointers are placeholders: refreshed every step)
+        earr, ws_bytes = nat.prepare_efb_batch(efb_entries, round_g=False)
+        return {'tier': tier, 'diag': darr, 'efb': earr, 'ws_bytes': ws_bytes, 'params': params, 'grads': flat,
+                'keep': (diag_entries, efb_entries)}
 
     def invert(self,
                add: Union[float, list, tuple] = 0.,
