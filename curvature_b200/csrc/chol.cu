@@ -11,7 +11,7 @@
 //
 // Blocked right-looking factorisation with 32-wide panels (diagonal blocks factored and inverted
 // in fp64 in shared memory, panel solves and trailing updates in fp32 FMA), followed by a
-// column-parallel blocked triangular inversion.  All matrices of a call advance together:
+// triangular inversion by recursive doubling (log-depth, all GEMM tiles).  All matrices of a call advance together:
 // gridDim.z indexes the matrix, CTAs of finished / smaller matrices exit at once.
 #include "common.cuh"
 #include <math.h>
@@ -172,57 +172,87 @@ __global__ void __launch_bounds__(256) chol_update_kernel(const MatDesc* __restr
   }
 }
 
-// ---- triangular inverse X = C^{-1}: one CTA per 16-column strip, forward over block rows ------
-constexpr int CW = 16;
-__global__ void __launch_bounds__(256) chol_trtri_kernel(const MatDesc* __restrict__ descs) {
+// ---- triangular inverse X = C^{-1} by recursive doubling ------------------------------------------
+// For a lower-triangular C = [[C11, 0], [C21, C22]]:  C^{-1} = [[X11, 0], [-X22 C21 X11, X22]].  Level 0 are the 32 x 32
+// diagonal blocks (inverted in fp64 by the factorisation, Dinv); level l merges neighbouring inverted blocks of size
+// b = 32 * 2^(l-1) with two GEMMs per pair -- T = C21 X11, then X21 = -X22 T -- and ALL pairs of all matrices of the call
+// are tiles of the same two launches: log2(D / 32) levels (8 for D = 4608) of fully parallel fp32 GEMM tiles instead of a
+// sequential sweep over block rows per column strip (which took 60 % of the whole invert).  The zero upper triangles of
+// X11 / X22 are skipped tile-wise (k range) and masked element-wise inside the diagonal tiles; T lives in the output
+// matrix L, which is only written by the epilogue.
+__global__ void __launch_bounds__(256) chol_trtri_init_kernel(const MatDesc* __restrict__ descs) {
   const MatDesc d = descs[blockIdx.z];
-  const int c0 = blockIdx.x * CW;
-  if (c0 >= d.D) return;
-  __shared__ float Cb[NB][NB + 1];
-  __shared__ float Xb[NB][CW + 1];
-  __shared__ float Tb[NB][CW + 1];
-  const int t = threadIdx.x;
-  const int ib0 = c0 / NB;
-  // each thread owns two accumulators of the (32 x 16) strip block: (r, c) and (r + 16, c)
-  const int r1 = t / CW, cc = t % CW;   // r1 in 0..15
-  for (int i = ib0; i < d.nb; ++i) {
-    float acc0 = 0.f, acc1 = 0.f;
-    for (int k = ib0; k < i; ++k) {
-      for (int e = t; e < NB * NB; e += 256) {
-        const int r = e / NB, c = e % NB;
-        Cb[r][c] = (i * NB + r < d.D && k * NB + c < d.D) ? d.W[(size_t)(i * NB + r) * d.D + k * NB + c] : 0.f;
-      }
-      for (int e = t; e < NB * CW; e += 256) {
-        const int r = e / CW, c = e % CW;
-        Xb[r][c] = (k * NB + r < d.D && c0 + c < d.D) ? d.X[(size_t)(k * NB + r) * d.D + c0 + c] : 0.f;
-      }
-      __syncthreads();
-#pragma unroll 8
-      for (int q = 0; q < NB; ++q) {
-        const float xv = Xb[q][cc];
-        acc0 = fmaf(Cb[r1][q], xv, acc0);
-        acc1 = fmaf(Cb[r1 + 16][q], xv, acc1);
-      }
-      __syncthreads();
+  const int i = blockIdx.x;
+  if (i >= d.nb) return;
+  for (int e = threadIdx.x; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    if (i * NB + r < d.D && i * NB + c < d.D) d.X[(size_t)(i * NB + r) * d.D + i * NB + c] = d.Dinv[(size_t)i * NB * NB + e];
+  }
+}
+
+// phase 0: T[bot, top] = C[bot, top] * X[top, top];  phase 1: X[bot, top] = -X[bot, bot] * T[bot, top]
+__global__ void __launch_bounds__(256) chol_trtri_merge_kernel(const MatDesc* __restrict__ descs, int b, int phase) {
+  const MatDesc d = descs[blockIdx.z];
+  const int tpp = max(1, b / 64);                      // 64-wide tiles per block edge
+  const int pair = blockIdx.x / (tpp * tpp);
+  const int tr = (blockIdx.x / tpp) % tpp, tc = blockIdx.x % tpp;
+  const int r0 = pair * 2 * b;                         // top block = [r0, r0 + b), bottom = [r0 + b, r0 + b + b2)
+  if (r0 + b >= d.D) return;
+  const int b2 = min(b, d.D - r0 - b);
+  const int rb = tr * 64, cb = tc * 64;                // tile origin inside the (b2 x b) output block
+  if (rb >= b2 || cb >= b) return;
+  __shared__ __align__(16) float As[16][68];           // As[k][row]
+  __shared__ __align__(16) float Bs[16][68];           // Bs[k][col]
+  const float* __restrict__ Am; const float* __restrict__ Bm; float* __restrict__ Om;
+  int a_r0, a_c0, b_r0, b_c0, klo, khi;
+  if (phase == 0) {        // A = C[bot][top], B = X[top][top] (lower triangular: rows k >= column)
+    Am = d.W; a_r0 = r0 + b; a_c0 = r0; Bm = d.X; b_r0 = r0; b_c0 = r0; Om = d.L;
+    klo = cb & ~15; khi = b;
+  } else {                 // A = X[bot][bot] (lower triangular: columns k <= row), B = T[bot][top]
+    Am = d.X; a_r0 = r0 + b; a_c0 = r0 + b; Bm = d.L; b_r0 = r0 + b; b_c0 = r0; Om = d.X;
+    klo = 0; khi = min(b2, rb + 64);
+  }
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  float acc[4][4] = {};
+  for (int k0 = klo; k0 < khi; k0 += 16) {
+    for (int e = t; e < 64 * 16; e += 256) {
+      const int kk = e & 15, rr = e >> 4;              // lanes along k: 64-byte runs of a row of A
+      const int gr = rb + rr, gk = k0 + kk;
+      float v = 0.f;
+      if (gr < b2 && gk < khi && !(phase == 1 && gk > gr)) v = Am[(size_t)(a_r0 + gr) * d.D + a_c0 + gk];
+      As[kk][rr] = v;
     }
-    // T = E_i - acc, then X_i = inv(C_ii) * T
-    Tb[r1][cc] = ((i * NB + r1) == (c0 + cc) ? 1.f : 0.f) - acc0;
-    Tb[r1 + 16][cc] = ((i * NB + r1 + 16) == (c0 + cc) ? 1.f : 0.f) - acc1;
-    for (int e = t; e < NB * NB; e += 256) Cb[e / NB][e % NB] = d.Dinv[(size_t)i * NB * NB + e];
+    for (int e = t; e < 64 * 16; e += 256) {
+      const int cc = e & 63, kk = e >> 6;              // lanes along the columns: contiguous rows of B
+      const int gc = cb + cc, gk = k0 + kk;
+      float v = 0.f;
+      if (gc < b && gk < khi && !(phase == 0 && gk < gc)) v = Bm[(size_t)(b_r0 + gk) * d.D + b_c0 + gc];
+      Bs[kk][cc] = v;
+    }
     __syncthreads();
-    float x0 = 0.f, x1 = 0.f;
-#pragma unroll 8
-    for (int q = 0; q < NB; ++q) {
-      const float tv = Tb[q][cc];
-      x0 = fmaf(Cb[r1][q], tv, x0);
-      x1 = fmaf(Cb[r1 + 16][q], tv, x1);
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
     }
-    if (c0 + cc < d.D) {
-      if (i * NB + r1 < d.D) d.X[(size_t)(i * NB + r1) * d.D + c0 + cc] = x0;
-      if (i * NB + r1 + 16 < d.D) d.X[(size_t)(i * NB + r1 + 16) * d.D + c0 + cc] = x1;
-    }
-    __threadfence_block();
     __syncthreads();
+  }
+  const float sign = phase == 0 ? 1.f : -1.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gr = rb + ty * 4 + i;
+    if (gr >= b2) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gc = cb + tx * 4 + j;
+      if (gc < b) Om[(size_t)(r0 + b + gr) * d.D + r0 + gc] = sign * acc[i][j];
+    }
   }
 }
 
@@ -299,7 +329,14 @@ int chol_inv_batched_launch(const float* const* F, const int* dims, int count, c
       chol_update_kernel<<<dim3(nt * (nt + 1) / 2, 1, count), 256, 0, s>>>(descs, j);
     }
   }
-  chol_trtri_kernel<<<dim3((maxD + CW - 1) / CW, 1, count), 256, 0, s>>>(descs);
+  chol_trtri_init_kernel<<<dim3(nbmax, 1, count), 256, 0, s>>>(descs);
+  for (int b = NB; b < maxD; b *= 2) {
+    const int tpp = b / 64 > 1 ? b / 64 : 1;
+    const int pairs = (maxD + 2 * b - 1) / (2 * b);
+    const dim3 grid((unsigned)(pairs * tpp * tpp), 1, count);
+    chol_trtri_merge_kernel<<<grid, 256, 0, s>>>(descs, b, 0);
+    chol_trtri_merge_kernel<<<grid, 256, 0, s>>>(descs, b, 1);
+  }
   chol_epilogue_kernel<<<dim3(ew, 1, count), 256, 0, s>>>(descs);
   CRV_CUDA(cudaGetLastError());
   return 0;

@@ -76,7 +76,8 @@ def test_inf_rank100_on_resnet18():
             o_qa, o_qg, o_lam = orc.INF._dim_reduction(QA, QG, lam_full, 100)
             assert torch.equal(o_qa.float(), qa.cpu()) and torch.equal(o_qg.float(), qg.cpu())       # same index selection
             assert rel_fro(lam, o_lam) <= 1e-6
-            o_corr = diag_vec - orc.INF._diagonal_accumulator(o_qa, o_qg, o_lam)
+            # (`invert` has already clamped the correction at 0 in place, like the reference, curvatures.py:523)
+            o_corr = (diag_vec - orc.INF._diagonal_accumulator(o_qa, o_qg, o_lam)).clamp_min(0)
             assert (corr.double().cpu() - o_corr).norm() <= 1e-5 * diag_vec.norm(), (li, "correction")
             o_corr = corr.double().cpu().clamp_min(0)                 # isolate invert / sample from that difference
             ric = torch.reciprocal(s_d * o_corr + n_d).sqrt()
