@@ -9,12 +9,14 @@
 // (C^{-T} alone -- the obvious "invert the Cholesky factor" -- is an upper factor of the same
 // covariance and gives different samples for the same noise)
 //
-// Blocked right-looking factorisation with 32-wide panels (diagonal blocks factored and inverted
-// in fp64 in shared memory, panel solves and trailing updates in fp32 FMA), followed by a
-// triangular inversion by recursive doubling (log-depth, all GEMM tiles).  All matrices of a call advance together:
+// Blocked right-looking factorisation, two levels: 32-wide inner panels (diagonal blocks factored and inverted in fp64
+// in shared memory by one warp, panel solve in the same launch, rank-32 fp32 updates confined to the 128-wide outer panel)
+// and one rank-128 fp32 update of the trailing matrix per outer panel; followed by a triangular inversion by recursive
+// doubling (log-depth, all GEMM tiles).  All matrices of a call advance together:
 // gridDim.z indexes the matrix, CTAs of finished / smaller matrices exit at once.
 #include "common.cuh"
 #include <math.h>
+#include <algorithm>
 
 namespace crv {
 namespace {
@@ -46,119 +48,120 @@ __global__ void __launch_bounds__(256) chol_prologue_kernel(const MatDesc* __res
   }
 }
 
-// ---- step 1: factor + invert the diagonal block of panel j (fp64 in smem) ----------------------
-__global__ void __launch_bounds__(256) chol_potf2_kernel(const MatDesc* __restrict__ descs, int j, int* info) {
-  const MatDesc d = descs[blockIdx.x];
+// ---- step 1 + 2: factor + invert the diagonal block of panel j, and solve the panel below it -------------------
+// One launch per 32-wide panel: CTA 0 owns the diagonal block (writes its inverse to Dinv and the failure flag), CTA
+// ib - j > 0 owns the 32-row block ib below it.  EVERY CTA factors the (same, read-only) diagonal block itself -- a
+// single warp, one lane per row, fp64 in shared memory, ~10 us -- instead of waiting for a separate launch to publish
+// it: the redundant work is nothing, the launch and the dependency it removes are a third of the critical path.  The
+// factored diagonal block itself is never written back: nothing reads it again (the triangular inversion starts from
+// Dinv, the updates read only rows below the block).
+__global__ void __launch_bounds__(128) chol_panel_kernel(const MatDesc* __restrict__ descs, int j, int* info) {
+  const MatDesc d = descs[blockIdx.z];
   if (j >= d.nb) return;
+  const int ib = j + blockIdx.x;
+  if (ib >= d.nb) return;
   __shared__ double S[NB][NB + 1];
   __shared__ double Iv[NB][NB + 1];
-  __shared__ int bad;
+  __shared__ float Ab[NB][NB + 1];
   const int o = j * NB;
   const int bs = min(NB, d.D - o);
-  const int t = threadIdx.x;
-  if (t == 0) bad = 0;
-  for (int e = t; e < NB * NB; e += 256) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int e = t; e < NB * NB; e += 128) {
     const int r = e / NB, c = e % NB;
     double v = 0.0;
     if (r < bs && c < bs && c <= r) v = (double)d.W[(size_t)(o + r) * d.D + o + c];
     if (r >= bs && r == c) v = 1.0;   // pad to a full 32x32 block with the identity
     S[r][c] = v;
+    if (ib > j) {
+      const int ro = ib * NB;
+      Ab[r][c] = (ro + r < d.D && o + c < d.D) ? d.W[(size_t)(ro + r) * d.D + o + c] : 0.f;
+    }
   }
   __syncthreads();
-  for (int c = 0; c < NB; ++c) {
-    if (t == 0) {
+  if (warp == 0) {
+    // right-looking Cholesky of the 32 x 32 block, lane = row
+    int bad = 0;
+    for (int c = 0; c < NB; ++c) {
       const double p = S[c][c];
-      if (!(p > 0.0)) { if (!bad) bad = o + c + 1; }
-      S[c][c] = sqrt(p);
+      if (!(p > 0.0) && !bad) bad = o + c + 1;
+      const double piv = sqrt(p);
+      __syncwarp();
+      if (lane == c) S[c][c] = piv;
+      if (lane > c) S[lane][c] /= piv;
+      __syncwarp();
+      if (lane > c) {
+        const double l = S[lane][c];
+        for (int cc = c + 1; cc <= lane; ++cc) S[lane][cc] -= l * S[cc][c];
+      }
+      __syncwarp();
     }
-    __syncthreads();
-    const double piv = S[c][c];
-    if (t > c && t < NB) S[t][c] /= piv;
-    __syncthreads();
-    // trailing update of the block: rows r > c, columns c < cc <= r
-    for (int e = t; e < NB * NB; e += 256) {
-      const int r = e / NB, cc = e % NB;
-      if (r > c && cc > c && cc <= r) S[r][cc] -= S[r][c] * S[cc][c];
+    // inverse of the lower-triangular block, lane = column (forward substitution)
+    {
+      const int c = lane;
+      for (int r = 0; r < NB; ++r) {
+        if (r < c) { Iv[r][c] = 0.0; continue; }
+        double acc = (r == c) ? 1.0 : 0.0;
+        for (int k = c; k < r; ++k) acc -= S[r][k] * Iv[k][c];
+        Iv[r][c] = acc / S[r][r];
+      }
     }
-    __syncthreads();
-  }
-  // inverse of the lower-triangular block, one column per thread (forward substitution)
-  if (t < NB) {
-    const int c = t;
-    for (int r = 0; r < NB; ++r) {
-      double acc = (r == c) ? 1.0 : 0.0;
-      if (r < c) { Iv[r][c] = 0.0; continue; }
-      for (int k = c; k < r; ++k) acc -= S[r][k] * Iv[k][c];
-      Iv[r][c] = acc / S[r][r];
-    }
+    if (ib == j && lane == 0 && bad && info[blockIdx.z] == 0) info[blockIdx.z] = bad;
   }
   __syncthreads();
-  for (int e = t; e < NB * NB; e += 256) {
-    const int r = e / NB, c = e % NB;
-    if (r < bs && c < bs) d.W[(size_t)(o + r) * d.D + o + c] = (c <= r) ? (float)S[r][c] : 0.f;
-    d.Dinv[(size_t)j * NB * NB + e] = (float)Iv[r][c];
+  if (ib == j) {
+    for (int e = t; e < NB * NB; e += 128) d.Dinv[(size_t)j * NB * NB + e] = (float)Iv[e / NB][e % NB];
+    return;
   }
-  if (t == 0 && bad && info[blockIdx.x] == 0) info[blockIdx.x] = bad;
-}
-
-// ---- step 2: panel solve  W[ib][j] <- W[ib][j] * inv(C_jj)^T  for ib > j -----------------------
-__global__ void __launch_bounds__(256) chol_trsm_kernel(const MatDesc* __restrict__ descs, int j) {
-  const MatDesc d = descs[blockIdx.z];
-  const int ib = j + 1 + blockIdx.x;
-  if (ib >= d.nb) return;
-  __shared__ float Ab[NB][NB + 1];
-  __shared__ float Iv[NB][NB + 1];
-  const int t = threadIdx.x;
-  const int ro = ib * NB, co = j * NB;
-  for (int e = t; e < NB * NB; e += 256) {
-    const int r = e / NB, c = e % NB;
-    Ab[r][c] = (ro + r < d.D && co + c < d.D) ? d.W[(size_t)(ro + r) * d.D + co + c] : 0.f;
-    Iv[r][c] = d.Dinv[(size_t)j * NB * NB + e];
-  }
-  __syncthreads();
-  for (int e = t; e < NB * NB; e += 256) {
+  // W[ib][j] <- W[ib][j] * inv(C_jj)^T
+  const int ro = ib * NB;
+  for (int e = t; e < NB * NB; e += 128) {
     const int r = e / NB, c = e % NB;
     float acc = 0.f;
 #pragma unroll 8
-    for (int k = 0; k < NB; ++k) acc = fmaf(Ab[r][k], Iv[c][k], acc);
-    if (ro + r < d.D && co + c < d.D) d.W[(size_t)(ro + r) * d.D + co + c] = acc;
+    for (int k = 0; k < NB; ++k) acc = fmaf(Ab[r][k], (float)Iv[c][k], acc);
+    if (ro + r < d.D && o + c < d.D) d.W[(size_t)(ro + r) * d.D + o + c] = acc;
   }
 }
 
-// ---- step 3: trailing update  W[I][K] -= C[I][j] * C[K][j]^T  on 64x64 tiles, I >= K -----------
-__global__ void __launch_bounds__(256) chol_update_kernel(const MatDesc* __restrict__ descs, int j) {
+// ---- step 3: symmetric rank-k update  W[r][c] -= sum_k W[r][kb + k] W[c][kb + k]  for cb <= c < ce, r >= c ----------
+// Two uses per 128-wide outer panel: after each 32-wide inner panel the columns still inside the outer panel get its
+// rank-32 update at once (the next inner panel needs them); everything beyond the outer panel gets ONE rank-128 update
+// when the outer panel is complete -- a quarter of the passes over the trailing matrix, four times the arithmetic per
+// byte.  64 x 64 tiles, lower triangle only (grid: row tile x column tile, relative to cb).
+__global__ void __launch_bounds__(256) chol_update_kernel(const MatDesc* __restrict__ descs, int kb, int klen, int cb, int ce) {
   const MatDesc d = descs[blockIdx.z];
-  const int start = (j + 1) * NB;          // first trailing row/col
-  if (start >= d.D) return;
-  const int nt = (d.D - start + 63) / 64;  // 64-wide tiles in the trailing matrix
-  const int p = blockIdx.x;
-  if (p >= nt * (nt + 1) / 2) return;
-  int ti = (int)((sqrtf(8.f * (float)p + 1.f) - 1.f) * 0.5f);
-  while (ti * (ti + 1) / 2 > p) --ti;
-  while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
-  const int tj = p - ti * (ti + 1) / 2;
+  if (cb >= d.D) return;
+  const int cend = min(ce, d.D);
+  const int ti = blockIdx.x, tj = blockIdx.y;
+  if (ti < tj) return;
+  const int r0 = cb + ti * 64, c0 = cb + tj * 64;
+  if (r0 >= d.D || c0 >= cend) return;
   __shared__ __align__(16) float Ps[NB][68];   // Ps[k][row]  panel rows of tile ti
   __shared__ __align__(16) float Qs[NB][68];   // Qs[k][row]  panel rows of tile tj
   const int t = threadIdx.x;
-  const int r0 = start + ti * 64, c0 = start + tj * 64, ko = j * NB;
-  for (int e = t; e < 64 * NB; e += 256) {
-    const int r = e / NB, k = e % NB;   // lanes along k: contiguous 128-byte panel rows
-    Ps[k][r] = (r0 + r < d.D) ? d.W[(size_t)(r0 + r) * d.D + ko + k] : 0.f;
-    Qs[k][r] = (c0 + r < d.D) ? d.W[(size_t)(c0 + r) * d.D + ko + k] : 0.f;
-  }
-  __syncthreads();
   const int ty = t >> 4, tx = t & 15;
   float acc[4][4] = {};
+  for (int k0 = 0; k0 < klen; k0 += NB) {
+    const int ko = kb + k0;
+    for (int e = t; e < 64 * NB; e += 256) {
+      const int r = e / NB, k = e % NB;   // lanes along k: contiguous 128-byte panel rows
+      const bool kv = k0 + k < klen && ko + k < d.D;
+      Ps[k][r] = (kv && r0 + r < d.D) ? d.W[(size_t)(r0 + r) * d.D + ko + k] : 0.f;
+      Qs[k][r] = (kv && c0 + r < d.D) ? d.W[(size_t)(c0 + r) * d.D + ko + k] : 0.f;
+    }
+    __syncthreads();
 #pragma unroll
-  for (int k = 0; k < NB; ++k) {
-    const float4 a4 = *reinterpret_cast<const float4*>(&Ps[k][ty * 4]);
-    const float4 b4 = *reinterpret_cast<const float4*>(&Qs[k][tx * 4]);
-    const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-    const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+    for (int k = 0; k < NB; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&Ps[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Qs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(a[i], b[jj], acc[i][jj]);
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(a[i], b[jj], acc[i][jj]);
+    }
+    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(256) chol_update_kernel(const MatDesc* __restr
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
       const int c = c0 + tx * 4 + jj;
-      if (c < d.D && c <= r) d.W[(size_t)r * d.D + c] -= acc[i][jj];
+      if (c < cend && c <= r) d.W[(size_t)r * d.D + c] -= acc[i][jj];
     }
   }
 }
@@ -320,13 +323,20 @@ int chol_inv_batched_launch(const float* const* F, const int* dims, int count, c
   const int nbmax = (maxD + NB - 1) / NB;
   const unsigned ew = (unsigned)min((size_t)1024, ((size_t)maxD * maxD + 255) / 256);
   chol_prologue_kernel<<<dim3(ew, 1, count), 256, 0, s>>>(descs);
-  for (int j = 0; j < nbmax; ++j) {
-    chol_potf2_kernel<<<count, 256, 0, s>>>(descs, j, info);
-    const int below = nbmax - j - 1;
-    if (below > 0) {
-      chol_trsm_kernel<<<dim3(below, 1, count), 256, 0, s>>>(descs, j);
-      const int nt = (maxD - (j + 1) * NB + 63) / 64;
-      chol_update_kernel<<<dim3(nt * (nt + 1) / 2, 1, count), 256, 0, s>>>(descs, j);
+  constexpr int NBO = 128;                               // outer panel: 4 inner panels of 32
+  for (int J = 0; J * NBO < maxD; ++J) {
+    const int oend = (J + 1) * NBO;
+    for (int j = J * (NBO / NB); j < (J + 1) * (NBO / NB) && j < nbmax; ++j) {
+      chol_panel_kernel<<<dim3(nbmax - j, 1, count), 128, 0, s>>>(descs, j, info);
+      const int cb = (j + 1) * NB;                       // columns of the outer panel that still need this inner panel's update
+      if (cb < oend && cb < maxD) {
+        const int ntr = (maxD - cb + 63) / 64, ntc = (std::min(oend, maxD) - cb + 63) / 64;
+        chol_update_kernel<<<dim3(ntr, ntc, count), 256, 0, s>>>(descs, j * NB, NB, cb, oend);
+      }
+    }
+    if (oend < maxD) {
+      const int nt = (maxD - oend + 63) / 64;
+      chol_update_kernel<<<dim3(nt, nt, count), 256, 0, s>>>(descs, J * NBO, NBO, oend, maxD);
     }
   }
   chol_trtri_init_kernel<<<dim3(nbmax, 1, count), 256, 0, s>>>(descs);
