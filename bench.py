@@ -654,7 +654,10 @@ def main():
         achieved = d["flops"] / (d["ms"] / 1e3) / 1e12
         traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            tr_path = os.path.join(ROOT, "profiles", "r2_traffic.json")        # ncu dram__bytes per launch, final code
+            if not os.path.exists(tr_path):
+                tr_path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+            tr = json.load(open(tr_path))
             traffic = tr.get(dom, {}).get("dram_bytes_per_launch")
         except Exception:
             pass

@@ -9,8 +9,11 @@ import csv
 import json
 
 CLASS_OF = (("syrk_nhwc_kernel<1>", "syrk_nhwc_bf16"), ("syrk_nhwc_kernel<0>", "syrk_nhwc_tf32"), ("syrk_tc_kernel", "syrk_staged_nchw"),
-            ("syrk_tc_tma_kernel", "syrk_staged_nchw"), ("syrk_tc_reduce_kernel", "syrk_split_reduce"), ("syrk_sk_reduce_kernel", "syrk_split_reduce"), ("cast_bf16_kernel", "cast_prepass"),
-            ("round_tf32_kernel", "cast_prepass"), ("syrk_simt_kernel", "syrk_simt_fp32"))
+            ("syrk_tc_tma_kernel", "syrk_staged_nchw"), ("syrk_tc_reduce_kernel", "syrk_split_reduce"), ("syrk_sk_reduce_kernel", "syrk_split_reduce"),
+            ("syrk_sk_reduce_taps_kernel", "syrk_split_reduce"), ("cast_bf16_kernel", "cast_prepass"),
+            ("round_tf32_kernel", "cast_prepass"), ("split_bf16_kernel", "cast_prepass"), ("nchw_to_nhwc_bf16_kernel", "cast_prepass"),
+            ("pack_smallc_kernel", "cast_prepass"), ("syrk_simt_kernel", "syrk_simt_fp32"), ("gemm_chain_kernel", "gemm_chain"),
+            ("gemm_tc_kernel", "gemm_tc"))
 
 
 def kclass(name):
