@@ -3,10 +3,10 @@ DLR-RM/curvature behind the reference's Python API.  Importing this package load
 library; it raises if the library has not been built (there is no fallback implementation)."""
 from . import _native
 from .curvatures import Curvature, Diagonal, KFAC, EFB, INF, FactorArena
-from .utils import get_eigenvectors, get_eigenvalues, kron
+from .utils import get_eigenvectors, get_eigenvalues, eigendecompose, kron
 from .parallel import allreduce_arena, shard_indices, invert_plan, allgather_segments
 from .io import save_factors, load_factors
 from .evaluate import eval_nn, eval_bnn
 
 __all__ = ["Curvature", "Diagonal", "KFAC", "EFB", "INF", "FactorArena", "get_eigenvectors", "get_eigenvalues",
-           "kron", "allreduce_arena", "shard_indices", "invert_plan", "allgather_segments", "save_factors", "load_factors", "eval_nn", "eval_bnn"]
+           "eigendecompose", "kron", "allreduce_arena", "shard_indices", "invert_plan", "allgather_segments", "save_factors", "load_factors", "eval_nn", "eval_bnn"]

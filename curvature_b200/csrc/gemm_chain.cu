@@ -290,30 +290,57 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
                          "r"(a[4 * k + 2]), "r"(a[4 * k + 3]) : "memory");
           }
           __syncwarp();
+          // Read the block back row-wise (lane -> row r4*4 + sub, 4 consecutive columns), then touch global memory in
+          // three batched phases -- all loads, all arithmetic, all stores -- so that a warp has 32 independent loads in
+          // flight instead of 32 dependent load-store round trips (the first version of this epilogue, `C += v*v` element
+          // by element, took longer than the MMAs of the tile: tensor pipe 17 % in profiles/r2_ncu_chain_before.md).
+          float v[8][4], old[8][4];
 #pragma unroll
           for (int r4 = 0; r4 < 8; ++r4) {
             const int r = r4 * 4 + sub;
-            float v[4];
             const uint32_t addr = stg + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) * 16);
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
-            const int gm = row0 + r;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[r4][0]), "=f"(v[r4][1]), "=f"(v[r4][2]), "=f"(v[r4][3])
+                         : "r"(addr) : "memory");
+          }
+          const int gn0 = sh.n0 + cc + ch * 4;
+          const int epi_kind = it.epi;
+          if (epi_kind != EPI_STORE) {
+#pragma unroll
+            for (int r4 = 0; r4 < 8; ++r4) {
+              const int gm = row0 + r4 * 4 + sub;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int gn = gn0 + j;
+                float o = 0.f;
+                if (gm < it.m && gn < it.n) {
+                  if (epi_kind == EPI_SQUARE_ACCUM) o = it.C[(size_t)gm * it.ldc + gn];
+                  else if (gn < it.se.K0) { if (it.se.w_out) o = __ldg(it.se.mu_w + (size_t)gm * it.se.K0 + gn); }
+                  else if (it.se.b_out) o = __ldg(it.se.mu_b + gm);
+                }
+                old[r4][j] = o;
+              }
+            }
+          }
+#pragma unroll
+          for (int r4 = 0; r4 < 8; ++r4) {
+            const int gm = row0 + r4 * 4 + sub;
             if (gm >= it.m) continue;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int gn = sh.n0 + cc + ch * 4 + j;
+              const int gn = gn0 + j;
               if (gn >= it.n) break;
-              if (it.epi == EPI_STORE) {
-                const float o = it.alpha * v[j];
+              if (epi_kind == EPI_STORE) {
+                const float o = it.alpha * v[r4][j];
                 it.C[(size_t)gm * it.ldc + gn] = it.round_out ? rna_tf32(o) : o;
-              } else if (it.epi == EPI_SQUARE_ACCUM) {
-                it.C[(size_t)gm * it.ldc + gn] += v[j] * v[j];
+              } else if (epi_kind == EPI_SQUARE_ACCUM) {
+                it.C[(size_t)gm * it.ldc + gn] = old[r4][j] + v[r4][j] * v[r4][j];
               } else {
-                const float sv = it.alpha * v[j];
+                const float sv = it.alpha * v[r4][j];
                 if (it.se.s_out) it.se.s_out[(size_t)gm * it.n + gn] = sv;
                 if (gn < it.se.K0) {
-                  if (it.se.w_out) it.se.w_out[(size_t)gm * it.se.K0 + gn] = it.se.mu_w[(size_t)gm * it.se.K0 + gn] + sv;
+                  if (it.se.w_out) it.se.w_out[(size_t)gm * it.se.K0 + gn] = old[r4][j] + sv;
                 } else {
-                  if (it.se.b_out) it.se.b_out[gm] = it.se.mu_b[gm] + sv;
+                  if (it.se.b_out) it.se.b_out[gm] = old[r4][j] + sv;
                 }
               }
             }

@@ -20,15 +20,33 @@ def get_eigenvectors(factors: Dict[Module, Tensor]) -> Dict[Module, Tensor]:
     return eigenvectors
 
 
+def eigendecompose(factors: Dict[Module, Tensor]):
+    """ONE eigensolve per factor for both consumers of the one-shot eigenbases: returns
+    `(eigvecs, eigvals)` with `eigvecs[layer] = (QA, QG)` exactly as `get_eigenvectors` (eigenvectors of `F + F^T`,
+    utils.py:45-60) and `eigvals[layer] = (wA, wG)` the spectra of `F` itself (what `get_eigenvalues`, utils.py:21-42,
+    computes with a second `symeig`): for the symmetric factors this path produces, `eig(F) = eig(F + F^T) / 2`."""
+    eigvecs, eigvals = dict(), dict()
+    for layer, (xxt, ggt) in factors.items():
+        wa, qa = torch.linalg.eigh(xxt + xxt.t(), UPLO='U')
+        wg, qg = torch.linalg.eigh(ggt + ggt.t(), UPLO='U')
+        eigvecs[layer] = (qa.contiguous(), qg.contiguous())
+        eigvals[layer] = (wa / 2, wg / 2)
+    return eigvecs, eigvals
+
+
 def get_eigenvalues(factors: List[Tensor],
-                    verbose: bool = False) -> Tensor:
+                    verbose: bool = False,
+                    eigvals: List = None) -> Tensor:
     """Eigenvalues of KFAC, EFB or diagonal factors (reference: utils.py:21-42): for a pair of Kronecker factors
-    the outer product of their spectra, otherwise the factor flattened."""
+    the outer product of their spectra, otherwise the factor flattened.  `eigvals` optionally supplies the spectra
+    already computed by `eigendecompose` (one per entry of `factors`, in order): no second eigensolve."""
     chunks = []
     for layer, factor in enumerate(factors):
         if verbose:
             print(f"Layer [{layer + 1}/{len(factors)}]")
-        if len(factor) == 2:
+        if len(factor) == 2 and eigvals is not None:
+            chunks.append(torch.outer(eigvals[layer][0], eigvals[layer][1]).contiguous().view(-1))
+        elif len(factor) == 2:
             xxt_eigvals = torch.linalg.eigvalsh(factor[0], UPLO='U')
             ggt_eigvals = torch.linalg.eigvalsh(factor[1], UPLO='U')
             chunks.append(torch.outer(xxt_eigvals, ggt_eigvals).contiguous().view(-1))

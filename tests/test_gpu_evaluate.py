@@ -63,3 +63,29 @@ def test_sample_many_equals_single_draws_and_eval_bnn(prec):
     assert p2.shape == (24, 10) and np.array_equal(l2, labels)
     for h in kfac.hooks:
         h.remove()
+
+
+def test_eigen_spectrum_tooling_shares_the_one_shot_eigensolve():
+    """`get_eigenvalues` (utils.py:21-42) and `get_eigenvectors` (utils.py:45-60) on device factors
+    against the oracle; `eigendecompose` gives both from ONE eigh per factor."""
+    model = small_net()
+    kfac = cb.KFAC(model)
+    orc.fisher_step(model, torch.randn(16, 3, 8, 8, device=DEV))
+    kfac.update(16)
+    factors = list(kfac.state.values())
+    host = [[f.cpu() for f in fs] for fs in factors]
+    want = orc.eigenvalues_of_factors(host)
+    got = cb.get_eigenvalues(factors)
+    assert got.is_cuda and rel_fro(got, want) <= 1e-4
+    eigvecs, eigvals = cb.eigendecompose(kfac.state)
+    shared = cb.get_eigenvalues(factors, eigvals=list(eigvals.values()))
+    assert rel_fro(shared, want) <= 1e-4
+    for layer, (qa, qg) in eigvecs.items():
+        A, G = kfac.state[layer]
+        wa, wg = eigvals[layer]
+        assert rel_fro(qa @ torch.diag(wa) @ qa.t(), A) <= 1e-4 and rel_fro(qg @ torch.diag(wg) @ qg.t(), G) <= 1e-4
+    ref = cb.get_eigenvectors(kfac.state)
+    for layer in ref:                       # same subspaces (eigenvectors are defined up to sign / rotation)
+        assert rel_fro(ref[layer][0] @ ref[layer][0].t(), eigvecs[layer][0] @ eigvecs[layer][0].t()) <= 1e-4
+    for h in kfac.hooks:
+        h.remove()
