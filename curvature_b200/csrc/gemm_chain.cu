@@ -110,7 +110,7 @@ __device__ __forceinline__ TileShape tile_shape(const ChainItemDev& it, const Ch
 
 __global__ void __launch_bounds__(C_THREADS, 1)
 gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __restrict__ tiles, const int* __restrict__ cta_begin,
-                  const CUtensorMap* __restrict__ maps, int* __restrict__ counters) {
+                  const CUtensorMap* __restrict__ maps, int* __restrict__ counters, long long* __restrict__ dbg) {
   extern __shared__ uint8_t raw[];
   const uint32_t sbase = (s32(raw) + 1023u) & ~1023u;
   const uint32_t epi = sbase + C_NSTAGE * C_STAGE;
@@ -119,6 +119,7 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw + (sbase - s32(raw)) + C_NSTAGE * C_STAGE + C_EPI + 8 * (2 * C_NSTAGE + 2));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t_begin = cta_begin[blockIdx.x], t_end = cta_begin[blockIdx.x + 1];
+  const long long t_start = dbg ? clock64() : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C_NSTAGE; ++s) {
@@ -153,6 +154,7 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(ma)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(mb)) : "memory");
       }
+      long long t_dep0 = dbg ? clock64() : 0;
       if (it.dep_counters >= 0) {
         // rows [m0, m0 + 256) of the A operand are rows [m0 / div, (m0 + 255) / div] of the producer GEMM's output:
         // written by its row tiles lo .. hi (one tile when div = 1)
@@ -168,6 +170,7 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
         }
         asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy writes of the other CTAs -> this CTA's TMA reads
       }
+      if (dbg && me == 0 && lane == 0) dbg[8 * blockIdx.x + 0] += clock64() - t_dep0;
       // boxes of one stage: A then B; K-major 16 KB boxes of 128 rows, MN-major 4 KB boxes of 32 rows
       const int na = it.a_mn ? (sh.rows + 31) / 32 : sh.mh;
       const int nb = it.b_mn ? (sh.ncols + 31) / 32 : (sh.ncols + 127) / 128;
@@ -220,14 +223,18 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
       const bool two = uni((uint32_t)sh.mh) == 2u;
       const int u_nk = (int)uni((uint32_t)sh.nk);
       if (ntile > 0) {                                       // the previous tile's accumulator has been drained
+        const long long t0 = dbg ? clock64() : 0;
         bar_wait(bar_tempty, (uint32_t)(ntile - 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (dbg && lane == 0) dbg[8 * blockIdx.x + 1] += clock64() - t0;
       }
       uint32_t acc = 0;
       for (int kb = 0; kb < u_nk; ++kb, ++git) {
         const uint32_t s = git % C_NSTAGE, ph = (git / C_NSTAGE) & 1u;
+        const long long t0 = dbg ? clock64() : 0;
         bar_wait(bars + 8 * s, ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (dbg && lane == 0) dbg[8 * blockIdx.x + 2] += clock64() - t0;
         const uint32_t sa = sbase + s * C_STAGE, sb = sa + 32768u;
         const uint32_t a0 = a_lo | ((sa >> 4) & 0x3FFFu), a1 = a_lo | (((sa + 16384u) >> 4) & 0x3FFFu);
         const uint32_t b0 = b_lo | ((sb >> 4) & 0x3FFFu);
@@ -265,8 +272,16 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
       const ChainTile t = tiles[ti];
       const ChainItemDev& it = items[t.item];
       const TileShape sh = tile_shape(it, t);
+      // the item's fields live in global memory: fetch what the epilogue needs once per tile
+      const int e_m = it.m, e_n = it.n, e_ldc = it.ldc, e_kind = it.epi, e_round = it.round_out, e_K0 = it.se.K0;
+      const float e_alpha = it.alpha;
+      float* const e_C = it.C;
+      float* const e_wout = it.se.w_out; float* const e_bout = it.se.b_out; float* const e_sout = it.se.s_out;
+      const float* const e_muw = it.se.mu_w; const float* const e_mub = it.se.mu_b;
+      const long long t_e0 = dbg ? clock64() : 0;
       bar_wait(bar_tfull, (uint32_t)ntile & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const long long t_e1 = dbg ? clock64() : 0;
       for (int h = 0; h < sh.mh; ++h) {
         const int row0 = sh.m0 + h * 128 + quad * 32;
         for (int cc = 0; cc < sh.ncols; cc += 32) {
@@ -303,44 +318,66 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
                          : "r"(addr) : "memory");
           }
           const int gn0 = sh.n0 + cc + ch * 4;
-          const int epi_kind = it.epi;
-          if (epi_kind != EPI_STORE) {
+          if (gn0 < e_n) {
+            // destination / read-modify-write source of this lane's 4-column group: (pointer, leading dimension, number of
+            // valid columns); 16-byte vector accesses whenever rows are 16-byte aligned
+            float* dst; const float* src; int ld, nv;
+            if (e_kind == 2) {
+              if (gn0 < e_K0) { dst = e_wout; src = e_muw; ld = e_K0; nv = min(4, e_K0 - gn0); }
+              else { dst = nullptr; src = nullptr; ld = 0; nv = 0; }          // the bias column: handled below
+            } else {
+              dst = e_C; src = e_kind == EPI_SQUARE_ACCUM ? e_C : nullptr; ld = e_ldc; nv = min(4, e_n - gn0);
+            }
+            const bool vec = nv == 4 && (ld & 3) == 0 && dst != nullptr && (((uintptr_t)dst) & 15) == 0;
+            if (src != nullptr) {
+#pragma unroll
+              for (int r4 = 0; r4 < 8; ++r4) {
+                const int gm = row0 + r4 * 4 + sub;
+                old[r4][0] = old[r4][1] = old[r4][2] = old[r4][3] = 0.f;
+                if (gm < e_m) {
+                  const float* p = src + (size_t)gm * ld + gn0;
+                  if (vec) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(p);
+                    old[r4][0] = t4.x; old[r4][1] = t4.y; old[r4][2] = t4.z; old[r4][3] = t4.w;
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (j < nv) old[r4][j] = p[j];
+                  }
+                }
+              }
+            }
 #pragma unroll
             for (int r4 = 0; r4 < 8; ++r4) {
               const int gm = row0 + r4 * 4 + sub;
+              if (gm >= e_m) continue;
+              float o[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const int gn = gn0 + j;
-                float o = 0.f;
-                if (gm < it.m && gn < it.n) {
-                  if (epi_kind == EPI_SQUARE_ACCUM) o = it.C[(size_t)gm * it.ldc + gn];
-                  else if (gn < it.se.K0) { if (it.se.w_out) o = __ldg(it.se.mu_w + (size_t)gm * it.se.K0 + gn); }
-                  else if (it.se.b_out) o = __ldg(it.se.mu_b + gm);
-                }
-                old[r4][j] = o;
+                const float x = v[r4][j];
+                if (e_kind == EPI_STORE) { const float y = e_alpha * x; o[j] = e_round ? rna_tf32(y) : y; }
+                else if (e_kind == EPI_SQUARE_ACCUM) o[j] = old[r4][j] + x * x;
+                else o[j] = old[r4][j] + e_alpha * x;
               }
-            }
-          }
+              if (dst != nullptr) {
+                float* p = dst + (size_t)gm * ld + gn0;
+                if (vec) *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+                else {
 #pragma unroll
-          for (int r4 = 0; r4 < 8; ++r4) {
-            const int gm = row0 + r4 * 4 + sub;
-            if (gm >= it.m) continue;
+                  for (int j = 0; j < 4; ++j) if (j < nv) p[j] = o[j];
+                }
+              }
+              if (e_kind == 2) {
+                if (e_sout) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int gn = gn0 + j;
-              if (gn >= it.n) break;
-              if (epi_kind == EPI_STORE) {
-                const float o = it.alpha * v[r4][j];
-                it.C[(size_t)gm * it.ldc + gn] = it.round_out ? rna_tf32(o) : o;
-              } else if (epi_kind == EPI_SQUARE_ACCUM) {
-                it.C[(size_t)gm * it.ldc + gn] = old[r4][j] + v[r4][j] * v[r4][j];
-              } else {
-                const float sv = it.alpha * v[r4][j];
-                if (it.se.s_out) it.se.s_out[(size_t)gm * it.n + gn] = sv;
-                if (gn < it.se.K0) {
-                  if (it.se.w_out) it.se.w_out[(size_t)gm * it.se.K0 + gn] = old[r4][j] + sv;
-                } else {
-                  if (it.se.b_out) it.se.b_out[gm] = old[r4][j] + sv;
+                  for (int j = 0; j < 4; ++j) if (gn0 + j < e_n) e_sout[(size_t)gm * e_n + gn0 + j] = e_alpha * v[r4][j];
+                }
+                if (e_bout) {                      // the bias column K0 (at most one per row) may sit in this group
+                  const int jb = e_K0 - gn0;
+                  if (jb >= 0 && jb < 4 && e_K0 < e_n) {
+                    float xb = v[r4][0];
+                    if (jb == 1) xb = v[r4][1]; else if (jb == 2) xb = v[r4][2]; else if (jb == 3) xb = v[r4][3];
+                    e_bout[gm] = __ldg(e_mub + gm) + e_alpha * xb;
+                  }
                 }
               }
             }
@@ -350,6 +387,11 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) bar_arrive(bar_tempty);
+      if (dbg && warp == 2 && lane == 0) {
+        dbg[8 * blockIdx.x + 3] += t_e1 - t_e0;            // epilogue waiting for the MMAs of the tile
+        dbg[8 * blockIdx.x + 4] += clock64() - t_e1;       // accumulator drain
+        dbg[8 * blockIdx.x + 5] += 1;                      // tiles
+      }
       if (it.counters >= 0) {
         // publish: every epilogue thread's stores -> gpu scope, then ONE increment of the row tile's counter
         __threadfence();
@@ -360,6 +402,7 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[8 * blockIdx.x + 6] = clock64() - t_start;
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
@@ -488,7 +531,10 @@ int gemm_chain_launch(const ChainGemm* gemms, int count, void* ws, size_t ws_byt
     for (int a = 0; a < tm_of[i]; ++a)
       for (int b = 0; b < tn_of[i]; ++b) {
         const int rows = std::min(CT, gemms[i].m - a * CT), cols = std::min(CT, gemms[i].n - b * CT);
-        const double c = (double)((rows + 127) / 128) * std::max(cols, 64) * gemms[i].k + 40000.0;
+        // cycles: MMA (4 k-steps x mh instructions of N/256 x 128 clocks per 32-deep stage) + accumulator drain (per warp
+        // mh x N/32 blocks of 32 x 32) + fixed; the two do not overlap (one accumulator)
+        const int mh = (rows + 127) / 128, nc = (cols + 15) / 16 * 16;
+        const double c = (double)((gemms[i].k + CK - 1) / CK) * mh * 2.0 * std::max(nc, 64) + (double)mh * ((nc + 31) / 32) * 1500.0 + 3000.0;
         all.push_back({i, a, b, gemms[i].dep >= 0 ? 1 : 0, c});
       }
   std::stable_sort(all.begin(), all.end(), [](const T& x, const T& y) {
@@ -528,7 +574,7 @@ int gemm_chain_launch(const ChainGemm* gemms, int count, void* ws, size_t ws_byt
     attr = true;
     CRV_CUDA(cudaFuncSetAttribute(gemm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));
   }
-  gemm_chain_kernel<<<G, C_THREADS, C_SMEM, s>>>(d_items, d_tiles, d_begin, d_maps, d_counters);
+  gemm_chain_kernel<<<G, C_THREADS, C_SMEM, s>>>(d_items, d_tiles, d_begin, d_maps, d_counters, debug_timeline_buffer());
   CRV_CUDA(cudaGetLastError());
   return 0;
 }
