@@ -32,9 +32,9 @@ namespace {
 constexpr int CT = 256;                       // tile edge
 constexpr int CK = 32;                        // contraction depth per stage (one 128-byte row of fp32)
 constexpr int C_STAGE = 64 * 1024, C_NSTAGE = 3;
-constexpr int C_EPI = 16 * 1024;
+constexpr int C_EPI = 32 * 1024;              // 8 epilogue warps x (32 rows x 128 B) staging
 constexpr int C_NPROD = 4;                    // TMA-issuing warps: 0, 6, 7, 8
-constexpr int C_THREADS = 9 * 32;             // warp 1: MMA + TMEM owner; warps 2-5: epilogue
+constexpr int C_THREADS = 13 * 32;            // warp 1: MMA + TMEM owner; warps 2-5 and 9-12: epilogue; 0, 6-8: TMA
 constexpr int C_SMEM = C_NSTAGE * C_STAGE + C_EPI + 1024 + 1024;
 constexpr uint32_t C_SPIN = 1u << 26;
 
@@ -127,7 +127,7 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
       bar_init(bars + 8 * (C_NSTAGE + s), 1);
     }
     bar_init(bar_tfull, 1);
-    bar_init(bar_tempty, 4);
+    bar_init(bar_tempty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -139,7 +139,7 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0 || warp >= 6) {
+  if (warp == 0 || (warp >= 6 && warp <= 8)) {
     // ---- TMA producers ----
     const uint32_t leader = elect_one();
     const int me = (int)uni((uint32_t)(warp == 0 ? 0 : warp - 5));       // 0 .. 3
@@ -263,9 +263,16 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
     }
     __syncwarp();
   } else {
-    // ---- epilogue warps 2..5: TMEM lane quadrant = warp & 3 ----
+    // ---- epilogue: EIGHT warps (2..5 and 9..12), two per TMEM lane quadrant (= warp & 3), each pair splitting the
+    // tile's 32-column blocks between them.  The accumulator drain is not overlapped with the next tile's MMAs (one
+    // accumulator fills TMEM), so it is on the critical path of every tile: the per-CTA cycle counters showed it as long
+    // as the MMAs themselves with four warps and load-after-drain read-modify-writes.  Per 32 x 32 block a warp now
+    // (1) issues the global loads of a read-modify-write epilogue FIRST (they do not depend on the accumulator),
+    // (2) moves the block TMEM -> registers -> swizzled shared memory, (3) reads it back row-wise, combines and stores
+    // with 16-byte accesses where rows are 16-byte aligned.
     const int quad = warp & 3;
-    const uint32_t stg = epi + (uint32_t)quad * 4096u;
+    const int eset = warp >= 9 ? 1 : 0;
+    const uint32_t stg = epi + (uint32_t)(eset * 4 + quad) * 4096u;
     const int sub = lane >> 3, ch = lane & 7;               // read-back role: row within a group of 4, 16-byte chunk
     int ntile = 0;
     for (int ti = t_begin; ti < t_end; ++ti, ++ntile) {
@@ -284,100 +291,93 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
       const long long t_e1 = dbg ? clock64() : 0;
       for (int h = 0; h < sh.mh; ++h) {
         const int row0 = sh.m0 + h * 128 + quad * 32;
-        for (int cc = 0; cc < sh.ncols; cc += 32) {
-          uint32_t a[32];
-          const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * 256 + cc);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-              : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
-                "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]),
-                "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]),
-                "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
-              : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          __syncwarp();                                     // the previous block has been read back
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((k ^ (lane & 7)) * 16);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a[4 * k]), "r"(a[4 * k + 1]),
-                         "r"(a[4 * k + 2]), "r"(a[4 * k + 3]) : "memory");
-          }
-          __syncwarp();
-          // Read the block back row-wise (lane -> row r4*4 + sub, 4 consecutive columns), then touch global memory in
-          // three batched phases -- all loads, all arithmetic, all stores -- so that a warp has 32 independent loads in
-          // flight instead of 32 dependent load-store round trips (the first version of this epilogue, `C += v*v` element
-          // by element, took longer than the MMAs of the tile: tensor pipe 17 % in profiles/r2_ncu_chain_before.md).
-          float v[8][4], old[8][4];
-#pragma unroll
-          for (int r4 = 0; r4 < 8; ++r4) {
-            const int r = r4 * 4 + sub;
-            const uint32_t addr = stg + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) * 16);
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[r4][0]), "=f"(v[r4][1]), "=f"(v[r4][2]), "=f"(v[r4][3])
-                         : "r"(addr) : "memory");
-          }
+        for (int cc = eset * 32; cc < sh.ncols; cc += 64) {
           const int gn0 = sh.n0 + cc + ch * 4;
+          // destination / read-modify-write source of this lane's 4-column group
+          float* dst = nullptr; const float* src = nullptr; int ld = 0, nv = 0;
           if (gn0 < e_n) {
-            // destination / read-modify-write source of this lane's 4-column group: (pointer, leading dimension, number of
-            // valid columns); 16-byte vector accesses whenever rows are 16-byte aligned
-            float* dst; const float* src; int ld, nv;
             if (e_kind == 2) {
               if (gn0 < e_K0) { dst = e_wout; src = e_muw; ld = e_K0; nv = min(4, e_K0 - gn0); }
-              else { dst = nullptr; src = nullptr; ld = 0; nv = 0; }          // the bias column: handled below
             } else {
               dst = e_C; src = e_kind == EPI_SQUARE_ACCUM ? e_C : nullptr; ld = e_ldc; nv = min(4, e_n - gn0);
             }
-            const bool vec = nv == 4 && (ld & 3) == 0 && dst != nullptr && (((uintptr_t)dst) & 15) == 0;
-            if (src != nullptr) {
+          }
+          const bool vec = nv == 4 && (ld & 3) == 0 && dst != nullptr && (((uintptr_t)dst) & 15) == 0;
+          // (1) loads of the old values, in flight during (2)
+          float old[8][4];
 #pragma unroll
-              for (int r4 = 0; r4 < 8; ++r4) {
-                const int gm = row0 + r4 * 4 + sub;
-                old[r4][0] = old[r4][1] = old[r4][2] = old[r4][3] = 0.f;
-                if (gm < e_m) {
-                  const float* p = src + (size_t)gm * ld + gn0;
-                  if (vec) {
-                    const float4 t4 = *reinterpret_cast<const float4*>(p);
-                    old[r4][0] = t4.x; old[r4][1] = t4.y; old[r4][2] = t4.z; old[r4][3] = t4.w;
-                  } else {
+          for (int r4 = 0; r4 < 8; ++r4) {
+            old[r4][0] = old[r4][1] = old[r4][2] = old[r4][3] = 0.f;
+            const int gm = row0 + r4 * 4 + sub;
+            if (src != nullptr && gm < e_m) {
+              const float* p = src + (size_t)gm * ld + gn0;
+              if (vec) {
+                const float4 t4 = *reinterpret_cast<const float4*>(p);
+                old[r4][0] = t4.x; old[r4][1] = t4.y; old[r4][2] = t4.z; old[r4][3] = t4.w;
+              } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) if (j < nv) old[r4][j] = p[j];
-                  }
-                }
+                for (int j = 0; j < 4; ++j) if (j < nv) old[r4][j] = p[j];
               }
             }
+          }
+          // (2) TMEM -> registers -> swizzled staging tile
+          {
+            uint32_t a[32];
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * 256 + cc);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+                  "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]),
+                  "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]),
+                  "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            __syncwarp();                                     // the previous block has been read back
 #pragma unroll
-            for (int r4 = 0; r4 < 8; ++r4) {
-              const int gm = row0 + r4 * 4 + sub;
-              if (gm >= e_m) continue;
-              float o[4];
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((k ^ (lane & 7)) * 16);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a[4 * k]), "r"(a[4 * k + 1]),
+                           "r"(a[4 * k + 2]), "r"(a[4 * k + 3]) : "memory");
+            }
+            __syncwarp();
+          }
+          // (3) read back row-wise, combine, store
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float x = v[r4][j];
-                if (e_kind == EPI_STORE) { const float y = e_alpha * x; o[j] = e_round ? rna_tf32(y) : y; }
-                else if (e_kind == EPI_SQUARE_ACCUM) o[j] = old[r4][j] + x * x;
-                else o[j] = old[r4][j] + e_alpha * x;
+          for (int r4 = 0; r4 < 8; ++r4) {
+            const int r = r4 * 4 + sub;
+            float v[4];
+            const uint32_t addr = stg + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) * 16);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
+            const int gm = row0 + r;
+            if (gm >= e_m || gn0 >= e_n) continue;
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (e_kind == EPI_STORE) { const float y = e_alpha * v[j]; o[j] = e_round ? rna_tf32(y) : y; }
+              else if (e_kind == EPI_SQUARE_ACCUM) o[j] = old[r4][j] + v[j] * v[j];
+              else o[j] = old[r4][j] + e_alpha * v[j];
+            }
+            if (dst != nullptr) {
+              float* p = dst + (size_t)gm * ld + gn0;
+              if (vec) *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+              else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j < nv) p[j] = o[j];
               }
-              if (dst != nullptr) {
-                float* p = dst + (size_t)gm * ld + gn0;
-                if (vec) *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
-                else {
+            }
+            if (e_kind == 2) {
+              if (e_sout) {
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) if (j < nv) p[j] = o[j];
-                }
+                for (int j = 0; j < 4; ++j) if (gn0 + j < e_n) e_sout[(size_t)gm * e_n + gn0 + j] = e_alpha * v[j];
               }
-              if (e_kind == 2) {
-                if (e_sout) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) if (gn0 + j < e_n) e_sout[(size_t)gm * e_n + gn0 + j] = e_alpha * v[r4][j];
-                }
-                if (e_bout) {                      // the bias column K0 (at most one per row) may sit in this group
-                  const int jb = e_K0 - gn0;
-                  if (jb >= 0 && jb < 4 && e_K0 < e_n) {
-                    float xb = v[r4][0];
-                    if (jb == 1) xb = v[r4][1]; else if (jb == 2) xb = v[r4][2]; else if (jb == 3) xb = v[r4][3];
-                    e_bout[gm] = __ldg(e_mub + gm) + e_alpha * xb;
-                  }
+              if (e_bout) {                      // the bias column K0 (at most one per row) may sit in this group
+                const int jb = e_K0 - gn0;
+                if (jb >= 0 && jb < 4 && e_K0 < e_n) {
+                  float xb = v[0];
+                  if (jb == 1) xb = v[1]; else if (jb == 2) xb = v[2]; else if (jb == 3) xb = v[3];
+                  e_bout[gm] = __ldg(e_mub + gm) + e_alpha * xb;
                 }
               }
             }
@@ -395,7 +395,7 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
       if (it.counters >= 0) {
         // publish: every epilogue thread's stores -> gpu scope, then ONE increment of the row tile's counter
         __threadfence();
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync 2, 256;" ::: "memory");
         if (warp == 2 && lane == 0) atomicAdd(counters + it.counters + t.tm, 1);
       }
     }
