@@ -108,7 +108,7 @@ __device__ __forceinline__ TileShape tile_shape(const ChainItemDev& it, const Ch
   return s;
 }
 
-__global__ void __launch_bounds__(C_THREADS, 1)
+__global__ void __maxnreg__(152)
 gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __restrict__ tiles, const int* __restrict__ cta_begin,
                   const CUtensorMap* __restrict__ maps, int* __restrict__ counters, long long* __restrict__ dbg) {
   extern __shared__ uint8_t raw[];
@@ -289,100 +289,118 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
       bar_wait(bar_tfull, (uint32_t)ntile & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const long long t_e1 = dbg ? clock64() : 0;
-      for (int h = 0; h < sh.mh; ++h) {
-        const int row0 = sh.m0 + h * 128 + quad * 32;
-        for (int cc = eset * 32; cc < sh.ncols; cc += 64) {
-          const int gn0 = sh.n0 + cc + ch * 4;
-          // destination / read-modify-write source of this lane's 4-column group
-          float* dst = nullptr; const float* src = nullptr; int ld = 0, nv = 0;
-          if (gn0 < e_n) {
-            if (e_kind == 2) {
-              if (gn0 < e_K0) { dst = e_wout; src = e_muw; ld = e_K0; nv = min(4, e_K0 - gn0); }
+      // this warp's 32 x 32 blocks of the tile: (row half h, column block cc), cc = eset * 32, + 64, ...
+      const int per_h = sh.ncols > eset * 32 ? (sh.ncols - eset * 32 + 63) / 64 : 0;
+      const int nblk = sh.mh * per_h;
+      // where this lane's 4-column group of block (h, cc) lives in global memory
+      struct Where { float* dst; const float* src; int ld, nv, row0, gn0; bool vec; };
+      auto where = [&](int idx) {
+        Where w;
+        const int h = idx / per_h, cc = eset * 32 + (idx - h * per_h) * 64;
+        w.row0 = sh.m0 + h * 128 + quad * 32;
+        w.gn0 = sh.n0 + cc + ch * 4;
+        w.dst = nullptr; w.src = nullptr; w.ld = 0; w.nv = 0;
+        if (w.gn0 < e_n) {
+          if (e_kind == 2) {
+            if (w.gn0 < e_K0) { w.dst = e_wout; w.src = e_muw; w.ld = e_K0; w.nv = min(4, e_K0 - w.gn0); }
+          } else {
+            w.dst = e_C; w.src = e_kind == EPI_SQUARE_ACCUM ? e_C : nullptr; w.ld = e_ldc; w.nv = min(4, e_n - w.gn0);
+          }
+        }
+        w.vec = w.nv == 4 && (w.ld & 3) == 0 && w.dst != nullptr && (((uintptr_t)w.dst) & 15) == 0;
+        return w;
+      };
+      // (1) the old values of a read-modify-write epilogue do not depend on the accumulator: the loads of block i + 1 are
+      // issued before block i is drained, so their latency hides behind the TMEM / shared-memory phase of block i
+      auto load_old = [&](const Where& w, float (&old)[8][4]) {
+#pragma unroll
+        for (int r4 = 0; r4 < 8; ++r4) {
+          old[r4][0] = old[r4][1] = old[r4][2] = old[r4][3] = 0.f;
+          const int gm = w.row0 + r4 * 4 + sub;
+          if (w.src != nullptr && gm < e_m) {
+            const float* p = w.src + (size_t)gm * w.ld + w.gn0;
+            if (w.vec) {
+              const float4 t4 = *reinterpret_cast<const float4*>(p);
+              old[r4][0] = t4.x; old[r4][1] = t4.y; old[r4][2] = t4.z; old[r4][3] = t4.w;
             } else {
-              dst = e_C; src = e_kind == EPI_SQUARE_ACCUM ? e_C : nullptr; ld = e_ldc; nv = min(4, e_n - gn0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) if (j < w.nv) old[r4][j] = p[j];
             }
           }
-          const bool vec = nv == 4 && (ld & 3) == 0 && dst != nullptr && (((uintptr_t)dst) & 15) == 0;
-          // (1) loads of the old values, in flight during (2)
-          float old[8][4];
+        }
+      };
+      float old[8][4], nxt[8][4];
+      if (nblk > 0) load_old(where(0), old);
+      for (int idx = 0; idx < nblk; ++idx) {
+        const Where w = where(idx);
+        const int h = idx / per_h, cc = eset * 32 + (idx - h * per_h) * 64;
+        if (idx + 1 < nblk) load_old(where(idx + 1), nxt);
+        // (2) TMEM -> registers -> swizzled staging tile
+        {
+          uint32_t a[32];
+          const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * 256 + cc);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+                "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]),
+                "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]),
+                "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          __syncwarp();                                     // the previous block has been read back
 #pragma unroll
-          for (int r4 = 0; r4 < 8; ++r4) {
-            old[r4][0] = old[r4][1] = old[r4][2] = old[r4][3] = 0.f;
-            const int gm = row0 + r4 * 4 + sub;
-            if (src != nullptr && gm < e_m) {
-              const float* p = src + (size_t)gm * ld + gn0;
-              if (vec) {
-                const float4 t4 = *reinterpret_cast<const float4*>(p);
-                old[r4][0] = t4.x; old[r4][1] = t4.y; old[r4][2] = t4.z; old[r4][3] = t4.w;
-              } else {
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((k ^ (lane & 7)) * 16);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a[4 * k]), "r"(a[4 * k + 1]),
+                         "r"(a[4 * k + 2]), "r"(a[4 * k + 3]) : "memory");
+          }
+          __syncwarp();
+        }
+        // (3) read back row-wise, combine, store
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (j < nv) old[r4][j] = p[j];
-              }
+        for (int r4 = 0; r4 < 8; ++r4) {
+          const int r = r4 * 4 + sub;
+          float v[4];
+          const uint32_t addr = stg + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) * 16);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
+          const int gm = w.row0 + r;
+          if (gm >= e_m || w.gn0 >= e_n) continue;
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (e_kind == EPI_STORE) { const float y = e_alpha * v[j]; o[j] = e_round ? rna_tf32(y) : y; }
+            else if (e_kind == EPI_SQUARE_ACCUM) o[j] = old[r4][j] + v[j] * v[j];
+            else o[j] = old[r4][j] + e_alpha * v[j];
+          }
+          if (w.dst != nullptr) {
+            float* p = w.dst + (size_t)gm * w.ld + w.gn0;
+            if (w.vec) *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+            else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) if (j < w.nv) p[j] = o[j];
             }
           }
-          // (2) TMEM -> registers -> swizzled staging tile
-          {
-            uint32_t a[32];
-            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * 256 + cc);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
-                  "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]),
-                  "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]),
-                  "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            __syncwarp();                                     // the previous block has been read back
+          if (e_kind == 2) {
+            if (e_sout) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((k ^ (lane & 7)) * 16);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a[4 * k]), "r"(a[4 * k + 1]),
-                           "r"(a[4 * k + 2]), "r"(a[4 * k + 3]) : "memory");
+              for (int j = 0; j < 4; ++j) if (w.gn0 + j < e_n) e_sout[(size_t)gm * e_n + w.gn0 + j] = e_alpha * v[j];
             }
-            __syncwarp();
-          }
-          // (3) read back row-wise, combine, store
-#pragma unroll
-          for (int r4 = 0; r4 < 8; ++r4) {
-            const int r = r4 * 4 + sub;
-            float v[4];
-            const uint32_t addr = stg + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) * 16);
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
-            const int gm = row0 + r;
-            if (gm >= e_m || gn0 >= e_n) continue;
-            float o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (e_kind == EPI_STORE) { const float y = e_alpha * v[j]; o[j] = e_round ? rna_tf32(y) : y; }
-              else if (e_kind == EPI_SQUARE_ACCUM) o[j] = old[r4][j] + v[j] * v[j];
-              else o[j] = old[r4][j] + e_alpha * v[j];
-            }
-            if (dst != nullptr) {
-              float* p = dst + (size_t)gm * ld + gn0;
-              if (vec) *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
-              else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) if (j < nv) p[j] = o[j];
-              }
-            }
-            if (e_kind == 2) {
-              if (e_sout) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) if (gn0 + j < e_n) e_sout[(size_t)gm * e_n + gn0 + j] = e_alpha * v[j];
-              }
-              if (e_bout) {                      // the bias column K0 (at most one per row) may sit in this group
-                const int jb = e_K0 - gn0;
-                if (jb >= 0 && jb < 4 && e_K0 < e_n) {
-                  float xb = v[0];
-                  if (jb == 1) xb = v[1]; else if (jb == 2) xb = v[2]; else if (jb == 3) xb = v[3];
-                  e_bout[gm] = __ldg(e_mub + gm) + e_alpha * xb;
-                }
+            if (e_bout) {                      // the bias column K0 (at most one per row) may sit in this group
+              const int jb = e_K0 - w.gn0;
+              if (jb >= 0 && jb < 4 && e_K0 < e_n) {
+                float xb = v[0];
+                if (jb == 1) xb = v[1]; else if (jb == 2) xb = v[2]; else if (jb == 3) xb = v[3];
+                e_bout[gm] = __ldg(e_mub + gm) + e_alpha * xb;
               }
             }
           }
         }
+#pragma unroll
+        for (int r4 = 0; r4 < 8; ++r4)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) old[r4][j] = nxt[r4][j];
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();

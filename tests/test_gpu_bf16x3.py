@@ -130,7 +130,7 @@ def test_bf16x3_resnet_shaped_factors_against_fp64(layer, layout):
     out = torch.zeros_like(want, dtype=torch.float32)
     nat.syrk_conv_accum(xd, (k, k), (s, s), (p, p), False, 1.0 / X.shape[1], out, X3)
     err = rel_fro(out, want)
-    assert err <= 1e-5, (name, err)
+    assert err <= 5e-6, (name, err)        # measured 0.7e-6 .. 1.3e-6 (post-ReLU data); the tier's statement is 1e-5
     print(f"[bf16x3 {name} {layout}] rel. Frobenius error {err:.3e}")
     OH = (H + 2 * p - k) // s + 1
     g = torch.randn(N, min(C, 1024), OH, OH, device=DEV) * 1e-3

@@ -537,10 +537,11 @@ def test_nhwc_resnet_shaped_factors_against_fp64(layer, prec):
     out = torch.zeros_like(want, dtype=torch.float32)
     nat.syrk_conv_accum(x, (k, k), (s, s), (p, p), False, 1.0 / X.shape[1], out, prec)
     err = rel_fro(out, want)
-    # both tensor-core tiers are stated 1e-3 tiers (FACTOR_TOL); measured on B200: round-to-nearest TF32 operands
-    # (tier tf32) land at 2e-6 .. 1.2e-5 on these post-ReLU distributions, raw fp32 words (tier tf32_tma, the
-    # tensor core truncates them) at a few 1e-4
-    assert err <= FACTOR_TOL[prec], (name, err)
+    # all of these are stated 1e-3 tiers (FACTOR_TOL); measured on B200 on these post-ReLU distributions (N = 2-4):
+    # round-to-nearest TF32 operands (tier tf32) 1.2e-5 .. 7.6e-5, bf16 copies 1e-4 .. 7e-4, raw fp32 words (tier
+    # tf32_tma, the tensor core truncates them) a systematic 7e-4.  The tf32 tier is held to 2e-4 here so that a
+    # regression to truncation (7e-4) cannot hide behind the stated tier.
+    assert err <= (2e-4 if prec == nat.PREC_TF32 else FACTOR_TOL[prec]), (name, err)
     print(f"[nhwc {name} tier {prec}] rel. Frobenius error {err:.3e}")
     assert torch.equal(out, out.t())
     OH = (H + 2 * p - k) // s + 1
