@@ -33,8 +33,9 @@ constexpr int CT = 256;                       // tile edge
 constexpr int CK = 32;                        // contraction depth per stage (one 128-byte row of fp32)
 constexpr int C_STAGE = 64 * 1024, C_NSTAGE = 3;
 constexpr int C_EPI = 32 * 1024;              // 8 epilogue warps x (32 rows x 128 B) staging
-constexpr int C_NPROD = 4;                    // TMA-issuing warps: 0, 6, 7, 8
-constexpr int C_THREADS = 13 * 32;            // warp 1: MMA + TMEM owner; warps 2-5 and 9-12: epilogue; 0, 6-8: TMA
+constexpr int C_NPROD = 3;                    // TMA-issuing warps: 0, 6, 7
+constexpr int C_THREADS = 12 * 32;            // warp 1: MMA + TMEM owner; warps 2-5 and 8-11: epilogue; 0, 6, 7: TMA
+                                              // (registers are allocated per 4 warps: 12 warps x 168 fit, 13 would cap at 128)
 constexpr int C_SMEM = C_NSTAGE * C_STAGE + C_EPI + 1024 + 1024;
 constexpr uint32_t C_SPIN = 1u << 26;
 
@@ -108,7 +109,7 @@ __device__ __forceinline__ TileShape tile_shape(const ChainItemDev& it, const Ch
   return s;
 }
 
-__global__ void __maxnreg__(152)
+__global__ void __launch_bounds__(C_THREADS, 1)
 gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __restrict__ tiles, const int* __restrict__ cta_begin,
                   const CUtensorMap* __restrict__ maps, int* __restrict__ counters, long long* __restrict__ dbg) {
   extern __shared__ uint8_t raw[];
@@ -139,10 +140,10 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0 || (warp >= 6 && warp <= 8)) {
+  if (warp == 0 || warp == 6 || warp == 7) {
     // ---- TMA producers ----
     const uint32_t leader = elect_one();
-    const int me = (int)uni((uint32_t)(warp == 0 ? 0 : warp - 5));       // 0 .. 3
+    const int me = (int)uni((uint32_t)(warp == 0 ? 0 : warp - 5));       // 0 .. 2
     uint32_t git = 0;                                                     // stage iterations since kernel start
     for (int ti = t_begin; ti < t_end; ++ti) {
       const ChainTile t = tiles[ti];
@@ -263,7 +264,7 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
     }
     __syncwarp();
   } else {
-    // ---- epilogue: EIGHT warps (2..5 and 9..12), two per TMEM lane quadrant (= warp & 3), each pair splitting the
+    // ---- epilogue: EIGHT warps (2..5 and 8..11), two per TMEM lane quadrant (= warp & 3), each pair splitting the
     // tile's 32-column blocks between them.  The accumulator drain is not overlapped with the next tile's MMAs (one
     // accumulator fills TMEM), so it is on the critical path of every tile: the per-CTA cycle counters showed it as long
     // as the MMAs themselves with four warps and load-after-drain read-modify-writes.  Per 32 x 32 block a warp now
@@ -271,7 +272,7 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
     // (2) moves the block TMEM -> registers -> swizzled shared memory, (3) reads it back row-wise, combines and stores
     // with 16-byte accesses where rows are 16-byte aligned.
     const int quad = warp & 3;
-    const int eset = warp >= 9 ? 1 : 0;
+    const int eset = warp >= 8 ? 1 : 0;
     const uint32_t stg = epi + (uint32_t)(eset * 4 + quad) * 4096u;
     const int sub = lane >> 3, ch = lane & 7;               // read-back role: row within a group of 4, 16-byte chunk
     int ntile = 0;
