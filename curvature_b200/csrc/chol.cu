@@ -55,11 +55,13 @@ __global__ void __launch_bounds__(256) chol_prologue_kernel(const MatDesc* __res
 // it: the redundant work is nothing, the launch and the dependency it removes are a third of the critical path.  The
 // factored diagonal block itself is never written back: nothing reads it again (the triangular inversion starts from
 // Dinv, the updates read only rows below the block).
+constexpr int PANEL_RB = 4;      // 32-row blocks solved per CTA of the panel kernel (amortises the redundant factorisation)
 __global__ void __launch_bounds__(128) chol_panel_kernel(const MatDesc* __restrict__ descs, int j, int* info) {
   const MatDesc d = descs[blockIdx.z];
   if (j >= d.nb) return;
-  const int ib = j + blockIdx.x;
-  if (ib >= d.nb) return;
+  const int ib0 = j + 1 + PANEL_RB * blockIdx.x;      // this CTA's row blocks: ib0 .. ib0 + PANEL_RB - 1 (CTA 0 also owns the diagonal)
+  if (ib0 >= d.nb && blockIdx.x > 0) return;
+  const int ib = blockIdx.x == 0 ? j : ib0;            // (`ib == j` marks the CTA that publishes Dinv and the failure flag)
   __shared__ double S[NB][NB + 1];
   __shared__ double Iv[NB][NB + 1];
   __shared__ float Ab[NB][NB + 1];
@@ -72,10 +74,6 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(const MatDesc* __restri
     if (r < bs && c < bs && c <= r) v = (double)d.W[(size_t)(o + r) * d.D + o + c];
     if (r >= bs && r == c) v = 1.0;   // pad to a full 32x32 block with the identity
     S[r][c] = v;
-    if (ib > j) {
-      const int ro = ib * NB;
-      Ab[r][c] = (ro + r < d.D && o + c < d.D) ? d.W[(size_t)(ro + r) * d.D + o + c] : 0.f;
-    }
   }
   __syncthreads();
   if (warp == 0) {
@@ -118,18 +116,24 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(const MatDesc* __restri
     if (ib == j && lane == 0 && bad && info[blockIdx.z] == 0) info[blockIdx.z] = bad;
   }
   __syncthreads();
-  if (ib == j) {
+  if (ib == j)
     for (int e = t; e < NB * NB; e += 128) d.Dinv[(size_t)j * NB * NB + e] = (float)Iv[e / NB][e % NB];
-    return;
-  }
-  // W[ib][j] <- W[ib][j] * inv(C_jj)^T
-  const int ro = ib * NB;
-  for (int e = t; e < NB * NB; e += 128) {
-    const int r = e / NB, c = e % NB;
-    float acc = 0.f;
+  // W[rb][j] <- W[rb][j] * inv(C_jj)^T for this CTA's row blocks
+  for (int rb = ib0; rb < ib0 + PANEL_RB && rb < d.nb; ++rb) {
+    const int ro = rb * NB;
+    __syncthreads();
+    for (int e = t; e < NB * NB; e += 128) {
+      const int r = e / NB, c = e % NB;
+      Ab[r][c] = (ro + r < d.D && o + c < d.D) ? d.W[(size_t)(ro + r) * d.D + o + c] : 0.f;
+    }
+    __syncthreads();
+    for (int e = t; e < NB * NB; e += 128) {
+      const int r = e / NB, c = e % NB;
+      float acc = 0.f;
 #pragma unroll 8
-    for (int k = 0; k < NB; ++k) acc = fmaf(Ab[r][k], (float)Iv[c][k], acc);
-    if (ro + r < d.D && o + c < d.D) d.W[(size_t)(ro + r) * d.D + o + c] = acc;
+      for (int k = 0; k < NB; ++k) acc = fmaf(Ab[r][k], (float)Iv[c][k], acc);
+      if (ro + r < d.D && o + c < d.D) d.W[(size_t)(ro + r) * d.D + o + c] = acc;
+    }
   }
 }
 
@@ -337,7 +341,7 @@ int chol_inv_batched_launch(const float* const* F, const int* dims, int count, c
   for (int J = 0; J * NBO < maxD; ++J) {
     const int oend = (J + 1) * NBO;
     for (int j = J * (NBO / NB); j < (J + 1) * (NBO / NB) && j < nbmax; ++j) {
-      chol_panel_kernel<<<dim3(nbmax - j, 1, count), 128, 0, s>>>(descs, j, info);
+      chol_panel_kernel<<<dim3((nbmax - j - 1 + PANEL_RB - 1) / PANEL_RB > 0 ? (nbmax - j - 1 + PANEL_RB - 1) / PANEL_RB : 1, 1, count), 128, 0, s>>>(descs, j, info);
       const int cb = (j + 1) * NB;                       // columns of the outer panel that still need this inner panel's update
       if (cb < oend && cb < maxD) {
         const int ntr = (maxD - cb + 63) / 64, ntc = (std::min(oend, maxD) - cb + 63) / 64;

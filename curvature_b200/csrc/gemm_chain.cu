@@ -172,6 +172,22 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
         asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy writes of the other CTAs -> this CTA's TMA reads
       }
       if (dbg && me == 0 && lane == 0) dbg[8 * blockIdx.x + 0] += clock64() - t_dep0;
+      // Read-modify-write epilogues (`C += acc^2`, `mean + sample`) read a 256 x 256 region whose rows are `ld` floats
+      // apart: one DRAM page per 1 KB row segment.  Left to the drain those reads stall the epilogue warps while the tensor
+      // pipe idles (drain as long as the MMAs in the per-CTA counters); the last producer warp instead asks for the tile's
+      // rows with L2 bulk prefetches NOW, a whole K loop before the drain needs them.
+      if (me == C_NPROD - 1 && it.epi != EPI_STORE) {
+        const float* src = it.epi == EPI_SQUARE_ACCUM ? it.C : it.se.mu_w;
+        const int ld = it.epi == EPI_SQUARE_ACCUM ? it.ldc : it.se.K0;
+        const int ncol = min(sh.ncols, (it.epi == EPI_SQUARE_ACCUM ? it.n : it.se.K0) - sh.n0);
+        if (src != nullptr && ncol >= 4 && (ld & 3) == 0 && ((uintptr_t)src & 15) == 0) {
+          const uint32_t bytes = (uint32_t)(ncol & ~3) * 4u;
+          for (int r = lane; r < sh.rows; r += 32) {
+            const float* p = src + (size_t)(sh.m0 + r) * ld + sh.n0;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+          }
+        }
+      }
       // boxes of one stage: A then B; K-major 16 KB boxes of 128 rows, MN-major 4 KB boxes of 32 rows
       const int na = it.a_mn ? (sh.rows + 31) / 32 : sh.mh;
       const int nb = it.b_mn ? (sh.ncols + 31) / 32 : (sh.ncols + 127) / 128;
