@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "../../include/curvature_b200.h"
 #include <cuda.h>
+#include <stdlib.h>
 #include <vector>
 #include <algorithm>
 
@@ -111,7 +112,7 @@ __device__ __forceinline__ TileShape tile_shape(const ChainItemDev& it, const Ch
 
 __global__ void __launch_bounds__(C_THREADS, 1)
 gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __restrict__ tiles, const int* __restrict__ cta_begin,
-                  const CUtensorMap* __restrict__ maps, int* __restrict__ counters, long long* __restrict__ dbg) {
+                  const CUtensorMap* __restrict__ maps, int* __restrict__ counters, long long* __restrict__ dbg, int flags) {
   extern __shared__ uint8_t raw[];
   const uint32_t sbase = (s32(raw) + 1023u) & ~1023u;
   const uint32_t epi = sbase + C_NSTAGE * C_STAGE;
@@ -351,9 +352,9 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
       for (int idx = 0; idx < nblk; ++idx) {
         const Where w = where(idx);
         const int h = idx / per_h, cc = eset * 32 + (idx - h * per_h) * 64;
-        if (idx + 1 < nblk) load_old(where(idx + 1), nxt);
+        if (idx + 1 < nblk && !(flags & 4)) load_old(where(idx + 1), nxt);
         // (2) TMEM -> registers -> swizzled staging tile
-        {
+        if (!(flags & 2)) {
           uint32_t a[32];
           const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * 256 + cc);
           asm volatile(
@@ -383,7 +384,7 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
           const uint32_t addr = stg + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) * 16);
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
           const int gm = w.row0 + r;
-          if (gm >= e_m || w.gn0 >= e_n) continue;
+          if (gm >= e_m || w.gn0 >= e_n || (flags & 1)) continue;
           float o[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -609,7 +610,8 @@ int gemm_chain_launch(const ChainGemm* gemms, int count, void* ws, size_t ws_byt
     attr = true;
     CRV_CUDA(cudaFuncSetAttribute(gemm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));
   }
-  gemm_chain_kernel<<<G, C_THREADS, C_SMEM, s>>>(d_items, d_tiles, d_begin, d_maps, d_counters, debug_timeline_buffer());
+  static const int dbg_flags = getenv("CURVATURE_B200_CHAIN_DBG") ? atoi(getenv("CURVATURE_B200_CHAIN_DBG")) : 0;   // (profiling ablations)
+  gemm_chain_kernel<<<G, C_THREADS, C_SMEM, s>>>(d_items, d_tiles, d_begin, d_maps, d_counters, debug_timeline_buffer(), dbg_flags);
   CRV_CUDA(cudaGetLastError());
   return 0;
 }
