@@ -1927,7 +1927,7 @@ void build_sk(const std::vector<const NhPlan*>& pls, int sms, GroupParams& gp, S
       }
       if (p.x3) { mma *= 3.0; bytes *= 2.0; }
       double c = std::max(mma, bytes / beta / 1.85);
-      if (pls.size() > 1 || p.T == 1) {
+      if ((pls.size() > 1 && pl.copy_bytes == 0) || p.T == 1) {
         // read-once operand: HBM time.  An off-diagonal pair of a two-block factor finds about half of its second block
         // in L2 (the diagonal pairs of the same factor stream it at the same time on neighbouring CTAs): measured 248 ns
         // per 16 KB k-group against 196 ns per 8 KB one (per-CTA timeline of the ResNet-50 group launch).
@@ -2230,7 +2230,11 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
   const bool bf16 = plans[idx[0]].bf16 != 0;
   size_t pairs = 0, copy_bytes = 0;
   for (int k = 0; k < cnt; ++k) { pairs += plans[idx[k]].pairs; copy_bytes += plans[idx[k]].copy_bytes; }
-  CRV_CHECK(cnt == 1 || copy_bytes == 0, "internal: operands with a pre-pass copy are launched one by one");
+  for (int k = 0; cnt > 1 && k < cnt; ++k)
+    CRV_CHECK(plans[idx[k]].copy_bytes == 0 || (plans[idx[k]].bf16 && !plans[idx[k]].p.x3 && !plans[idx[k]].pack),
+              "internal: only single-plane bf16 copies share a launch");
+  copy_bytes = 0;
+  for (int k = 0; k < cnt; ++k) copy_bytes += (plans[idx[k]].copy_bytes + 1023) & ~(size_t)1023;
   const size_t partial_bytes = (size_t)(SK_MAXG + pairs) * TILE_ELEMS * sizeof(float);
   // Workspace layout of a batch: [partial tiles 0 | partial tiles 1 | copy slot 0 | ... | copy slot ncopy-1]; partial
   // buffers are `copy_off` bytes (the largest partial-tile region of any launch of the batch), copy slots `max_copy`.
@@ -2271,7 +2275,9 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
     gp.dbg = d ? atoi(d) : 0;
   }
   double flops = 0.0, bytes = 0.0, fbytes = 0.0;
-  int used_slot = -1;                  // copy slot this launch's contraction reads (launches with a copy are groups of one)
+  int used_slot = -1;                  // copy slot this launch's contraction reads (one slot per launch: the copies of
+  size_t slot_off = 0;                 // a launch's operands sit behind one another in it)
+  cudaStream_t cast_stream = nullptr;
   std::vector<const NhPlan*> pls(cnt);
   for (int k = 0; k < cnt; ++k) {
     const ConvGeom& g = gs[idx[k]];
@@ -2283,18 +2289,23 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
     const float* src = g.x;
     int cslot = -1;
     if (pl.copy_bytes) {   // pre-pass: bf16 copy (tiers bf16 / bf16x3) / TF32 round-to-nearest copy (tier tf32), or pack
-      cslot = use_side ? st->ctoggle : 0;
-      if (use_side) st->ctoggle = (st->ctoggle + 1) % ncopy;
-      float* copy = (float*)(base + (size_t)npart * copy_off + (size_t)cslot * slot_bytes);
-      const size_t n4 = (size_t)g.N * g.C * g.H * g.W / 4;
       cudaStream_t cs = s;
       const bool side_cast = use_side && st->forked;
       if (side_cast) cs = st->cast;
-      // the contraction that last read this slot (ncopy pre-passes ago) must have finished
-      if (use_side && st->used_pending[cslot]) {
-        CRV_CUDA(cudaStreamWaitEvent(cs, st->ev_used[cslot], 0));
-        st->used_pending[cslot] = false;
+      if (used_slot < 0) {
+        cslot = use_side ? st->ctoggle : 0;
+        if (use_side) st->ctoggle = (st->ctoggle + 1) % ncopy;
+        // the contraction that last read this slot (ncopy launches with a copy ago) must have finished
+        if (use_side && st->used_pending[cslot]) {
+          CRV_CUDA(cudaStreamWaitEvent(cs, st->ev_used[cslot], 0));
+          st->used_pending[cslot] = false;
+        }
+      } else {
+        cslot = used_slot;
       }
+      float* copy = (float*)(base + (size_t)npart * copy_off + (size_t)cslot * slot_bytes + slot_off);
+      slot_off += (pl.copy_bytes + 1023) & ~(size_t)1023;
+      const size_t n4 = (size_t)g.N * g.C * g.H * g.W / 4;
       if (pl.pack) {
         const ConvGeom& q = pl.gq;
         const long long nt = (long long)q.N * q.H * q.W * 2;
@@ -2327,10 +2338,7 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
       }
       profile_end(cs);
       CRV_CUDA(cudaGetLastError());
-      if (side_cast) {
-        CRV_CUDA(cudaEventRecord(st->ev_cast[cslot], cs));
-        CRV_CUDA(cudaStreamWaitEvent(s, st->ev_cast[cslot], 0));
-      }
+      if (side_cast) cast_stream = cs;
       src = copy;
       used_slot = cslot;
     }
@@ -2341,6 +2349,10 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
     flops += (double)g.R * g.D * (g.D + 1);
     bytes += pl.pack ? 2.0 * pl.gq.N * pl.gq.C * pl.gq.H * pl.gq.W : (pl.bf16 ? 2.0 : 4.0) * g.N * g.C * g.H * g.W;
     fbytes += 8.0 * g.D * g.D;
+  }
+  if (cast_stream) {                            // the contraction waits for the (last) pre-pass of its launch
+    CRV_CUDA(cudaEventRecord(st->ev_cast[used_slot], cast_stream));
+    CRV_CUDA(cudaStreamWaitEvent(s, st->ev_cast[used_slot], 0));
   }
   if (cached_valid && *cached_valid) {          // same batch geometry as last time: the partition is unchanged
     sk = *cached_sk;
@@ -2469,13 +2481,40 @@ int plan_batch_uncached(const ConvGeom* gs, int n, int precision, std::vector<Nh
   plans.resize(n);
   std::vector<int> grp;
   static const int grp_max = getenv("CURVATURE_B200_GROUP") ? std::max(1, std::min(GRP_MAXF, atoi(getenv("CURVATURE_B200_GROUP")))) : GRP_MAXF;
+  // Light re-read factors (the 1x1 convolutions of the 14^2 and 7^2 stages: 53 GF each, 30 us of tensor time against
+  // ~30 us of ramp, accumulator flush and tail) CAN share launches (CURVATURE_B200_BF16_GROUP = operands per launch), but
+  // it does not pay and is off by default: with four 103 MB copies live at once the operands no longer stay in L2
+  // between the pairs that re-read them, and the launch becomes DRAM-bound (4 x 70 us apart -> 270-307 us together,
+  // profiles/r2_bf16_grouping_ab.txt).
+  static const int lgrp_max = getenv("CURVATURE_B200_BF16_GROUP") ? std::max(1, std::min(8, atoi(getenv("CURVATURE_B200_BF16_GROUP")))) : 1;
+  static const double light_flops = getenv("CURVATURE_B200_BF16_GROUP_GF") ? atof(getenv("CURVATURE_B200_BF16_GROUP_GF")) * 1e9 : 120e9;
+  size_t max_single_copy = 0;
   for (int i = 0; i < n; ++i) {
     CRV_CHECK(nhwc_plan(gs[i], precision, sms, plans[i]),
               "channels-last SYRK: unsupported geometry (needs no bias row, C %% 4 == 0, C >= 32, C %% 32 == 0 for k x k; "
               "bf16x3 tier and NCHW-dense sources: C >= 64, C %% 8 == 0, C %% 64 == 0 for k x k)");
-    if (rides_in_group(plans[i])) {
+    max_single_copy = std::max(max_single_copy, plans[i].copy_bytes);
+  }
+  int open_light = -1;                  // index into `launches` of the light-bf16 launch that still has room
+  size_t open_copy = 0, open_pairs = 0;
+  for (int i = 0; i < n; ++i) {
+    const NhPlan& pl = plans[i];
+    const bool light = lgrp_max > 1 && pl.bf16 && !pl.p.x3 && !pl.pack && pl.copy_bytes > 0 &&
+                       (double)gs[i].R * gs[i].D * (gs[i].D + 1) <= light_flops;
+    if (rides_in_group(pl)) {
       grp.push_back(i);
       if ((int)grp.size() == grp_max) { launches.push_back(grp); grp.clear(); }
+    } else if (light) {
+      const size_t cb = (pl.copy_bytes + 1023) & ~(size_t)1023;
+      if (open_light >= 0 && (int)launches[open_light].size() < lgrp_max && open_copy + cb <= max_single_copy &&
+          open_pairs + (size_t)pl.pairs <= 160) {
+        launches[open_light].push_back(i);
+        open_copy += cb; open_pairs += (size_t)pl.pairs;
+      } else {
+        launches.push_back(std::vector<int>(1, i));
+        open_light = (int)launches.size() - 1;
+        open_copy = cb; open_pairs = (size_t)pl.pairs;
+      }
     } else {
       launches.push_back(std::vector<int>(1, i));
     }
@@ -2526,7 +2565,7 @@ void batch_layout(const std::vector<NhPlan>& plans, const std::vector<std::vecto
   max_copy = 0;
   for (const auto& l : launches) {
     size_t pairs = 0, copy = 0;
-    for (int i : l) { pairs += plans[i].pairs; copy += plans[i].copy_bytes; }
+    for (int i : l) { pairs += plans[i].pairs; copy += (plans[i].copy_bytes + 1023) & ~(size_t)1023; }
     max_partial = std::max(max_partial, (size_t)(SK_MAXG + pairs) * TILE_ELEMS * sizeof(float));
     max_copy = std::max(max_copy, copy);
   }
