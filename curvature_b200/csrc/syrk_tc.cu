@@ -2068,7 +2068,15 @@ struct SideState {
   cudaStream_t hp = nullptr;         // contraction kernels between fork and join: highest priority, so that the block
                                      // scheduler places a SYRK CTA on every SM first and fills the rest of the SM with
                                      // reduction / pre-pass CTAs (queued earlier, they would otherwise crowd it out)
-  cudaEvent_t ev_hp = nullptr;
+  cudaStream_t hp2 = nullptr;        // second contraction stream: consecutive contraction launches ALTERNATE between hp
+                                     // and hp2, so launch k + 1 does not wait for the last CTA of launch k -- its CTAs
+                                     // start on every SM a CTA of launch k has left (the factors are independent; the
+                                     // workspace rings are ordered by events, not by stream order).  A stream-K launch
+                                     // ends ragged (CTAs with two accumulator flushes finish 10-15 us after the median)
+                                     // and a dependent launch costs another 5-15 us: ~40 such seams per ResNet-50 update.
+  bool two_hp = true;
+  int hp_toggle = 0;
+  cudaEvent_t ev_hp = nullptr, ev_hp2 = nullptr;
   // Workspace rings.  Partial tiles: npart buffers -- contraction j writes buffer j % npart and first waits for reduction
   // j - npart (3 by default: the reduction of a 4608^2 factor outlasts the next, short contraction).
   // Pre-pass copies: NCOPY slots of their own -- pre-pass c (the c-th launch that has one) writes slot c % ncopy and waits
@@ -2102,11 +2110,15 @@ SideState* side_state() {
       bool ok = cudaStreamCreateWithPriority(&st.side, cudaStreamNonBlocking, least) == cudaSuccess &&
                 cudaStreamCreateWithPriority(&st.cast, cudaStreamNonBlocking, least) == cudaSuccess &&
                 cudaStreamCreateWithPriority(&st.hp, cudaStreamNonBlocking, greatest) == cudaSuccess &&
+                cudaStreamCreateWithPriority(&st.hp2, cudaStreamNonBlocking, greatest) == cudaSuccess &&
                 cudaEventCreateWithFlags(&st.ev_hp, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&st.ev_hp2, cudaEventDisableTiming) == cudaSuccess &&
                 cudaEventCreateWithFlags(&st.ev_fork, cudaEventDisableTiming) == cudaSuccess;
       for (int i = 0; i < SideState::NPART_MAX && ok; ++i)
         ok = cudaEventCreateWithFlags(&st.ev_main[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&st.ev_red[i], cudaEventDisableTiming) == cudaSuccess;
+      const char* h2 = getenv("CURVATURE_B200_HP2");
+      st.two_hp = !(h2 && atoi(h2) == 0);
       const char* np = getenv("CURVATURE_B200_NPART");
       if (np) st.npart = std::max(2, std::min((int)SideState::NPART_MAX, atoi(np)));
       for (int i = 0; i < SideState::NCOPY_MAX && ok; ++i)
@@ -2133,8 +2145,11 @@ int syrk_stream_join(cudaStream_t s) {
   if (st->forked) {          // the contraction kernels of the fork ran on the internal high-priority stream
     CRV_CUDA(cudaEventRecord(st->ev_hp, st->hp));
     CRV_CUDA(cudaStreamWaitEvent(s, st->ev_hp, 0));
+    CRV_CUDA(cudaEventRecord(st->ev_hp2, st->hp2));
+    CRV_CUDA(cudaStreamWaitEvent(s, st->ev_hp2, 0));
   }
   st->forked = false;
+  st->hp_toggle = 0;
   return 0;
 }
 
@@ -2155,6 +2170,7 @@ static void side_abort(cudaStream_t s) {
   st->ctoggle = 0;
   if (st->forked) {
     if (cudaEventRecord(st->ev_hp, st->hp) == cudaSuccess) cudaStreamWaitEvent(s, st->ev_hp, 0);
+    if (cudaEventRecord(st->ev_hp2, st->hp2) == cudaSuccess) cudaStreamWaitEvent(s, st->ev_hp2, 0);
     if (cudaEventRecord(st->ev_fork, st->cast) == cudaSuccess) cudaStreamWaitEvent(s, st->ev_fork, 0);
   }
   st->forked = false;
@@ -2171,7 +2187,9 @@ int syrk_stream_fork(cudaStream_t s) {
   CRV_CUDA(cudaEventRecord(st->ev_fork, s));
   CRV_CUDA(cudaStreamWaitEvent(st->cast, st->ev_fork, 0));
   CRV_CUDA(cudaStreamWaitEvent(st->hp, st->ev_fork, 0));
+  CRV_CUDA(cudaStreamWaitEvent(st->hp2, st->ev_fork, 0));
   st->forked = true;
+  st->hp_toggle = 0;
   return 0;
 }
 
@@ -2250,7 +2268,11 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
   // times the kernel alone, not the kernel plus whatever shares the SMs with it)
   const bool use_side = st && st->enabled && !profile_on();
   // between fork and join the contraction kernels run on the internal high-priority stream (see SideState::hp)
-  cudaStream_t s = (use_side && st->forked) ? st->hp : caller;
+  cudaStream_t s = caller;
+  if (use_side && st->forked) {
+    s = (st->two_hp && st->hp_toggle) ? st->hp2 : st->hp;
+    st->hp_toggle ^= 1;
+  }
   int buf = 0;
   if (use_side) {
     buf = st->toggle;
@@ -2605,10 +2627,13 @@ int syrk_nhwc_batch_launch(const ConvGeom* gs, const float* alphas, float* const
         if (st->red_pending[b]) CRV_CUDA(cudaStreamWaitEvent(w, st->ev_red[b], 0));
         if (st->main_pending[b]) CRV_CUDA(cudaStreamWaitEvent(w, st->ev_main[b], 0));
       }
-      if (st->forked) {        // pre-passes of this batch run on the cast stream: order it behind the same events
+      if (st->forked) {        // pre-passes of this batch run on the cast stream, every other contraction on the second
+                               // contraction stream: order them behind the same events
         for (int b = 0; b < SideState::NPART_MAX; ++b) {
           if (st->red_pending[b]) CRV_CUDA(cudaStreamWaitEvent(st->cast, st->ev_red[b], 0));
           if (st->main_pending[b]) CRV_CUDA(cudaStreamWaitEvent(st->cast, st->ev_main[b], 0));
+          if (st->red_pending[b]) CRV_CUDA(cudaStreamWaitEvent(st->hp2, st->ev_red[b], 0));
+          if (st->main_pending[b]) CRV_CUDA(cudaStreamWaitEvent(st->hp2, st->ev_main[b], 0));
         }
       }
       memcpy(st->sig, sig, sizeof(sig));
