@@ -18,8 +18,9 @@
 //   epilogue  4 warps drain TMEM through a swizzled shared-memory tile and touch global memory in whole 128-byte row
 //             segments; epilogues: store (optionally rounded to TF32 for the next GEMM), accumulate the square, add the
 //             posterior mean and split weight / bias columns;
-//   schedule  static: the host assigns tiles to CTAs (longest first within a phase) and every CTA walks its list in global
-//             order, so a waiting tile only ever waits for tiles that are earlier in the global order -- no deadlock.
+//   schedule  dynamic: the host sorts the tiles (first GEMMs before the GEMMs that consume them, longest first within each)
+//             and the CTAs claim them in that order from an atomic cursor; a waiting tile only ever waits for tiles that were
+//             claimed earlier -- no deadlock.
 #include "common.cuh"
 #include "../../include/curvature_b200.h"
 #include <cuda.h>
@@ -37,6 +38,7 @@ constexpr int C_EPI = 32 * 1024;              // 8 epilogue warps x (32 rows x 1
 constexpr int C_NPROD = 3;                    // TMA-issuing warps: 0, 6, 7
 constexpr int C_THREADS = 12 * 32;            // warp 1: MMA + TMEM owner; warps 2-5 and 8-11: epilogue; 0, 6, 7: TMA
                                               // (registers are allocated per 4 warps: 12 warps x 168 fit, 13 would cap at 128)
+constexpr int C_NSCHED = 4;                    // entries of the CTA's tile queue
 constexpr int C_SMEM = C_NSTAGE * C_STAGE + C_EPI + 1024 + 1024;
 constexpr uint32_t C_SPIN = 1u << 26;
 
@@ -111,16 +113,20 @@ __device__ __forceinline__ TileShape tile_shape(const ChainItemDev& it, const Ch
 }
 
 __global__ void __launch_bounds__(C_THREADS, 1)
-gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __restrict__ tiles, const int* __restrict__ cta_begin,
+gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __restrict__ tiles, int ntiles, int* __restrict__ cursor,
                   const CUtensorMap* __restrict__ maps, int* __restrict__ counters, long long* __restrict__ dbg, int flags) {
   extern __shared__ uint8_t raw[];
   const uint32_t sbase = (s32(raw) + 1023u) & ~1023u;
   const uint32_t epi = sbase + C_NSTAGE * C_STAGE;
   const uint32_t bars = epi + C_EPI;                         // full[3] | empty[3] | tmem_full | tmem_empty
   const uint32_t bar_tfull = bars + 8 * (2 * C_NSTAGE), bar_tempty = bar_tfull + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw + (sbase - s32(raw)) + C_NSTAGE * C_STAGE + C_EPI + 8 * (2 * C_NSTAGE + 2));
+  // the CTA's tile queue: a ring of C_NSCHED entries (tile index, -1 = no more work) filled by the fetcher (one lane of
+  // producer warp 0, atomicAdd on the global cursor) and read by all twelve warps
+  const uint32_t sched_full = bar_tempty + 8, sched_empty = sched_full + 8 * C_NSCHED;
+  const uint32_t sched_idx = sched_empty + 8 * C_NSCHED;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw + (sbase - s32(raw)) + C_NSTAGE * C_STAGE + C_EPI + 8 * (2 * C_NSTAGE + 2) +
+                                                    8 * (2 * C_NSCHED) + 4 * C_NSCHED);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t_begin = cta_begin[blockIdx.x], t_end = cta_begin[blockIdx.x + 1];
   const long long t_start = dbg ? clock64() : 0;
 
   if (threadIdx.x == 0) {
@@ -130,6 +136,10 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
     }
     bar_init(bar_tfull, 1);
     bar_init(bar_tempty, 8);
+    for (int i = 0; i < C_NSCHED; ++i) {
+      bar_init(sched_full + 8 * i, 1);
+      bar_init(sched_empty + 8 * i, C_THREADS / 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -140,13 +150,38 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
+  // Dynamic schedule: the tiles of the call are ONE list in a dependency-respecting order (first GEMMs, then the GEMMs that
+  // consume them; the most expensive first within each) and every CTA takes the next unclaimed one.  Whatever a tile
+  // really costs -- cold operands from HBM, a dependency that is late, a plain-store epilogue -- the CTAs finish within
+  // one tile of each other (the static longest-first deal left them 416 k .. 522 k cycles apart), and a tile only ever
+  // waits for tiles that were claimed before it: no deadlock.
+  auto next_tile = [&](int it, bool fetcher) -> int {
+    const uint32_t slot = (uint32_t)it % C_NSCHED, ph = ((uint32_t)it / C_NSCHED) & 1u;
+    if (fetcher) {
+      bar_wait(sched_empty + 8 * slot, ph ^ 1u);            // every warp has read the entry this one replaces
+      if (lane == 0) {
+        int idx = atomicAdd(cursor, 1);
+        if (idx >= ntiles) idx = -1;
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(sched_idx + 4 * slot), "r"(idx) : "memory");
+        bar_arrive(sched_full + 8 * slot);
+      }
+    }
+    bar_wait(sched_full + 8 * slot, ph);
+    int idx;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(idx) : "r"(sched_idx + 4 * slot) : "memory");
+    __syncwarp();
+    if (lane == 0) bar_arrive(sched_empty + 8 * slot);
+    return idx;
+  };
 
   if (warp == 0 || warp == 6 || warp == 7) {
     // ---- TMA producers ----
     const uint32_t leader = elect_one();
     const int me = (int)uni((uint32_t)(warp == 0 ? 0 : warp - 5));       // 0 .. 2
     uint32_t git = 0;                                                     // stage iterations since kernel start
-    for (int ti = t_begin; ti < t_end; ++ti) {
+    for (int it_ = 0;; ++it_) {
+      const int ti = next_tile(it_, warp == 0);
+      if (ti < 0) break;
       const ChainTile t = tiles[ti];
       const ChainItemDev& it = items[t.item];
       const TileShape sh = tile_shape(it, t);
@@ -229,7 +264,9 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
     const uint32_t u_tmem = uni(tmem);
     uint32_t git = 0;
     int ntile = 0;
-    for (int ti = t_begin; ti < t_end; ++ti, ++ntile) {
+    for (;; ++ntile) {
+      const int ti = (int)uni((uint32_t)(next_tile(ntile, false) + 1)) - 1;
+      if (ti < 0) break;
       const ChainTile t = tiles[ti];
       const ChainItemDev& it = items[t.item];
       const TileShape sh = tile_shape(it, t);
@@ -294,7 +331,9 @@ gemm_chain_kernel(const ChainItemDev* __restrict__ items, const ChainTile* __res
     const uint32_t stg = epi + (uint32_t)(eset * 4 + quad) * 4096u;
     const int sub = lane >> 3, ch = lane & 7;               // read-back role: row within a group of 4, 16-byte chunk
     int ntile = 0;
-    for (int ti = t_begin; ti < t_end; ++ti, ++ntile) {
+    for (;; ++ntile) {
+      const int ti = next_tile(ntile, false);
+      if (ti < 0) break;
       const ChainTile t = tiles[ti];
       const ChainItemDev& it = items[t.item];
       const TileShape sh = tile_shape(it, t);
@@ -608,7 +647,7 @@ bool same_gemm(const ChainGemm& a, const ChainGemm& b) {
 // loop: same factors, same buffers) is one asynchronous copy and one launch -- no tensor-map encoding, no scheduling.
 struct TableCache {
   std::vector<ChainGemm> key;
-  int sms = 0, grid = 0;
+  int sms = 0, grid = 0, dev = -1, ntiles = 0;
   char* pinned = nullptr;
   size_t bytes = 0, cap = 0, counters_off = 0;
   cudaEvent_t used = nullptr;      // the last copy out of `pinned` has executed
@@ -643,17 +682,20 @@ int gemm_chain_launch(const ChainGemm* gemms, int count, void* ws, size_t ws_byt
     size_t off = 0;
     const ChainItemDev* d_items = (const ChainItemDev*)(base + off); off += al(sizeof(ChainItemDev) * (size_t)count);
     const ChainTile* d_tiles = (const ChainTile*)(base + off);
-    const int* d_begin = (const int*)(base + tc.counters_off - al(sizeof(CUtensorMap) * 3 * (size_t)count) - al(sizeof(int) * (SK_MAX_CTAS + 1)));
+    int* d_cursor = (int*)(base + tc.counters_off - al(sizeof(CUtensorMap) * 3 * (size_t)count) - al(sizeof(int) * (SK_MAX_CTAS + 1)));
     const CUtensorMap* d_maps = (const CUtensorMap*)(base + tc.counters_off - al(sizeof(CUtensorMap) * 3 * (size_t)count));
     int* d_counters = (int*)(base + tc.counters_off);
-    gemm_chain_kernel<<<tc.grid, C_THREADS, C_SMEM, s>>>(d_items, d_tiles, d_begin, d_maps, d_counters, debug_timeline_buffer(), dbg_flags);
+    gemm_chain_kernel<<<tc.grid, C_THREADS, C_SMEM, s>>>(d_items, d_tiles, tc.ntiles, d_cursor, d_maps, d_counters,
+                                                         debug_timeline_buffer(), dbg_flags);
     CRV_CUDA(cudaGetLastError());
     return 0;
   };
   TableCache* slot = nullptr;
+  int dev = 0;
+  CRV_CUDA(cudaGetDevice(&dev));
   if (use_cache) {
     for (auto& tc : g_tables) {
-      if (tc.pinned == nullptr || tc.sms != sms || (int)tc.key.size() != count) continue;
+      if (tc.pinned == nullptr || tc.dev != dev || tc.sms != sms || (int)tc.key.size() != count) continue;
       bool same = true;
       for (int i = 0; i < count && same; ++i) same = same_gemm(tc.key[i], gemms[i]);
       if (!same) continue;
@@ -712,42 +754,34 @@ int gemm_chain_launch(const ChainGemm* gemms, int count, void* ws, size_t ws_byt
       items[i].dep_div = div;
       items[i].dep_rows = gemms[p].m;
     }
-  // global order: producers (GEMMs somebody waits for, and independent ones) first, then consumers; within each phase
-  // the most expensive tiles first.  Tiles are dealt to the CTAs in that order, always to the least loaded CTA; every CTA
-  // keeps its tiles in global order.
+  // global order: producers (GEMMs somebody waits for, and independent ones) first, then consumers; within each phase the
+  // most expensive tiles first.  The CTAs claim tiles from this list at run time (see next_tile in the kernel).
   struct T { int item, tm, tn, phase; double cost; };
   std::vector<T> all;
+  std::vector<int> depth(count, 0);                // length of the dependency chain behind a GEMM (producers come earlier)
+  for (int i = 0; i < count; ++i)
+    if (gemms[i].dep >= 0) {
+      const int np = gemms[i].dep_count > 1 ? gemms[i].dep_count : 1;
+      for (int j = gemms[i].dep; j < gemms[i].dep + np; ++j) depth[i] = std::max(depth[i], depth[j] + 1);
+    }
   for (int i = 0; i < count; ++i)
     for (int a = 0; a < tm_of[i]; ++a)
       for (int b = 0; b < tn_of[i]; ++b) {
         const int rows = std::min(CT, gemms[i].m - a * CT), cols = std::min(CT, gemms[i].n - b * CT);
         // cycles: MMA (4 k-steps x mh instructions of N/256 x 128 clocks per 32-deep stage) + accumulator drain (per warp
-        // mh x N/32 blocks of 32 x 32; about half as long through the TMA unit) + fixed; the two do not overlap (one
-        // accumulator)
+        // mh x N/32 blocks of 32 x 32; about half as long through the TMA unit) + fixed
         const int mh = (rows + 127) / 128, nc = (cols + 15) / 16 * 16;
         const double per_blk = items[i].mapC >= 0 ? 700.0 : 1500.0;
         const double c = (double)((gemms[i].k + CK - 1) / CK) * mh * 2.0 * std::max(nc, 64) + (double)mh * ((nc + 31) / 32) * per_blk + 3000.0;
-        all.push_back({i, a, b, gemms[i].dep >= 0 ? 1 : 0, c});
+        all.push_back({i, a, b, depth[i], c});
       }
   std::stable_sort(all.begin(), all.end(), [](const T& x, const T& y) {
     if (x.phase != y.phase) return x.phase < y.phase;
     return x.cost > y.cost;
   });
-  std::vector<std::vector<int>> lists(G);
-  std::vector<double> load(G, 0.0);
-  for (size_t e = 0; e < all.size(); ++e) {
-    int best = 0;
-    for (int c = 1; c < G; ++c) if (load[c] < load[best]) best = c;
-    lists[best].push_back((int)e);
-    load[best] += all[e].cost;
-  }
   std::vector<ChainTile> tiles;
-  std::vector<int> begin(SK_MAX_CTAS + 1, 0);
-  for (int c = 0; c < G; ++c) {
-    begin[c] = (int)tiles.size();
-    for (int e : lists[c]) tiles.push_back({all[e].item, all[e].tm, all[e].tn, 0});
-  }
-  for (int c = G; c <= SK_MAX_CTAS; ++c) begin[c] = (int)tiles.size();
+  for (const T& t : all) tiles.push_back({t.item, t.tm, t.tn, 0});
+  std::vector<int> begin(SK_MAX_CTAS + 1, 0);      // (first word: the tile cursor, zero at launch)
   // the workspace prefix: items | tiles | CTA ranges | tensor maps | counters (zero)
   const size_t o_items = 0, o_tiles = o_items + al(sizeof(ChainItemDev) * (size_t)count);
   const size_t o_begin = o_tiles + al(sizeof(ChainTile) * tiles.size());
@@ -759,8 +793,13 @@ int gemm_chain_launch(const ChainGemm* gemms, int count, void* ws, size_t ws_byt
   std::vector<char> pageable;
   char* host;
   if (slot) {
-    if (tc.used) CRV_CUDA(cudaEventSynchronize(tc.used));        // an earlier copy may still be reading the old tables
-    else CRV_CUDA(cudaEventCreateWithFlags(&tc.used, cudaEventDisableTiming));
+    if (tc.used) {
+      CRV_CUDA(cudaEventSynchronize(tc.used));                   // an earlier copy may still be reading the old tables
+      if (tc.dev != dev) { cudaEventDestroy(tc.used); tc.used = nullptr; }      // (an event belongs to its device)
+    }
+    tc.key.clear();                                              // (not a valid entry until it is filled again below)
+    if (!tc.used) CRV_CUDA(cudaEventCreateWithFlags(&tc.used, cudaEventDisableTiming));
+    tc.dev = dev;
     if (tc.cap < total) {
       if (tc.pinned) CRV_CUDA(cudaFreeHost(tc.pinned));
       tc.pinned = nullptr; tc.cap = 0;
@@ -777,7 +816,7 @@ int gemm_chain_launch(const ChainGemm* gemms, int count, void* ws, size_t ws_byt
   memcpy(host + o_tiles, tiles.data(), sizeof(ChainTile) * tiles.size());
   memcpy(host + o_begin, begin.data(), sizeof(int) * (SK_MAX_CTAS + 1));
   memcpy(host + o_maps, maps.data(), sizeof(CUtensorMap) * maps.size());
-  tc.sms = sms; tc.grid = G; tc.bytes = total; tc.counters_off = o_counters;
+  tc.sms = sms; tc.grid = std::min(G, (int)tiles.size()); tc.bytes = total; tc.counters_off = o_counters; tc.ntiles = (int)tiles.size();
   if (slot) { tc.key.assign(gemms, gemms + count); tc.stamp = ++g_table_clock; }
   CRV_CUDA(cudaMemcpyAsync(base, host, total, cudaMemcpyHostToDevice, s));   // (pageable: staged before the call returns)
   if (slot) CRV_CUDA(cudaEventRecord(tc.used, s));
