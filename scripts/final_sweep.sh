@@ -1,3 +1,5 @@
+# Everything the round-2 tables in DESIGN.md / profiles/ were filled from, in one gpurun call (one B200):
+#   gpurun --timeout 1500 -- 'bash scripts/final_sweep.sh'   -> gpurun_out/f1/
 mkdir -p gpurun_out/f1
 O=gpurun_out/f1
 timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base function -k regex:gemm_chain_kernel -s 6 -c 3 -o $O/chain python scripts/bench_chain.py > $O/ncu_chain.log 2>&1
@@ -17,6 +19,6 @@ python scripts/bench_chain.py > $O/chain.json 2>/dev/null
 python scripts/bench_k3k5.py > $O/k3k5.json 2>/dev/null
 python scripts/chain_timeline.py > $O/chain_timeline.txt 2>&1
 python scripts/step_trace.py > $O/step_trace.txt 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-context > $O/launches_run.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --kernel-name-base function -k regex:"syrk|cast_bf16|round_tf32|split_bf16|pack_smallc|nchw_to_nhwc" -c 600 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-context > $O/launches_run.log 2>&1
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference.json 2>/dev/null
 tail -5 $O/tests.log; cat $O/smoke.log | tail -2; cat $O/bench_resnet50.json | head -c 600; echo; ls -la $O
