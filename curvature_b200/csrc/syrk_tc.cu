@@ -354,6 +354,52 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ItemShape& t, uin
   }
 }
 
+// The same drain with the global side handed to the TMA unit (experiment, off by default: CURVATURE_B200_DBG=8): a
+// 32 x 32 block goes TMEM -> registers -> the SWIZZLE_128B staging tile and one lane issues a tensor store of the 4 KB
+// tile into the partial-tile buffer (`part`: see GroupMaps; rows of the slot start at `slot_row0`).  In the chain kernel
+// this halved the drain (profiles/r2_chain_ablation.txt); here it does not pay (profiles/r2_syrk_tma_flush_ab.txt:
+// 24.36 k img/s against 24.53 k with the warps' own stores) -- all 148 CTAs flush their 256 KB accumulators at the same
+// moment at the end of a launch, and 38 MB in ~11 us is what L2 takes, whoever issues the stores.
+__device__ __forceinline__ void epilogue_store_tma(const ItemShape& t, uint32_t bar_tmem_full, uint32_t parity, uint32_t tmem,
+                                                   const CUtensorMap* part, int slot_row0, int quad, int lane, uint32_t stg) {
+  mbar_wait(bar_tmem_full, parity);
+  tc_fence_after();
+  for (int h = 0; h < t.mh; ++h) {
+    const int row0 = h * 128 + quad * 32;
+    if (row0 >= t.rowsA) continue;                        // (warp-uniform)
+    const int nc = h == 0 ? t.ncols0 : t.ncols;
+    for (int cc = 0; cc < nc; cc += 32) {
+      uint32_t a[32];
+      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * 256 + cc);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+            "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]),
+            "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]),
+            "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the previous block's store has read the tile
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((k ^ (lane & 7)) * 16);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a[4 * k]), "r"(a[4 * k + 1]),
+                     "r"(a[4 * k + 2]), "r"(a[4 * k + 3]) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                     ::"l"(reinterpret_cast<uint64_t>(part)), "r"(cc), "r"(slot_row0 + row0), "r"(stg) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+  }
+}
+
 // ---- TMA-fed kernel ---------------------------------------------------------------------------------
 // Same tiles, same MMA loop, same epilogue; the operands are fetched by the TMA unit instead of by threads:
 // one cp.async.bulk.tensor.4d per (filter tap, channel segment) box of [channels][bh x bw positions] lands
@@ -920,7 +966,11 @@ struct GroupParams {
   int qbeg[GRP_MAXF + 1];
   NhParams f[GRP_MAXF];
 };
-struct alignas(64) GroupMaps { CUtensorMap m[GRP_MAXF]; };
+struct alignas(64) GroupMaps {
+  CUtensorMap m[GRP_MAXF];
+  CUtensorMap part;          // the launch's partial-tile buffer as a [(slots x 256) rows][256 columns] fp32 tensor, boxes of
+                             // 32 x 32 in SWIZZLE_128B form: the accumulator flush goes out through the TMA unit
+};
 
 // MN-major descriptor for 32-bit operands.  tcgen05 accepts exactly one shared-memory layout for MN-major TF32
 // (measured with scripts/experiments/mn_major_probe.cu; CUTLASS calls it SW128_32B): 128-byte rows (32 fp32 along
@@ -1293,14 +1343,20 @@ syrk_nhwc_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       ItemShape t;
       t.mh = g.mh; t.ncols = g.ncols; t.rowsA = g.pk ? g.poff + g.rowsA : g.rowsA;
       t.ncols0 = (g.diag && g.mh == 2 && !(gp.dbg & 4)) ? 128 : g.ncols;
-      epilogue_store_coalesced(t, bar_tmem_full, (uint32_t)nseg & 1u, tmem, gp.ws + (size_t)(blockIdx.x + q) * TILE_ELEMS,
-                               warp & 3, lane, epi + (uint32_t)(warp & 3) * 4096u);
+      if (gp.dbg & 8)          // (A/B switch, CURVATURE_B200_DBG=8: flush through the TMA unit -- measured no faster here)
+        epilogue_store_tma(t, bar_tmem_full, (uint32_t)nseg & 1u, tmem, &maps.part, (int)(blockIdx.x + q) * TB, warp & 3, lane,
+                           epi + (uint32_t)(warp & 3) * 4096u);
+      else
+        epilogue_store_coalesced(t, bar_tmem_full, (uint32_t)nseg & 1u, tmem, gp.ws + (size_t)(blockIdx.x + q) * TILE_ELEMS,
+                                 warp & 3, lane, epi + (uint32_t)(warp & 3) * 4096u);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tmem_empty);
       ++nseg;
       if (tl && warp == 2 && lane == 0) tl[4] = (long long)gtimer();
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // this warp's tensor stores have landed
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -2371,6 +2427,14 @@ int launch_group(const ConvGeom* gs, const float* alphas, float* const* Fs, cons
     flops += (double)g.R * g.D * (g.D + 1);
     bytes += pl.pack ? 2.0 * pl.gq.N * pl.gq.C * pl.gq.H * pl.gq.W : (pl.bf16 ? 2.0 : 4.0) * g.N * g.C * g.H * g.W;
     fbytes += 8.0 * g.D * g.D;
+  }
+  {
+    const cuuint64_t gd[2] = {(cuuint64_t)TB, (cuuint64_t)(SK_MAXG + pairs) * TB}, gs[1] = {(cuuint64_t)TB * sizeof(float)};
+    const cuuint32_t box[2] = {32, 32}, es[2] = {1, 1};
+    const CUresult rc = tensor_map_encoder()(&maps.part, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wsb, gd, gs, box, es,
+                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CRV_CHECK(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled(partial tiles) failed: %d", (int)rc);
   }
   if (cast_stream) {                            // the contraction waits for the (last) pre-pass of its launch
     CRV_CUDA(cudaEventRecord(st->ev_cast[used_slot], cast_stream));
