@@ -74,6 +74,13 @@ _gemm = _sig("crv_gemm", c_int, _f32p, c_int, c_int, _f32p, c_int, c_int, _f32p,
 
 
 
+class SyrkDenseItem(ctypes.Structure):
+    """crv_syrk_dense_item (include/curvature_b200.h, K1f)."""
+    _fields_ = [("x", c_void_p), ("N", c_int), ("C", c_int), ("H", c_int), ("W", c_int), ("kh", c_int), ("kw", c_int),
+                ("sh", c_int), ("sw", c_int), ("ph", c_int), ("pw", c_int), ("has_bias", c_int), ("alpha", c_float),
+                ("F", c_void_p)]
+
+
 class SyrkItem(ctypes.Structure):
     """crv_syrk_item (include/curvature_b200.h)"""
     _fields_ = [("x", c_void_p), ("N", c_int), ("C", c_int), ("H", c_int), ("W", c_int), ("kh", c_int), ("kw", c_int),
@@ -123,11 +130,13 @@ _debug_partition = _sig("crv_debug_partition", c_int, POINTER(SyrkItem), c_int, 
 _syrk_batch_ws = _sig("crv_syrk_batch_nhwc_workspace", c_size_t, POINTER(SyrkItem), c_int, c_int)
 _syrk_batch = _sig("crv_syrk_batch_nhwc", c_int, POINTER(SyrkItem), c_int, c_void_p, c_size_t, c_int, c_void_p)
 
+_syrk_batch_dense = _sig("crv_syrk_batch_dense", c_int, POINTER(SyrkDenseItem), c_int, c_void_p)
+
 ABI_VERSION = _abi_version()
 EXPORTED_SYMBOLS = (
     "crv_abi_version", "crv_last_error", "crv_device_sm_count", "crv_workspace_bytes", "crv_profile_enable",
     "crv_profile_collect", "crv_debug_timeline", "crv_debug_trace", "crv_debug_trace_count",
-    "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc", "crv_syrk_batch_nhwc", "crv_syrk_batch_nhwc_workspace", "crv_debug_partition", "crv_stream_join", "crv_stream_fork",
+    "crv_syrk_conv_accum", "crv_syrk_rows_accum", "crv_syrk_conv_accum_nhwc", "crv_syrk_rows_accum_nhwc", "crv_syrk_batch_nhwc", "crv_syrk_batch_nhwc_workspace", "crv_syrk_batch_dense", "crv_debug_partition", "crv_stream_join", "crv_stream_fork",
     "crv_diag_accum", "crv_diag_accum_batch", "crv_efb_project_accum", "crv_efb_project_batch",
     "crv_efb_project_batch_workspace", "crv_sample_matrix_normal_batch", "crv_sample_matrix_normal_batch_workspace",
     "crv_sample_matrix_normal_multi", "crv_sample_matrix_normal_multi_workspace",
@@ -318,6 +327,39 @@ def syrk_conv_accum(x, kernel_size, stride, padding, has_bias, alpha, out, preci
     _check(_syrk_conv(_dev(x, "activation"), N, C, H, W, kh, kw, sh, sw, ph, pw, int(bool(has_bias)),
                       float(alpha), _dev(out, "factor"), ws.data_ptr(), ws.numel(), precision, _stream(x)),
            "crv_syrk_conv_accum")
+
+
+def dense_item(x, kernel_size, stride, padding, has_bias, alpha, out):
+    """crv_syrk_dense_item of a DENSE operand (K1f), or None: x is the (N,C,H,W) activation of a convolution
+    (`kernel_size` given) or an (N, M, ...) rows operand (`kernel_size` None: output gradient / Linear input)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+        return None
+    if kernel_size is None:
+        N, M = x.shape[0], x.shape[1]
+        L = 1
+        for d in x.shape[2:]:
+            L *= d
+        dims = (N, M, L, 1, 1, 1, 1, 1, 0, 0)
+    else:
+        if x.dim() != 4:
+            return None
+        dims = (*x.shape, *kernel_size, *stride, *padding)
+    D = dims[1] * dims[4] * dims[5] + int(bool(has_bias))
+    if tuple(out.shape) != (D, D) or not out.is_contiguous():
+        return None
+    return SyrkDenseItem(x.data_ptr(), *[int(d) for d in dims], int(bool(has_bias)), float(alpha), out.data_ptr())
+
+
+def syrk_dense_array(items):
+    return (SyrkDenseItem * len(items))(*items)
+
+
+def syrk_batch_dense(arr, n, device):
+    """One launch for every factor of a small model (K1f, exact fp32 products on the CUDA cores)."""
+    global launch_calls
+    launch_calls += 1
+    with torch.cuda.device(device):
+        _check(_syrk_batch_dense(arr, n, torch.cuda.current_stream(device).cuda_stream), "crv_syrk_batch_dense")
 
 
 def syrk_rows_accum(g, has_bias, alpha, out, precision=PREC_FP32, join=True):

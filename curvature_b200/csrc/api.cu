@@ -291,6 +291,22 @@ int crv_syrk_batch_nhwc(const crv_syrk_item* items, int n, void* ws, size_t ws_b
   return syrk_nhwc_batch_launch(gs.data(), alphas.data(), Fs.data(), n, precision, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+int crv_syrk_batch_dense(const crv_syrk_dense_item* items, int n, crv_stream_t stream) {
+  ApiGuard guard_(items && n > 0 ? items[0].x : nullptr, (cudaStream_t)stream);
+  CRV_CHECK(items != nullptr && n > 0, "empty batch");
+  std::vector<ConvGeom> gs(n);
+  std::vector<float> alphas(n);
+  std::vector<float*> Fs(n);
+  for (int i = 0; i < n; ++i) {
+    const crv_syrk_dense_item& it = items[i];
+    if (int rc = make_geom(gs[i], it.x, it.N, it.C, it.H, it.W, it.kh, it.kw, it.sh, it.sw, it.ph, it.pw, it.has_bias ? 1 : 0))
+      return rc;
+    alphas[i] = it.alpha;
+    Fs[i] = it.F;
+  }
+  return syrk_simt_batch_launch(gs.data(), alphas.data(), Fs.data(), n, (cudaStream_t)stream);
+}
+
 int crv_stream_join(crv_stream_t stream) {
   ApiGuard guard_(nullptr, (cudaStream_t)stream); return syrk_stream_join((cudaStream_t)stream); }
 int crv_stream_fork(crv_stream_t stream) {

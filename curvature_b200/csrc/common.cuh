@@ -105,6 +105,7 @@ void profile_end(cudaStream_t s);
 
 // ---- kernel launchers (one per .cu file) -------------------------------------------------
 int syrk_simt_launch(const ConvGeom& g, float alpha, float* F, cudaStream_t s);
+int syrk_simt_batch_launch(const ConvGeom* gs, const float* alphas, float* const* Fs, int n, cudaStream_t s);
 int syrk_tc_launch(const ConvGeom& g, float alpha, float* F, int precision, void* ws, size_t ws_bytes,
                    cudaStream_t s);
 size_t syrk_tc_workspace(const ConvGeom& g, int precision);

@@ -336,6 +336,11 @@ class Diagonal(Curvature):
                         b_out=None if bias is None else bias.data)
 
 
+# factors with fewer multiply-adds than this (R D^2) ride in the one-launch dense batch (K1f) when the TMA-fed kernel
+# cannot take them; larger ones keep their own launch (tensor cores on the 1e-3 tiers)
+_DENSE_BATCH_FLOPS = 5e8
+
+
 class KFAC(Curvature):
     r"""Kronecker-factored Fisher (reference: curvatures.py:264-392).
 
@@ -433,7 +438,12 @@ class KFAC(Curvature):
         for slot, li, which in plan['slots']:                  # refresh the operand pointers of the batch items
             arr[slot].x = recorded[li][1 + which].data_ptr()
         try:
-            for li, which, args in plan['fallback']:           # operands the channels-last kernel cannot take
+            if plan['dense'] is not None:                      # small factors the channels-last kernel cannot take: one launch
+                darr, dslots = plan['dense']
+                for slot, li, which in dslots:
+                    darr[slot].x = recorded[li][1 + which].data_ptr()
+                nat.syrk_batch_dense(darr, len(dslots), device)
+            for li, which, args in plan['fallback']:           # the others, one by one
                 t = recorded[li][1 + which]
                 if args[0] == 'conv':
                     nat.syrk_conv_accum(t, *args[1:], join=False)
@@ -452,8 +462,9 @@ class KFAC(Curvature):
 
     def _plan_update(self, recorded, sig):
         """Which factor goes where (see `update`): the crv_syrk_item array of the batch call, the (slot, layer, operand)
-        triples whose pointer must be refreshed every step, and the per-factor calls for everything else."""
-        items, slots, fallback = [], [], []
+        triples whose pointer must be refreshed every step, the one-launch dense batch of small factors and the
+        per-factor calls for everything else."""
+        specs = []        # (li, which, tensor, geometry or None, has_bias, alpha, out, zero_mean, R)
         for li, (layer, x, g) in enumerate(recorded):
             if layer not in self.state:
                 self.state[layer] = self._views[layer]
@@ -466,30 +477,61 @@ class KFAC(Curvature):
                 sh, sw = _pair(layer.stride)
                 ph, pw = _pair(layer.padding)
                 r_x = N * ((H + 2 * ph - kh) // sh + 1) * ((W + 2 * pw - kw) // sw + 1)
-                item = nat.nhwc_item(x, (kh, kw), (sh, sw), (ph, pw), has_bias, 1.0 / r_x, first, self.precision)
-                if item is None:
-                    fallback.append((li, 0, ('conv', (kh, kw), (sh, sw), (ph, pw), has_bias, 1.0 / r_x, first, self.precision)))
+                specs.append((li, 0, x, ((kh, kw), (sh, sw), (ph, pw)), has_bias, 1.0 / r_x, first, None, r_x))
                 r_g = n_g * g.shape[2] * g.shape[3]
             else:
                 if x.dim() != 2:
                     raise NotImplementedError("KFAC supports 2-D Linear inputs only (as the reference)")
-                item = nat.nhwc_item(x, None, None, None, has_bias, 1.0 / x.size(0), first, self.precision, zero_mean=False)
-                if item is None:
-                    fallback.append((li, 0, ('rows', has_bias, 1.0 / x.size(0), first, self.precision)))
+                specs.append((li, 0, x, None, has_bias, 1.0 / x.size(0), first, False, x.size(0)))
                 r_g = n_g
-            if item is not None:
-                slots.append((len(items), li, 0))
-                items.append(item)
             # reference: (g * N)(g * N)^T / R  ==  g g^T * N^2 / R
-            alpha_g = float(n_g) * float(n_g) / float(r_g)
-            item = nat.nhwc_item(g, None, None, None, False, alpha_g, second, self.precision)
+            specs.append((li, 1, g, None, False, float(n_g) * float(n_g) / float(r_g), second, None, r_g))
+
+        def dense_of(spec):
+            li, which, t, geom, has_bias, alpha, out, _, R = spec
+            if float(R) * out.shape[0] * out.shape[0] > _DENSE_BATCH_FLOPS:
+                return None
+            return nat.dense_item(t, *(geom if geom is not None else (None, None, None)), has_bias, alpha, out)
+
+        # A SMALL model (LeNet-5, BASELINE configs[0]: ten factors, 0.3 GFLOP per update) is launch-bound on any
+        # per-factor or per-group path: all of its factors go into ONE launch of the exact-fp32 CUDA-core kernel (K1f;
+        # exact products satisfy every tier).
+        all_dense = [dense_of(sp) for sp in specs]
+        if len(specs) >= 2 and all(d is not None for d in all_dense):
+            arr, ws_bytes = nat.syrk_item_array([], self.precision)
+            dslots = [(i, sp[0], sp[1]) for i, sp in enumerate(specs)]
+            return {'sig': sig, 'arr': arr, 'n': 0, 'ws_bytes': ws_bytes, 'slots': [], 'fallback': [],
+                    'dense': (nat.syrk_dense_array(all_dense), dslots)}
+
+        items, slots, fallback, dense, dslots = [], [], [], [], []
+        simt_tier = self.precision in (nat.PREC_FP32, nat.PREC_BF16X3)
+        for sp, d in zip(specs, all_dense):
+            li, which, t, geom, has_bias, alpha, out, zero_mean, R = sp
+            kw = {} if zero_mean is None else {'zero_mean': zero_mean}
+            item = nat.nhwc_item(t, *(geom if geom is not None else (None, None, None)), has_bias, alpha, out, self.precision, **kw)
             if item is not None:
-                slots.append((len(items), li, 1))
+                slots.append((len(items), li, which))
                 items.append(item)
+            elif d is not None and simt_tier:   # small dense operands the channels-last kernel cannot take share one launch
+                                                # too (on the tiers whose per-factor fallback is that CUDA-core kernel anyway;
+                                                # the 1e-3 tiers keep the thread-staged tensor-core kernel, whose fixed-order
+                                                # reduction gives exactly symmetric factors)
+                dslots.append((len(dense), li, which))
+                dense.append(d)
+            elif geom is not None:
+                fallback.append((li, which, ('conv', *geom, has_bias, alpha, out, self.precision)))
             else:
-                fallback.append((li, 1, ('rows', False, alpha_g, second, self.precision)))
+                fallback.append((li, which, ('rows', has_bias, alpha, out, self.precision)))
+        if len(dense) == 1:               # (a single one: its own call, which may use the tensor cores)
+            _, li, which = dslots[0]
+            sp = next(s_ for s_ in specs if s_[0] == li and s_[1] == which)
+            geom = sp[3]
+            fallback.append((li, which, ('conv', *geom, sp[4], sp[5], sp[6], self.precision) if geom is not None
+                             else ('rows', sp[4], sp[5], sp[6], self.precision)))
+            dense, dslots = [], []
         arr, ws_bytes = nat.syrk_item_array(items, self.precision)
-        return {'sig': sig, 'arr': arr, 'n': len(items), 'ws_bytes': ws_bytes, 'slots': slots, 'fallback': fallback}
+        return {'sig': sig, 'arr': arr, 'n': len(items), 'ws_bytes': ws_bytes, 'slots': slots, 'fallback': fallback,
+                'dense': (nat.syrk_dense_array(dense), dslots) if dense else None}
 
     def invert(self,
                add: Union[float, list, tuple] = 0.,

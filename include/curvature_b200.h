@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CRV_ABI_VERSION 4
+#define CRV_ABI_VERSION 5
 
 typedef void* crv_stream_t; /* cudaStream_t */
 
@@ -153,6 +153,21 @@ typedef struct {
 size_t crv_syrk_batch_nhwc_workspace(const crv_syrk_item* items, int n, int precision);
 int crv_syrk_batch_nhwc(const crv_syrk_item* items, int n, void* ws, size_t ws_bytes, int precision,
                         crv_stream_t stream);
+/* K1f -- the factors of a SMALL model in ONE launch: F_i += alpha_i * X_i X_i^T for NCHW-dense operands exactly as K1a
+ * (a rows operand (N, M, L) of K1b is the item C = M, H = L, W = 1, 1x1 kernel), on the CUDA cores with exact fp32
+ * products -- every tier's tolerance holds.  For models whose factors are too small or too oddly shaped for the
+ * TMA-fed kernel (LeNet-5, BASELINE configs[0]: ten factors, C = 1 / 6, bias rows), where the loop over layers of
+ * curvature/curvatures.py:312-350 is launch-bound when every factor is a launch of its own. */
+typedef struct {
+  const float* x;
+  int N, C, H, W;
+  int kh, kw, sh, sw, ph, pw;
+  int has_bias;
+  float alpha;
+  float* F;
+} crv_syrk_dense_item;
+int crv_syrk_batch_dense(const crv_syrk_dense_item* items, int n, crv_stream_t stream);
+
 /* Host-only view of the K1e scheduler for `sms` SMs (no device needed; x / F of the items are not dereferenced but x must
  * be non-null and 16-byte aligned): launch_of_item[i] = the launch item i rides in, *n_launches, and for launch `which`
  * the stream-K boundary table -- CTA c starts at (pair q[c], box b[c]), c <= *G, (q[*G], b[*G]) = (*pairs, 0) -- plus

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/curvature_b200.h but not exported"
     assert sorted(nat.EXPORTED_SYMBOLS) == declared
-    assert nat.ABI_VERSION == 4
+    assert nat.ABI_VERSION == 5
 
 
 def test_workspace_queries_are_host_only():

@@ -664,6 +664,84 @@ def test_batch_call_equals_item_by_item_calls(prec):
         assert torch.equal(out.cpu().double(), 2 * want)
 
 
+def test_dense_batch_one_launch_bit_exact_on_integers():
+    """K1f (crv_syrk_batch_dense): every factor of a small model in ONE CUDA-core launch -- convolutions with bias rows,
+    ragged geometries, rows operands, more items than one launch's table holds -- exact on integer inputs, accumulating."""
+    gen = torch.Generator().manual_seed(13)
+    items, outs, wants, keep = [], [], [], []
+    for (N, C, H, W, k, s, p, bias) in GEOMS + [(100, 1, 28, 28, (5, 5), (1, 1), (2, 2), True), (100, 6, 14, 14, (5, 5), (1, 1), (0, 0), True)]:
+        x = torch.randint(-2, 3, (N, C, H, W), generator=gen).float()
+        want, _ = oracle_A(x, k, s, p, bias)
+        out = torch.zeros(want.shape[0], want.shape[0], device=DEV)
+        xd = x.to(DEV)
+        it = nat.dense_item(xd, k, s, p, bias, 1.0, out)
+        assert it is not None
+        items.append(it); outs.append(out); wants.append(want); keep.append(xd)
+    shapes = [(100, 400), (100, 120), (100, 84), (100, 10), (100, 16, 10, 10), (100, 6, 28, 28), (1, 7)]
+    shapes += [(3 + i % 4, 5 + 7 * (i % 9)) for i in range(70)]                    # > 64 items: two launches
+    for i, shape in enumerate(shapes):
+        g = torch.randint(-3, 4, shape, generator=gen).float()
+        M = shape[1]
+        bias = (i % 2 == 0) and len(shape) == 2
+        X = g.reshape(shape[0], M, -1).permute(1, 0, 2).reshape(M, -1).double()
+        if bias:
+            X = torch.cat([X, torch.ones_like(X[:1])], 0)
+        gd = g.to(DEV)
+        out = torch.zeros(X.shape[0], X.shape[0], device=DEV)
+        it = nat.dense_item(gd, None, None, None, bias, 1.0, out)
+        assert it is not None
+        items.append(it); outs.append(out); wants.append(X @ X.t()); keep.append(gd)
+    before = nat.launch_calls
+    nat.syrk_batch_dense(nat.syrk_dense_array(items), len(items), DEV)
+    assert nat.launch_calls == before + 1
+    for i, (out, want) in enumerate(zip(outs, wants)):
+        assert torch.equal(out.cpu().double(), want), f"item {i}: max diff {(out.cpu().double() - want).abs().max()}"
+    nat.syrk_batch_dense(nat.syrk_dense_array(items), len(items), DEV)       # accumulates
+    for out, want in zip(outs, wants):
+        assert torch.equal(out.cpu().double(), 2 * want)
+    assert nat.dense_item(keep[0].permute(0, 1, 3, 2), (3, 3), (1, 1), (1, 1), True, 1.0, outs[0]) is None      # not dense
+
+
+def test_lenet_update_is_one_launch():
+    """BASELINE configs[0]: the ten factors of a LeNet-5 update (C = 1 / 6 convolutions, bias rows) are one K1f launch
+    (plus nothing else), whatever the tier, and equal the per-factor fp32 path to 1e-6."""
+    import torch.nn as nn
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Conv2d(1, 6, 5, padding=2), nn.ReLU(), nn.MaxPool2d(2), nn.Conv2d(6, 16, 5), nn.ReLU(), nn.MaxPool2d(2),
+                          nn.Flatten(), nn.Linear(400, 120), nn.ReLU(), nn.Linear(120, 84), nn.ReLU(), nn.Linear(84, 10)).to(DEV)
+    x = torch.randn(100, 1, 28, 28, device=DEV)
+    states = {}
+    for prec in ("fp32", "bf16x3", "bf16"):
+        kfac = cb.KFAC(model, precision=prec)
+        out = model(x)
+        lab = torch.distributions.Categorical(logits=out).sample()
+        torch.manual_seed(1)
+        F.cross_entropy(model(x), lab).backward()
+        before = nat.launch_calls
+        kfac.update(100)
+        assert nat.launch_calls - before == 1, (prec, nat.launch_calls - before)
+        states[prec] = [[f.clone() for f in v] for v in kfac.state.values()]
+        for h in kfac.hooks:
+            h.remove()
+        model.zero_grad()
+    import curvature_b200.curvatures as cv
+    old, cv._DENSE_BATCH_FLOPS = cv._DENSE_BATCH_FLOPS, 0.0          # per-factor path
+    try:
+        kfac = cb.KFAC(model, precision="fp32")
+        out = model(x)
+        F.cross_entropy(out, torch.distributions.Categorical(logits=out).sample()).backward()
+        kfac.update(100)
+    finally:
+        cv._DENSE_BATCH_FLOPS = old
+    for h in kfac.hooks:
+        h.remove()
+    # (different sampled labels between the passes: compare the label-independent A factors)
+    for a, b in zip(states["fp32"], [[f for f in v] for v in kfac.state.values()]):
+        assert rel_fro(a[0], b[0]) <= 1e-6
+    for a, b in zip(states["fp32"], states["bf16"]):
+        assert rel_fro(a[0], b[0]) <= 1e-6
+
+
 def test_resnet_stem_factor_against_fp64():
     """The 3 -> 64, 7x7, stride-2 stem at 224^2 through the packed path (bf16 operands, stated 1e-3 tier)."""
     torch.manual_seed(5)
