@@ -206,7 +206,7 @@ def cpu_reference_run(args, steps, warmup, model_name, batch):
             times.append(t1 - t0)
     total = sum(times)
     return {"value": batch * len(times) / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{model_name} KFAC.update on one {batch}-image 224^2 batch x {len(times)} timed calls "
+            "sample": f"{model_name} KFAC.update on one {batch}-image {shape[-1]}^2 batch x {len(times)} timed calls "
                       f"({warmup} warm-up), torch {torch.__version__} CPU, {os.cpu_count()} logical cpus",
             "ms_per_step": 1e3 * total / len(times)}
 
