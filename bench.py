@@ -346,12 +346,13 @@ def invert_mode(args, rank, world, local):
         barrier()
         unsharded = e0.elapsed_time(e1) / max(1, args.steps // 2)
     if rank == 0:
-        plan = cb.invert_plan(dims, world)
+        plan = cb.invert_plan_two_rounds(dims, world) if world > 1 else cb.invert_plan(dims, world)
         line = {"metric": f"{args.model} KFAC invert ms (all factors, README damping)", "value": ms, "unit": "ms",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{args.model} KFAC.invert{(add, mul)}: {len(dims)} matrices, orders {min(dims)}..{max(dims)} "
-                                       "(BASELINE configs[4])", "network": args.model, "parallelism": f"layer-sharded x{world}",
+                                       "(BASELINE configs[4])", "network": args.model,
+                           "parallelism": f"layer-sharded x{world}" + (", exchange in two rounds, the first beside every rank's largest matrix" if world > 1 else ""),
                            "arena_bytes": 4 * plan["total"]},
                 "unsharded_ms_per_invert_on_every_rank": unsharded, "clocks": clocks,
                 "gpu_launches": None}

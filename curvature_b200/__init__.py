@@ -4,9 +4,9 @@ library; it raises if the library has not been built (there is no fallback imple
 from . import _native
 from .curvatures import Curvature, Diagonal, KFAC, EFB, INF, FactorArena
 from .utils import get_eigenvectors, get_eigenvalues, eigendecompose, kron
-from .parallel import allreduce_arena, shard_indices, invert_plan, allgather_segments
+from .parallel import allreduce_arena, shard_indices, invert_plan, invert_plan_two_rounds, allgather_segments
 from .io import save_factors, load_factors
 from .evaluate import eval_nn, eval_bnn
 
 __all__ = ["Curvature", "Diagonal", "KFAC", "EFB", "INF", "FactorArena", "get_eigenvectors", "get_eigenvalues",
-           "eigendecompose", "kron", "allreduce_arena", "shard_indices", "invert_plan", "allgather_segments", "save_factors", "load_factors", "eval_nn", "eval_bnn"]
+           "eigendecompose", "kron", "allreduce_arena", "shard_indices", "invert_plan", "invert_plan_two_rounds", "allgather_segments", "save_factors", "load_factors", "eval_nn", "eval_bnn"]

@@ -608,9 +608,14 @@ def sample_matrix_normal_multi(entries, S, precision):
            "crv_sample_matrix_normal_multi")
 
 
-def chol_inv_batched(factors, adds, muls, outs):
+def chol_inv_workspace_bytes(dims):
+    return workspace_bytes(OP_CHOL_INV, [len(dims)] + [int(d) for d in dims])
+
+
+def chol_inv_batched(factors, adds, muls, outs, ws=None):
     """outs[i] = chol_lower(inv(sym(sqrt(mul_i) F_i + sqrt(add_i) I)))  (K4).  Returns the device
-    int32 info tensor (0 = ok)."""
+    int32 info tensor (0 = ok).  `ws`: a caller-owned uint8 workspace of chol_inv_workspace_bytes(dims) bytes (for a call
+    that runs on another stream beside one that uses the binding's shared workspace); default: the shared one."""
     global launch_calls
     count = len(factors)
     dev = factors[0].device
@@ -624,9 +629,13 @@ def chol_inv_batched(factors, adds, muls, outs):
     ad = (c_float * count)(*[float(a) for a in adds])
     mu = (c_float * count)(*[float(m) for m in muls])
     info = torch.empty(count, dtype=torch.int32, device=dev)
-    ws = workspace(workspace_bytes(OP_CHOL_INV, [count] + dims), dev)
+    nb = workspace_bytes(OP_CHOL_INV, [count] + dims)
+    if ws is None:
+        ws = workspace(nb, dev)
+    elif ws.numel() * ws.element_size() < nb or ws.device != dev:
+        raise ValueError("chol_inv_batched: workspace too small or on another device")
     launch_calls += 4 + 3 * ((max(dims) + 31) // 32)
-    _check(_chol_inv(Fp, dm, count, ad, mu, Lp, info.data_ptr(), ws.data_ptr(), ws.numel(),
+    _check(_chol_inv(Fp, dm, count, ad, mu, Lp, info.data_ptr(), ws.data_ptr(), ws.numel() * ws.element_size(),
                      torch.cuda.current_stream(dev).cuda_stream), "crv_chol_inv_batched")
     return info
 

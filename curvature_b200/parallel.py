@@ -65,6 +65,37 @@ def invert_plan(dims, world_size: int, align: int = 64):
             "total": segment * world_size}
 
 
+def invert_plan_two_rounds(dims, world_size: int, align: int = 64):
+    """`invert_plan` with the exchange step overlapped with compute.  A rank's time is dominated by its largest matrix (the
+    blocked Cholesky is a sequential chain of panels: a 4608^2 factor takes 10 ms on a whole B200 however little else the
+    rank has to do), while the bytes to exchange are dominated by everything else (ResNet-152: 1.6 of 1.9 GB).  So every
+    rank inverts its matrices in two rounds -- all but its largest, then its largest -- and the arena has two rank-major
+    regions: region 1 (segments of `segment` floats) is all-gathered WHILE round 2 computes, region 2 (one matrix per rank,
+    `segment2` floats each, starting at float `base2`) after it.  Same owners as `invert_plan`.
+    Returns dict(owner, offset, late=[bool per factor], segment, base2, segment2, total)."""
+    base = invert_plan(dims, world_size, align)
+    owner = base["owner"]
+    count = len(dims)
+    late = [False] * count
+    for r in range(world_size):
+        mine = [i for i in range(count) if owner[i] == r]
+        if mine:
+            late[max(mine, key=lambda i: (int(dims[i]), -i))] = True
+    fill = [0] * world_size
+    local = [0] * count
+    for i in range(count):
+        if not late[i]:
+            local[i] = fill[owner[i]]
+            n = int(dims[i]) ** 2
+            fill[owner[i]] += (n + align - 1) // align * align
+    segment = max(max(fill), align)
+    segment2 = max([(int(dims[i]) ** 2 + align - 1) // align * align for i in range(count) if late[i]] + [align])
+    base2 = segment * world_size
+    offset = [(base2 + owner[i] * segment2) if late[i] else (owner[i] * segment + local[i]) for i in range(count)]
+    return {"owner": owner, "offset": offset, "late": late, "segment": segment, "base2": base2, "segment2": segment2,
+            "total": base2 + segment2 * world_size}
+
+
 def allgather_segments(flat: torch.Tensor, segment: int, group: Optional["dist.ProcessGroup"] = None):
     """In-place all-gather of a rank-major arena: rank r contributes flat[r * segment : (r + 1) * segment].  One collective."""
     if not dist.is_available() or not dist.is_initialized():

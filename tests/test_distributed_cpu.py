@@ -129,3 +129,15 @@ def test_invert_plan_is_a_balanced_partition():
             assert r * plan["segment"] <= o and o + d * d <= (r + 1) * plan["segment"]
         load = [sum(d ** 3 for d, r in zip(dims, plan["owner"]) if r == q) for q in range(world)]
         assert max(load) <= 1.1 * sum(load) / world, (world, load)                       # LPT by D^3: within 10 % of even
+        # two rounds (exchange overlapped with every rank's largest matrix): same owners, two rank-major regions
+        p2 = cb.invert_plan_two_rounds(dims, world)
+        assert p2["owner"] == plan["owner"] and sum(p2["late"]) == world
+        spans = sorted((o, o + d * d) for o, d in zip(p2["offset"], dims))
+        assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= p2["total"]
+        for i, (o, d) in enumerate(zip(p2["offset"], dims)):
+            r = p2["owner"][i]
+            if p2["late"][i]:
+                assert d == max(dd for dd, rr in zip(dims, p2["owner"]) if rr == r)
+                assert p2["base2"] + r * p2["segment2"] <= o and o + d * d <= p2["base2"] + (r + 1) * p2["segment2"]
+            else:
+                assert r * p2["segment"] <= o and o + d * d <= (r + 1) * p2["segment"] <= p2["base2"]

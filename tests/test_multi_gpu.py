@@ -46,9 +46,15 @@ def _worker(rank, world, port, out_dir):
     # layer-sharded invert + one all-gather == every rank inverting everything
     kfac.invert(0.5, 1.0)                                   # sharded: torch.distributed is initialised, world 2
     sharded = [[t.clone() for t in v] for v in kfac.inv_state.values()]
+    import curvature_b200.curvatures as cv
+    old_floats, cv._TWO_ROUND_FLOATS = cv._TWO_ROUND_FLOATS, 0          # ... and the two-round plan (exchange overlapped
+    kfac.invert(0.5, 1.0)                                               # with every rank's largest matrix) on this model
+    cv._TWO_ROUND_FLOATS = old_floats
+    two_round = [[t.clone() for t in v] for v in kfac.inv_state.values()]
     kfac.invert(0.5, 1.0, shard=False)
-    for a, b in zip(sharded, kfac.inv_state.values()):
+    for a, c, b in zip(sharded, two_round, kfac.inv_state.values()):
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        assert torch.equal(c[0], b[0]) and torch.equal(c[1], b[1])
     kfac.sample_and_replace()                               # posterior samples: per-rank RNG, no communication
     # a model on a device that is not the current one (the C ABI switches to the operand's device itself)
     other = (rank + 1) % world
