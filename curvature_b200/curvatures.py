@@ -548,7 +548,9 @@ class KFAC(Curvature):
         With `torch.distributed` initialised on more than one rank (and `shard` not False) the factors are sharded over
         the ranks of `group` by their D^3 cost, every rank inverts its own and ONE all-gather of the rank-major inverse
         arena gives every rank all of `inv_state` (the state must already be merged, see
-        `allreduce_arena`).  The result is the same as every rank inverting everything."""
+        `allreduce_arena`).  Arenas of 1 GiB and more are exchanged in two rounds, the first beside the inversion of every
+        rank's largest matrix (`parallel.invert_plan_two_rounds`).  The result is the same as every rank inverting
+        everything."""
         assert self.state, "State dict is empty. Did you call 'update' prior to this?"
         if self.inv_state:
             Warning("State has already been inverted. Is this expected?")
