@@ -196,12 +196,6 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-
 // K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in bits
 // [0,14), leading byte offset (unused for one swizzle atom along K) in [16,30), stride byte offset
 // = 1024 B between 8-row groups in [32,46), descriptor version 1 in [46,48), swizzle mode 2 (128 B)
@@ -994,15 +988,6 @@ __device__ __forceinline__ uint64_t umma_desc_mn16(uint32_t saddr, uint32_t lbo_
 // D = fp32, A = B = BF16 (format 1), both MN-major
 __device__ __forceinline__ uint32_t umma_idesc_mn16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
 }
 
 // ---- stream-K work partition -----------------------------------------------------------------------------
@@ -2266,10 +2251,6 @@ int group_max_t() {
   return t;
 }
 bool rides_in_group(const NhPlan& pl) { return !pl.bf16 && pl.p.T <= group_max_t() && pl.copy_bytes == 0; }
-
-size_t launch_need(size_t pairs, size_t copy_bytes) {
-  return (size_t)(SK_MAXG + pairs) * TILE_ELEMS * sizeof(float) + 4096 + copy_bytes;
-}
 
 int make_tensor_map(const ConvGeom& g, const NhPlan& pl, const void* src, CUtensorMap* map) {
   const NhParams& p = pl.p;
