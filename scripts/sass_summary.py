@@ -10,7 +10,7 @@ import sys
 LIB = "curvature_b200/libcurvature_b200.so"
 COLS = ["UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMACCTL", "UBLKPF", "SYNCS", "HMMA", "FFMA", "DFMA", "ATOM/RED"]
 PAT = {c: re.compile(r"\b" + c) for c in COLS if c != "ATOM/RED"}
-PAT["ATOM/RED"] = re.compile(r"\b(ATOMG|ATOM|RED)\b")
+PAT["ATOM/RED"] = re.compile(r"\b(ATOMG|REDG)\b")
 
 
 def demangle(names):
@@ -54,12 +54,14 @@ def main():
 Legend: UTCHMMA = tcgen05.mma (kind::f16 / kind::tf32); UTCBAR = tcgen05.commit; LDTM = tcgen05.ld (TMEM -> registers);
 UTMALDG = cp.async.bulk.tensor load (TMA); UTMASTG = cp.async.bulk.tensor store; UTMAREDG = cp.reduce.async.bulk.tensor
 (reduce-add applied in L2); UTMACCTL = tensor-map prefetch (prefetch.tensormap); UBLKPF = cp.async.bulk.prefetch.L2; SYNCS = mbarrier;
-HMMA = legacy mma.sync; FFMA / DFMA = fp32 / fp64 FMA; ATOM/RED = global atomics.
+HMMA = legacy mma.sync; FFMA / DFMA = fp32 / fp64 FMA; ATOM/RED = global atomics (ATOMG / REDG).
 
 No HMMA anywhere: no kernel falls back to the legacy mma.sync path.  The tensor-core kernels (syrk_nhwc_kernel<bf16|tf32>,
 syrk_tc_kernel, syrk_tc_tma_kernel, gemm_tc_kernel, gemm_chain_kernel) issue UTCHMMA from TMA-filled shared memory (UTMALDG)
 into TMEM and drain it with LDTM; gemm_chain_kernel writes its results back through the TMA unit (UTMASTG / UTMAREDG).
-The one global atomic is the per-row-tile dependency counter of gemm_chain_kernel.""")
+syrk_nhwc_kernel also carries the (optional, off by default) TMA-store flush of its accumulator.  Global atomics
+(ATOMG / REDG): the tile cursor and the per-row-tile dependency counters of gemm_chain_kernel, the fp32 merge of the
+contraction splits in the CUDA-core SYRK kernels (syrk_simt*), and the debug trace slots (64-bit min / max).""")
 
 
 if __name__ == "__main__":
