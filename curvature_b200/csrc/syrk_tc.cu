@@ -2119,10 +2119,11 @@ struct SideState {
   int hp_toggle = 0;
   cudaEvent_t ev_hp = nullptr, ev_hp2 = nullptr;
   // Workspace rings.  Partial tiles: npart buffers -- contraction j writes buffer j % npart and first waits for reduction
-  // j - npart (3 by default: the reduction of a 4608^2 factor outlasts the next, short contraction).
-  // Pre-pass copies: NCOPY slots of their own -- pre-pass c (the c-th launch that has one) writes slot c % ncopy and waits
-  // only for the CONTRACTION that last read that slot (c - ncopy): pre-passes run up to ncopy - 1 launches ahead of the
-  // contractions, whatever the reductions are doing.
+  // j - npart.  Pre-pass copies: NCOPY slots of their own -- pre-pass c (the c-th launch that has one) writes slot
+  // c % ncopy and waits only for the CONTRACTION that last read that slot (c - ncopy): pre-passes run up to ncopy - 1
+  // launches ahead of the contractions, whatever the reductions are doing.  Two and two by default: a pre-pass one
+  // launch ahead is enough to hide it, and its bf16 copy (51-411 MB) is then still largely in the 126 MB L2 when the
+  // contraction reads it -- with deeper rings two more copies and their partial tiles pass through L2 in between.
   static constexpr int NCOPY_MAX = 6;
   static constexpr int NPART_MAX = 4;
   cudaEvent_t ev_main[NPART_MAX] = {}, ev_red[NPART_MAX] = {};
@@ -2131,7 +2132,7 @@ struct SideState {
   bool red_pending[NPART_MAX] = {}, main_pending[NPART_MAX] = {};
   bool used_pending[NCOPY_MAX] = {};
   bool forked = false;
-  int toggle = 0, ctoggle = 0, ncopy = 3, npart = 3;
+  int toggle = 0, ctoggle = 0, ncopy = 2, npart = 2;   // (deeper rings measured 1.5-2.5 % slower: profiles/r2_ring_depth_ab.txt)
   size_t sig[4] = {0, 0, 0, 0};      // workspace layout of the last batch (base, bytes, partial size, copy size)
   bool enabled = true, init = false;
 };
